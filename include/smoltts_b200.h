@@ -141,9 +141,13 @@ int smol_prefill(SmolModel* m, const SmolBatch* b, int32_t batch, const int32_t*
  * increments seq_len. */
 int smol_slow_step(SmolModel* m, const SmolBatch* b, int32_t batch, int32_t advance, void* stream);
 
-/* forward_generate_fast (M:194-220): one depth step at position depth_pos on the stream
- * buffer; writes fp32 codebook logits [B, C]. */
-int smol_fast_step(SmolModel* m, const SmolBatch* b, int32_t batch, int32_t depth_pos, void* stream);
+/* forward_generate_fast (M:194-220): one depth step at position depth_pos; writes fp32 codebook
+ * logits [B, C] into depth_logits[:, depth_pos].  Input of the step: from_xf == 0 -> the slow
+ * hidden state (depth_pos 0) or the embedding of the code stored by smol_fast_embed for
+ * depth_pos-1 (G:136-140);  from_xf != 0 -> whatever the caller put in the "xf" buffer
+ * (the MLX signature passes x explicitly). */
+int smol_fast_step(SmolModel* m, const SmolBatch* b, int32_t batch, int32_t depth_pos, int32_t from_xf,
+                   void* stream);
 
 /* fast_embeddings lookup feeding the next depth step (G:136-140): d_codes [B] int32. */
 int smol_fast_embed(SmolModel* m, int32_t batch, const int32_t* d_codes, int32_t depth_pos, void* stream);
@@ -157,18 +161,37 @@ int smol_sample(SmolModel* m, const SmolBatch* b, int32_t batch, const float* d_
  * sequence: slow step, slow sample, depth loop with sampling, frame assembly, stop rule. */
 int smol_decode_frame(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s, void* stream);
 
-/* The loop of generate_blocking (G:200-205) without host round trips: captures
- * smol_decode_frame in a CUDA graph (re-captured when batch/sampling/state pointers
- * change) and launches it n_frames times. */
+/* The loop of generate_blocking (G:200-205) without host round trips.  mode 0: ONE persistent
+ * launch walks n_frames frames;  mode 1: the frame's per-phase launches are captured in a CUDA
+ * graph (re-captured when batch / sampling / state pointers change) and replayed n_frames times. */
 int smol_decode_frames(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s,
                        int32_t n_frames, void* stream);
 
-/* Introspection for parity tests and benchmarks. name: "x" (stream buffer [B,D] bf16),
- * "xq" [B,H*64] bf16, "attn" [B,D] bf16, "act" [B,F] bf16, "token_logits" [B,V] f32,
- * "depth_logits" [B,Nf,C] f32, "frame_tokens" [B,R] i32. Returns NULL if unknown. */
+/* Teacher forcing / greedy-with-resync: d_force [B, R] int32 ids that replace the sampled ones
+ * after their logits were produced (NULL switches it off).  Borrowed pointer. */
+int smol_set_force(SmolModel* m, const int32_t* d_force);
+
+/* Runs phases [phase_begin, phase_end) of one frame's program (see smol_phase_count and DESIGN.md
+ * "Phase program") - op-level parity tests and per-phase profiling. */
+int smol_run_phases(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s,
+                    int32_t phase_begin, int32_t phase_end, void* stream);
+int32_t smol_phase_count(const SmolModel* m);
+
+/* Options: "mode" 0 = one persistent cooperative kernel per call (default), 1 = one launch per
+ * phase, a frame captured in a CUDA graph;  "n_ctas" = grid size (default: one CTA per SM). */
+int smol_set_option(SmolModel* m, const char* name, int64_t value);
+int64_t smol_get_option(const SmolModel* m, const char* name);
+
+/* Introspection for parity tests and benchmarks. name: "x" (slow stream [B,D] bf16), "h" [B,D] bf16,
+ * "xf" (fast stream [B,Df] bf16), "q" [B,H*64] bf16, "attn" [B,D] bf16, "act" [B,F] bf16, "fkv"
+ * [B,Lf,2,depth,Hkv*64] bf16, "token_logits" [B,V] f32, "depth_logits" [B,Nf,C] f32,
+ * "frame_tokens" [B,R] i32. Returns NULL if unknown. */
 void* smol_debug_buffer(SmolModel* m, const char* name);
-/* Kernel launches issued by the most recent smol_decode_frame (the count baked into a graph). */
+/* Kernel launches issued for one frame in the current mode (mode 0: one launch covers all the
+ * frames of a call). */
 int32_t smol_launches_per_frame(const SmolModel* m);
+/* Total kernel launches issued by this model so far. */
+int64_t smol_launch_count(const SmolModel* m);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,496 @@
+// C ABI of the B200 DualAR decode engine (include/smoltts_b200.h).  Host-side only: shape checks,
+// workspace carving, launch geometry and the two launch modes (persistent cooperative kernel /
+// per-phase launches replayed from a CUDA graph).  No torch types, no allocation after create,
+// no device synchronisation: every compute entry point only enqueues work on the caller's stream.
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smoltts_b200.h"
+#include "dev_model.h"
+
+namespace smol {
+size_t decode_smem_bytes(const DevModel& M);
+cudaError_t decode_configure(size_t smem);
+cudaError_t decode_max_ctas(size_t smem, int* per_sm);
+cudaError_t decode_launch(const DevModel& M, const CallArgs& A, int n_ctas, size_t smem, cudaStream_t stream);
+cudaError_t sample_launch(const float* logits, int n, int batch, const SmolSampling& s, int stream_id,
+                          const int32_t* seq_id, const int32_t* step, int32_t* out, cudaStream_t stream);
+cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int batch, int n_rows, int row,
+                               cudaStream_t stream);
+}  // namespace smol
+
+using smol::CallArgs;
+using smol::DevModel;
+
+struct GraphKey {
+    SmolBatch b;
+    SmolSampling s;
+    int batch;
+    const int32_t* force;
+};
+
+struct SmolModel {
+    SmolConfig cfg;
+    DevModel dm;
+    bool weights_bound = false, ws_bound = false, kv_bound = false, configured = false;
+    int device = 0, n_sms = 0, n_ctas = 0, n_ctas_override = 0;
+    size_t smem = 0;
+    int mode = 0;
+    int64_t launches = 0;
+    // mode 1: cached CUDA graph of one frame
+    cudaGraphExec_t frame_graph = nullptr;
+    GraphKey frame_key;
+    bool frame_key_valid = false;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return SMOL_ERR_CUDA;
+}
+#define CU(call)                                         \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+struct WsLayout {
+    size_t x, h, xf, q, attn, act, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier, total;
+};
+
+static WsLayout ws_layout(const SmolConfig& c, int depth) {
+    WsLayout L;
+    const size_t B = (size_t)c.max_batch;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    const int dmax = imax(c.dim, c.fast_dim);
+    L.x = take(B * c.dim * 2);
+    L.h = take(B * dmax * 2);
+    L.xf = take(B * c.fast_dim * 2);
+    L.q = take(B * imax(c.n_head, c.fast_n_head) * 64 * 2);
+    L.attn = take(B * dmax * 2);
+    L.act = take(B * imax(c.intermediate_size, c.fast_intermediate_size) * 2);
+    L.fkv = take(B * c.n_fast_layer * 2 * depth * c.fast_n_local_heads * 64 * 2);
+    L.token_logits = take(B * c.vocab_size * 4);
+    L.depth_logits = take(B * depth * c.codebook_size * 4);
+    L.frame_tokens = take(B * (1 + depth) * 4);
+    L.partial = take(B * c.n_head * smol::kMaxSplits * smol::kPartialStride * 4);
+    L.split_count = take(B * c.n_local_heads * 4);
+    L.barrier = take(256);
+    L.total = off;
+    return L;
+}
+
+static int depth_of(const SmolConfig& c) { return c.num_codebooks - (c.duplicate_code_0 ? 0 : 1); }
+
+extern "C" {
+
+int smol_abi_version(void) { return SMOL_ABI_VERSION; }
+const char* smol_last_error(void) { return g_err.c_str(); }
+
+int smol_create(const SmolConfig* cfg, SmolModel** out) {
+    if (!cfg || !out) return fail(SMOL_ERR_INVALID, "smol_create: null argument");
+    const SmolConfig& c = *cfg;
+    auto bad = [&](const char* m) { return fail(SMOL_ERR_UNSUPPORTED, std::string("smol_create: ") + m); };
+    if (c.dim <= 0 || c.n_layer <= 0 || c.n_head <= 0 || c.n_local_heads <= 0) return fail(SMOL_ERR_INVALID, "smol_create: bad shape");
+    if (c.n_layer > SMOL_MAX_LAYERS || c.n_fast_layer > SMOL_MAX_FAST_LAYERS) return bad("too many layers");
+    if (c.head_dim != 64 || c.fast_head_dim != 64) return bad("head_dim must be 64");
+    if (c.dim != c.n_head * 64 || c.fast_dim != c.fast_n_head * 64) return bad("dim must equal n_head * 64");
+    if (c.fast_dim != c.dim) return bad("fast_project_in (fast_dim != dim) is not on the built path");
+    if (c.n_head % c.n_local_heads || c.fast_n_head % c.fast_n_local_heads) return bad("n_head must be a multiple of n_local_heads");
+    if (c.n_head / c.n_local_heads > smol::kMaxGroup) return bad("more than 4 query heads per kv head");
+    if (c.dim % 8 || c.intermediate_size % 8 || c.fast_intermediate_size % 8) return bad("dims must be multiples of 8");
+    if (imax(imax(c.dim, c.intermediate_size), c.fast_intermediate_size) > 3072) return bad("reduction dims above 3072");
+    if (c.vocab_size > smol::kThreads * 8 || c.codebook_size > smol::kThreads * 8) return bad("vocab / codebook above 4096 rows");
+    const int depth = depth_of(c);
+    if (depth < 1 || depth > smol::kMaxDepth) return bad("depth out of range");
+    if (c.page_size <= 0 || c.max_batch <= 0 || c.max_seq_len <= 0) return fail(SMOL_ERR_INVALID, "smol_create: bad capacity");
+    if (!c.tie_word_embeddings) { /* output.weight must be bound */ }
+
+    SmolModel* m = new SmolModel();
+    m->cfg = c;
+    DevModel& d = m->dm;
+    std::memset(&d, 0, sizeof(d));
+    d.dim = c.dim; d.n_layer = c.n_layer; d.n_head = c.n_head; d.n_kv = c.n_local_heads; d.inter = c.intermediate_size;
+    d.vocab = c.vocab_size;
+    d.fdim = c.fast_dim; d.n_flayer = c.n_fast_layer; d.fn_head = c.fast_n_head; d.fn_kv = c.fast_n_local_heads;
+    d.finter = c.fast_intermediate_size;
+    d.codebook_size = c.codebook_size; d.num_codebooks = c.num_codebooks; d.depth = depth; d.n_rows = 1 + depth;
+    d.dup0 = c.duplicate_code_0; d.depthwise_wte = c.depthwise_wte; d.depthwise_output = c.depthwise_output;
+    d.max_seq_len = c.max_seq_len; d.max_batch = c.max_batch; d.page_size = c.page_size;
+    d.semantic_start = c.semantic_start_id; d.semantic_end = c.semantic_end_id; d.im_end = c.im_end_id;
+    d.mlx_embed_mask = c.mlx_embed_mask; d.eps = c.norm_eps;
+    *out = m;
+    return SMOL_OK;
+}
+
+void smol_destroy(SmolModel* m) {
+    if (!m) return;
+    if (m->frame_graph) cudaGraphExecDestroy(m->frame_graph);
+    delete m;
+}
+
+int smol_bind_weights(SmolModel* m, const SmolWeights* w) {
+    if (!m || !w) return fail(SMOL_ERR_INVALID, "smol_bind_weights: null argument");
+    const SmolConfig& c = m->cfg;
+    DevModel& d = m->dm;
+    auto need = [&](const void* p, const char* name) {
+        if (!p) { g_err = std::string("smol_bind_weights: missing ") + name; return false; }
+        if (((uintptr_t)p) & 15) { g_err = std::string("smol_bind_weights: not 16-byte aligned: ") + name; return false; }
+        return true;
+    };
+    if (!need(w->embeddings, "embeddings") || !need(w->codebook_embeddings, "codebook_embeddings") || !need(w->norm, "norm") ||
+        !need(w->fast_embeddings, "fast_embeddings") || !need(w->fast_norm, "fast_norm") || !need(w->fast_output, "fast_output") ||
+        !need(w->rope, "rope") || !need(w->fast_rope, "fast_rope"))
+        return SMOL_ERR_INVALID;
+    if (!c.tie_word_embeddings && !need(w->output, "output")) return SMOL_ERR_INVALID;
+    auto u16 = [](const void* p) { return reinterpret_cast<const uint16_t*>(p); };
+    d.embeddings = u16(w->embeddings); d.codebook_embeddings = u16(w->codebook_embeddings); d.norm = u16(w->norm);
+    d.head = c.tie_word_embeddings ? u16(w->embeddings) : u16(w->output);
+    d.fast_embeddings = u16(w->fast_embeddings); d.fast_norm = u16(w->fast_norm); d.fast_output = u16(w->fast_output);
+    d.rope = u16(w->rope); d.fast_rope = u16(w->fast_rope);
+    auto bind_layer = [&](const SmolLayerWeights& s, smol::DevLayer& t, const char* what) {
+        if (!need(s.wqkv, what) || !need(s.wo, what) || !need(s.w1, what) || !need(s.w3, what) || !need(s.w2, what) ||
+            !need(s.attention_norm, what) || !need(s.ffn_norm, what))
+            return false;
+        t.wqkv = u16(s.wqkv); t.wo = u16(s.wo); t.w1 = u16(s.w1); t.w3 = u16(s.w3); t.w2 = u16(s.w2);
+        t.attention_norm = u16(s.attention_norm); t.ffn_norm = u16(s.ffn_norm);
+        return true;
+    };
+    for (int l = 0; l < c.n_layer; ++l)
+        if (!bind_layer(w->layers[l], d.layers[l], "layers[*]")) return SMOL_ERR_INVALID;
+    for (int l = 0; l < c.n_fast_layer; ++l)
+        if (!bind_layer(w->fast_layers[l], d.fast_layers[l], "fast_layers[*]")) return SMOL_ERR_INVALID;
+    m->weights_bound = true;
+    m->frame_key_valid = false;
+    return SMOL_OK;
+}
+
+size_t smol_workspace_bytes(const SmolModel* m) {
+    if (!m) return 0;
+    return ws_layout(m->cfg, m->dm.depth).total;
+}
+
+int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
+    if (!m || !d_workspace) return fail(SMOL_ERR_INVALID, "smol_bind_workspace: null argument");
+    const WsLayout L = ws_layout(m->cfg, m->dm.depth);
+    if (bytes < L.total) return fail(SMOL_ERR_CAPACITY, "smol_bind_workspace: buffer smaller than smol_workspace_bytes()");
+    if (((uintptr_t)d_workspace) & 255) return fail(SMOL_ERR_INVALID, "smol_bind_workspace: buffer must be 256-byte aligned");
+    char* base = reinterpret_cast<char*>(d_workspace);
+    DevModel& d = m->dm;
+    d.x = (uint16_t*)(base + L.x); d.h = (uint16_t*)(base + L.h); d.xf = (uint16_t*)(base + L.xf);
+    d.q = (uint16_t*)(base + L.q); d.attn = (uint16_t*)(base + L.attn); d.act = (uint16_t*)(base + L.act);
+    d.fkv = (uint16_t*)(base + L.fkv);
+    d.token_logits = (float*)(base + L.token_logits); d.depth_logits = (float*)(base + L.depth_logits);
+    d.frame_tokens = (int32_t*)(base + L.frame_tokens);
+    d.partial = (float*)(base + L.partial); d.split_count = (uint32_t*)(base + L.split_count);
+    d.barrier = (uint32_t*)(base + L.barrier);
+    // split counters and the barrier words must start at zero (setup-time, synchronous)
+    CU(cudaMemset(base + L.split_count, 0, L.total - L.split_count));
+    CU(cudaMemset(base + L.frame_tokens, 0, L.partial - L.frame_tokens));
+    m->ws_bound = true;
+    m->frame_key_valid = false;
+    return SMOL_OK;
+}
+
+size_t smol_kv_page_bytes(const SmolModel* m) {
+    if (!m) return 0;
+    return (size_t)m->cfg.n_layer * 2 * m->cfg.n_local_heads * m->cfg.page_size * 64 * 2;
+}
+
+int smol_kv_bind(SmolModel* m, void* d_kv_pool, int32_t n_pages) {
+    if (!m || !d_kv_pool || n_pages <= 0) return fail(SMOL_ERR_INVALID, "smol_kv_bind: bad argument");
+    if (((uintptr_t)d_kv_pool) & 15) return fail(SMOL_ERR_INVALID, "smol_kv_bind: pool must be 16-byte aligned");
+    m->dm.kv_pool = reinterpret_cast<uint16_t*>(d_kv_pool);
+    m->dm.n_pages = n_pages;
+    m->kv_bound = true;
+    m->frame_key_valid = false;
+    return SMOL_OK;
+}
+
+}  // extern "C"
+
+// ---- launch plumbing -------------------------------------------------------------------------------
+static int ensure_configured(SmolModel* m) {
+    if (!m->weights_bound || !m->ws_bound || !m->kv_bound)
+        return fail(SMOL_ERR_UNBOUND, "weights, workspace and KV pool must be bound before compute calls");
+    if (m->configured) return SMOL_OK;
+    CU(cudaGetDevice(&m->device));
+    int coop = 0;
+    CU(cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, m->device));
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
+    if (!coop) return fail(SMOL_ERR_UNSUPPORTED, "device does not support cooperative launch");
+    m->smem = smol::decode_smem_bytes(m->dm);
+    CU(smol::decode_configure(m->smem));
+    int per_sm = 0;
+    CU(smol::decode_max_ctas(m->smem, &per_sm));
+    if (per_sm < 1) return fail(SMOL_ERR_UNSUPPORTED, "decode kernel does not fit on an SM");
+    m->n_ctas = m->n_sms;
+    if (m->n_ctas_override > 0 && m->n_ctas_override < m->n_ctas) m->n_ctas = m->n_ctas_override;
+    m->configured = true;
+    return SMOL_OK;
+}
+
+static int check_batch(const SmolModel* m, const SmolBatch* b, int batch) {
+    if (!b) return fail(SMOL_ERR_INVALID, "null SmolBatch");
+    if (batch <= 0 || batch > m->cfg.max_batch) return fail(SMOL_ERR_CAPACITY, "batch outside [1, max_batch]");
+    if (!b->tokens || !b->seq_len || !b->block_table || b->max_pages <= 0)
+        return fail(SMOL_ERR_INVALID, "SmolBatch needs tokens, seq_len and block_table");
+    return SMOL_OK;
+}
+
+// Enqueue `n_iter` iterations of phases [begin, end).  mode 0: one cooperative launch.
+// mode 1: one launch per phase (optionally the caller wraps a frame in a graph).
+static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream) {
+    if (m->mode == 0) {
+        A.cooperative = 1;
+        CU(smol::decode_launch(m->dm, A, m->n_ctas, m->smem, stream));
+        m->launches += 1;
+        return SMOL_OK;
+    }
+    const int n_iter = A.n_iter, begin = A.phase_begin, end = A.phase_end;
+    const int finalize = A.finalize, advance = A.advance, base = A.iter_base;
+    A.cooperative = 0;
+    if (n_iter == 0 && finalize) {
+        A.n_iter = 0;
+        CU(smol::decode_launch(m->dm, A, 1, m->smem, stream));
+        m->launches += 1;
+        return SMOL_OK;
+    }
+    for (int it = 0; it < n_iter; ++it) {
+        for (int p = begin; p < end; ++p) {
+            const bool last = (it == n_iter - 1) && (p == end - 1);
+            A.n_iter = 1;
+            A.iter_base = base + it;
+            A.phase_begin = p;
+            A.phase_end = p + 1;
+            A.finalize = last ? finalize : 0;
+            A.advance = (p == end - 1) ? advance : 0;
+            CU(smol::decode_launch(m->dm, A, m->n_ctas, m->smem, stream));
+            m->launches += 1;
+        }
+    }
+    return SMOL_OK;
+}
+
+static CallArgs base_args(const SmolBatch* b, int batch, const SmolSampling* s) {
+    CallArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.b = *b;
+    if (s) A.s = *s;
+    else { A.s.temp = 0.f; A.s.fast_temp = 0.f; A.s.top_p = 1.f; A.s.ignore_stop = 1; }
+    A.batch = batch;
+    A.n_iter = 1;
+    return A;
+}
+
+extern "C" {
+
+int smol_prefill(SmolModel* m, const SmolBatch* b, int32_t batch, const int32_t* d_prompt,
+                 const int32_t* d_prompt_len, int32_t s_max, void* stream) {
+    if (!m) return fail(SMOL_ERR_INVALID, "null model");
+    int rc = ensure_configured(m);
+    if (rc) return rc;
+    if ((rc = check_batch(m, b, batch))) return rc;
+    if (!d_prompt || !d_prompt_len || s_max < 1) return fail(SMOL_ERR_INVALID, "smol_prefill: bad prompt");
+    CallArgs A = base_args(b, batch, nullptr);
+    A.mode = 1;
+    A.n_iter = s_max - 1;
+    A.finalize = 1;
+    A.phase_begin = 0;
+    A.phase_end = smol::phases_per_prefill_step(m->dm.n_layer);
+    A.prompt = d_prompt;
+    A.prompt_len = d_prompt_len;
+    A.s_max = s_max;
+    return enqueue(m, A, (cudaStream_t)stream);
+}
+
+int smol_slow_step(SmolModel* m, const SmolBatch* b, int32_t batch, int32_t advance, void* stream) {
+    if (!m) return fail(SMOL_ERR_INVALID, "null model");
+    int rc = ensure_configured(m);
+    if (rc) return rc;
+    if ((rc = check_batch(m, b, batch))) return rc;
+    CallArgs A = base_args(b, batch, nullptr);
+    A.phase_begin = 0;
+    A.phase_end = 5 * m->dm.n_layer + 1;  // slow layers + LM head
+    A.advance = advance ? 1 : 0;
+    return enqueue(m, A, (cudaStream_t)stream);
+}
+
+int smol_fast_step(SmolModel* m, const SmolBatch* b, int32_t batch, int32_t depth_pos, int32_t from_xf, void* stream) {
+    if (!m) return fail(SMOL_ERR_INVALID, "null model");
+    int rc = ensure_configured(m);
+    if (rc) return rc;
+    if ((rc = check_batch(m, b, batch))) return rc;
+    if (depth_pos < 0 || depth_pos >= m->dm.depth) return fail(SMOL_ERR_INVALID, "smol_fast_step: depth_pos out of range");
+    CallArgs A = base_args(b, batch, nullptr);
+    const int per = 4 * m->dm.n_flayer + 2;
+    A.phase_begin = 5 * m->dm.n_layer + 2 + depth_pos * per;
+    A.phase_end = A.phase_begin + 4 * m->dm.n_flayer + 1;  // fast layers + depth head
+    A.fast_from_xf = from_xf ? 1 : 0;
+    return enqueue(m, A, (cudaStream_t)stream);
+}
+
+int smol_fast_embed(SmolModel* m, int32_t batch, const int32_t* d_codes, int32_t depth_pos, void* stream) {
+    if (!m || !d_codes) return fail(SMOL_ERR_INVALID, "smol_fast_embed: null argument");
+    if (!m->ws_bound) return fail(SMOL_ERR_UNBOUND, "workspace not bound");
+    if (batch <= 0 || batch > m->cfg.max_batch) return fail(SMOL_ERR_CAPACITY, "batch outside [1, max_batch]");
+    if (depth_pos < 0 || depth_pos >= m->dm.depth) return fail(SMOL_ERR_INVALID, "smol_fast_embed: depth_pos out of range");
+    CU(smol::store_codes_launch(m->dm.frame_tokens, d_codes, batch, m->dm.n_rows, 1 + depth_pos, (cudaStream_t)stream));
+    m->launches += 1;
+    return SMOL_OK;
+}
+
+int smol_sample(SmolModel* m, const SmolBatch* b, int32_t batch, const float* d_logits, int32_t n,
+                const SmolSampling* s, int32_t stream_id, int32_t* d_out, void* stream) {
+    if (!m || !d_logits || !s || !d_out) return fail(SMOL_ERR_INVALID, "smol_sample: null argument");
+    if (n <= 0 || n > smol::kThreads * 8) return fail(SMOL_ERR_UNSUPPORTED, "smol_sample: n outside [1, 4096]");
+    if (batch <= 0) return fail(SMOL_ERR_INVALID, "smol_sample: bad batch");
+    CU(smol::sample_launch(d_logits, n, batch, *s, stream_id, b ? b->seq_id : nullptr, b ? b->step : nullptr, d_out,
+                           (cudaStream_t)stream));
+    m->launches += 1;
+    return SMOL_OK;
+}
+
+int smol_run_phases(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s, int32_t phase_begin,
+                    int32_t phase_end, void* stream) {
+    if (!m) return fail(SMOL_ERR_INVALID, "null model");
+    int rc = ensure_configured(m);
+    if (rc) return rc;
+    if ((rc = check_batch(m, b, batch))) return rc;
+    const int total = smol::phases_per_frame(m->dm.n_layer, m->dm.n_flayer, m->dm.depth);
+    if (phase_begin < 0 || phase_end > total || phase_begin >= phase_end) return fail(SMOL_ERR_INVALID, "smol_run_phases: bad range");
+    CallArgs A = base_args(b, batch, s);
+    A.phase_begin = phase_begin;
+    A.phase_end = phase_end;
+    return enqueue(m, A, (cudaStream_t)stream);
+}
+
+int32_t smol_phase_count(const SmolModel* m) {
+    return m ? smol::phases_per_frame(m->dm.n_layer, m->dm.n_flayer, m->dm.depth) : 0;
+}
+
+int smol_decode_frames(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s, int32_t n_frames,
+                       void* stream_v) {
+    if (!m || !s) return fail(SMOL_ERR_INVALID, "null argument");
+    int rc = ensure_configured(m);
+    if (rc) return rc;
+    if ((rc = check_batch(m, b, batch))) return rc;
+    if (n_frames < 1) return fail(SMOL_ERR_INVALID, "n_frames must be >= 1");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CallArgs A = base_args(b, batch, s);
+    A.phase_begin = 0;
+    A.phase_end = smol::phases_per_frame(m->dm.n_layer, m->dm.n_flayer, m->dm.depth);
+    if (m->mode == 0) {
+        A.n_iter = n_frames;
+        return enqueue(m, A, stream);
+    }
+    // mode 1: one frame = phase_end launches, captured once per (batch, state pointers, sampling)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(stream, &cs));
+    if (cs != cudaStreamCaptureStatusNone) {  // the caller is capturing: just enqueue
+        A.n_iter = n_frames;
+        return enqueue(m, A, stream);
+    }
+    GraphKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.b = *b; key.s = *s; key.batch = batch; key.force = m->dm.force;
+    if (!m->frame_key_valid || std::memcmp(&key, &m->frame_key, sizeof(key)) != 0) {
+        if (m->frame_graph) { cudaGraphExecDestroy(m->frame_graph); m->frame_graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        A.n_iter = 1;
+        const int64_t before = m->launches;
+        rc = enqueue(m, A, stream);
+        m->launches = before;
+        cudaError_t e = cudaStreamEndCapture(stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+        e = cudaGraphInstantiate(&m->frame_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+        m->frame_key = key;
+        m->frame_key_valid = true;
+    }
+    for (int f = 0; f < n_frames; ++f) CU(cudaGraphLaunch(m->frame_graph, stream));
+    m->launches += (int64_t)n_frames * A.phase_end;
+    return SMOL_OK;
+}
+
+int smol_decode_frame(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s, void* stream) {
+    return smol_decode_frames(m, b, batch, s, 1, stream);
+}
+
+int smol_set_force(SmolModel* m, const int32_t* d_force) {
+    if (!m) return fail(SMOL_ERR_INVALID, "null model");
+    m->dm.force = d_force;
+    return SMOL_OK;
+}
+
+int smol_set_option(SmolModel* m, const char* name, int64_t value) {
+    if (!m || !name) return fail(SMOL_ERR_INVALID, "null argument");
+    if (!std::strcmp(name, "mode")) {
+        if (value != 0 && value != 1) return fail(SMOL_ERR_INVALID, "mode must be 0 or 1");
+        m->mode = (int)value;
+        return SMOL_OK;
+    }
+    if (!std::strcmp(name, "n_ctas")) {
+        if (value < 0) return fail(SMOL_ERR_INVALID, "n_ctas must be >= 0");
+        m->n_ctas_override = (int)value;
+        m->configured = false;
+        m->frame_key_valid = false;
+        return SMOL_OK;
+    }
+    return fail(SMOL_ERR_INVALID, std::string("unknown option ") + name);
+}
+
+int64_t smol_get_option(const SmolModel* m, const char* name) {
+    if (!m || !name) return -1;
+    if (!std::strcmp(name, "mode")) return m->mode;
+    if (!std::strcmp(name, "n_ctas")) return m->n_ctas;
+    if (!std::strcmp(name, "n_sms")) return m->n_sms;
+    if (!std::strcmp(name, "smem_bytes")) return (int64_t)m->smem;
+    return -1;
+}
+
+void* smol_debug_buffer(SmolModel* m, const char* name) {
+    if (!m || !name || !m->ws_bound) return nullptr;
+    const DevModel& d = m->dm;
+    if (!std::strcmp(name, "x")) return d.x;
+    if (!std::strcmp(name, "h")) return d.h;
+    if (!std::strcmp(name, "xf")) return d.xf;
+    if (!std::strcmp(name, "q")) return d.q;
+    if (!std::strcmp(name, "attn")) return d.attn;
+    if (!std::strcmp(name, "act")) return d.act;
+    if (!std::strcmp(name, "fkv")) return d.fkv;
+    if (!std::strcmp(name, "token_logits")) return d.token_logits;
+    if (!std::strcmp(name, "depth_logits")) return d.depth_logits;
+    if (!std::strcmp(name, "frame_tokens")) return d.frame_tokens;
+    return nullptr;
+}
+
+int32_t smol_launches_per_frame(const SmolModel* m) {
+    if (!m) return 0;
+    return m->mode == 0 ? 1 : smol::phases_per_frame(m->dm.n_layer, m->dm.n_flayer, m->dm.depth);
+}
+
+int64_t smol_launch_count(const SmolModel* m) { return m ? m->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// Device-visible description of one bound model: shapes, borrowed weight pointers and the
+// activation workspace carved out of the caller's buffer.  Uploaded once (capi.cu) and read by
+// every CTA of the decode kernel through a const pointer.
+#pragma once
+
+#include <stdint.h>
+
+#include "../../include/smoltts_b200.h"
+
+namespace smol {
+
+constexpr int kThreads = 512;          // 16 warps per CTA, one CTA per SM
+constexpr int kWarps = kThreads / 32;
+constexpr int kBatchTile = 8;          // sequences whose activations sit in shared memory at once
+constexpr int kMaxSplits = 32;         // split-KV partials per (sequence, kv head)
+constexpr int kSplitMin = 64;          // minimum positions per split
+constexpr int kMaxGroup = 4;           // q heads per kv head
+constexpr int kMaxDepth = 16;          // depth positions of the fast transformer
+constexpr int kPartialStride = 66;     // (m, l, o[64]) per attention partial
+
+struct DevLayer {
+    const uint16_t* wqkv;
+    const uint16_t* wo;
+    const uint16_t* w1;
+    const uint16_t* w3;
+    const uint16_t* w2;
+    const uint16_t* attention_norm;
+    const uint16_t* ffn_norm;
+};
+
+struct DevModel {
+    // shapes (RQTransformerModelArgs)
+    int dim, n_layer, n_head, n_kv, inter, vocab;
+    int fdim, n_flayer, fn_head, fn_kv, finter;
+    int codebook_size, num_codebooks, depth, n_rows;  // depth = max_fast_seqlen, n_rows = 1 + depth
+    int dup0, depthwise_wte, depthwise_output;
+    int max_seq_len, max_batch, page_size;
+    int semantic_start, semantic_end, im_end;
+    int mlx_embed_mask;
+    float eps;
+
+    // weights (borrowed, bf16 as raw 16-bit)
+    const uint16_t* embeddings;
+    const uint16_t* codebook_embeddings;
+    const uint16_t* norm;
+    const uint16_t* head;  // output.weight or the tied embeddings
+    const uint16_t* fast_embeddings;
+    const uint16_t* fast_norm;
+    const uint16_t* fast_output;
+    const uint16_t* rope;       // [max_seq_len][32][2]
+    const uint16_t* fast_rope;  // [depth][32][2]
+    DevLayer layers[SMOL_MAX_LAYERS];
+    DevLayer fast_layers[SMOL_MAX_FAST_LAYERS];
+
+    // paged KV pool  [n_pages][n_layer][2][n_kv][page_size][64] bf16
+    uint16_t* kv_pool;
+    int n_pages;
+
+    // workspace (all [max_batch, ...])
+    uint16_t* x;        // slow residual stream            [B][dim]
+    uint16_t* h;        // post-attention stream (slow+fast) [B][max(dim,fdim)]
+    uint16_t* xf;       // fast residual stream            [B][fdim]
+    uint16_t* q;        // rotated queries                 [B][max(n_head,fn_head)*64]
+    uint16_t* attn;     // attention output                [B][max(dim,fdim)]
+    uint16_t* act;      // silu(w1 x) * w3 x               [B][max(inter,finter)]
+    uint16_t* fkv;      // fast KV  [B][n_flayer][2][depth][fn_kv*64]
+    float* token_logits;  // [B][vocab]           (bf16-rounded values)
+    float* depth_logits;  // [B][depth][codebook] (bf16-rounded values)
+    int32_t* frame_tokens;  // [B][n_rows] ids chosen in the current frame
+    float* partial;       // [B][n_head][kMaxSplits][66]
+    uint32_t* split_count;  // [B][n_kv]
+    uint32_t* barrier;    // [0] arrivals, [1] base of the next launch
+    const int32_t* force; // optional [B][n_rows] ids that override the sampled ones (teacher forcing)
+};
+
+// Per-launch arguments (passed by value).
+struct CallArgs {
+    SmolBatch b;
+    SmolSampling s;
+    int batch;
+    int mode;         // 0 decode frames, 1 prefill steps
+    int n_iter;       // frames (decode) or prompt positions (prefill) in this launch
+    int iter_base;    // prefill: prompt position of iteration 0
+    int finalize;     // prefill: this launch ends the prompt -> publish the last column as pending input
+    int phase_begin;  // phases [begin, end) of every iteration
+    int phase_end;
+    int cooperative;  // 1: grid barrier between phases; 0: exactly one phase per launch
+    int advance;      // slow-only launches: bump seq_len after the last phase
+    int fast_from_xf; // depth-step launches: layer 0 reads the caller-filled xf buffer
+    const int32_t* prompt;      // prefill: [B][n_rows][s_max]
+    const int32_t* prompt_len;  // prefill: [B]
+    int s_max;
+};
+
+// Phase kinds of one decode frame, in program order.
+enum PhaseKind {
+    PH_QKV = 0,   // [embed] + RMSNorm + wqkv + RoPE + KV append
+    PH_ATTN,      // paged split-KV attention (slow layers only)
+    PH_WO,        // [fast: attention over <= depth positions] + wo + residual
+    PH_W13,       // RMSNorm + w1/w3 + silu*mul
+    PH_W2,        // w2 + residual
+    PH_HEAD,      // final norm + LM head / depth head
+    PH_SAMPLE     // argmax / sampling (+ frame assembly after the last depth code)
+};
+
+struct Phase {
+    int kind;
+    int fast;   // 0 slow, 1 fast
+    int layer;
+    int depth_pos;
+};
+
+__host__ __device__ inline int phases_per_frame(int n_layer, int n_flayer, int depth) {
+    return 5 * n_layer + 2 + depth * (4 * n_flayer + 2);
+}
+__host__ __device__ inline int phases_per_prefill_step(int n_layer) { return 5 * n_layer; }
+
+__host__ __device__ inline Phase decode_phase(int p, int n_layer, int n_flayer) {
+    Phase ph;
+    ph.fast = 0; ph.layer = 0; ph.depth_pos = 0; ph.kind = PH_QKV;
+    const int n_slow = 5 * n_layer;
+    if (p < n_slow) {
+        ph.layer = p / 5;
+        ph.kind = p % 5;
+        return ph;
+    }
+    if (p == n_slow) { ph.kind = PH_HEAD; return ph; }
+    if (p == n_slow + 1) { ph.kind = PH_SAMPLE; return ph; }
+    const int q = p - (n_slow + 2);
+    const int per = 4 * n_flayer + 2;
+    ph.fast = 1;
+    ph.depth_pos = q / per;
+    const int r = q % per;
+    if (r < 4 * n_flayer) {
+        ph.layer = r / 4;
+        const int k = r % 4;
+        ph.kind = (k == 0) ? PH_QKV : (k == 1) ? PH_WO : (k == 2) ? PH_W13 : PH_W2;
+    } else if (r == 4 * n_flayer) {
+        ph.kind = PH_HEAD;
+    } else {
+        ph.kind = PH_SAMPLE;
+    }
+    return ph;
+}
+
+}  // namespace smol

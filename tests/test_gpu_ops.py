@@ -1,0 +1,209 @@
+"""Op-level parity on the GPU: every phase of a slow layer and of a depth step is run on its own
+(smol_run_phases) on inputs copied bit-for-bit from the CPU oracle's trace, and its output is
+compared with the oracle's next tensor.  With identical inputs only the fp32 summation order
+differs, so the bar is: every element within 2 bf16 ulps and >= 98% of elements bit-identical."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import close_report, model_and_oracle
+from smoltts_b200.synth import teacher_grid
+
+pytestmark = pytest.mark.gpu
+
+SIZES = ["smoltts_byte_tiny", "smoltts_byte_70m", "smoltts_byte_150m"]
+
+
+def _load_cache_into_pool(model, batch, cache, B):
+    """oracle LayerCache [B, Hkv, L, 64] per layer -> the paged pool through the block table."""
+    kv = model.kv_view()  # [pages, L, 2, Hkv, ps, 64]
+    ps = model.page_size
+    table = batch.block_table.cpu()
+    for l, lc in enumerate(cache):
+        L = lc.k.shape[2]
+        for b in range(B):
+            for p0 in range(0, L, ps):
+                n = min(ps, L - p0)
+                page = int(table[b, p0 // ps])
+                kv[page, l, 0, :, :n] = lc.k[b, :, p0:p0 + n].to(kv.device)
+                kv[page, l, 1, :, :n] = lc.v[b, :, p0:p0 + n].to(kv.device)
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("B,T", [(1, 70), (3, 37)])
+def test_slow_layer_phases_match_oracle_trace(size, B, T):
+    cfg, sd, model, orc = model_and_oracle(size)
+    # B == 3: the traced column itself has row-1 code 0 (PyTorch embed-mask quirk)
+    grid = teacher_grid(cfg, n_text=T - 6, n_audio=8, batch=B, seed=11, zero_code_at=6 if B == 3 else 2)  # [B, R, T+2]
+    with torch.no_grad():
+        cache = orc.new_cache()
+        orc.slow_forward(grid[:, :, :T], cache, all_positions=True)
+        # keep a copy of the prefix cache: the traced step appends position T to `cache`
+        prefix = [type(c)(k=c.k.clone(), v=c.v.clone(), offset=c.offset) for c in cache]
+        trace = {}
+        logits, hidden = orc.slow_forward(grid[:, :, T:T + 1], cache, trace=trace)
+    batch = model.new_batch(B, max_positions=256)
+    try:
+        _load_cache_into_pool(model, batch, prefix, B)
+        batch.seq_len.fill_(T)
+        batch.tokens.copy_(grid[:, :, T].to(torch.int32))
+        s = model.sampling()
+        dev = model.device
+        D, H, Hkv = cfg.dim, cfg.n_head, cfg.n_local_heads
+        xbuf, hbuf = model.debug_buffer("x", B), model.debug_buffer("h", B)
+        qbuf, abuf, actbuf = model.debug_buffer("q", B), model.debug_buffer("attn", B), model.debug_buffer("act", B)
+        kv = model.kv_view()
+        table = batch.block_table.cpu()
+        ps = model.page_size
+        for l in range(cfg.n_layer):
+            tag = f"l{l}."
+            if l > 0:
+                xbuf.copy_(trace[f"l{l-1}.out"].to(dev))
+            model.run_phases(batch, s, 5 * l, 5 * l + 1)  # QKV (+ embed at l == 0)
+            torch.cuda.synchronize()
+            if l == 0:
+                close_report("embed", xbuf, trace["embed"], max_ulp=0.0, min_exact=1.0)
+            close_report(tag + "q", qbuf[:, : H * 64], trace[tag + "q"])
+            knew = torch.stack([kv[int(table[b, T // ps]), l, 0, :, T % ps].reshape(-1) for b in range(B)])
+            vnew = torch.stack([kv[int(table[b, T // ps]), l, 1, :, T % ps].reshape(-1) for b in range(B)])
+            close_report(tag + "k", knew, trace[tag + "k"])
+            close_report(tag + "v", vnew, trace[tag + "v"])
+            # identical inputs for attention: the oracle's q and its K/V at position T
+            qbuf[:, : H * 64].copy_(trace[tag + "q"].to(dev))
+            for b in range(B):
+                page = int(table[b, T // ps])
+                kv[page, l, 0, :, T % ps] = trace[tag + "k"][b].view(Hkv, 64).to(dev)
+                kv[page, l, 1, :, T % ps] = trace[tag + "v"][b].view(Hkv, 64).to(dev)
+            model.run_phases(batch, s, 5 * l + 1, 5 * l + 2)  # ATTN
+            torch.cuda.synchronize()
+            # softmax(exp) implementations differ slightly: 3 ulps, 95% exact
+            close_report(tag + "attn", abuf[:, :D], trace[tag + "attn"], max_ulp=3.0, min_exact=0.95)
+            abuf[:, :D].copy_(trace[tag + "attn"].to(dev))
+            model.run_phases(batch, s, 5 * l + 2, 5 * l + 3)  # WO + residual
+            torch.cuda.synchronize()
+            close_report(tag + "h", hbuf[:, :D], trace[tag + "h"])
+            hbuf[:, :D].copy_(trace[tag + "h"].to(dev))
+            model.run_phases(batch, s, 5 * l + 3, 5 * l + 4)  # W13
+            torch.cuda.synchronize()
+            close_report(tag + "act", actbuf[:, : cfg.intermediate_size], trace[tag + "act"])
+            actbuf[:, : cfg.intermediate_size].copy_(trace[tag + "act"].to(dev))
+            model.run_phases(batch, s, 5 * l + 4, 5 * l + 5)  # W2 + residual
+            torch.cuda.synchronize()
+            close_report(tag + "out", xbuf, trace[tag + "out"])
+        # LM head on the oracle's hidden state
+        xbuf.copy_(hidden.to(dev))
+        model.run_phases(batch, s, 5 * cfg.n_layer, 5 * cfg.n_layer + 1)
+        torch.cuda.synchronize()
+        close_report("token_logits", model.debug_buffer("token_logits", B), logits)
+    finally:
+        batch.release()
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_depth_step_phases_match_oracle_trace(size):
+    """All depth positions of one frame: per fast layer QKV / WO(+attention) / W13 / W2, then the
+    depth head, each on the oracle's inputs; the fast KV written by the engine is what later
+    positions read (on-chip cache parity)."""
+    B = 2
+    cfg, sd, model, orc = model_and_oracle(size)
+    g = torch.Generator().manual_seed(5)
+    hidden = (torch.randn(B, cfg.dim, generator=g) * 0.8).to(torch.bfloat16)
+    codes = torch.randint(0, cfg.codebook_size, (B, cfg.max_fast_seqlen), generator=g)
+    batch = model.new_batch(B, max_positions=64)
+    try:
+        s = model.sampling()
+        dev = model.device
+        Df, Ff, Lf = cfg.fast_dim, cfg.fast_intermediate_size, cfg.n_fast_layer
+        xf, hbuf = model.debug_buffer("xf", B), model.debug_buffer("h", B)
+        actbuf, fkv = model.debug_buffer("act", B), model.debug_buffer("fkv", B)
+        base = 5 * cfg.n_layer + 2
+        per = 4 * Lf + 2
+        fcache = orc.new_fast_cache()
+        x = hidden
+        for i in range(cfg.max_fast_seqlen):
+            trace = {}
+            with torch.no_grad():
+                want_logits = orc.fast_step(x, i, fcache, trace=trace)
+            p0 = base + i * per
+            if i == 0:
+                model.debug_buffer("x", B).copy_(hidden.to(dev))
+            else:
+                model.fast_embed(batch, codes[:, i - 1].to(device=dev, dtype=torch.int32), i - 1)
+            for l in range(Lf):
+                tag = f"f{i}.l{l}."
+                if l > 0:
+                    xf.copy_(trace[f"f{i}.l{l-1}.out"].to(dev))
+                model.run_phases(batch, s, p0 + 4 * l, p0 + 4 * l + 1)  # QKV (layer 0: input gather)
+                torch.cuda.synchronize()
+                if l == 0:
+                    close_report(f"f{i}.input", xf, x, max_ulp=0.0, min_exact=1.0)
+                close_report(tag + "k", fkv[:, l, 0, i], trace[tag + "k"])
+                close_report(tag + "v", fkv[:, l, 1, i], trace[tag + "v"])
+                close_report(tag + "q", model.debug_buffer("q", B)[:, : cfg.fast_n_head * 64], trace[tag + "q"])
+                # identical attention inputs
+                model.debug_buffer("q", B)[:, : cfg.fast_n_head * 64].copy_(trace[tag + "q"].to(dev))
+                fkv[:, l, 0, i].copy_(trace[tag + "k"].to(dev))
+                fkv[:, l, 1, i].copy_(trace[tag + "v"].to(dev))
+                model.run_phases(batch, s, p0 + 4 * l + 1, p0 + 4 * l + 2)  # attention + WO + residual
+                torch.cuda.synchronize()
+                close_report(tag + "h", hbuf[:, :Df], trace[tag + "h"], max_ulp=3.0, min_exact=0.95)
+                hbuf[:, :Df].copy_(trace[tag + "h"].to(dev))
+                model.run_phases(batch, s, p0 + 4 * l + 2, p0 + 4 * l + 3)
+                torch.cuda.synchronize()
+                close_report(tag + "act", actbuf[:, :Ff], trace[tag + "act"])
+                actbuf[:, :Ff].copy_(trace[tag + "act"].to(dev))
+                model.run_phases(batch, s, p0 + 4 * l + 3, p0 + 4 * l + 4)
+                torch.cuda.synchronize()
+                close_report(tag + "out", xf, trace[tag + "out"])
+            xf.copy_(trace[f"f{i}.l{Lf-1}.out"].to(dev))
+            model.run_phases(batch, s, p0 + 4 * Lf, p0 + 4 * Lf + 1)  # depth head i
+            torch.cuda.synchronize()
+            close_report(f"depth_logits[{i}]", model.debug_buffer("depth_logits", B)[:, i], want_logits)
+            if i + 1 < cfg.max_fast_seqlen:
+                x = orc.fast_embed(codes[:, i], i)
+    finally:
+        batch.release()
+
+
+@pytest.mark.parametrize("L", [1, 63, 64, 65, 300, 1000])
+def test_split_kv_attention_lengths(L):
+    """Paged split-KV attention against fp32 softmax attention on random q/K/V for context lengths
+    around the split boundaries (1 split, exactly 64, many splits, many pages)."""
+    size = "smoltts_byte_tiny"
+    cfg, sd, model, orc = model_and_oracle(size, max_batch=4, max_seq_len=1024)
+    B = 3
+    batch = model.new_batch(B, max_positions=1024)
+    try:
+        dev = model.device
+        g = torch.Generator().manual_seed(L)
+        H, Hkv = cfg.n_head, cfg.n_local_heads
+        lens = [L, max(1, L // 2), max(1, L - 1)]
+        q = (torch.randn(B, H, 64, generator=g)).to(torch.bfloat16)
+        K = (torch.randn(B, Hkv, L, 64, generator=g)).to(torch.bfloat16)
+        V = (torch.randn(B, Hkv, L, 64, generator=g)).to(torch.bfloat16)
+        kv = model.kv_view()
+        table = batch.block_table.cpu()
+        ps = model.page_size
+        layer = 1
+        for b in range(B):
+            for p0 in range(0, lens[b], ps):
+                n = min(ps, lens[b] - p0)
+                page = int(table[b, p0 // ps])
+                kv[page, layer, 0, :, :n] = K[b, :, p0:p0 + n].to(dev)
+                kv[page, layer, 1, :, :n] = V[b, :, p0:p0 + n].to(dev)
+        model.debug_buffer("q", B)[:, : H * 64].copy_(q.view(B, -1).to(dev))
+        batch.seq_len.copy_(torch.tensor([n - 1 for n in lens], dtype=torch.int32))
+        model.run_phases(batch, model.sampling(), 5 * layer + 1, 5 * layer + 2)
+        torch.cuda.synchronize()
+        got = model.debug_buffer("attn", B)[:, : H * 64].float().cpu().view(B, H, 64)
+        G = H // Hkv
+        for b in range(B):
+            n = lens[b]
+            kb = K[b, :, :n].float().repeat_interleave(G, dim=0)
+            vb = V[b, :, :n].float().repeat_interleave(G, dim=0)
+            sc = torch.einsum("hd,hld->hl", q[b].float(), kb) * 0.125
+            want = torch.einsum("hl,hld->hd", torch.softmax(sc, dim=-1), vb)
+            err = (got[b] - want).abs().max().item()
+            assert err <= 2.0 ** -7 * max(1.0, want.abs().max().item()), f"L={n}: max err {err}"
+    finally:
+        batch.release()
