@@ -79,6 +79,7 @@ PROTOTYPES = {
     "smol_decode_frames": (C.c_int, [C.c_void_p, C.POINTER(SmolBatch), C.c_int32, C.POINTER(SmolSampling), C.c_int32,
                                      C.c_void_p]),
     "smol_set_force": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "smol_set_profile": (C.c_int, [C.c_void_p, C.c_void_p]),
     "smol_run_phases": (C.c_int, [C.c_void_p, C.POINTER(SmolBatch), C.c_int32, C.POINTER(SmolSampling), C.c_int32,
                                   C.c_int32, C.c_void_p]),
     "smol_phase_count": (C.c_int32, [C.c_void_p]),

@@ -44,6 +44,7 @@ struct SmolModel {
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
     cudaGraphExec_t frame_graph = nullptr;
+    cudaStream_t capture_stream = nullptr;  // the caller's stream may be the legacy default stream, which cannot capture
     GraphKey frame_key;
     bool frame_key_valid = false;
 };
@@ -55,6 +56,7 @@ static int fail(int code, const std::string& msg) {
     return code;
 }
 static int cuda_fail(cudaError_t e, const char* what) {
+    (void)cudaGetLastError();  // launch-configuration errors are not sticky: do not leave them for the next caller
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return SMOL_ERR_CUDA;
 }
@@ -144,6 +146,7 @@ int smol_create(const SmolConfig* cfg, SmolModel** out) {
 void smol_destroy(SmolModel* m) {
     if (!m) return;
     if (m->frame_graph) cudaGraphExecDestroy(m->frame_graph);
+    if (m->capture_stream) cudaStreamDestroy(m->capture_stream);
     delete m;
 }
 
@@ -415,12 +418,13 @@ int smol_decode_frames(SmolModel* m, const SmolBatch* b, int32_t batch, const Sm
     if (!m->frame_key_valid || std::memcmp(&key, &m->frame_key, sizeof(key)) != 0) {
         if (m->frame_graph) { cudaGraphExecDestroy(m->frame_graph); m->frame_graph = nullptr; }
         cudaGraph_t g = nullptr;
-        CU(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        if (!m->capture_stream) CU(cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking));
+        CU(cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeThreadLocal));
         A.n_iter = 1;
         const int64_t before = m->launches;
-        rc = enqueue(m, A, stream);
+        rc = enqueue(m, A, m->capture_stream);
         m->launches = before;
-        cudaError_t e = cudaStreamEndCapture(stream, &g);
+        cudaError_t e = cudaStreamEndCapture(m->capture_stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
         e = cudaGraphInstantiate(&m->frame_graph, g, 0);
@@ -441,6 +445,13 @@ int smol_decode_frame(SmolModel* m, const SmolBatch* b, int32_t batch, const Smo
 int smol_set_force(SmolModel* m, const int32_t* d_force) {
     if (!m) return fail(SMOL_ERR_INVALID, "null model");
     m->dm.force = d_force;
+    return SMOL_OK;
+}
+
+int smol_set_profile(SmolModel* m, uint64_t* d_phase_ns) {
+    if (!m) return fail(SMOL_ERR_INVALID, "null model");
+    m->dm.prof = reinterpret_cast<unsigned long long*>(d_phase_ns);
+    m->frame_key_valid = false;
     return SMOL_OK;
 }
 

@@ -78,6 +78,12 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t& target, ui
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct Ctx {
     int cta, n_ctas, warp, lane, tid;
     float* xs;          // dynamic shared memory
@@ -316,19 +322,33 @@ __device__ __forceinline__ void fast_attention_rows(const DevModel& M, const Ctx
         const float q0 = bf_lo(qp), q1 = bf_hi(qp);
         const uint16_t* kb = M.fkv + ((size_t)(bg * M.n_flayer + layer) * 2) * M.depth * kvw + kvh * kHeadDim + 2 * c.lane;
         const uint16_t* vb = kb + (size_t)M.depth * kvw;
-        float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-        for (int j = 0; j <= depth_pos; ++j) {
-            const uint32_t kp = ldcg_u32(kb + (size_t)j * kvw);
-            const uint32_t vp = ldcg_u32(vb + (size_t)j * kvw);
-            float s = fmaf(q0, bf_lo(kp), q1 * bf_hi(kp));
-            s = warp_sum(s) * 0.125f;
-            const float mn = fmaxf(m, s);
-            const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
-            const float pe = expf(s - mn);
-            l = fmaf(l, corr, pe);
-            o0 = fmaf(o0, corr, pe * bf_lo(vp));
-            o1 = fmaf(o1, corr, pe * bf_hi(vp));
-            m = mn;
+        // <= kMaxDepth positions: scores first, then one softmax with the global max.  The probabilities
+        // are rounded to bf16 before the PV product and the row sum keeps the unrounded values, which is
+        // what the reference's fused SDPA does for bf16 inputs (flash kernels, CPU and CUDA alike).
+        float sj[kMaxDepth];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kMaxDepth; ++j) {
+            sj[j] = -INFINITY;
+            if (j <= depth_pos) {
+                const uint32_t kp = ldcg_u32(kb + (size_t)j * kvw);
+                float s = fmaf(q0, bf_lo(kp), q1 * bf_hi(kp));
+                s = warp_sum(s) * 0.125f;
+                sj[j] = s;
+                m = fmaxf(m, s);
+            }
+        }
+        float l = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxDepth; ++j) {
+            if (j <= depth_pos) {
+                const uint32_t vp = ldcg_u32(vb + (size_t)j * kvw);
+                const float pe = expf(sj[j] - m);
+                l += pe;
+                const float pb = bf16_round(pe);
+                o0 = fmaf(pb, bf_lo(vp), o0);
+                o1 = fmaf(pb, bf_hi(vp), o1);
+            }
         }
         const float inv = 1.0f / l;
         float* row = c.xs + (size_t)b * D;
@@ -735,11 +755,19 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
     if (A.cooperative) target = ldcg_u32(M.barrier + 1);
     const int per_iter = (A.mode == 1) ? phases_per_prefill_step(M.n_layer)
                                        : phases_per_frame(M.n_layer, M.n_flayer, M.depth);
+    const bool prof_cta = (M.prof != nullptr) && c.cta == 0;  // CTA-uniform
+    const bool prof = prof_cta && c.tid == 0;
+    unsigned long long t0 = 0, t1 = 0;
     for (int it = 0; it < A.n_iter; ++it) {
         c.iter = it;
         for (int p = A.phase_begin; p < A.phase_end; ++p) {
             const Phase ph = decode_phase(p, M.n_layer, M.n_flayer);
+            if (prof) t0 = globaltimer_ns();
             run_phase(M, A, c, ph);
+            if (prof_cta) {
+                __syncthreads();
+                if (prof) t1 = globaltimer_ns();
+            }
             if (c.cta == 0 && p == per_iter - 1 && A.mode == 1) {
                 // prefill bookkeeping: sequences still inside their prompt advance one position
                 for (int b = c.tid; b < A.batch; b += kThreads)
@@ -750,6 +778,11 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
             }
             const bool last = (it == A.n_iter - 1) && (p == A.phase_end - 1);
             if (A.cooperative && !last) grid_barrier(M.barrier, target, (uint32_t)c.n_ctas);
+            if (prof) {  // [2p] CTA 0's own time in the phase, [2p+1] its wait at the barrier that follows
+                const unsigned long long t2 = globaltimer_ns();
+                M.prof[2 * p] += t1 - t0;
+                M.prof[2 * p + 1] += t2 - t1;
+            }
         }
     }
     if (A.mode == 1 && A.finalize && c.cta == 0) {
@@ -815,8 +848,13 @@ size_t decode_smem_bytes(const DevModel& M) {
     return m > cbytes ? m : cbytes;
 }
 
+// The attribute is per function, not per model: it only ever grows (several models may coexist).
+static size_t g_smem_configured = 0;
 cudaError_t decode_configure(size_t smem) {
-    return cudaFuncSetAttribute(smol_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem <= g_smem_configured) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(smol_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) g_smem_configured = smem;
+    return e;
 }
 
 cudaError_t decode_max_ctas(size_t smem, int* per_sm) {

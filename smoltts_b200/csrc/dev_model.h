@@ -70,6 +70,7 @@ struct DevModel {
     float* partial;       // [B][n_head][kMaxSplits][66]
     uint32_t* split_count;  // [B][n_kv]
     uint32_t* barrier;    // [0] arrivals, [1] base of the next launch
+    unsigned long long* prof;  // optional [2 * phases_per_frame] ns accumulators (CTA 0: work, barrier wait)
     const int32_t* force; // optional [B][n_rows] ids that override the sampled ones (teacher forcing)
 };
 

@@ -316,6 +316,16 @@ class RQTransformer:
         self._force = force
         _capi.check(self.lib.smol_set_force(self._h, C.c_void_p(force.data_ptr()) if force is not None else None))
 
+    def set_profile(self, enable: bool = True) -> Optional[torch.Tensor]:
+        """Per-phase ns accumulators [phase_count, 2] (CTA 0: work, barrier wait); None switches off."""
+        if not enable:
+            _capi.check(self.lib.smol_set_profile(self._h, None))
+            self._prof = None
+            return None
+        self._prof = torch.zeros(self.phase_count, 2, dtype=torch.int64, device=self.device)
+        _capi.check(self.lib.smol_set_profile(self._h, C.c_void_p(self._prof.data_ptr())))
+        return self._prof
+
     def prefill(self, batch: DecodeBatch, prompts: torch.Tensor, lengths: torch.Tensor) -> None:
         """prompts [B, R, s_max] int32 (device), lengths [B] int32 (device).  Leaves every
         sequence with its first len-1 columns cached and the last column pending."""

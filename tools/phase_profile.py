@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Per-phase time breakdown of the persistent decode kernel (in-kernel %globaltimer, CTA 0).
+
+usage: python tools/phase_profile.py [--model smoltts_byte_150m] [--batch 1] [--frames 256] [--out profiles/x.json]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from smoltts_b200 import RQTransformer, named_config  # noqa: E402
+from smoltts_b200.generate import GenerationSettings, _sampling, pack_prompts  # noqa: E402
+from smoltts_b200.synth import byte_prompt, make_state_dict, prompt_grid  # noqa: E402
+
+KINDS = ["QKV", "ATTN", "WO", "W13", "W2", "HEAD", "SAMPLE"]
+
+
+def phase_kind(p, n_layer, n_flayer):
+    n_slow = 5 * n_layer
+    if p < n_slow:
+        return "slow." + KINDS[p % 5]
+    if p == n_slow:
+        return "slow.HEAD"
+    if p == n_slow + 1:
+        return "slow.SAMPLE"
+    r = (p - n_slow - 2) % (4 * n_flayer + 2)
+    if r < 4 * n_flayer:
+        return "fast." + ["QKV", "WO", "W13", "W2"][r % 4]
+    return "fast.HEAD" if r == 4 * n_flayer else "fast.SAMPLE"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="smoltts_byte_150m")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--prompt-bytes", type=int, default=200)
+    ap.add_argument("--sampled", action="store_true")
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    cfg = named_config(a.model)
+    need = a.prompt_bytes + 12 + a.frames + 8
+    model = RQTransformer(cfg, max_batch=a.batch, max_seq_len=max(need, 256))
+    model.load_state_dict(make_state_dict(cfg, seed=0))
+    prompts = [prompt_grid(byte_prompt(a.prompt_bytes, seed=1 + b), cfg) for b in range(a.batch)]
+    padded, lens = pack_prompts(model, prompts)
+    batch = model.new_batch(a.batch, max_positions=need, max_frames=a.frames)
+    gs = (GenerationSettings(default_temp=0.7, default_fast_temp=0.7, top_k=50, top_p=0.9, seed=1234) if a.sampled
+          else GenerationSettings(default_temp=0.0, default_fast_temp=0.0))
+    s = _sampling(model, gs, True, ignore_stop=True)
+    model.prefill(batch, padded, lens)
+    model.decode_frames(batch, s, 8)  # warm
+    torch.cuda.synchronize()
+    prof = model.set_profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    model.decode_frames(batch, s, a.frames)
+    e1.record()
+    torch.cuda.synchronize()
+    model.set_profile(False)
+    ns = prof.cpu().numpy().astype(float) / a.frames  # per frame
+    agg = {}
+    for p in range(ns.shape[0]):
+        k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
+        w, b, n = agg.get(k, (0.0, 0.0, 0))
+        agg[k] = (w + ns[p, 0], b + ns[p, 1], n + 1)
+    total = ns.sum()
+    print(f"{a.model} bs={a.batch} frames={a.frames}: {e0.elapsed_time(e1) * 1e3 / a.frames:.1f} us/frame by events, "
+          f"{total / 1e3:.1f} us/frame by in-kernel timers (CTA 0)")
+    print(f"{'phase':14s} {'count':>5s} {'work us':>9s} {'wait us':>9s} {'per-phase work':>15s} {'per-phase wait':>15s}")
+    rows = {}
+    for k, (w, b, n) in sorted(agg.items(), key=lambda kv: -(kv[1][0] + kv[1][1])):
+        print(f"{k:14s} {n:5d} {w / 1e3:9.1f} {b / 1e3:9.1f} {w / n / 1e3:15.2f} {b / n / 1e3:15.2f}")
+        rows[k] = {"count": n, "work_us": w / 1e3, "wait_us": b / 1e3}
+    if a.out:
+        with open(a.out, "w") as f:
+            json.dump({"model": a.model, "batch": a.batch, "frames": a.frames,
+                       "us_per_frame_events": e0.elapsed_time(e1) * 1e3 / a.frames, "by_phase": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
