@@ -14,10 +14,13 @@
 #include "dev_model.h"
 
 namespace smol {
-size_t decode_smem_bytes(const DevModel& M);
-cudaError_t decode_configure(size_t smem);
-cudaError_t decode_max_ctas(size_t smem, int* per_sm);
-cudaError_t decode_launch(const DevModel& M, const CallArgs& A, int n_ctas, size_t smem, cudaStream_t stream);
+size_t decode_xs_bytes(const DevModel& M, int bt);
+size_t decode_stage_bytes(const DevModel& M, int n_ctas);
+int decode_batch_tile(int batch);
+cudaError_t decode_configure(int bt, size_t smem);
+cudaError_t decode_max_ctas(int bt, size_t smem, int* per_sm);
+cudaError_t decode_launch(const DevModel& M, const CallArgs& A, int bt, int n_ctas, size_t smem, int xs_bytes,
+                          cudaStream_t stream);
 cudaError_t sample_launch(const float* logits, int n, int batch, const SmolSampling& s, int stream_id,
                           const int32_t* seq_id, const int32_t* step, int32_t* out, cudaStream_t stream);
 cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int batch, int n_rows, int row,
@@ -39,7 +42,8 @@ struct SmolModel {
     DevModel dm;
     bool weights_bound = false, ws_bound = false, kv_bound = false, configured = false;
     int device = 0, n_sms = 0, n_ctas = 0, n_ctas_override = 0;
-    size_t smem = 0;
+    size_t smem[9] = {0}, xs_bytes[9] = {0};  // indexed by batch tile (1, 2, 4, 8)
+    bool tile_ready[9] = {false};
     int mode = 0;
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
@@ -120,6 +124,7 @@ int smol_create(const SmolConfig* cfg, SmolModel** out) {
     if (c.n_head / c.n_local_heads > smol::kMaxGroup) return bad("more than 4 query heads per kv head");
     if (c.dim % 8 || c.intermediate_size % 8 || c.fast_intermediate_size % 8) return bad("dims must be multiples of 8");
     if (imax(imax(c.dim, c.intermediate_size), c.fast_intermediate_size) > 3072) return bad("reduction dims above 3072");
+    if (c.dim > 768) return bad("model dim above 768");
     if (c.vocab_size > smol::kThreads * 8 || c.codebook_size > smol::kThreads * 8) return bad("vocab / codebook above 4096 rows");
     const int depth = depth_of(c);
     if (depth < 1 || depth > smol::kMaxDepth) return bad("depth out of range");
@@ -139,6 +144,9 @@ int smol_create(const SmolConfig* cfg, SmolModel** out) {
     d.max_seq_len = c.max_seq_len; d.max_batch = c.max_batch; d.page_size = c.page_size;
     d.semantic_start = c.semantic_start_id; d.semantic_end = c.semantic_end_id; d.im_end = c.im_end_id;
     d.mlx_embed_mask = c.mlx_embed_mask; d.eps = c.norm_eps;
+    const int n_prog = smol::phases_per_frame(d.n_layer, d.n_flayer, d.depth);
+    if (n_prog > smol::kMaxProg) { delete m; return bad("frame program longer than 512 phases"); }
+    for (int p = 0; p < n_prog; ++p) d.prog[p] = smol::pack_phase(smol::decode_phase(p, d.n_layer, d.n_flayer));
     *out = m;
     return SMOL_OK;
 }
@@ -240,14 +248,25 @@ static int ensure_configured(SmolModel* m) {
     CU(cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, m->device));
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
     if (!coop) return fail(SMOL_ERR_UNSUPPORTED, "device does not support cooperative launch");
-    m->smem = smol::decode_smem_bytes(m->dm);
-    CU(smol::decode_configure(m->smem));
-    int per_sm = 0;
-    CU(smol::decode_max_ctas(m->smem, &per_sm));
-    if (per_sm < 1) return fail(SMOL_ERR_UNSUPPORTED, "decode kernel does not fit on an SM");
     m->n_ctas = m->n_sms;
     if (m->n_ctas_override > 0 && m->n_ctas_override < m->n_ctas) m->n_ctas = m->n_ctas_override;
+    for (int i = 0; i < 9; ++i) m->tile_ready[i] = false;
     m->configured = true;
+    return SMOL_OK;
+}
+
+// Shared-memory budget and function attributes of the kernel variant for this batch tile.
+static int ensure_tile(SmolModel* m, int bt) {
+    if (m->tile_ready[bt]) return SMOL_OK;
+    m->xs_bytes[bt] = smol::decode_xs_bytes(m->dm, bt);
+    m->smem[bt] = m->xs_bytes[bt] + smol::decode_stage_bytes(m->dm, m->n_ctas);
+    if (m->smem[bt] > 227 * 1024)
+        return fail(SMOL_ERR_UNSUPPORTED, "activation tile + weight stage exceed 227 KB of shared memory");
+    CU(smol::decode_configure(bt, m->smem[bt]));
+    int per_sm = 0;
+    CU(smol::decode_max_ctas(bt, m->smem[bt], &per_sm));
+    if (per_sm < 1) return fail(SMOL_ERR_UNSUPPORTED, "decode kernel does not fit on an SM");
+    m->tile_ready[bt] = true;
     return SMOL_OK;
 }
 
@@ -262,9 +281,12 @@ static int check_batch(const SmolModel* m, const SmolBatch* b, int batch) {
 // Enqueue `n_iter` iterations of phases [begin, end).  mode 0: one cooperative launch.
 // mode 1: one launch per phase (optionally the caller wraps a frame in a graph).
 static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream) {
+    const int bt = smol::decode_batch_tile(A.batch);
+    int rc = ensure_tile(m, bt);
+    if (rc) return rc;
     if (m->mode == 0) {
         A.cooperative = 1;
-        CU(smol::decode_launch(m->dm, A, m->n_ctas, m->smem, stream));
+        CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
         m->launches += 1;
         return SMOL_OK;
     }
@@ -273,7 +295,7 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream) {
     A.cooperative = 0;
     if (n_iter == 0 && finalize) {
         A.n_iter = 0;
-        CU(smol::decode_launch(m->dm, A, 1, m->smem, stream));
+        CU(smol::decode_launch(m->dm, A, bt, 1, m->smem[bt], (int)m->xs_bytes[bt], stream));
         m->launches += 1;
         return SMOL_OK;
     }
@@ -286,7 +308,7 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream) {
             A.phase_end = p + 1;
             A.finalize = last ? finalize : 0;
             A.advance = (p == end - 1) ? advance : 0;
-            CU(smol::decode_launch(m->dm, A, m->n_ctas, m->smem, stream));
+            CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
             m->launches += 1;
         }
     }
@@ -477,7 +499,7 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!std::strcmp(name, "mode")) return m->mode;
     if (!std::strcmp(name, "n_ctas")) return m->n_ctas;
     if (!std::strcmp(name, "n_sms")) return m->n_sms;
-    if (!std::strcmp(name, "smem_bytes")) return (int64_t)m->smem;
+    if (!std::strcmp(name, "smem_bytes")) return (int64_t)m->smem[1];
     return -1;
 }
 

@@ -17,11 +17,17 @@
 // (P = modeling/model/rq_transformer.py, M = mlx lm/rq_transformer.py, G = mlx lm/generate.py,
 //  K = mlx lm/cache.py of the reference.)
 //
-// All matrix work at this batch size is weight streaming: each warp owns whole weight rows, issues
-// all of a row's 16-byte loads up front (ld.global.nc, no L1 allocation) and reduces with
-// shuffles; activations of up to 8 sequences sit in shared memory as fp32.  Rounding points follow
-// the reference's eager bf16 forward exactly (bf16 after every Linear, each RMSNorm stage, RoPE,
-// SDPA, silu, the product and each residual add; fp32 inside), so only summation order differs.
+// Weight streaming.  At this batch size every matrix op is a GEMV bounded by HBM latency/bandwidth,
+// and weights do not depend on activations.  So each CTA owns a fixed set of weight rows per phase
+// and fetches them ONE PHASE AHEAD: as soon as a phase's math is done, one lane per warp issues
+// TMA bulk copies (cp.async.bulk global->shared, completion on a per-warp mbarrier) for the rows the
+// warp needs in the next weight phase.  The copies fly while the CTA sits in the grid barrier and
+// runs the next phase's prologue (activation gather + RMSNorm), so the GEMV itself reads weights
+// and activations from shared memory only.
+//
+// Rounding points follow the reference's eager bf16 forward exactly (bf16 after every Linear, each
+// RMSNorm stage, RoPE, SDPA, silu, the product and each residual add; fp32 inside), so only
+// summation order differs.
 //
 // The same kernel launched non-cooperatively runs exactly one phase (phase_end == phase_begin+1):
 // that is the "one kernel per op" mode used for CUDA-graph capture, per-phase profiling and tests.
@@ -63,6 +69,12 @@ __device__ __forceinline__ void store_chunk(float* row, int K, int c, const floa
     *reinterpret_cast<float4*>(row + (K >> 1) + c * 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Release/acquire grid barrier.  All CTAs are co-resident (cooperative launch).  `target` is the
 // cumulative arrival count this barrier completes at; the counter only ever grows (wrap-safe compare).
 __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t& target, uint32_t n_ctas) {
@@ -78,29 +90,106 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t& target, ui
     __syncthreads();
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
+// ---- mbarrier + TMA bulk copy (global -> shared) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct Ctx {
     int cta, n_ctas, warp, lane, tid;
-    float* xs;          // dynamic shared memory
-    int iter;           // frame (decode) or prompt position (prefill) inside this launch
+    float* xs;            // activations of the batch tile, fp32 (dynamic shared memory)
+    unsigned char* stage; // weight rows of the current / next weight phase (dynamic shared memory)
+    int iter;             // frame (decode) or prompt position (prefill) inside this launch
 };
 
 __shared__ SampleScratch g_sc;
-__shared__ float g_red[kWarps * kBatchTile];
-__shared__ float g_rstd[kBatchTile];
 __shared__ int g_pos[kBatchTile];
+__shared__ float g_part[kWarps];
 __shared__ int g_flag;
+__shared__ __align__(8) uint64_t g_mbar[kWarps];
+
+// ------------------------------------------------------------------------------------------------
+// weight plan of a phase and its staging
+// ------------------------------------------------------------------------------------------------
+// A phase's GEMV is `n_units` units of R weight rows of K elements; unit u lands in slot
+// (u - cta) / n_ctas of the CTA's stage buffer as R contiguous rows.
+struct Plan {
+    const uint16_t* w0;
+    const uint16_t* w1;  // second row source (w3) for the gated MLP, else nullptr
+    int K, n_units, R;
+};
+
+__device__ __forceinline__ Plan phase_plan(const DevModel& M, const Phase& ph) {
+    Plan pl;
+    pl.w0 = nullptr; pl.w1 = nullptr; pl.K = 0; pl.n_units = 0; pl.R = 1;
+    const bool fast = ph.fast != 0;
+    const int D = fast ? M.fdim : M.dim, F = fast ? M.finter : M.inter;
+    const DevLayer& L = fast ? M.fast_layers[ph.layer] : M.layers[ph.layer];
+    switch (ph.kind) {
+        case PH_QKV: {
+            const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
+            pl.w0 = L.wqkv; pl.K = D; pl.R = 2; pl.n_units = (Hq + 2 * Hkv) * kHeadDim / 2;
+        } break;
+        case PH_WO: pl.w0 = L.wo; pl.K = D; pl.n_units = D; break;
+        case PH_W13: pl.w0 = L.w1; pl.w1 = L.w3; pl.K = D; pl.R = 2; pl.n_units = F; break;
+        case PH_W2: pl.w0 = L.w2; pl.K = F; pl.n_units = D; break;
+        case PH_HEAD: {
+            const int N = fast ? M.codebook_size : M.vocab;
+            pl.w0 = fast ? M.fast_output + (M.depthwise_output ? (size_t)ph.depth_pos * N * D : 0) : M.head;
+            pl.K = D; pl.n_units = N;
+        } break;
+        default: break;
+    }
+    return pl;
+}
+
+// One lane per warp issues the bulk copies of the warp's units; the bytes complete on the warp's
+// own mbarrier.  Callers guarantee (block barrier) that nobody still reads the stage buffer.
+__device__ __forceinline__ void stage_issue(const Ctx& c, const Plan& pl) {
+    if (c.lane != 0 || pl.n_units == 0) return;
+    const uint32_t row_bytes = (uint32_t)pl.K * 2u, slot_bytes = row_bytes * pl.R;
+    int mine = 0;
+    for (int u = c.cta + c.warp * c.n_ctas; u < pl.n_units; u += kWarps * c.n_ctas) ++mine;
+    if (mine == 0) return;
+    fence_proxy_async();
+    mbar_expect_tx(&g_mbar[c.warp], (uint32_t)mine * slot_bytes);
+    int j = c.warp;
+    for (int u = c.cta + c.warp * c.n_ctas; u < pl.n_units; u += kWarps * c.n_ctas, j += kWarps) {
+        unsigned char* dst = c.stage + (size_t)j * slot_bytes;
+        if (pl.w1 != nullptr) {
+            bulk_g2s(dst, pl.w0 + (size_t)u * pl.K, row_bytes, &g_mbar[c.warp]);
+            bulk_g2s(dst + row_bytes, pl.w1 + (size_t)u * pl.K, row_bytes, &g_mbar[c.warp]);
+        } else {
+            bulk_g2s(dst, pl.w0 + (size_t)u * pl.R * pl.K, slot_bytes, &g_mbar[c.warp]);
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // activation staging
 // ------------------------------------------------------------------------------------------------
 
-// xs[b][:] = rows[b][0:K] (bf16 in global, read through L2), b < nb.
+// xs[b][:] = rows[b][0:K] (bf16 in global, read through L2), b < nb; all threads cooperate.
 template <class RowPtr>
 __device__ __forceinline__ void fill_rows(const Ctx& c, int K, int nb, RowPtr rowptr) {
     const int nch = K >> 3;
@@ -113,113 +202,93 @@ __device__ __forceinline__ void fill_rows(const Ctx& c, int K, int nb, RowPtr ro
     }
 }
 
-// In-place RMSNorm of xs rows (reference RMSNorm.forward :607-613): fp32 normalise, round to
-// bf16, multiply by the bf16 weight, round again.  Every CTA does this redundantly for the
-// sequences of the current batch tile.
-__device__ __forceinline__ void rmsnorm_rows(const Ctx& c, int K, int nb, const uint16_t* w, float eps) {
-    float ss[kBatchTile];
-#pragma unroll
-    for (int b = 0; b < kBatchTile; ++b) ss[b] = 0.f;
-    for (int i = c.tid; i < K; i += kThreads) {
-#pragma unroll
-        for (int b = 0; b < kBatchTile; ++b)
-            if (b < nb) { const float v = c.xs[(size_t)b * K + i]; ss[b] = fmaf(v, v, ss[b]); }
-    }
-#pragma unroll
-    for (int b = 0; b < kBatchTile; ++b) ss[b] = warp_sum(ss[b]);
-    if (c.lane == 0) {
-#pragma unroll
-        for (int b = 0; b < kBatchTile; ++b) g_red[c.warp * kBatchTile + b] = ss[b];
-    }
-    __syncthreads();
-    if (c.tid < nb) {
-        float t = 0.f;
-        for (int wi = 0; wi < kWarps; ++wi) t += g_red[wi * kBatchTile + c.tid];
-        const float mean = __fdiv_rn(t, (float)K);
-        g_rstd[c.tid] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
-    }
-    __syncthreads();
+// RMSNorm (reference RMSNorm.forward :607-613: fp32 normalise, round to bf16, multiply by the bf16
+// weight, round again) of nb rows gathered by `load_chunk(b, ch, f)` straight into xs.  One thread per
+// 16-byte chunk: a row occupies ceil(K/256) warps, the sum of squares goes through shuffles and one
+// shared-memory hop, and the thread that loaded a chunk normalises and stores it -- one round trip to
+// L2 and two block barriers, with only the warps that hold data issuing instructions.
+// If `spill` is set (CTA 0 on layer 0) the raw row is also written to global as the residual stream.
+template <class LoadChunk>
+__device__ __forceinline__ void norm_rows(const Ctx& c, int K, int nb, LoadChunk load_chunk, const uint16_t* w, float eps,
+                                          uint16_t* spill, int b0) {
     const int nch = K >> 3;
-    for (int idx = c.tid; idx < nch * 2; idx += kThreads) {
-        // idx walks the physical layout: first half-row then second half-row, 4 elements at a time
-        const int half = idx / nch, ch = idx - half * nch;
-        const int k0 = ch * 8 + half * 4;
-        const uint2 wv = __ldg(reinterpret_cast<const uint2*>(w + k0));
-        const float w0 = bf_lo(wv.x), w1 = bf_hi(wv.x), w2 = bf_lo(wv.y), w3 = bf_hi(wv.y);
+    const int wpr = (nch + 31) >> 5;         // warps per row (<= 3: K <= 768)
+    const int rows_per_pass = kWarps / wpr;
+    const int wr = c.warp / wpr, wi = c.warp - wr * wpr;
+    const int ch = wi * 32 + c.lane;
+    for (int bp = 0; bp < nb; bp += rows_per_pass) {
+        const int b = bp + wr;
+        const bool act = (wr < rows_per_pass) && (b < nb) && (ch < nch);
+        float x[8];
+        float ss = 0.f;
+        uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+        if (act) {
+            wv = __ldg(reinterpret_cast<const uint4*>(w + ch * 8));
+            load_chunk(b, ch, x);
 #pragma unroll
-        for (int b = 0; b < kBatchTile; ++b) {
-            if (b < nb) {
-                float4* p = reinterpret_cast<float4*>(c.xs + (size_t)b * K + half * (K >> 1) + ch * 4);
-                float4 v = *p;
-                const float r = g_rstd[b];
-                v.x = bf16_round(__fmul_rn(bf16_round(__fmul_rn(v.x, r)), w0));
-                v.y = bf16_round(__fmul_rn(bf16_round(__fmul_rn(v.y, r)), w1));
-                v.z = bf16_round(__fmul_rn(bf16_round(__fmul_rn(v.z, r)), w2));
-                v.w = bf16_round(__fmul_rn(bf16_round(__fmul_rn(v.w, r)), w3));
-                *p = v;
-            }
+            for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
         }
-    }
-    __syncthreads();
-}
-
-// Copies the raw (pre-norm) xs rows to a global bf16 buffer [.. + b][K] (only CTA 0 calls it).
-__device__ __forceinline__ void spill_rows(const Ctx& c, int K, int nb, uint16_t* dst, int b0) {
-    for (int idx = c.tid; idx < nb * (K >> 1); idx += kThreads) {
-        const int b = idx / (K >> 1), k = (idx - b * (K >> 1)) * 2;
-        const float lo = c.xs[(size_t)b * K + xs_index(k, K)];
-        const float hi = c.xs[(size_t)b * K + xs_index(k + 1, K)];
-        *reinterpret_cast<uint32_t*>(dst + (size_t)(b0 + b) * K + k) = pack_bf16(lo, hi);
+        ss = warp_sum(ss);
+        if (c.lane == 0) g_part[c.warp] = ss;
+        __syncthreads();
+        if (act) {
+            float t = 0.f;
+            for (int i = 0; i < wpr; ++i) t += g_part[wr * wpr + i];
+            const float mean = __fdiv_rn(t, (float)K);
+            const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+            if (spill != nullptr) {
+                uint4 pk;
+                pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
+                pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
+                *reinterpret_cast<uint4*>(spill + (size_t)(b0 + b) * K + ch * 8) = pk;
+            }
+            float wf[8], o[8];
+            unpack8(wv, wf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = bf16_round(__fmul_rn(bf16_round(__fmul_rn(x[e], r)), wf[e]));
+            store_chunk(c.xs + (size_t)b * K, K, ch, o);
+        }
+        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight-streaming GEMV over the units owned by this CTA
+// GEMV over the units owned by this CTA, weights and activations both in shared memory
 // ------------------------------------------------------------------------------------------------
-// unit u -> R weight rows of `nchunks` 16-byte chunks.  Units are dealt round-robin to CTAs, and a
-// CTA's units round-robin to its warps.  acc[r][b] = sum_k W_r[k] * xs[b][k], reduced over the warp.
-template <int BT, int NCH, int R, class RowFn, class Epi>
-__device__ __forceinline__ void gemv_units(const Ctx& c, int n_units, int K, RowFn rows, Epi epi) {
+// acc[r][b] = sum_k W_r[k] * xs[b][k], reduced over the warp; lane b receives sequence b's sums.
+// Only <BT, R> are compile-time: the chunk loop is a runtime loop so that the whole frame program
+// stays small enough for the instruction cache (every phase runs once per frame).
+template <int BT, int R, class Epi>
+__device__ __forceinline__ void gemv_units(const Ctx& c, int n_units, int K, Epi epi) {
     const int nchunks = K >> 3;
     const int half = K >> 1;
-    for (int u = c.cta + c.warp * c.n_ctas; u < n_units; u += kWarps * c.n_ctas) {
-        const uint16_t* rp[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) rp[r] = rows(u, r);
-        uint4 wv[R][NCH];
-#pragma unroll
-        for (int it = 0; it < NCH; ++it) {
-            const int ch = c.lane + 32 * it;
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                wv[r][it] = (ch < nchunks) ? ldg_stream(rp[r] + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        float acc[R][BT];
+    const size_t slot_bytes = (size_t)K * 2 * R;
+    int j = c.warp;
+    for (int u = c.cta + c.warp * c.n_ctas; u < n_units; u += kWarps * c.n_ctas, j += kWarps) {
+        const uint4* wrow = reinterpret_cast<const uint4*>(c.stage + (size_t)j * slot_bytes);
+        float acc0[R][BT], acc1[R][BT];
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int b = 0; b < BT; ++b) acc[r][b] = 0.f;
+            for (int b = 0; b < BT; ++b) { acc0[r][b] = 0.f; acc1[r][b] = 0.f; }
+#pragma unroll(BT <= 2 ? 3 : 1)
+        for (int ch = c.lane; ch < nchunks; ch += 32) {
+            float wf[R][8];
 #pragma unroll
-        for (int it = 0; it < NCH; ++it) {
-            const int ch = c.lane + 32 * it;
-            if (ch < nchunks) {
-                float wf[R][8];
+            for (int r = 0; r < R; ++r) unpack8(wrow[r * nchunks + ch], wf[r]);
 #pragma unroll
-                for (int r = 0; r < R; ++r) unpack8(wv[r][it], wf[r]);
+            for (int b = 0; b < BT; ++b) {
+                const float* xr = c.xs + (size_t)b * K + ch * 4;
+                const float4 x0 = *reinterpret_cast<const float4*>(xr);
+                const float4 x1 = *reinterpret_cast<const float4*>(xr + half);
 #pragma unroll
-                for (int b = 0; b < BT; ++b) {
-                    const float* xr = c.xs + (size_t)b * K + ch * 4;
-                    const float4 x0 = *reinterpret_cast<const float4*>(xr);
-                    const float4 x1 = *reinterpret_cast<const float4*>(xr + half);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float a = acc[r][b];
-                        a = fmaf(wf[r][0], x0.x, a); a = fmaf(wf[r][1], x0.y, a);
-                        a = fmaf(wf[r][2], x0.z, a); a = fmaf(wf[r][3], x0.w, a);
-                        a = fmaf(wf[r][4], x1.x, a); a = fmaf(wf[r][5], x1.y, a);
-                        a = fmaf(wf[r][6], x1.z, a); a = fmaf(wf[r][7], x1.w, a);
-                        acc[r][b] = a;
-                    }
+                for (int r = 0; r < R; ++r) {
+                    float a0 = acc0[r][b], a1 = acc1[r][b];
+                    a0 = fmaf(wf[r][0], x0.x, a0); a1 = fmaf(wf[r][4], x1.x, a1);
+                    a0 = fmaf(wf[r][1], x0.y, a0); a1 = fmaf(wf[r][5], x1.y, a1);
+                    a0 = fmaf(wf[r][2], x0.z, a0); a1 = fmaf(wf[r][6], x1.z, a1);
+                    a0 = fmaf(wf[r][3], x0.w, a0); a1 = fmaf(wf[r][7], x1.w, a1);
+                    acc0[r][b] = a0; acc1[r][b] = a1;
                 }
             }
         }
@@ -229,35 +298,20 @@ __device__ __forceinline__ void gemv_units(const Ctx& c, int n_units, int K, Row
             mine[r] = 0.f;
 #pragma unroll
             for (int b = 0; b < BT; ++b) {
-                const float s = warp_sum(acc[r][b]);
+                const float s = warp_sum(acc0[r][b] + acc1[r][b]);
                 if (c.lane == b) mine[r] = s;
             }
         }
-        epi(u, mine);  // lane b holds the sums of sequence b of the tile
+        epi(u, mine);
     }
 }
 
-template <int R, class RowFn, class Epi>
-__device__ __forceinline__ void gemv_dispatch(const Ctx& c, int nb, int n_units, int K, RowFn rows, Epi epi) {
-    const int need = ((K >> 3) + 31) / 32;
-#define SMOL_GEMV_BT(NCH)                                                                 \
-    do {                                                                                  \
-        if (nb == 1) gemv_units<1, NCH, R>(c, n_units, K, rows, epi);                     \
-        else if (nb == 2) gemv_units<2, NCH, R>(c, n_units, K, rows, epi);                \
-        else if (nb <= 4) gemv_units<4, NCH, R>(c, n_units, K, rows, epi);                \
-        else gemv_units<8, NCH, R>(c, n_units, K, rows, epi);                             \
-    } while (0)
-    if (R == 2) {
-        if (need <= 1) SMOL_GEMV_BT(1);
-        else if (need <= 3) SMOL_GEMV_BT(3);
-        else SMOL_GEMV_BT(6);
-    } else {
-        if (need <= 1) SMOL_GEMV_BT(1);
-        else if (need <= 3) SMOL_GEMV_BT(3);
-        else if (need <= 6) SMOL_GEMV_BT(6);
-        else SMOL_GEMV_BT(12);
+// Waits until this warp's staged weight rows have landed (if it owns any unit of the phase).
+__device__ __forceinline__ void stage_wait(const Ctx& c, int n_units, uint32_t& parity) {
+    if (c.cta + c.warp * c.n_ctas < n_units) {
+        mbar_wait(&g_mbar[c.warp], parity);
+        parity ^= 1u;
     }
-#undef SMOL_GEMV_BT
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,75 +333,114 @@ __device__ __forceinline__ int input_token(const DevModel& M, const CallArgs& A,
     return ldcg_i32(A.b.tokens + (size_t)bg * M.n_rows + r);
 }
 
-// BaseTransformer.embed (P:205-221): text row + sum of the codebook rows, zeroed by the
-// PyTorch rule (row-1 code == 0) or the MLX rule (row-0 id outside the semantic range, M:162-169).
-__device__ __forceinline__ void embed_rows(const DevModel& M, const CallArgs& A, const Ctx& c, int b0, int nb) {
-    const int D = M.dim, nch = D >> 3;
-    for (int idx = c.tid; idx < nb * nch; idx += kThreads) {
-        const int b = idx / nch, ch = idx - b * nch, bg = b0 + b;
-        const int t0 = input_token(M, A, c, bg, 0);
-        float f[8];
-        unpack8(ldcg_v4(M.embeddings + (size_t)t0 * D + ch * 8), f);
-        bool use_vq;
-        if (M.mlx_embed_mask) use_vq = (t0 >= M.semantic_start && t0 <= M.semantic_end);
-        else use_vq = input_token(M, A, c, bg, 1) != 0;
-        if (use_vq) {
-            float s[8];
+// BaseTransformer.embed (P:205-221) for one 8-element chunk: text row + sum of the codebook rows,
+// zeroed by the PyTorch rule (row-1 code == 0) or the MLX rule (row-0 id outside the semantic range,
+// M:162-169).
+__device__ __forceinline__ void embed_chunk(const DevModel& M, const CallArgs& A, const Ctx& c, int bg, int ch,
+                                            float (&f)[8]) {
+    const int D = M.dim;
+    const int t0 = input_token(M, A, c, bg, 0);
+    unpack8(ldcg_v4(M.embeddings + (size_t)t0 * D + ch * 8), f);
+    bool use_vq;
+    if (M.mlx_embed_mask) use_vq = (t0 >= M.semantic_start && t0 <= M.semantic_end);
+    else use_vq = input_token(M, A, c, bg, 1) != 0;
+    if (use_vq) {
+        float s[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s[e] = 0.f;
-            for (int r = 1; r < M.n_rows; ++r) {
-                const int code = input_token(M, A, c, bg, r);
-                const int row = code + (M.dup0 ? (r - 1) : r) * M.codebook_size;
-                float g[8];
-                unpack8(ldcg_v4(M.codebook_embeddings + (size_t)row * D + ch * 8), g);
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        for (int r = 1; r < M.n_rows; ++r) {
+            const int code = input_token(M, A, c, bg, r);
+            const int row = code + (M.dup0 ? (r - 1) : r) * M.codebook_size;
+            float g[8];
+            unpack8(ldcg_v4(M.codebook_embeddings + (size_t)row * D + ch * 8), g);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) s[e] = __fadd_rn(s[e], g[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = bf16_round(__fadd_rn(f[e], bf16_round(s[e])));
+            for (int e = 0; e < 8; ++e) s[e] = __fadd_rn(s[e], g[e]);
         }
-        store_chunk(c.xs + (size_t)b * D, D, ch, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = bf16_round(__fadd_rn(f[e], bf16_round(s[e])));
     }
 }
 
 // Attention of the fast transformer for the current batch tile, computed redundantly by every CTA
-// straight into xs (the input of the wo GEMV): <= depth cached positions per sequence.
+// straight into xs (the input of the wo GEMV): <= kMaxDepth cached positions per sequence.  One warp
+// per (sequence, head).  Scores: 4 lanes per position (16 dims each), two positions per lane group
+// when depth > 8.  One softmax with the global max; the probabilities are rounded to bf16 before the
+// PV product while the row sum keeps the unrounded values -- what the reference's fused SDPA does
+// for bf16 inputs (flash kernels, CPU and CUDA alike).
 __device__ __forceinline__ void fast_attention_rows(const DevModel& M, const Ctx& c, int layer, int depth_pos,
                                                     int b0, int nb) {
     const int Hq = M.fn_head, Hkv = M.fn_kv, G = Hq / Hkv, D = M.fdim;
     const int kvw = Hkv * kHeadDim;
+    const int jl = c.lane >> 2, part = c.lane & 3;
     for (int pair = c.warp; pair < nb * Hq; pair += kWarps) {
         const int b = pair / Hq, hq = pair - b * Hq, bg = b0 + b, kvh = hq / G;
-        const uint32_t qp = ldcg_u32(M.q + (size_t)bg * Hq * kHeadDim + hq * kHeadDim + 2 * c.lane);
-        const float q0 = bf_lo(qp), q1 = bf_hi(qp);
-        const uint16_t* kb = M.fkv + ((size_t)(bg * M.n_flayer + layer) * 2) * M.depth * kvw + kvh * kHeadDim + 2 * c.lane;
+        const uint16_t* qp = M.q + (size_t)bg * Hq * kHeadDim + hq * kHeadDim + part * 16;
+        const uint16_t* kb = M.fkv + ((size_t)(bg * M.n_flayer + layer) * 2) * M.depth * kvw + kvh * kHeadDim;
         const uint16_t* vb = kb + (size_t)M.depth * kvw;
-        // <= kMaxDepth positions: scores first, then one softmax with the global max.  The probabilities
-        // are rounded to bf16 before the PV product and the row sum keeps the unrounded values, which is
-        // what the reference's fused SDPA does for bf16 inputs (flash kernels, CPU and CUDA alike).
-        float sj[kMaxDepth];
-        float m = -INFINITY;
+        float qf[16];
+        {
+            float t0[8], t1[8];
+            unpack8(ldcg_v4(qp), t0);
+            unpack8(ldcg_v4(qp + 8), t1);
 #pragma unroll
-        for (int j = 0; j < kMaxDepth; ++j) {
-            sj[j] = -INFINITY;
-            if (j <= depth_pos) {
-                const uint32_t kp = ldcg_u32(kb + (size_t)j * kvw);
-                float s = fmaf(q0, bf_lo(kp), q1 * bf_hi(kp));
-                s = warp_sum(s) * 0.125f;
-                sj[j] = s;
-                m = fmaxf(m, s);
+            for (int e = 0; e < 8; ++e) { qf[e] = t0[e]; qf[8 + e] = t1[e]; }
+        }
+        const bool deep = depth_pos >= 8;  // warp-uniform: second position per lane group only then
+        float sc[2];
+        bool ok[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = jl + 8 * h2;
+            ok[h2] = j <= depth_pos;
+            sc[h2] = -INFINITY;
+            if (h2 == 0 || deep) {
+                float s = 0.f;
+                if (ok[h2]) {
+                    float k0[8], k1[8];
+                    unpack8(ldcg_v4(kb + (size_t)j * kvw + part * 16), k0);
+                    unpack8(ldcg_v4(kb + (size_t)j * kvw + part * 16 + 8), k1);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s = fmaf(qf[e], k0[e], s);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s = fmaf(qf[8 + e], k1[e], s);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (ok[h2]) sc[h2] = s * 0.125f;
             }
         }
-        float l = 0.f, o0 = 0.f, o1 = 0.f;
+        float m = fmaxf(sc[0], sc[1]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        const float pe0 = ok[0] ? expf(sc[0] - m) : 0.f;
+        const float pe1 = ok[1] ? expf(sc[1] - m) : 0.f;
+        float l = pe0 + pe1;
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        const float pb0 = bf16_round(pe0), pb1 = bf16_round(pe1);
+        // PV: lane owns dims 2*lane, 2*lane+1
+        float o0 = 0.f, o1 = 0.f;
+        {
+            uint32_t vv[8];
 #pragma unroll
-        for (int j = 0; j < kMaxDepth; ++j) {
-            if (j <= depth_pos) {
-                const uint32_t vp = ldcg_u32(vb + (size_t)j * kvw);
-                const float pe = expf(sj[j] - m);
-                l += pe;
-                const float pb = bf16_round(pe);
-                o0 = fmaf(pb, bf_lo(vp), o0);
-                o1 = fmaf(pb, bf_hi(vp), o1);
+            for (int j = 0; j < 8; ++j) vv[j] = (j <= depth_pos) ? ldcg_u32(vb + (size_t)j * kvw + 2 * c.lane) : 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = __shfl_sync(0xffffffffu, pb0, j * 4);
+                o0 = fmaf(p, bf_lo(vv[j]), o0);
+                o1 = fmaf(p, bf_hi(vv[j]), o1);
+            }
+        }
+        if (deep) {
+            for (int j = 8; j < kMaxDepth; ++j) {
+                const float p = __shfl_sync(0xffffffffu, pb1, (j & 7) * 4);
+                if (j <= depth_pos) {
+                    const uint32_t v = ldcg_u32(vb + (size_t)j * kvw + 2 * c.lane);
+                    o0 = fmaf(p, bf_lo(v), o0);
+                    o1 = fmaf(p, bf_hi(v), o1);
+                }
             }
         }
         const float inv = 1.0f / l;
@@ -358,87 +451,13 @@ __device__ __forceinline__ void fast_attention_rows(const DevModel& M, const Ctx
     }
 }
 
-__device__ void phase_qkv(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
-    const bool fast = ph.fast != 0;
-    const int D = fast ? M.fdim : M.dim;
-    const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
-    const DevLayer& L = fast ? M.fast_layers[ph.layer] : M.layers[ph.layer];
-    const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
-    const int n_units = (Hq + 2 * Hkv) * kHeadDim / 2;
-    const uint16_t* table = fast ? M.fast_rope : M.rope;
-    for (int b0 = 0; b0 < A.batch; b0 += kBatchTile) {
-        const int nb = min(kBatchTile, A.batch - b0);
-        if (!fast && ph.layer == 0) {
-            embed_rows(M, A, c, b0, nb);
-            __syncthreads();
-            if (c.cta == 0) spill_rows(c, D, nb, M.x, b0);
-        } else if (fast && ph.layer == 0 && !A.fast_from_xf) {
-            if (ph.depth_pos == 0) {
-                fill_rows(c, D, nb, [&](int b) { return M.x + (size_t)(b0 + b) * D; });
-            } else {
-                fill_rows(c, D, nb, [&](int b) {
-                    const int code = ldcg_i32(M.frame_tokens + (size_t)(b0 + b) * M.n_rows + ph.depth_pos);
-                    const int off = M.depthwise_wte ? (M.dup0 ? ph.depth_pos - 1 : ph.depth_pos) * M.codebook_size : 0;
-                    return M.fast_embeddings + (size_t)(code + off) * D;
-                });
-            }
-            __syncthreads();
-            if (c.cta == 0) spill_rows(c, D, nb, M.xf, b0);
-        } else {
-            const uint16_t* src = fast ? M.xf : M.x;
-            fill_rows(c, D, nb, [&](int b) { return src + (size_t)(b0 + b) * D; });
-        }
-        if (c.tid < nb) g_pos[c.tid] = fast ? ph.depth_pos : ldcg_i32(A.b.seq_len + b0 + c.tid);
-        __syncthreads();
-        rmsnorm_rows(c, D, nb, L.attention_norm, M.eps);
-
-        auto rows = [&](int u, int r) { return L.wqkv + (size_t)(2 * u + r) * D; };
-        auto epi = [&](int u, const float (&acc)[2]) {
-            if (c.lane >= nb) return;
-            const int bg = b0 + c.lane, n0 = 2 * u, pos = g_pos[c.lane];
-            float v0 = bf16_round(acc[0]), v1 = bf16_round(acc[1]);
-            if (n0 < k_end) {  // q and k rows: interleaved-pair RoPE with the bf16 table (P:616-640)
-                const int j = (n0 & (kHeadDim - 1)) >> 1;
-                const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + ((size_t)pos * (kHeadDim / 2) + j) * 2));
-                const float co = bf_lo(cs), si = bf_hi(cs);
-                const float r0 = bf16_round(__fsub_rn(__fmul_rn(v0, co), __fmul_rn(v1, si)));
-                const float r1 = bf16_round(__fadd_rn(__fmul_rn(v1, co), __fmul_rn(v0, si)));
-                v0 = r0; v1 = r1;
-            }
-            const uint32_t packed = pack_bf16(v0, v1);
-            if (n0 < q_rows) {
-                *reinterpret_cast<uint32_t*>(M.q + (size_t)bg * q_rows + n0) = packed;
-                return;
-            }
-            const int is_v = n0 >= k_end ? 1 : 0;
-            const int n1 = n0 - (is_v ? k_end : q_rows);
-            const int kvh = n1 / kHeadDim, d = n1 & (kHeadDim - 1);
-            if (fast) {
-                uint16_t* dst = M.fkv + (((size_t)(bg * M.n_flayer + ph.layer) * 2 + is_v) * M.depth + ph.depth_pos) * (Hkv * kHeadDim)
-                                + kvh * kHeadDim + d;
-                *reinterpret_cast<uint32_t*>(dst) = packed;
-            } else {
-                if (!seq_active(M, A, c, bg)) return;
-                const int ps = M.page_size;
-                if (pos >= A.b.max_pages * ps) return;
-                const int page = ldcg_i32(A.b.block_table + (size_t)bg * A.b.max_pages + pos / ps);
-                uint16_t* dst = M.kv_pool + ((((size_t)page * M.n_layer + ph.layer) * 2 + is_v) * Hkv + kvh) * ((size_t)ps * kHeadDim)
-                                + (size_t)(pos % ps) * kHeadDim + d;
-                *reinterpret_cast<uint32_t*>(dst) = packed;
-            }
-        };
-        gemv_dispatch<2>(c, nb, n_units, D, rows, epi);
-        __syncthreads();
-    }
-}
-
 // Split-KV decode attention over the paged cache.  Unit = (sequence, kv head, split); the G query
 // heads of a kv head share every K/V read.  Each 8-lane group owns one cached position per step
 // and keeps its own online-softmax state; states are merged across groups, warps and (through a
 // last-arriver fix-up in global memory) splits, always in a fixed order.
-template <int G>
 __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, int s_max) {
-    const int Hq = M.n_head, Hkv = M.n_kv, ps = M.page_size;
+    constexpr int GM = kMaxGroup;
+    const int Hq = M.n_head, Hkv = M.n_kv, ps = M.page_size, G = Hq / Hkv;
     const int dch = c.lane & 7, psub = c.lane >> 3;
     float* red = c.xs;  // [kWarps][G][kPartialStride]
     const int n_units = A.batch * Hkv * s_max;
@@ -454,16 +473,18 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
         const int chunk = (Lb + ns - 1) / ns;
         const int p0 = s * chunk, p1 = min(Lb, p0 + chunk);
 
-        float qf[G][8];
+        float qf[GM][8];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
+        for (int g = 0; g < GM; ++g) {
+            if (g >= G) continue;
             unpack8(ldcg_v4(M.q + (size_t)b * Hq * kHeadDim + (kvh * G + g) * kHeadDim + dch * 8), qf[g]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) qf[g][e] *= 0.125f;  // 1/sqrt(64), exact
         }
-        float m[G], l[G], acc[G][8];
+        float m[GM], l[GM], acc[GM][8];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
+        for (int g = 0; g < GM; ++g) {
+            if (g >= G) continue;
             m[g] = -INFINITY; l[g] = 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
@@ -485,7 +506,8 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
             unpack8(kk, kf);
             unpack8(vv, vf);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
+            for (int g = 0; g < GM; ++g) {
+            if (g >= G) continue;
                 float sc = 0.f;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) sc = fmaf(qf[g][e], kf[e], sc);
@@ -507,7 +529,8 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
+            for (int g = 0; g < GM; ++g) {
+            if (g >= G) continue;
                 const float mo = __shfl_xor_sync(0xffffffffu, m[g], o);
                 const float lo = __shfl_xor_sync(0xffffffffu, l[g], o);
                 const float mn = fmaxf(m[g], mo);
@@ -524,7 +547,8 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
         }
         if (psub == 0) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
+            for (int g = 0; g < GM; ++g) {
+            if (g >= G) continue;
                 float* dst = red + (c.warp * G + g) * kPartialStride;
                 if (dch == 0) { dst[0] = m[g]; dst[1] = l[g]; }
 #pragma unroll
@@ -594,96 +618,126 @@ __device__ int attn_splits(const DevModel& M, int batch, int n_ctas) {
 }
 
 __device__ void phase_attn(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
-    const int s_max = attn_splits(M, A.batch, c.n_ctas);
-    switch (M.n_head / M.n_kv) {
-        case 1: phase_attn_g<1>(M, A, c, ph, s_max); break;
-        case 2: phase_attn_g<2>(M, A, c, ph, s_max); break;
-        case 3: phase_attn_g<3>(M, A, c, ph, s_max); break;
-        default: phase_attn_g<4>(M, A, c, ph, s_max); break;
-    }
+    phase_attn_g(M, A, c, ph, attn_splits(M, A.batch, c.n_ctas));
 }
 
-__device__ void phase_wo(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
+// Every phase that streams weights: [gather / RMSNorm / fast attention] -> staged-weight GEMV ->
+// epilogue.  One function so that each building block is instantiated exactly once (code size is what
+// the instruction cache sees: every phase runs once per frame).
+template <int BT>
+__device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, uint32_t& parity) {
     const bool fast = ph.fast != 0;
-    const int D = fast ? M.fdim : M.dim;
-    const DevLayer& L = fast ? M.fast_layers[ph.layer] : M.layers[ph.layer];
-    const uint16_t* res = fast ? M.xf : M.x;
-    for (int b0 = 0; b0 < A.batch; b0 += kBatchTile) {
-        const int nb = min(kBatchTile, A.batch - b0);
-        if (fast) fast_attention_rows(M, c, ph.layer, ph.depth_pos, b0, nb);
-        else fill_rows(c, D, nb, [&](int b) { return M.attn + (size_t)(b0 + b) * D; });
-        __syncthreads();
-        auto rows = [&](int u, int) { return L.wo + (size_t)u * D; };
-        auto epi = [&](int u, const float (&acc)[1]) {
-            if (c.lane >= nb) return;
-            const size_t o = (size_t)(b0 + c.lane) * D + u;
-            M.h[o] = f_to_bf(__fadd_rn(bf_to_f(ldcg_u16(res + o)), bf16_round(acc[0])));
-        };
-        gemv_dispatch<1>(c, nb, D, D, rows, epi);
-        __syncthreads();
-    }
-}
-
-__device__ void phase_w13(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
-    const bool fast = ph.fast != 0;
+    const int kind = ph.kind;
     const int D = fast ? M.fdim : M.dim, F = fast ? M.finter : M.inter;
+    const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
     const DevLayer& L = fast ? M.fast_layers[ph.layer] : M.layers[ph.layer];
-    for (int b0 = 0; b0 < A.batch; b0 += kBatchTile) {
-        const int nb = min(kBatchTile, A.batch - b0);
-        fill_rows(c, D, nb, [&](int b) { return M.h + (size_t)(b0 + b) * D; });
-        __syncthreads();
-        rmsnorm_rows(c, D, nb, L.ffn_norm, M.eps);
-        auto rows = [&](int u, int r) { return (r == 0 ? L.w1 : L.w3) + (size_t)u * D; };
-        auto epi = [&](int u, const float (&acc)[2]) {
-            if (c.lane >= nb) return;
-            const float a = bf16_round(acc[0]), g = bf16_round(acc[1]);
-            const float s = bf16_round(__fdiv_rn(a, __fadd_rn(1.0f, expf(-a))));  // F.silu in fp32, bf16 out
-            M.act[(size_t)(b0 + c.lane) * F + u] = f_to_bf(__fmul_rn(s, g));
-        };
-        gemv_dispatch<2>(c, nb, F, D, rows, epi);
-        __syncthreads();
-    }
-}
+    const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
+    const int n_head_rows = fast ? M.codebook_size : M.vocab;
+    const int K = (kind == PH_W2) ? F : D;
+    const int n_units = kind == PH_QKV ? (Hq + 2 * Hkv) * kHeadDim / 2 : kind == PH_W13 ? F : kind == PH_HEAD ? n_head_rows : D;
+    const bool normed = kind == PH_QKV || kind == PH_W13 || kind == PH_HEAD;
+    const uint16_t* norm_w = kind == PH_QKV ? L.attention_norm : kind == PH_W13 ? L.ffn_norm : (fast ? M.fast_norm : M.norm);
+    const uint16_t* table = fast ? M.fast_rope : M.rope;
+    uint16_t* stream = fast ? M.xf : M.x;
+    for (int b0 = 0; b0 < A.batch; b0 += BT) {
+        const int nb = min(BT, A.batch - b0);
+        if (kind == PH_QKV && c.tid < nb) g_pos[c.tid] = fast ? ph.depth_pos : ldcg_i32(A.b.seq_len + b0 + c.tid);
+        if (normed) {
+            // where the row of sequence b comes from: 0 token embedding (P:205-221), 1 slow hidden state,
+            // 2 embedding of the previous depth code (G:136-140), 3 a stream buffer
+            int src_kind = 3;
+            const uint16_t* base = kind == PH_W13 ? M.h : stream;
+            uint16_t* spill = nullptr;
+            if (kind == PH_QKV && ph.layer == 0) {
+                if (!fast) { src_kind = 0; spill = M.x; }
+                else if (!A.fast_from_xf) { src_kind = ph.depth_pos == 0 ? 1 : 2; spill = M.xf; }
+            }
+            if (c.cta != 0) spill = nullptr;
+            norm_rows(c, D, nb, [&](int b, int ch, float (&f)[8]) {
+                if (src_kind == 0) { embed_chunk(M, A, c, b0 + b, ch, f); return; }
+                const uint16_t* src;
+                if (src_kind == 1) {
+                    src = M.x + (size_t)(b0 + b) * D;
+                } else if (src_kind == 2) {
+                    const int code = ldcg_i32(M.frame_tokens + (size_t)(b0 + b) * M.n_rows + ph.depth_pos);
+                    const int off = M.depthwise_wte ? (M.dup0 ? ph.depth_pos - 1 : ph.depth_pos) * M.codebook_size : 0;
+                    src = M.fast_embeddings + (size_t)(code + off) * D;
+                } else {
+                    src = base + (size_t)(b0 + b) * D;
+                }
+                unpack8(ldcg_v4(src + ch * 8), f);
+            }, norm_w, M.eps, spill, b0);
+        } else if (kind == PH_WO && fast) {
+            fast_attention_rows(M, c, ph.layer, ph.depth_pos, b0, nb);
+            __syncthreads();
+        } else {
+            const uint16_t* src = kind == PH_WO ? M.attn : M.act;
+            fill_rows(c, K, nb, [&](int b) { return src + (size_t)(b0 + b) * K; });
+            __syncthreads();
+        }
+        if (b0 == 0) stage_wait(c, n_units, parity);
 
-__device__ void phase_w2(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
-    const bool fast = ph.fast != 0;
-    const int D = fast ? M.fdim : M.dim, F = fast ? M.finter : M.inter;
-    const DevLayer& L = fast ? M.fast_layers[ph.layer] : M.layers[ph.layer];
-    uint16_t* dst = fast ? M.xf : M.x;
-    for (int b0 = 0; b0 < A.batch; b0 += kBatchTile) {
-        const int nb = min(kBatchTile, A.batch - b0);
-        fill_rows(c, F, nb, [&](int b) { return M.act + (size_t)(b0 + b) * F; });
-        __syncthreads();
-        auto rows = [&](int u, int) { return L.w2 + (size_t)u * F; };
-        auto epi = [&](int u, const float (&acc)[1]) {
-            if (c.lane >= nb) return;
-            const size_t o = (size_t)(b0 + c.lane) * D + u;
-            dst[o] = f_to_bf(__fadd_rn(bf_to_f(ldcg_u16(M.h + o)), bf16_round(acc[0])));
-        };
-        gemv_dispatch<1>(c, nb, D, F, rows, epi);
-        __syncthreads();
-    }
-}
-
-__device__ void phase_head(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
-    const bool fast = ph.fast != 0;
-    const int D = fast ? M.fdim : M.dim;
-    const int N = fast ? M.codebook_size : M.vocab;
-    const uint16_t* W = fast ? M.fast_output + (M.depthwise_output ? (size_t)ph.depth_pos * N * D : 0) : M.head;
-    const uint16_t* src = fast ? M.xf : M.x;
-    for (int b0 = 0; b0 < A.batch; b0 += kBatchTile) {
-        const int nb = min(kBatchTile, A.batch - b0);
-        fill_rows(c, D, nb, [&](int b) { return src + (size_t)(b0 + b) * D; });
-        __syncthreads();
-        rmsnorm_rows(c, D, nb, fast ? M.fast_norm : M.norm, M.eps);
-        auto rows = [&](int u, int) { return W + (size_t)u * D; };
-        auto epi = [&](int u, const float (&acc)[1]) {
-            if (c.lane >= nb) return;
-            const int bg = b0 + c.lane;
-            float* out = fast ? M.depth_logits + ((size_t)bg * M.depth + ph.depth_pos) * N : M.token_logits + (size_t)bg * N;
-            out[u] = bf16_round(acc[0]);
-        };
-        gemv_dispatch<1>(c, nb, N, D, rows, epi);
+        if (kind == PH_QKV || kind == PH_W13) {
+            auto epi = [&](int u, const float (&acc)[2]) {
+                if (c.lane >= nb) return;
+                const int bg = b0 + c.lane;
+                if (kind == PH_W13) {
+                    const float a = bf16_round(acc[0]), g = bf16_round(acc[1]);
+                    const float sg = bf16_round(__fdiv_rn(a, __fadd_rn(1.0f, expf(-a))));  // F.silu in fp32, bf16 out
+                    M.act[(size_t)bg * F + u] = f_to_bf(__fmul_rn(sg, g));
+                    return;
+                }
+                const int n0 = 2 * u, pos = g_pos[c.lane];
+                float v0 = bf16_round(acc[0]), v1 = bf16_round(acc[1]);
+                if (n0 < k_end) {  // q and k rows: interleaved-pair RoPE with the bf16 table (P:616-640)
+                    const int j = (n0 & (kHeadDim - 1)) >> 1;
+                    const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + ((size_t)pos * (kHeadDim / 2) + j) * 2));
+                    const float co = bf_lo(cs), si = bf_hi(cs);
+                    const float r0 = bf16_round(__fsub_rn(__fmul_rn(v0, co), __fmul_rn(v1, si)));
+                    const float r1 = bf16_round(__fadd_rn(__fmul_rn(v1, co), __fmul_rn(v0, si)));
+                    v0 = r0; v1 = r1;
+                }
+                const uint32_t packed = pack_bf16(v0, v1);
+                if (n0 < q_rows) {
+                    *reinterpret_cast<uint32_t*>(M.q + (size_t)bg * q_rows + n0) = packed;
+                    return;
+                }
+                const int is_v = n0 >= k_end ? 1 : 0;
+                const int n1 = n0 - (is_v ? k_end : q_rows);
+                const int kvh = n1 / kHeadDim, d = n1 & (kHeadDim - 1);
+                if (fast) {
+                    uint16_t* dst = M.fkv + (((size_t)(bg * M.n_flayer + ph.layer) * 2 + is_v) * M.depth + ph.depth_pos) * (Hkv * kHeadDim)
+                                    + kvh * kHeadDim + d;
+                    *reinterpret_cast<uint32_t*>(dst) = packed;
+                } else {
+                    if (!seq_active(M, A, c, bg)) return;
+                    const int ps = M.page_size;
+                    if (pos >= A.b.max_pages * ps) return;
+                    const int page = ldcg_i32(A.b.block_table + (size_t)bg * A.b.max_pages + pos / ps);
+                    uint16_t* dst = M.kv_pool + ((((size_t)page * M.n_layer + ph.layer) * 2 + is_v) * Hkv + kvh) * ((size_t)ps * kHeadDim)
+                                    + (size_t)(pos % ps) * kHeadDim + d;
+                    *reinterpret_cast<uint32_t*>(dst) = packed;
+                }
+            };
+            gemv_units<BT, 2>(c, n_units, K, epi);
+        } else {
+            auto epi = [&](int u, const float (&acc)[1]) {
+                if (c.lane >= nb) return;
+                const int bg = b0 + c.lane;
+                if (kind == PH_HEAD) {
+                    float* out = fast ? M.depth_logits + ((size_t)bg * M.depth + ph.depth_pos) * n_head_rows
+                                      : M.token_logits + (size_t)bg * n_head_rows;
+                    out[u] = bf16_round(acc[0]);
+                    return;
+                }
+                // wo: h = stream + wo(attn)   (P:499)      w2: stream = h + w2(act)   (P:500)
+                const uint16_t* res = kind == PH_WO ? stream : M.h;
+                uint16_t* dst = kind == PH_WO ? M.h : stream;
+                const size_t o = (size_t)bg * D + u;
+                dst[o] = f_to_bf(__fadd_rn(bf_to_f(ldcg_u16(res + o)), bf16_round(acc[0])));
+            };
+            gemv_units<BT, 1>(c, n_units, K, epi);
+        }
         __syncthreads();
     }
 }
@@ -730,40 +784,71 @@ __device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c,
     }
 }
 
-__device__ __forceinline__ void run_phase(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
-    switch (ph.kind) {
-        case PH_QKV: phase_qkv(M, A, c, ph); break;
-        case PH_ATTN: phase_attn(M, A, c, ph); break;
-        case PH_WO: phase_wo(M, A, c, ph); break;
-        case PH_W13: phase_w13(M, A, c, ph); break;
-        case PH_W2: phase_w2(M, A, c, ph); break;
-        case PH_HEAD: phase_head(M, A, c, ph); break;
-        default: phase_sample(M, A, c, ph); break;
+template <int BT>
+__device__ __forceinline__ void run_phase(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph,
+                                          uint32_t& parity) {
+    if (ph.kind == PH_ATTN) phase_attn(M, A, c, ph);
+    else if (ph.kind == PH_SAMPLE) phase_sample(M, A, c, ph);
+    else phase_gemv<BT>(M, A, c, ph, parity);
+}
+
+// Flat index (iteration, phase) of the next phase of this launch that streams weights, or -1.
+__device__ __forceinline__ bool next_weight_phase(const DevModel& M, const CallArgs& A, int& it, int& p) {
+    for (;;) {
+        ++p;
+        if (p >= A.phase_end) { p = A.phase_begin; ++it; }
+        if (it >= A.n_iter) return false;
+        const int k = (int)(M.prog[p] & 15u);
+        if (k != PH_ATTN && k != PH_SAMPLE) return true;
     }
 }
 
+template <int BT>
 __global__ void __launch_bounds__(kThreads, 1)
-smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallArgs A) {
-    extern __shared__ __align__(16) float smem_dyn[];
+smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallArgs A, const int xs_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
     Ctx c;
     c.cta = blockIdx.x; c.n_ctas = gridDim.x; c.tid = threadIdx.x;
     c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
-    c.xs = smem_dyn;
+    c.xs = reinterpret_cast<float*>(smem_dyn);
+    c.stage = smem_dyn + xs_bytes;
     c.iter = 0;
+
+    if (c.tid == 0) {
+        for (int w = 0; w < kWarps; ++w) mbar_init(&g_mbar[w], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     uint32_t target = 0;
     if (A.cooperative) target = ldcg_u32(M.barrier + 1);
+    uint32_t parity = 0;
     const int per_iter = (A.mode == 1) ? phases_per_prefill_step(M.n_layer)
                                        : phases_per_frame(M.n_layer, M.n_flayer, M.depth);
     const bool prof_cta = (M.prof != nullptr) && c.cta == 0;  // CTA-uniform
     const bool prof = prof_cta && c.tid == 0;
     unsigned long long t0 = 0, t1 = 0;
+    int st_it = -1, st_p = -1;  // (iteration, phase) whose weights are staged / in flight
     for (int it = 0; it < A.n_iter; ++it) {
         c.iter = it;
         for (int p = A.phase_begin; p < A.phase_end; ++p) {
-            const Phase ph = decode_phase(p, M.n_layer, M.n_flayer);
+            const Phase ph = unpack_phase(M.prog[p]);
+            const bool has_w = ph.kind != PH_ATTN && ph.kind != PH_SAMPLE;
             if (prof) t0 = globaltimer_ns();
-            run_phase(M, A, c, ph);
+            if (has_w && !(st_it == it && st_p == p)) {  // cold start of a launch
+                stage_issue(c, phase_plan(M, ph));
+                st_it = it; st_p = p;
+            }
+            run_phase<BT>(M, A, c, ph, parity);
+            if (has_w) {
+                // every warp is past its last read of the stage buffer (phases end with a block
+                // barrier): stream the next weight phase in behind the grid barrier
+                int nit = it, np = p;
+                if (next_weight_phase(M, A, nit, np)) {
+                    stage_issue(c, phase_plan(M, unpack_phase(M.prog[np])));
+                    st_it = nit; st_p = np;
+                }
+            }
             if (prof_cta) {
                 __syncthreads();
                 if (prof) t1 = globaltimer_ns();
@@ -800,7 +885,8 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
 __global__ void __launch_bounds__(kThreads, 1)
 smol_sample_kernel(const float* logits, int n, int batch, SmolSampling s, int stream_id, const int32_t* seq_id,
                    const int32_t* step, int32_t* out) {
-    extern __shared__ __align__(16) float smem_dyn[];
+    extern __shared__ __align__(16) float smem_sample[];
+    float* smem_dyn = smem_sample;
     for (int b = blockIdx.x; b < batch; b += gridDim.x) {
         for (int i = threadIdx.x; i < n; i += kThreads) smem_dyn[i] = logits[(size_t)b * n + i];
         __syncthreads();
@@ -835,39 +921,72 @@ cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int 
 }
 
 // ---- host-side launch helpers (called from capi.cu) ----------------------------------------------
-size_t decode_smem_bytes(const DevModel& M) {
+// Activation region: the batch tile's rows in fp32 (also the attention merge scratch and the
+// sampler's logits row).  Sized for the batch the model was created for.
+size_t decode_xs_bytes(const DevModel& M, int bt) {
     int kmax = M.dim;
     if (M.inter > kmax) kmax = M.inter;
     if (M.fdim > kmax) kmax = M.fdim;
     if (M.finter > kmax) kmax = M.finter;
-    size_t a = (size_t)kBatchTile * kmax * sizeof(float);
+    size_t a = (size_t)bt * kmax * sizeof(float);
     size_t b = (size_t)kWarps * kMaxGroup * kPartialStride * sizeof(float);
     int nl = M.vocab > M.codebook_size ? M.vocab : M.codebook_size;
     size_t cbytes = (size_t)nl * sizeof(float);
     size_t m = a > b ? a : b;
-    return m > cbytes ? m : cbytes;
+    m = m > cbytes ? m : cbytes;
+    return (m + 127) / 128 * 128;
 }
 
+// Stage region: the weight rows one CTA owns in the heaviest phase.
+size_t decode_stage_bytes(const DevModel& M, int n_ctas) {
+    auto per = [&](long units, long slot) { return (size_t)((units + n_ctas - 1) / n_ctas) * (size_t)slot; };
+    size_t m = 0;
+    auto upd = [&](size_t v) { if (v > m) m = v; };
+    upd(per((M.n_head + 2 * M.n_kv) * kHeadDim / 2, 4L * M.dim));
+    upd(per(M.dim, 2L * M.dim));
+    upd(per(M.inter, 4L * M.dim));
+    upd(per(M.dim, 2L * M.inter));
+    upd(per(M.vocab, 2L * M.dim));
+    upd(per((M.fn_head + 2 * M.fn_kv) * kHeadDim / 2, 4L * M.fdim));
+    upd(per(M.fdim, 2L * M.fdim));
+    upd(per(M.finter, 4L * M.fdim));
+    upd(per(M.fdim, 2L * M.finter));
+    upd(per(M.codebook_size, 2L * M.fdim));
+    return (m + 127) / 128 * 128;
+}
+
+// Kernel variant by batch tile (sequences whose activations share one pass over the weights).
+static int tile_index(int bt) { return bt <= 1 ? 0 : bt <= 2 ? 1 : bt <= 4 ? 2 : 3; }
+static const void* decode_fn(int bt) {
+    switch (tile_index(bt)) {
+        case 0: return (const void*)smol_decode_kernel<1>;
+        case 1: return (const void*)smol_decode_kernel<2>;
+        case 2: return (const void*)smol_decode_kernel<4>;
+        default: return (const void*)smol_decode_kernel<8>;
+    }
+}
+int decode_batch_tile(int batch) { return batch <= 1 ? 1 : batch <= 2 ? 2 : batch <= 4 ? 4 : 8; }
+
 // The attribute is per function, not per model: it only ever grows (several models may coexist).
-static size_t g_smem_configured = 0;
-cudaError_t decode_configure(size_t smem) {
-    if (smem <= g_smem_configured) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(smol_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) g_smem_configured = smem;
+static size_t g_smem_configured[4] = {0, 0, 0, 0};
+cudaError_t decode_configure(int bt, size_t smem) {
+    size_t& cur = g_smem_configured[tile_index(bt)];
+    if (smem <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(decode_fn(bt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) cur = smem;
     return e;
 }
 
-cudaError_t decode_max_ctas(size_t smem, int* per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, smol_decode_kernel, kThreads, smem);
+cudaError_t decode_max_ctas(int bt, size_t smem, int* per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, decode_fn(bt), kThreads, smem);
 }
 
-cudaError_t decode_launch(const DevModel& M, const CallArgs& A, int n_ctas, size_t smem, cudaStream_t stream) {
-    if (A.cooperative) {
-        void* args[2] = {(void*)&M, (void*)&A};
-        return cudaLaunchCooperativeKernel((const void*)smol_decode_kernel, dim3(n_ctas), dim3(kThreads), args, smem, stream);
-    }
-    smol_decode_kernel<<<n_ctas, kThreads, smem, stream>>>(M, A);
-    return cudaGetLastError();
+cudaError_t decode_launch(const DevModel& M, const CallArgs& A, int bt, int n_ctas, size_t smem, int xs_bytes,
+                          cudaStream_t stream) {
+    void* args[3] = {(void*)&M, (void*)&A, (void*)&xs_bytes};
+    if (A.cooperative)
+        return cudaLaunchCooperativeKernel(decode_fn(bt), dim3(n_ctas), dim3(kThreads), args, smem, stream);
+    return cudaLaunchKernel(decode_fn(bt), dim3(n_ctas), dim3(kThreads), args, smem, stream);
 }
 
 }  // namespace smol

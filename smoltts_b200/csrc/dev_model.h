@@ -17,6 +17,7 @@ constexpr int kSplitMin = 64;          // minimum positions per split
 constexpr int kMaxGroup = 4;           // q heads per kv head
 constexpr int kMaxDepth = 16;          // depth positions of the fast transformer
 constexpr int kPartialStride = 66;     // (m, l, o[64]) per attention partial
+constexpr int kMaxProg = 512;          // phases of one frame's program
 
 struct DevLayer {
     const uint16_t* wqkv;
@@ -70,6 +71,7 @@ struct DevModel {
     float* partial;       // [B][n_head][kMaxSplits][66]
     uint32_t* split_count;  // [B][n_kv]
     uint32_t* barrier;    // [0] arrivals, [1] base of the next launch
+    uint32_t prog[kMaxProg];   // the frame's phase program, packed (pack_phase), built on the host
     unsigned long long* prof;  // optional [2 * phases_per_frame] ns accumulators (CTA 0: work, barrier wait)
     const int32_t* force; // optional [B][n_rows] ids that override the sampled ones (teacher forcing)
 };
@@ -141,6 +143,15 @@ __host__ __device__ inline Phase decode_phase(int p, int n_layer, int n_flayer) 
     } else {
         ph.kind = PH_SAMPLE;
     }
+    return ph;
+}
+
+__host__ __device__ inline uint32_t pack_phase(const Phase& ph) {
+    return (uint32_t)ph.kind | ((uint32_t)ph.fast << 4) | ((uint32_t)ph.layer << 8) | ((uint32_t)ph.depth_pos << 16);
+}
+__host__ __device__ inline Phase unpack_phase(uint32_t w) {
+    Phase ph;
+    ph.kind = (int)(w & 15u); ph.fast = (int)((w >> 4) & 1u); ph.layer = (int)((w >> 8) & 255u); ph.depth_pos = (int)((w >> 16) & 255u);
     return ph;
 }
 

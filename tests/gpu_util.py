@@ -47,8 +47,11 @@ def close_report(name: str, got: torch.Tensor, want: torch.Tensor, max_ulp: floa
     # an absolute slack of one ulp of the tensor's typical magnitude
     scale = want.abs().mean().item() + 1e-12
     bad = (ulps > max_ulp) & ((got - want).abs() > scale * 2.0 ** -7)
-    assert not bad.any(), (f"{name}: {int(bad.sum())} elements differ by more than {max_ulp} bf16 ulps "
-                           f"(max {ulps.max().item():.1f} ulps, max abs {float((got - want).abs().max()):.3g})")
+    if bad.any():
+        idx = bad.nonzero()[:6].tolist()
+        detail = "; ".join(f"{tuple(i)}: got {got[tuple(i)].item():.6g} want {want[tuple(i)].item():.6g}" for i in idx)
+        raise AssertionError(f"{name}: {int(bad.sum())} elements differ by more than {max_ulp} bf16 ulps "
+                             f"(max {ulps.max().item():.1f} ulps, max abs {float((got - want).abs().max()):.3g}): {detail}")
     assert exact >= min_exact, f"{name}: only {exact:.4f} of elements bit-exact (need {min_exact})"
     return exact, float(ulps.max())
 

@@ -88,7 +88,8 @@ def test_slow_layer_phases_match_oracle_trace(size, B, T):
             hbuf[:, :D].copy_(trace[tag + "h"].to(dev))
             model.run_phases(batch, s, 5 * l + 3, 5 * l + 4)  # W13
             torch.cuda.synchronize()
-            close_report(tag + "act", actbuf[:, : cfg.intermediate_size], trace[tag + "act"])
+            # silu(a) * b: each factor may sit one bf16 ulp away -> up to 4 ulps on the product
+            close_report(tag + "act", actbuf[:, : cfg.intermediate_size], trace[tag + "act"], max_ulp=4.0)
             actbuf[:, : cfg.intermediate_size].copy_(trace[tag + "act"].to(dev))
             model.run_phases(batch, s, 5 * l + 4, 5 * l + 5)  # W2 + residual
             torch.cuda.synchronize()
@@ -154,7 +155,7 @@ def test_depth_step_phases_match_oracle_trace(size):
                 hbuf[:, :Df].copy_(trace[tag + "h"].to(dev))
                 model.run_phases(batch, s, p0 + 4 * l + 2, p0 + 4 * l + 3)
                 torch.cuda.synchronize()
-                close_report(tag + "act", actbuf[:, :Ff], trace[tag + "act"])
+                close_report(tag + "act", actbuf[:, :Ff], trace[tag + "act"], max_ulp=4.0)
                 actbuf[:, :Ff].copy_(trace[tag + "act"].to(dev))
                 model.run_phases(batch, s, p0 + 4 * l + 3, p0 + 4 * l + 4)
                 torch.cuda.synchronize()
