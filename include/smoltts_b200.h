@@ -177,9 +177,10 @@ int smol_run_phases(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolS
                     int32_t phase_begin, int32_t phase_end, void* stream);
 int32_t smol_phase_count(const SmolModel* m);
 
-/* Per-phase timing (profiling aid): d_phase_ns [2 * smol_phase_count()] uint64 accumulators, zeroed by
- * the caller; CTA 0 adds [2p] = ns it spent inside phase p and [2p+1] = ns it then waited at the grid
- * barrier.  NULL switches it off. */
+/* Per-phase timing (profiling aid): d_phase_ns [2 * 512 + 64] uint64 accumulators, zeroed by the
+ * caller; CTA 0 adds [2p] = ns it spent inside phase p and [2p+1] = ns it then waited at the grid
+ * barrier; [1024 + 4 * (kind + 8 * fast) + s] = ns in segment s (prologue, weight-stage wait,
+ * GEMV + epilogue, closing block barrier) of the weight phases.  NULL switches it off. */
 int smol_set_profile(SmolModel* m, uint64_t* d_phase_ns);
 
 /* Options: "mode" 0 = one persistent cooperative kernel per call (default), 1 = one launch per

@@ -45,6 +45,7 @@ struct SmolModel {
     size_t smem[9] = {0}, xs_bytes[9] = {0};  // indexed by batch tile (1, 2, 4, 8)
     bool tile_ready[9] = {false};
     int mode = 0;
+    int repeat = 0;
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
     cudaGraphExec_t frame_graph = nullptr;
@@ -284,6 +285,7 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream) {
     const int bt = smol::decode_batch_tile(A.batch);
     int rc = ensure_tile(m, bt);
     if (rc) return rc;
+    A.repeat = m->repeat;
     if (m->mode == 0) {
         A.cooperative = 1;
         CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
@@ -482,6 +484,11 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
     if (!std::strcmp(name, "mode")) {
         if (value != 0 && value != 1) return fail(SMOL_ERR_INVALID, "mode must be 0 or 1");
         m->mode = (int)value;
+        return SMOL_OK;
+    }
+    if (!std::strcmp(name, "repeat")) {
+        m->repeat = value > 0 ? (int)value : 0;
+        m->frame_key_valid = false;
         return SMOL_OK;
     }
     if (!std::strcmp(name, "n_ctas")) {

@@ -75,13 +75,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// Release/acquire grid barrier.  All CTAs are co-resident (cooperative launch).  `target` is the
-// cumulative arrival count this barrier completes at; the counter only ever grows (wrap-safe compare).
-__device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t& target, uint32_t n_ctas) {
+// Release/acquire grid barrier, split into arrive and wait so that work which does not depend on the
+// other CTAs (issuing the next phase's weight copies) sits between the two.  All CTAs are co-resident
+// (cooperative launch).  `target` is the cumulative arrival count this barrier completes at; the
+// counter only ever grows (wrap-safe compare).
+__device__ __forceinline__ void grid_arrive(uint32_t* ctr, uint32_t& target, uint32_t n_ctas) {
     target += n_ctas;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0)
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void grid_wait(uint32_t* ctr, uint32_t target) {
+    if (threadIdx.x == 0) {
         uint32_t v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -639,6 +644,12 @@ __device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, c
     const uint16_t* norm_w = kind == PH_QKV ? L.attention_norm : kind == PH_W13 ? L.ffn_norm : (fast ? M.fast_norm : M.norm);
     const uint16_t* table = fast ? M.fast_rope : M.rope;
     uint16_t* stream = fast ? M.xf : M.x;
+    const bool prof = (M.prof != nullptr) && c.cta == 0 && c.tid == 0;
+    unsigned long long* seg = M.prof + 2 * kMaxProg + (size_t)(kind + (fast ? 8 : 0)) * 4;
+    unsigned long long ts = 0;
+    if (prof) ts = globaltimer_ns();
+    // A.repeat > 0 (profiling only): the idempotent body runs again with a warm instruction cache
+    for (int rep = 0; rep <= A.repeat; ++rep)
     for (int b0 = 0; b0 < A.batch; b0 += BT) {
         const int nb = min(BT, A.batch - b0);
         if (kind == PH_QKV && c.tid < nb) g_pos[c.tid] = fast ? ph.depth_pos : ldcg_i32(A.b.seq_len + b0 + c.tid);
@@ -675,7 +686,9 @@ __device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, c
             fill_rows(c, K, nb, [&](int b) { return src + (size_t)(b0 + b) * K; });
             __syncthreads();
         }
-        if (b0 == 0) stage_wait(c, n_units, parity);
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[0] += t - ts; ts = t; }
+        if (b0 == 0 && rep == 0) stage_wait(c, n_units, parity);
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[1] += t - ts; ts = t; }
 
         if (kind == PH_QKV || kind == PH_W13) {
             auto epi = [&](int u, const float (&acc)[2]) {
@@ -738,7 +751,9 @@ __device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, c
             };
             gemv_units<BT, 1>(c, n_units, K, epi);
         }
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[2] += t - ts; ts = t; }
         __syncthreads();
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[3] += t - ts; ts = t; }
     }
 }
 
@@ -840,15 +855,6 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
                 st_it = it; st_p = p;
             }
             run_phase<BT>(M, A, c, ph, parity);
-            if (has_w) {
-                // every warp is past its last read of the stage buffer (phases end with a block
-                // barrier): stream the next weight phase in behind the grid barrier
-                int nit = it, np = p;
-                if (next_weight_phase(M, A, nit, np)) {
-                    stage_issue(c, phase_plan(M, unpack_phase(M.prog[np])));
-                    st_it = nit; st_p = np;
-                }
-            }
             if (prof_cta) {
                 __syncthreads();
                 if (prof) t1 = globaltimer_ns();
@@ -862,7 +868,18 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
                 for (int b = c.tid; b < A.batch; b += kThreads) A.b.seq_len[b] = ldcg_i32(A.b.seq_len + b) + 1;
             }
             const bool last = (it == A.n_iter - 1) && (p == A.phase_end - 1);
-            if (A.cooperative && !last) grid_barrier(M.barrier, target, (uint32_t)c.n_ctas);
+            const bool sync = A.cooperative && !last;
+            if (sync) grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
+            if (has_w) {
+                // Every warp is past its last read of the stage buffer (phases end with a block barrier):
+                // stream the next weight phase in while the other CTAs arrive at the grid barrier.
+                int nit = it, np = p;
+                if (next_weight_phase(M, A, nit, np)) {
+                    stage_issue(c, phase_plan(M, unpack_phase(M.prog[np])));
+                    st_it = nit; st_p = np;
+                }
+            }
+            if (sync) grid_wait(M.barrier, target);
             if (prof) {  // [2p] CTA 0's own time in the phase, [2p+1] its wait at the barrier that follows
                 const unsigned long long t2 = globaltimer_ns();
                 M.prof[2 * p] += t1 - t0;

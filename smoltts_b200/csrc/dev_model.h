@@ -90,6 +90,7 @@ struct CallArgs {
     int cooperative;  // 1: grid barrier between phases; 0: exactly one phase per launch
     int advance;      // slow-only launches: bump seq_len after the last phase
     int fast_from_xf; // depth-step launches: layer 0 reads the caller-filled xf buffer
+    int repeat;       // profiling only: run the body of every weight phase 1 + repeat times
     const int32_t* prompt;      // prefill: [B][n_rows][s_max]
     const int32_t* prompt_len;  // prefill: [B]
     int s_max;

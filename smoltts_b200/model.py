@@ -322,7 +322,8 @@ class RQTransformer:
             _capi.check(self.lib.smol_set_profile(self._h, None))
             self._prof = None
             return None
-        self._prof = torch.zeros(self.phase_count, 2, dtype=torch.int64, device=self.device)
+        # [0 : 2*512] per-phase (work, wait) pairs, then 16 x 4 sub-phase segments of the weight phases
+        self._prof = torch.zeros(2 * 512 + 64, dtype=torch.int64, device=self.device)
         _capi.check(self.lib.smol_set_profile(self._h, C.c_void_p(self._prof.data_ptr())))
         return self._prof
 

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--prompt-bytes", type=int, default=200)
     ap.add_argument("--sampled", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--repeat", type=int, default=0, help="profiling: run every weight-phase body 1+repeat times")
     a = ap.parse_args()
     cfg = named_config(a.model)
     need = a.prompt_bytes + 12 + a.frames + 8
@@ -57,6 +58,7 @@ def main():
     model.prefill(batch, padded, lens)
     model.decode_frames(batch, s, 8)  # warm
     torch.cuda.synchronize()
+    model.set_option("repeat", a.repeat)
     prof = model.set_profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -64,7 +66,9 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     model.set_profile(False)
-    ns = prof.cpu().numpy().astype(float) / a.frames  # per frame
+    raw = prof.cpu().numpy().astype(float) / a.frames  # per frame
+    ns = raw[: 2 * model.phase_count].reshape(-1, 2)
+    seg = raw[2 * 512:].reshape(16, 4)
     agg = {}
     for p in range(ns.shape[0]):
         k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
@@ -78,6 +82,11 @@ def main():
     for k, (w, b, n) in sorted(agg.items(), key=lambda kv: -(kv[1][0] + kv[1][1])):
         print(f"{k:14s} {n:5d} {w / 1e3:9.1f} {b / 1e3:9.1f} {w / n / 1e3:15.2f} {b / n / 1e3:15.2f}")
         rows[k] = {"count": n, "work_us": w / 1e3, "wait_us": b / 1e3}
+    print("sub-phase segments of the weight phases, us per frame (CTA 0 thread 0): prologue | stage wait | gemv+epilogue | final sync")
+    for k in range(16):
+        if seg[k].sum() > 0:
+            name = ("fast." if k >= 8 else "slow.") + KINDS[k % 8]
+            print(f"  {name:12s} " + " ".join(f"{v / 1e3:8.1f}" for v in seg[k]))
     if a.out:
         with open(a.out, "w") as f:
             json.dump({"model": a.model, "batch": a.batch, "frames": a.frames,
