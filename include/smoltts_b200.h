@@ -161,7 +161,7 @@ int smol_sample(SmolModel* m, const SmolBatch* b, int32_t batch, const float* d_
  * sequence: slow step, slow sample, depth loop with sampling, frame assembly, stop rule. */
 int smol_decode_frame(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s, void* stream);
 
-/* The loop of generate_blocking (G:200-205) without host round trips.  mode 0: ONE persistent
+/* The loop of generate_blocking (G:200-205) without host round trips.  mode 2 / 0: ONE persistent
  * launch walks n_frames frames;  mode 1: the frame's per-phase launches are captured in a CUDA
  * graph (re-captured when batch / sampling / state pointers change) and replayed n_frames times. */
 int smol_decode_frames(SmolModel* m, const SmolBatch* b, int32_t batch, const SmolSampling* s,
@@ -183,8 +183,10 @@ int32_t smol_phase_count(const SmolModel* m);
  * GEMV + epilogue, closing block barrier) of the weight phases.  NULL switches it off. */
 int smol_set_profile(SmolModel* m, uint64_t* d_phase_ns);
 
-/* Options: "mode" 0 = one persistent cooperative kernel per call (default), 1 = one launch per
- * phase, a frame captured in a CUDA graph;  "n_ctas" = grid size (default: one CTA per SM). */
+/* Options: "mode" 2 (default) = data-flow persistent kernel (flag-carrying activation words, TMA
+ * producer warp; whole frames / prefill at batch <= 8, larger batches fall back to mode 0),
+ * 0 = persistent cooperative kernel with a grid barrier per phase, 1 = one launch per phase, a frame
+ * captured in a CUDA graph;  "n_ctas" = grid size (default: one CTA per SM). */
 int smol_set_option(SmolModel* m, const char* name, int64_t value);
 int64_t smol_get_option(const SmolModel* m, const char* name);
 

@@ -25,6 +25,12 @@ cudaError_t sample_launch(const float* logits, int n, int batch, const SmolSampl
                           const int32_t* seq_id, const int32_t* step, int32_t* out, cudaStream_t stream);
 cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int batch, int n_rows, int row,
                                cudaStream_t stream);
+// data-flow kernel (ll_kernel.cu)
+size_t ll_smem_plan(const DevModel& M, int bt, int n_ctas, int* xs_bytes, int* res_bytes, int* scratch_bytes, int* ring_bytes);
+cudaError_t ll_configure(int bt, size_t smem);
+cudaError_t ll_max_ctas(int bt, size_t smem, int* per_sm);
+cudaError_t ll_launch(const DevModel& M, const CallArgs& A, int bt, int n_ctas, size_t smem, int xs_bytes, int res_bytes,
+                      int scratch_bytes, int ring_bytes, cudaStream_t stream);
 }  // namespace smol
 
 using smol::CallArgs;
@@ -44,7 +50,11 @@ struct SmolModel {
     int device = 0, n_sms = 0, n_ctas = 0, n_ctas_override = 0;
     size_t smem[9] = {0}, xs_bytes[9] = {0};  // indexed by batch tile (1, 2, 4, 8)
     bool tile_ready[9] = {false};
-    int mode = 0;
+    // data-flow kernel, indexed by batch tile
+    size_t ll_smem[9] = {0};
+    int ll_xs[9] = {0}, ll_res[9] = {0}, ll_scratch[9] = {0}, ll_ring[9] = {0};
+    int ll_state[9] = {0};  // 0 unknown, 1 ready, -1 does not fit
+    int mode = 2;
     int repeat = 0;
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
@@ -75,8 +85,28 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int imax(int a, int b) { return a > b ? a : b; }
 
 struct WsLayout {
-    size_t x, h, xf, q, attn, act, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier, total;
+    size_t x, h, xf, q, attn, act, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
+    size_t ll, ll_partial, ll_tok, ll_epoch, total;
 };
+
+static int ll_batch_of(const SmolConfig& c) { return c.max_batch < smol::kLLMaxBatch ? c.max_batch : smol::kLLMaxBatch; }
+
+// Word offsets of every phase's LL region for `bl` sequences x kLLRep replicas; returns the total words.
+static size_t ll_regions(const SmolConfig& c, int depth, int bl, uint32_t* off, uint16_t* len) {
+    const int n_prog = smol::phases_per_frame(c.n_layer, c.n_fast_layer, depth);
+    size_t words = 0;
+    for (int p = 0; p < n_prog; ++p) {
+        const smol::Phase ph = smol::decode_phase(p, c.n_layer, c.n_fast_layer);
+        const int n = ph.fast ? smol::ll_phase_words(ph.kind, 1, c.fast_dim, c.fast_n_head, c.fast_n_local_heads,
+                                                     c.fast_intermediate_size, c.codebook_size)
+                              : smol::ll_phase_words(ph.kind, 0, c.dim, c.n_head, c.n_local_heads, c.intermediate_size,
+                                                     c.vocab_size);
+        if (off) off[p] = (uint32_t)words;
+        if (len) len[p] = (uint16_t)n;
+        words += (size_t)n * bl * smol::kLLRep;
+    }
+    return words;
+}
 
 static WsLayout ws_layout(const SmolConfig& c, int depth) {
     WsLayout L;
@@ -101,6 +131,11 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.partial = take(B * c.n_head * smol::kMaxSplits * smol::kPartialStride * 4);
     L.split_count = take(B * c.n_local_heads * 4);
     L.barrier = take(256);
+    const int bl = ll_batch_of(c);
+    L.ll = take(ll_regions(c, depth, bl, nullptr, nullptr) * 8);
+    L.ll_partial = take((size_t)2 * bl * c.n_head * smol::kMaxSplits * smol::kPartialStride * 8);
+    L.ll_tok = take((size_t)bl * (1 + depth) * smol::kLLMaxCtas * 8);
+    L.ll_epoch = take(256);
     L.total = off;
     return L;
 }
@@ -148,6 +183,8 @@ int smol_create(const SmolConfig* cfg, SmolModel** out) {
     const int n_prog = smol::phases_per_frame(d.n_layer, d.n_flayer, d.depth);
     if (n_prog > smol::kMaxProg) { delete m; return bad("frame program longer than 512 phases"); }
     for (int p = 0; p < n_prog; ++p) d.prog[p] = smol::pack_phase(smol::decode_phase(p, d.n_layer, d.n_flayer));
+    d.ll_batch = ll_batch_of(c);
+    ll_regions(c, depth, d.ll_batch, d.ll_off, d.ll_len);
     *out = m;
     return SMOL_OK;
 }
@@ -214,7 +251,10 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     d.frame_tokens = (int32_t*)(base + L.frame_tokens);
     d.partial = (float*)(base + L.partial); d.split_count = (uint32_t*)(base + L.split_count);
     d.barrier = (uint32_t*)(base + L.barrier);
-    // split counters and the barrier words must start at zero (setup-time, synchronous)
+    d.ll = (unsigned long long*)(base + L.ll); d.ll_partial = (unsigned long long*)(base + L.ll_partial);
+    d.ll_tok = (unsigned long long*)(base + L.ll_tok); d.ll_epoch = (uint32_t*)(base + L.ll_epoch);
+    // split counters, barrier words and every LL word (epoch 0 = never written) must start at zero
+    // (setup-time, synchronous)
     CU(cudaMemset(base + L.split_count, 0, L.total - L.split_count));
     CU(cudaMemset(base + L.frame_tokens, 0, L.partial - L.frame_tokens));
     m->ws_bound = true;
@@ -251,7 +291,7 @@ static int ensure_configured(SmolModel* m) {
     if (!coop) return fail(SMOL_ERR_UNSUPPORTED, "device does not support cooperative launch");
     m->n_ctas = m->n_sms;
     if (m->n_ctas_override > 0 && m->n_ctas_override < m->n_ctas) m->n_ctas = m->n_ctas_override;
-    for (int i = 0; i < 9; ++i) m->tile_ready[i] = false;
+    for (int i = 0; i < 9; ++i) { m->tile_ready[i] = false; m->ll_state[i] = 0; }
     m->configured = true;
     return SMOL_OK;
 }
@@ -281,12 +321,36 @@ static int check_batch(const SmolModel* m, const SmolBatch* b, int batch) {
 
 // Enqueue `n_iter` iterations of phases [begin, end).  mode 0: one cooperative launch.
 // mode 1: one launch per phase (optionally the caller wraps a frame in a graph).
-static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream) {
+// Shared-memory plan of the data-flow kernel for this batch tile; ll_state -1 = it does not fit this model.
+static int ensure_ll_tile(SmolModel* m, int bt) {
+    if (m->ll_state[bt] != 0) return SMOL_OK;
+    m->ll_smem[bt] = smol::ll_smem_plan(m->dm, bt, m->n_ctas, &m->ll_xs[bt], &m->ll_res[bt], &m->ll_scratch[bt], &m->ll_ring[bt]);
+    if (m->ll_smem[bt] == 0 || m->n_ctas > smol::kLLMaxCtas) { m->ll_state[bt] = -1; return SMOL_OK; }
+    CU(smol::ll_configure(bt, m->ll_smem[bt]));
+    int per_sm = 0;
+    CU(smol::ll_max_ctas(bt, m->ll_smem[bt], &per_sm));
+    m->ll_state[bt] = per_sm >= 1 ? 1 : -1;
+    return SMOL_OK;
+}
+
+// whole_iters: the call runs complete frames / complete prefill positions (what the data-flow kernel carries).
+static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_iters = false) {
     const int bt = smol::decode_batch_tile(A.batch);
-    int rc = ensure_tile(m, bt);
+    int rc;
+    if (m->mode == 2 && whole_iters && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
+        if ((rc = ensure_ll_tile(m, bt))) return rc;
+        if (m->ll_state[bt] == 1) {
+            if (A.n_iter == 0 && !A.finalize) return SMOL_OK;
+            CU(smol::ll_launch(m->dm, A, bt, m->n_ctas, m->ll_smem[bt], m->ll_xs[bt], m->ll_res[bt], m->ll_scratch[bt],
+                               m->ll_ring[bt], stream));
+            m->launches += 1;
+            return SMOL_OK;
+        }
+    }
+    rc = ensure_tile(m, bt);
     if (rc) return rc;
     A.repeat = m->repeat;
-    if (m->mode == 0) {
+    if (m->mode != 1) {
         A.cooperative = 1;
         CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
         m->launches += 1;
@@ -346,7 +410,7 @@ int smol_prefill(SmolModel* m, const SmolBatch* b, int32_t batch, const int32_t*
     A.prompt = d_prompt;
     A.prompt_len = d_prompt_len;
     A.s_max = s_max;
-    return enqueue(m, A, (cudaStream_t)stream);
+    return enqueue(m, A, (cudaStream_t)stream, true);
 }
 
 int smol_slow_step(SmolModel* m, const SmolBatch* b, int32_t batch, int32_t advance, void* stream) {
@@ -425,9 +489,9 @@ int smol_decode_frames(SmolModel* m, const SmolBatch* b, int32_t batch, const Sm
     CallArgs A = base_args(b, batch, s);
     A.phase_begin = 0;
     A.phase_end = smol::phases_per_frame(m->dm.n_layer, m->dm.n_flayer, m->dm.depth);
-    if (m->mode == 0) {
+    if (m->mode != 1) {
         A.n_iter = n_frames;
-        return enqueue(m, A, stream);
+        return enqueue(m, A, stream, true);
     }
     // mode 1: one frame = phase_end launches, captured once per (batch, state pointers, sampling)
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -482,7 +546,7 @@ int smol_set_profile(SmolModel* m, uint64_t* d_phase_ns) {
 int smol_set_option(SmolModel* m, const char* name, int64_t value) {
     if (!m || !name) return fail(SMOL_ERR_INVALID, "null argument");
     if (!std::strcmp(name, "mode")) {
-        if (value != 0 && value != 1) return fail(SMOL_ERR_INVALID, "mode must be 0 or 1");
+        if (value < 0 || value > 2) return fail(SMOL_ERR_INVALID, "mode must be 0, 1 or 2");
         m->mode = (int)value;
         return SMOL_OK;
     }
@@ -507,6 +571,9 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!std::strcmp(name, "n_ctas")) return m->n_ctas;
     if (!std::strcmp(name, "n_sms")) return m->n_sms;
     if (!std::strcmp(name, "smem_bytes")) return (int64_t)m->smem[1];
+    if (!std::strcmp(name, "ll_smem_bytes")) return (int64_t)m->ll_smem[1];
+    if (!std::strcmp(name, "ll_ring_bytes")) return (int64_t)m->ll_ring[1];
+    if (!std::strcmp(name, "ll_ready")) return (int64_t)m->ll_state[1];
     return -1;
 }
 
@@ -528,7 +595,7 @@ void* smol_debug_buffer(SmolModel* m, const char* name) {
 
 int32_t smol_launches_per_frame(const SmolModel* m) {
     if (!m) return 0;
-    return m->mode == 0 ? 1 : smol::phases_per_frame(m->dm.n_layer, m->dm.n_flayer, m->dm.depth);
+    return m->mode != 1 ? 1 : smol::phases_per_frame(m->dm.n_layer, m->dm.n_flayer, m->dm.depth);
 }
 
 int64_t smol_launch_count(const SmolModel* m) { return m ? m->launches : 0; }

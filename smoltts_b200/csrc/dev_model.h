@@ -18,6 +18,13 @@ constexpr int kMaxGroup = 4;           // q heads per kv head
 constexpr int kMaxDepth = 16;          // depth positions of the fast transformer
 constexpr int kPartialStride = 66;     // (m, l, o[64]) per attention partial
 constexpr int kMaxProg = 512;          // phases of one frame's program
+constexpr int kMaxRows = kMaxDepth + 1; // rows of one token column
+
+// ---- data-flow ("LL") decode kernel (ll_kernel.cu) ----
+constexpr int kLLThreads = kThreads + 32; // 16 consumer warps + 1 TMA producer warp
+constexpr int kLLMaxBatch = 8;         // sequences the data-flow kernel carries (one batch tile)
+constexpr int kLLRep = 4;              // replicas of every broadcast vector (spreads the polls over L2 slices)
+constexpr int kLLMaxCtas = 256;        // token words are published once per CTA
 
 struct DevLayer {
     const uint16_t* wqkv;
@@ -74,7 +81,33 @@ struct DevModel {
     uint32_t prog[kMaxProg];   // the frame's phase program, packed (pack_phase), built on the host
     unsigned long long* prof;  // optional [2 * phases_per_frame] ns accumulators (CTA 0: work, barrier wait)
     const int32_t* force; // optional [B][n_rows] ids that override the sampled ones (teacher forcing)
+
+    // data-flow kernel: every phase publishes its output as 8-byte words {payload, epoch} that the
+    // consumers poll ("LL" protocol: the flag travels with the data, no barrier, no fence)
+    unsigned long long* ll;          // phase p, sequence b, replica r: ll + ll_off[p] + (b * kLLRep + r) * ll_len[p]
+    unsigned long long* ll_partial;  // split-KV partials [2][ll_batch][n_head][kMaxSplits][66] words
+    unsigned long long* ll_tok;      // sampled ids [ll_batch][n_rows][kLLMaxCtas] words
+    uint32_t* ll_epoch;              // [0] phases executed by earlier launches (epochs never repeat)
+    int ll_batch;
+    uint32_t ll_off[kMaxProg];
+    uint16_t ll_len[kMaxProg];
 };
+
+// Words (8 bytes, two bf16 + epoch) one sequence publishes in a phase; multiples of 16 words (128 B).
+__host__ __device__ inline int ll_phase_words(int kind, int fast, int dim, int n_head, int n_kv, int inter, int n_out) {
+    int n = 0;
+    switch (kind) {
+        case 0: n = (n_head + 2 * n_kv) * 64 / 2; break;  // PH_QKV
+        case 1: n = dim / 2; break;                      // PH_ATTN (attention output)
+        case 2: n = dim / 2; break;                      // PH_WO
+        case 3: n = inter / 2; break;                    // PH_W13
+        case 4: n = dim / 2; break;                      // PH_W2
+        case 5: n = n_out / 2; break;                    // PH_HEAD
+        default: n = 0; break;
+    }
+    (void)fast;
+    return (n + 15) / 16 * 16;
+}
 
 // Per-launch arguments (passed by value).
 struct CallArgs {

@@ -11,6 +11,12 @@
 #include "common.cuh"
 #include "dev_model.h"
 
+// Block barrier over the kThreads sampling threads.  The data-flow kernel (ll_kernel.cu) runs an extra
+// producer warp next to them and substitutes a named barrier.
+#ifndef SMOL_BLOCK_SYNC
+#define SMOL_BLOCK_SYNC() __syncthreads()
+#endif
+
 namespace smol {
 
 constexpr int kSampleMaxPerThread = 8;  // rows up to kThreads * 8 = 4096 entries
@@ -28,9 +34,9 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     if (lane == 0) sc.u64[warp] = v;
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     unsigned long long t = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) t += sc.u64[w];
@@ -40,9 +46,9 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 __device__ __forceinline__ float block_max_f32(float v, SampleScratch& sc) {
     v = warp_max(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     if (lane == 0) sc.f32[warp] = v;
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     float t = sc.f32[0];
 #pragma unroll
     for (int w = 1; w < kWarps; ++w) t = fmaxf(t, sc.f32[w]);
@@ -69,9 +75,9 @@ __device__ __forceinline__ int block_argmax(const float* lg, int n, SampleScratc
         if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     if (lane == 0) { sc.f32[warp] = bv; sc.i32[warp] = bi; }
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     float tv = sc.f32[0];
     int ti = sc.i32[0];
 #pragma unroll
@@ -84,7 +90,7 @@ __device__ __forceinline__ int block_argmax(const float* lg, int n, SampleScratc
 }
 
 // All kThreads threads call this.  lg: shared memory, n <= kThreads * kSampleMaxPerThread.
-__device__ int sample_row(const float* lg, int n, float temp, int top_k, float top_p, float min_p,
+static __device__ __forceinline__ int sample_row(const float* lg, int n, float temp, int top_k, float top_p, float min_p,
                           unsigned long long seed, uint32_t step, uint32_t seq_id, uint32_t stream,
                           SampleScratch& sc) {
     if (temp == 0.0f) return block_argmax(lg, n, sc);
@@ -174,9 +180,9 @@ __device__ int sample_row(const float* lg, int n, float temp, int top_k, float t
         const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += up;
     }
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     if (lane == 31) sc.u64[warp] = incl;
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     unsigned long long warp_base = 0, total = 0;
 #pragma unroll
     for (int wi = 0; wi < kWarps; ++wi) {
@@ -192,7 +198,7 @@ __device__ int sample_row(const float* lg, int n, float temp, int top_k, float t
     const unsigned long long target = __umul64hi(r64, total);
 
     if (threadIdx.x == 0) sc.bcast_i32 = n - 1;  // unreachable fallback (total > target always)
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     if (mine > 0 && excl <= target && target < excl + mine) {
         unsigned long long run = excl;
         int pick = -1;
@@ -205,7 +211,7 @@ __device__ int sample_row(const float* lg, int n, float temp, int top_k, float t
         }
         sc.bcast_i32 = pick;
     }
-    __syncthreads();
+    SMOL_BLOCK_SYNC();
     return sc.bcast_i32;
 }
 

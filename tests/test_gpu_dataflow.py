@@ -1,0 +1,125 @@
+"""The data-flow (LL flag) kernel against the grid-barrier kernel: same phase program, same arithmetic,
+same summation order -> every logit, every id, every cached K/V value must be BIT-identical, for
+greedy and sampled decoding, batch 1..8, contexts that cross the split-KV and page boundaries, and
+for prefill.  This is the regression net for the hand-off protocol (a missed or stale word shows up as
+a bit difference)."""
+import pytest
+import torch
+
+from gpu_util import model_and_oracle
+from smoltts_b200.generate import pack_prompts
+from smoltts_b200.synth import byte_prompt, prompt_grid
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(model, mode, prompts, n_frames, chunk, seq_ids, **skw):
+    model.set_option("mode", mode)
+    try:
+        B = len(prompts)
+        padded, lens = pack_prompts(model, prompts)
+        batch = model.new_batch(B, max_positions=int(padded.shape[2]) + n_frames + 1, max_frames=n_frames, seq_ids=seq_ids)
+        try:
+            model.kv_view()[torch.tensor(batch.pages, device=model.device)] = 0  # leftovers of earlier runs
+            model.prefill(batch, padded, lens)
+            torch.cuda.synchronize()
+            kv_prefill = model.kv_view()[torch.tensor(batch.pages, device=model.device)].clone()
+            s = model.sampling(ignore_stop=True, **skw)
+            done = 0
+            logits = []
+            while done < n_frames:
+                n = min(chunk, n_frames - done)
+                model.decode_frames(batch, s, n)
+                torch.cuda.synchronize()
+                logits.append((model.debug_buffer("token_logits", B).clone(), model.debug_buffer("depth_logits", B).clone()))
+                done += n
+            out = dict(codes=batch.out_codes.clone(), tokens=batch.tokens.clone(), seq_len=batch.seq_len.clone(),
+                       step=batch.step.clone(), kv_prefill=kv_prefill,
+                       kv=model.kv_view()[torch.tensor(batch.pages, device=model.device)].clone(), logits=logits)
+        finally:
+            batch.release()
+        return out
+    finally:
+        model.set_option("mode", 2)
+
+
+def _same(a, b, what):
+    for k in ("codes", "tokens", "seq_len", "step"):
+        assert torch.equal(a[k], b[k]), f"{what}: {k} differ"
+    assert torch.equal(a["kv_prefill"].view(torch.int16), b["kv_prefill"].view(torch.int16)), f"{what}: prefill KV differs"
+    assert torch.equal(a["kv"].view(torch.int16), b["kv"].view(torch.int16)), f"{what}: KV differs"
+    for i, ((ta, da), (tb, db)) in enumerate(zip(a["logits"], b["logits"])):
+        assert torch.equal(ta, tb), f"{what}: token logits differ after chunk {i}"
+        assert torch.equal(da, db), f"{what}: depth logits differ after chunk {i}"
+
+
+@pytest.mark.parametrize("size,B,n_prompt,n_frames,chunk", [
+    ("smoltts_byte_tiny", 1, 20, 40, 7),
+    ("smoltts_byte_tiny", 3, 50, 30, 30),
+    ("smoltts_byte_tiny", 8, 30, 12, 5),
+    ("smoltts_byte_70m", 1, 100, 24, 24),
+    ("smoltts_byte_70m", 2, 60, 10, 3),
+    ("smoltts_byte_150m", 1, 180, 16, 16),
+    ("smoltts_byte_150m", 4, 40, 6, 6),
+])
+def test_dataflow_equals_barrier_kernel_greedy(size, B, n_prompt, n_frames, chunk):
+    cfg, sd, model, orc = model_and_oracle(size)
+    assert model.get_option("mode") == 2
+    prompts = [prompt_grid(byte_prompt(n_prompt + 5 * b, seed=40 + b), cfg) for b in range(B)]
+    ids = list(range(3, 3 + B))
+    ref = _run(model, 0, prompts, n_frames, chunk, ids)
+    got = _run(model, 2, prompts, n_frames, chunk, ids)
+    assert model.get_option("ll_ready") == 1 or B > 1
+    _same(ref, got, f"{size} B={B}")
+
+
+@pytest.mark.parametrize("size,B", [("smoltts_byte_tiny", 1), ("smoltts_byte_tiny", 5), ("smoltts_byte_70m", 1)])
+def test_dataflow_equals_barrier_kernel_sampled(size, B):
+    cfg, sd, model, orc = model_and_oracle(size)
+    prompts = [prompt_grid(byte_prompt(25 + 4 * b, seed=60 + b), cfg) for b in range(B)]
+    kw = dict(temp=0.8, fast_temp=0.6, top_k=40, top_p=0.9, seed=99)
+    ref = _run(model, 0, prompts, 14, 4, None, **kw)
+    got = _run(model, 2, prompts, 14, 4, None, **kw)
+    _same(ref, got, f"{size} sampled B={B}")
+
+
+def test_dataflow_long_context_many_splits():
+    """Context past 64 * splits and across many KV pages: the combiner path with several splits."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=2, max_seq_len=2304)
+    prompts = [prompt_grid(byte_prompt(2100 - 400 * b, seed=70 + b), cfg) for b in range(2)]
+    ref = _run(model, 0, prompts, 6, 6, None)
+    got = _run(model, 2, prompts, 6, 6, None)
+    _same(ref, got, "long context")
+
+
+def test_dataflow_stop_rule_and_force():
+    """<|im_end|> forced on sequence 1 in frame 2: it must freeze (tokens, seq_len, step) exactly as in
+    the barrier kernel while sequence 0 keeps decoding inside the same launch."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny")
+    B, R = 2, cfg.n_rows
+    prompts = [prompt_grid(byte_prompt(12 + b, seed=80 + b), cfg) for b in range(B)]
+    res = {}
+    for mode in (0, 2):
+        model.set_option("mode", mode)
+        padded, lens = pack_prompts(model, prompts)
+        batch = model.new_batch(B, max_positions=64, max_frames=8)
+        try:
+            model.prefill(batch, padded, lens)
+            s = model.sampling(audio_only=True)
+            model.decode_frames(batch, s, 1)
+            force = torch.zeros(B, R, dtype=torch.int32, device=model.device)
+            force[:, 0] = 400
+            force[1, 0] = model.token_config.im_end_id
+            model.set_force(force)
+            model.decode_frames(batch, s, 1)
+            model.set_force(None)
+            model.decode_frames(batch, s, 4)
+            torch.cuda.synchronize()
+            res[mode] = (batch.tokens.clone(), batch.seq_len.clone(), batch.step.clone(), batch.finished.clone(), batch.out_codes.clone())
+        finally:
+            model.set_force(None)
+            model.set_option("mode", 2)
+            batch.release()
+    assert res[0][3].tolist() == [0, 1] and res[0][2].tolist() == [6, 2]
+    for a, b in zip(res[0], res[2]):
+        assert torch.equal(a, b)

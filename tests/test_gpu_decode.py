@@ -157,13 +157,17 @@ def test_modes_and_batch_composition_are_bit_identical():
     cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=16)
     prompts = [prompt_grid(byte_prompt(10 + 3 * b, seed=20 + b), cfg) for b in range(11)]
     gs = GenerationSettings(default_temp=0.8, default_fast_temp=0.6, top_k=40, top_p=0.9, seed=77)
-    ref = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=20, chunk=7)
-    model.set_option("mode", 1)
+    model.set_option("mode", 0)
     try:
+        ref = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=20, chunk=7)
+        model.set_option("mode", 1)
         alt = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=20, chunk=20)
     finally:
-        model.set_option("mode", 0)
+        model.set_option("mode", 2)  # default: data-flow kernel up to 8 sequences, barrier kernel above
     for a, b in zip(ref, alt):
+        assert torch.equal(a, b)
+    dflt = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=20, chunk=9)
+    for a, b in zip(ref, dflt):
         assert torch.equal(a, b)
     solo = generate_batch(model, prompts[4:5], gs, audio_only=False, fixed_frames=20, seq_ids=[4])
     assert torch.equal(solo[0], ref[4])
