@@ -58,7 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_current():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB_PATH, "-lcudart"]
+    extra = os.environ.get("SMOL_EXTRA_NVCC", "").split()
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB_PATH, "-lcudart"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:

@@ -89,7 +89,7 @@ struct WsLayout {
     size_t ll, ll_partial, ll_tok, ll_epoch, total;
 };
 
-static int ll_batch_of(const SmolConfig& c) { return c.max_batch < smol::kLLMaxBatch ? c.max_batch : smol::kLLMaxBatch; }
+static int ll_batch_of(const SmolConfig& c) { (void)c; return smol::kLLMaxBatch; }
 
 // Word offsets of every phase's LL region for `bl` sequences x kLLRep replicas; returns the total words.
 static size_t ll_regions(const SmolConfig& c, int depth, int bl, uint32_t* off, uint16_t* len) {
@@ -185,6 +185,10 @@ int smol_create(const SmolConfig* cfg, SmolModel** out) {
     for (int p = 0; p < n_prog; ++p) d.prog[p] = smol::pack_phase(smol::decode_phase(p, d.n_layer, d.n_flayer));
     d.ll_batch = ll_batch_of(c);
     ll_regions(c, depth, d.ll_batch, d.ll_off, d.ll_len);
+    {
+        const int first = 5 * d.n_layer + 2, per = 4 * d.n_flayer + 2;
+        d.ll_step_words = depth > 1 ? d.ll_off[first + per] - d.ll_off[first] : 0;
+    }
     *out = m;
     return SMOL_OK;
 }

@@ -541,11 +541,11 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
                 const float mn = fmaxf(m[g], mo);
                 const float c1 = (m[g] == -INFINITY) ? 0.f : expf(m[g] - mn);
                 const float c2 = (mo == -INFINITY) ? 0.f : expf(mo - mn);
-                l[g] = l[g] * c1 + lo * c2;
+                l[g] = fmaf(l[g], c1, __fmul_rn(lo, c2));  // explicit: ll_kernel.cu must contract identically
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float ao = __shfl_xor_sync(0xffffffffu, acc[g][e], o);
-                    acc[g][e] = acc[g][e] * c1 + ao * c2;
+                    acc[g][e] = fmaf(acc[g][e], c1, __fmul_rn(ao, c2));
                 }
                 m[g] = mn;
             }
@@ -771,7 +771,7 @@ __device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c,
         const uint32_t step = A.b.step ? (uint32_t)ldcg_i32(A.b.step + b) : 0u;
         const uint32_t seq_id = A.b.seq_id ? (uint32_t)ldcg_i32(A.b.seq_id + b) : (uint32_t)b;
         const float temp = fast ? A.s.fast_temp : A.s.temp;
-        int tok = sample_row(c.xs, N, temp, fast ? 0 : A.s.top_k, fast ? 1.0f : A.s.top_p, A.s.min_p, A.s.seed,
+        int tok = sample_row<kThreads>(c.xs, N, temp, fast ? 0 : A.s.top_k, fast ? 1.0f : A.s.top_p, A.s.min_p, A.s.seed,
                              step, seq_id, (uint32_t)r, g_sc);
         if (M.force != nullptr) tok = ldcg_i32(M.force + (size_t)b * R + r);
         if (c.tid == 0) {
@@ -908,7 +908,7 @@ smol_sample_kernel(const float* logits, int n, int batch, SmolSampling s, int st
         for (int i = threadIdx.x; i < n; i += kThreads) smem_dyn[i] = logits[(size_t)b * n + i];
         __syncthreads();
         const bool fast = stream_id != 0;
-        const int tok = sample_row(smem_dyn, n, fast ? s.fast_temp : s.temp, fast ? 0 : s.top_k, fast ? 1.0f : s.top_p,
+        const int tok = sample_row<kThreads>(smem_dyn, n, fast ? s.fast_temp : s.temp, fast ? 0 : s.top_k, fast ? 1.0f : s.top_p,
                                    s.min_p, s.seed, step ? (uint32_t)step[b] : 0u, seq_id ? (uint32_t)seq_id[b] : (uint32_t)b,
                                    (uint32_t)stream_id, g_sc);
         if (threadIdx.x == 0) out[b] = tok;

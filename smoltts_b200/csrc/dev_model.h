@@ -21,9 +21,11 @@ constexpr int kMaxProg = 512;          // phases of one frame's program
 constexpr int kMaxRows = kMaxDepth + 1; // rows of one token column
 
 // ---- data-flow ("LL") decode kernel (ll_kernel.cu) ----
-constexpr int kLLThreads = kThreads + 32; // 16 consumer warps + 1 TMA producer warp
-constexpr int kLLMaxBatch = 8;         // sequences the data-flow kernel carries (one batch tile)
-constexpr int kLLRep = 4;              // replicas of every broadcast vector (spreads the polls over L2 slices)
+constexpr int kLLWarps = 11;             // consumer warps of the data-flow kernel; warp 11 is the TMA producer
+constexpr int kLLThreads = (kLLWarps + 1) * 32;  // 12 warps: 3 per scheduler -> 168 registers per thread, no spills (local
+                                         // memory misses L1 next to 227 KB of shared memory: a spill costs an L2 round trip)
+constexpr int kLLMaxBatch = 1;         // sequences the data-flow kernel carries (the bs=1 latency path)
+constexpr int kLLRep = 8;              // replicas of every broadcast vector (spreads the polls over L2 slices)
 constexpr int kLLMaxCtas = 256;        // token words are published once per CTA
 
 struct DevLayer {
@@ -89,6 +91,7 @@ struct DevModel {
     unsigned long long* ll_tok;      // sampled ids [ll_batch][n_rows][kLLMaxCtas] words
     uint32_t* ll_epoch;              // [0] phases executed by earlier launches (epochs never repeat)
     int ll_batch;
+    uint32_t ll_step_words;          // words between the regions of the same phase of two consecutive depth steps
     uint32_t ll_off[kMaxProg];
     uint16_t ll_len[kMaxProg];
 };

@@ -30,6 +30,7 @@ struct SampleScratch {
     int bcast_i32;
 };
 
+template <int NT>
 __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, SampleScratch& sc) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -39,10 +40,11 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
     SMOL_BLOCK_SYNC();
     unsigned long long t = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += sc.u64[w];
+    for (int w = 0; w < (NT / 32); ++w) t += sc.u64[w];
     return t;
 }
 
+template <int NT>
 __device__ __forceinline__ float block_max_f32(float v, SampleScratch& sc) {
     v = warp_max(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -51,13 +53,14 @@ __device__ __forceinline__ float block_max_f32(float v, SampleScratch& sc) {
     SMOL_BLOCK_SYNC();
     float t = sc.f32[0];
 #pragma unroll
-    for (int w = 1; w < kWarps; ++w) t = fmaxf(t, sc.f32[w]);
+    for (int w = 1; w < (NT / 32); ++w) t = fmaxf(t, sc.f32[w]);
     return t;
 }
 
 // First index of the maximum (torch / mx argmax tie rule).  lg in shared memory.
+template <int NT>
 __device__ __forceinline__ int block_argmax(const float* lg, int n, SampleScratch& sc) {
-    const int per = (n + kThreads - 1) / kThreads;
+    const int per = (n + NT - 1) / NT;
     const int i0 = threadIdx.x * per;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
@@ -81,7 +84,7 @@ __device__ __forceinline__ int block_argmax(const float* lg, int n, SampleScratc
     float tv = sc.f32[0];
     int ti = sc.i32[0];
 #pragma unroll
-    for (int w = 1; w < kWarps; ++w) {
+    for (int w = 1; w < (NT / 32); ++w) {
         const float ov = sc.f32[w];
         const int oi = sc.i32[w];
         if (oi != 0x7fffffff && (ti == 0x7fffffff || ov > tv || (ov == tv && oi < ti))) { tv = ov; ti = oi; }
@@ -89,13 +92,14 @@ __device__ __forceinline__ int block_argmax(const float* lg, int n, SampleScratc
     return ti;
 }
 
-// All kThreads threads call this.  lg: shared memory, n <= kThreads * kSampleMaxPerThread.
+// All NT threads call this.  lg: shared memory, n <= NT * kSampleMaxPerThread.
+template <int NT>
 static __device__ __forceinline__ int sample_row(const float* lg, int n, float temp, int top_k, float top_p, float min_p,
                           unsigned long long seed, uint32_t step, uint32_t seq_id, uint32_t stream,
                           SampleScratch& sc) {
-    if (temp == 0.0f) return block_argmax(lg, n, sc);
+    if (temp == 0.0f) return block_argmax<NT>(lg, n, sc);
 
-    const int per = (n + kThreads - 1) / kThreads;
+    const int per = (n + NT - 1) / NT;
     const int i0 = threadIdx.x * per;
     const float inv_temp = __fdiv_rn(1.0f, temp);
 
@@ -110,7 +114,7 @@ static __device__ __forceinline__ int sample_row(const float* lg, int n, float t
             zmax = fmaxf(zmax, z[e]);
         }
     }
-    zmax = block_max_f32(zmax, sc);
+    zmax = block_max_f32<NT>(zmax, sc);
 
     uint32_t w[kSampleMaxPerThread];
     bool keep[kSampleMaxPerThread];
@@ -130,7 +134,7 @@ static __device__ __forceinline__ int sample_row(const float* lg, int n, float t
             unsigned long long c = 0;
 #pragma unroll
             for (int e = 0; e < kSampleMaxPerThread; ++e) c += (keep[e] && w[e] >= mid) ? 1ull : 0ull;
-            c = block_sum_u64(c, sc);
+            c = block_sum_u64<NT>(c, sc);
             if (c >= (unsigned long long)top_k) lo = mid; else hi = mid;
         }
 #pragma unroll
@@ -144,7 +148,7 @@ static __device__ __forceinline__ int sample_row(const float* lg, int n, float t
         unsigned long long tsum = 0;
 #pragma unroll
         for (int e = 0; e < kSampleMaxPerThread; ++e) tsum += keep[e] ? (unsigned long long)w[e] : 0ull;
-        tsum = block_sum_u64(tsum, sc);
+        tsum = block_sum_u64<NT>(tsum, sc);
         // need = max(1, (T * P32) >> 32) with a 96-bit product
         const unsigned long long hi64 = __umul64hi(tsum, p32), lo64 = tsum * p32;
         unsigned long long need = (hi64 << 32) | (lo64 >> 32);
@@ -155,7 +159,7 @@ static __device__ __forceinline__ int sample_row(const float* lg, int n, float t
             unsigned long long s = 0;
 #pragma unroll
             for (int e = 0; e < kSampleMaxPerThread; ++e) s += (keep[e] && w[e] >= mid) ? (unsigned long long)w[e] : 0ull;
-            s = block_sum_u64(s, sc);
+            s = block_sum_u64<NT>(s, sc);
             if (s >= need) lo = mid; else hi = mid;
         }
 #pragma unroll
@@ -185,7 +189,7 @@ static __device__ __forceinline__ int sample_row(const float* lg, int n, float t
     SMOL_BLOCK_SYNC();
     unsigned long long warp_base = 0, total = 0;
 #pragma unroll
-    for (int wi = 0; wi < kWarps; ++wi) {
+    for (int wi = 0; wi < (NT / 32); ++wi) {
         const unsigned long long t = sc.u64[wi];
         if (wi < warp) warp_base += t;
         total += t;

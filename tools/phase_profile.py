@@ -68,7 +68,8 @@ def main():
     model.set_profile(False)
     raw = prof.cpu().numpy().astype(float) / a.frames  # per frame
     ns = raw[: 2 * model.phase_count].reshape(-1, 2)
-    seg = raw[2 * 512:].reshape(16, 4)
+    seg = raw[2 * 512: 2 * 512 + 64].reshape(16, 4)
+    trace = prof.cpu().numpy()[2 * 512 + 64:].reshape(2, 512, 8)
     agg = {}
     for p in range(ns.shape[0]):
         k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
@@ -87,6 +88,30 @@ def main():
         if seg[k].sum() > 0:
             name = ("fast." if k >= 8 else "slow.") + KINDS[k % 8]
             print(f"  {name:12s} " + " ".join(f"{v / 1e3:8.1f}" for v in seg[k]))
+    if trace.any():
+        names = ["poll", "norm/fill", "bar", "gemv", "publish", "release", "total", "wts@"]
+        print("cycle trace of the last frame (data-flow kernel), mean cycles per phase kind: " + " | ".join(names))
+        for slot, label in ((0, "CTA 0"), (1, "CTA n/2")):
+            acc = {}
+            for p in range(model.phase_count):
+                t = trace[slot, p].astype(float)
+                if t[0] == 0:
+                    continue
+                k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
+                if t[2] == 0:  # attention / sample: start and end only
+                    d = [0, 0, 0, 0, 0, 0, t[6] - t[0], 0]
+                else:
+                    t5 = t[5] if t[5] else t[2]
+                    t4 = t[4] if t[4] else t[2]
+                    # wts@ = when the last consumer warp saw the weights, relative to the phase start of warp 0
+                    d = [t[1] - t[0], t[7] - t[1], t[2] - t[7], t4 - t[2], t5 - t4, t[6] - t5, t[6] - t[0], (t[3] - t[0]) if t[3] else 0]
+                a0, n0 = acc.get(k, ([0.0] * 8, 0))
+                acc[k] = ([x + y for x, y in zip(a0, d)], n0 + 1)
+            tot = 0.0
+            for k, (v, n) in acc.items():
+                print(f"  {label:8s} {k:12s} x{n:3d} " + " ".join(f"{x / n:8.0f}" for x in v))
+                tot += v[6]
+            print(f"  {label}: {tot:.0f} cycles per frame in phases")
     if a.out:
         with open(a.out, "w") as f:
             json.dump({"model": a.model, "batch": a.batch, "frames": a.frames,
