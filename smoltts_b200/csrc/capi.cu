@@ -86,7 +86,7 @@ static int imax(int a, int b) { return a > b ? a : b; }
 
 struct WsLayout {
     size_t x, h, xf, q, attn, act, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
-    size_t ll, ll_partial, ll_tok, ll_epoch, total;
+    size_t ll, ll_partial, ll_tok, ll_cand, ll_epoch, total;
 };
 
 static int ll_batch_of(const SmolConfig& c) { (void)c; return smol::kLLMaxBatch; }
@@ -135,6 +135,7 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.ll = take(ll_regions(c, depth, bl, nullptr, nullptr) * 8);
     L.ll_partial = take((size_t)2 * bl * c.n_head * smol::kMaxSplits * smol::kPartialStride * 8);
     L.ll_tok = take((size_t)bl * (1 + depth) * smol::kLLMaxCtas * 8);
+    L.ll_cand = take((size_t)(1 + depth) * smol::kLLRep * smol::kLLMaxCtas * 8);
     L.ll_epoch = take(256);
     L.total = off;
     return L;
@@ -257,6 +258,7 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     d.barrier = (uint32_t*)(base + L.barrier);
     d.ll = (unsigned long long*)(base + L.ll); d.ll_partial = (unsigned long long*)(base + L.ll_partial);
     d.ll_tok = (unsigned long long*)(base + L.ll_tok); d.ll_epoch = (uint32_t*)(base + L.ll_epoch);
+    d.ll_cand = (unsigned long long*)(base + L.ll_cand);
     // split counters, barrier words and every LL word (epoch 0 = never written) must start at zero
     // (setup-time, synchronous)
     CU(cudaMemset(base + L.split_count, 0, L.total - L.split_count));
@@ -341,6 +343,7 @@ static int ensure_ll_tile(SmolModel* m, int bt) {
 static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_iters = false) {
     const int bt = smol::decode_batch_tile(A.batch);
     int rc;
+    A.repeat = m->repeat;  // barrier kernel: profiling repeat count; data-flow kernel: experiment switches
     if (m->mode == 2 && whole_iters && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
         if ((rc = ensure_ll_tile(m, bt))) return rc;
         if (m->ll_state[bt] == 1) {

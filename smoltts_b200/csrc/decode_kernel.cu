@@ -271,41 +271,54 @@ __device__ __forceinline__ void gemv_units(const Ctx& c, int n_units, int K, Epi
     int j = c.warp;
     for (int u = c.cta + c.warp * c.n_ctas; u < n_units; u += kWarps * c.n_ctas, j += kWarps) {
         const uint4* wrow = reinterpret_cast<const uint4*>(c.stage + (size_t)j * slot_bytes);
-        float acc0[R][BT], acc1[R][BT];
+        // K is summed in slices of 128 chunks (1024 elements): inside a slice lane-strided chunks with two
+        // accumulator chains and a butterfly warp sum, slices added in order.  (The data-flow kernel gives the
+        // slices of a long row to different warps; the order of the additions is the same.)
+        float tot[R][BT];
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int b = 0; b < BT; ++b) { acc0[r][b] = 0.f; acc1[r][b] = 0.f; }
+            for (int b = 0; b < BT; ++b) tot[r][b] = 0.f;
+        for (int c0 = 0; c0 < nchunks; c0 += 128) {
+            const int c1 = min(c0 + 128, nchunks);
+            float acc0[R][BT], acc1[R][BT];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) { acc0[r][b] = 0.f; acc1[r][b] = 0.f; }
 #pragma unroll(BT <= 2 ? 3 : 1)
-        for (int ch = c.lane; ch < nchunks; ch += 32) {
-            float wf[R][8];
+            for (int ch = c0 + c.lane; ch < c1; ch += 32) {
+                float wf[R][8];
 #pragma unroll
-            for (int r = 0; r < R; ++r) unpack8(wrow[r * nchunks + ch], wf[r]);
+                for (int r = 0; r < R; ++r) unpack8(wrow[r * nchunks + ch], wf[r]);
 #pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                const float* xr = c.xs + (size_t)b * K + ch * 4;
-                const float4 x0 = *reinterpret_cast<const float4*>(xr);
-                const float4 x1 = *reinterpret_cast<const float4*>(xr + half);
+                for (int b = 0; b < BT; ++b) {
+                    const float* xr = c.xs + (size_t)b * K + ch * 4;
+                    const float4 x0 = *reinterpret_cast<const float4*>(xr);
+                    const float4 x1 = *reinterpret_cast<const float4*>(xr + half);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float a0 = acc0[r][b], a1 = acc1[r][b];
-                    a0 = fmaf(wf[r][0], x0.x, a0); a1 = fmaf(wf[r][4], x1.x, a1);
-                    a0 = fmaf(wf[r][1], x0.y, a0); a1 = fmaf(wf[r][5], x1.y, a1);
-                    a0 = fmaf(wf[r][2], x0.z, a0); a1 = fmaf(wf[r][6], x1.z, a1);
-                    a0 = fmaf(wf[r][3], x0.w, a0); a1 = fmaf(wf[r][7], x1.w, a1);
-                    acc0[r][b] = a0; acc1[r][b] = a1;
+                    for (int r = 0; r < R; ++r) {
+                        float a0 = acc0[r][b], a1 = acc1[r][b];
+                        a0 = fmaf(wf[r][0], x0.x, a0); a1 = fmaf(wf[r][4], x1.x, a1);
+                        a0 = fmaf(wf[r][1], x0.y, a0); a1 = fmaf(wf[r][5], x1.y, a1);
+                        a0 = fmaf(wf[r][2], x0.z, a0); a1 = fmaf(wf[r][6], x1.z, a1);
+                        a0 = fmaf(wf[r][3], x0.w, a0); a1 = fmaf(wf[r][7], x1.w, a1);
+                        acc0[r][b] = a0; acc1[r][b] = a1;
+                    }
                 }
             }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) tot[r][b] = __fadd_rn(tot[r][b], warp_sum(acc0[r][b] + acc1[r][b]));
         }
         float mine[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             mine[r] = 0.f;
 #pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                const float s = warp_sum(acc0[r][b] + acc1[r][b]);
-                if (c.lane == b) mine[r] = s;
-            }
+            for (int b = 0; b < BT; ++b)
+                if (c.lane == b) mine[r] = tot[r][b];
         }
         epi(u, mine);
     }

@@ -89,6 +89,7 @@ struct DevModel {
     unsigned long long* ll;          // phase p, sequence b, replica r: ll + ll_off[p] + (b * kLLRep + r) * ll_len[p]
     unsigned long long* ll_partial;  // split-KV partials [2][ll_batch][n_head][kMaxSplits][66] words
     unsigned long long* ll_tok;      // sampled ids [ll_batch][n_rows][kLLMaxCtas] words
+    unsigned long long* ll_cand;     // greedy candidates (best logit | index) of every CTA [n_rows][kLLRep][kLLMaxCtas] words
     uint32_t* ll_epoch;              // [0] phases executed by earlier launches (epochs never repeat)
     int ll_batch;
     uint32_t ll_step_words;          // words between the regions of the same phase of two consecutive depth steps

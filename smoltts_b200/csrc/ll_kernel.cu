@@ -160,6 +160,8 @@ __shared__ __align__(8) uint64_t s_full[kStages];
 __shared__ __align__(8) uint64_t s_empty[kStages];
 __shared__ SampleScratch s_sc;
 __shared__ float s_part[kWarps];
+__shared__ float s_kpart[64];          // partial sums of the K slices of long rows (w2)
+__shared__ uint32_t s_cand[kWarps];    // greedy candidates of the warps (bf16 logit << 16 | 4095 - index... see cand_pack)
 __shared__ int s_pos, s_step, s_fin;   // cached positions (seq_len) / frames emitted / stop flag, tracked locally
 __shared__ int s_tok[kMaxRows];        // pending input column
 __shared__ int s_nw[kMaxRows];         // ids sampled in the current frame
@@ -316,11 +318,26 @@ __device__ __forceinline__ int sample_phase_index(const DevModel& M, int r) {  /
 __device__ __forceinline__ int token_word_get(const DevModel& M, int r, uint32_t epoch) {
     return (int)ll_get(M.ll_tok + (size_t)r * kLLMaxCtas + blockIdx.x, epoch);
 }
+// Greedy rows (temperature 0) and forced ids need no sampler CTA: every CTA works the id out itself (argmax over
+// the published logits / the forced id) -- no SAMPLE hand-off on the critical path.
+__device__ __forceinline__ bool row_is_local(const DevModel& M, const CallArgs& A, int r) {
+    if (A.repeat & 2) return false;  // experiment switch: always go through the sampler CTA
+    return M.force != nullptr || (r == 0 ? A.s.temp : A.s.fast_temp) == 0.0f;
+}
+// Greedy candidate = (logit, index) packed so that unsigned max picks the larger logit and, among equal logits, the
+// smaller index (torch / mx argmax tie rule): an order-preserving map of the bf16 logit in the high 16 bits, the
+// inverted index in the low 16.  Logits are bf16-rounded, so nothing is lost.
+__device__ __forceinline__ uint32_t cand_pack(float v, int idx) {
+    uint32_t b = __float_as_uint(v) >> 16;
+    b = (b & 0x8000u) ? (~b & 0xffffu) : (b | 0x8000u);
+    return (b << 16) | (uint32_t)(0xffff - idx);
+}
+__device__ __forceinline__ int cand_index(uint32_t c) { return 0xffff - (int)(c & 0xffffu); }
 // frame boundary: adopt the ids sampled in the previous frame (G:143-166).  e_prev0 = epoch of phase 0 of
 // the previous frame.
 __device__ __noinline__ void frame_boundary(const DevModel& M, const CallArgs& A, uint32_t e_prev0) {
     const int tid = threadIdx.x;
-    if (tid < M.n_rows) s_nw[tid] = token_word_get(M, tid, e_prev0 + (uint32_t)sample_phase_index(M, tid));
+    if (tid < M.n_rows && !row_is_local(M, A, tid)) s_nw[tid] = token_word_get(M, tid, e_prev0 + (uint32_t)sample_phase_index(M, tid));
     csync();
     if (tid == 0 && s_fin == 0) {
         for (int r = 0; r < M.n_rows; ++r) s_tok[r] = s_nw[r];
@@ -585,29 +602,74 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, in
 // ---- sampling (G:88-99 slow, G:118-132 depth) + frame assembly and the stop rule (G:143-166) ------------
 __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, int is_fast, int depth_pos, int p, uint32_t epoch,
                                           float* lg) {
-    if (blockIdx.x != 0) return;
     const int tid = threadIdx.x, n_ctas = gridDim.x;
     const bool fast = is_fast != 0;
     const int N = fast ? M.codebook_size : M.vocab;
     const int r = fast ? 1 + depth_pos : 0;
     const int R = M.n_rows;
-    const unsigned long long* src = M.ll + M.ll_off[p - 1];  // replica 0 of the HEAD phase
-    for (int i = tid; i < N / 4; i += kCons) {
-        uint4 v;
-        uint32_t spins = 0;
-        do { LL_SPIN_GUARD(spins); v = ld_relaxed_v4(src + 2 * i); } while (v.y != epoch - 1 || v.w != epoch - 1);
-        *reinterpret_cast<float4*>(lg + 4 * i) = make_float4(bf_lo(v.x), bf_hi(v.x), bf_lo(v.z), bf_hi(v.z));
+    const bool local = row_is_local(M, A, r);
+    if (!local && blockIdx.x != 0) return;  // sampled rows: CTA 0 is the sampler, the others pick the id up when they need it
+    int tok;
+    if (M.force != nullptr) {
+        tok = ldcg_i32(M.force + r);
+    } else if (local) {
+        // greedy: every CTA published its best (logit, index) with the HEAD phase's epoch; warp 0 reduces them
+        if (tid < 32) {
+            const unsigned long long* src = M.ll_cand + ((size_t)r * kLLRep + (blockIdx.x % kLLRep)) * kLLMaxCtas;
+            // all of the lane's words in flight before the first epoch is looked at (kLLMaxCtas / 32 = 8 per lane)
+            uint2 v[kLLMaxCtas / 32];
+#pragma unroll
+            for (int k = 0; k < kLLMaxCtas / 32; ++k) {
+                v[k] = make_uint2(0u, epoch - 1);
+                if (tid + 32 * k < n_ctas) v[k] = ld_relaxed_v2(src + tid + 32 * k);
+            }
+            uint32_t spins = 0;
+            for (;;) {
+                bool ready = true;
+#pragma unroll
+                for (int k = 0; k < kLLMaxCtas / 32; ++k)
+                    if (v[k].y != epoch - 1) { ready = false; v[k] = ld_relaxed_v2(src + tid + 32 * k); }
+                if (ready) break;
+                LL_SPIN_GUARD(spins);
+            }
+            uint32_t best = 0u;
+#pragma unroll
+            for (int k = 0; k < kLLMaxCtas / 32; ++k) best = v[k].x > best ? v[k].x : best;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+                best = ob > best ? ob : best;
+            }
+            if (tid == 0) s_cand[0] = best;
+        }
+        csync();
+        tok = cand_index(s_cand[0]);
+    } else {
+        const unsigned long long* src = ll_src(M, p - 1, 0);  // the HEAD phase's logits (replica 0)
+        for (int i = tid; i < N / 4; i += kCons) {
+            uint4 v = ld_relaxed_v4(src + 2 * i);
+            uint32_t spins = 0;
+            while (v.y != epoch - 1 || v.w != epoch - 1) { LL_SPIN_GUARD(spins); v = ld_relaxed_v4(src + 2 * i); }
+            *reinterpret_cast<float4*>(lg + 4 * i) = make_float4(bf_lo(v.x), bf_hi(v.x), bf_lo(v.z), bf_hi(v.z));
+        }
+        csync();
+        const float temp = fast ? A.s.fast_temp : A.s.temp;
+        if (temp == 0.0f) {
+            tok = block_argmax<kCons>(lg, N, s_sc);
+        } else {
+            const uint32_t seq_id = A.b.seq_id ? (uint32_t)ldcg_i32(A.b.seq_id) : 0u;
+            tok = sample_row<kCons>(lg, N, temp, fast ? 0 : A.s.top_k, fast ? 1.0f : A.s.top_p, A.s.min_p, A.s.seed,
+                                    (uint32_t)s_step, seq_id, (uint32_t)r, s_sc);
+        }
     }
-    csync();
-    const float temp = fast ? A.s.fast_temp : A.s.temp;
-    const uint32_t seq_id = A.b.seq_id ? (uint32_t)ldcg_i32(A.b.seq_id) : 0u;
-    int tok = sample_row<kCons>(lg, N, temp, fast ? 0 : A.s.top_k, fast ? 1.0f : A.s.top_p, A.s.min_p, A.s.seed,
-                         (uint32_t)s_step, seq_id, (uint32_t)r, s_sc);
-    if (M.force != nullptr) tok = ldcg_i32(M.force + r);
     const bool last = fast && depth_pos == M.depth - 1;
-    if (last) __threadfence();  // frame boundary: keep the release chain cumulative
-    if (tid < n_ctas) st_relaxed_v2(M.ll_tok + (size_t)r * kLLMaxCtas + tid, (uint32_t)tok, epoch);
-    if (tid == 0) {
+    if (local) {
+        if (tid == 0) s_nw[r] = tok;
+    } else {
+        if (last) __threadfence();  // frame boundary: keep the release chain cumulative
+        if (tid < n_ctas) st_relaxed_v2(M.ll_tok + (size_t)r * kLLMaxCtas + tid, (uint32_t)tok, epoch);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
         M.frame_tokens[r] = tok;
         if (last && s_fin == 0) {
             // frame assembly for the host and the next launch; every CTA applies the same update locally
@@ -616,7 +678,7 @@ __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, 
             for (int rr = 0; rr < R; ++rr) {
                 int v;
                 if (rr == r) v = tok;
-                else if (rr == 0) v = token_word_get(M, 0, epoch - (uint32_t)(p - sample_phase_index(M, 0)));
+                else if (rr == 0 && !row_is_local(M, A, 0)) v = token_word_get(M, 0, epoch - (uint32_t)(p - sample_phase_index(M, 0)));
                 else v = s_nw[rr];
                 if (rr == 0) slow = v;
                 A.b.tokens[rr] = v;
@@ -634,13 +696,13 @@ __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, 
 // acc_r = sum_k W_r[k] * x[k]: lane-strided 8-element chunks, two accumulator chains per row (elements
 // 0-3 / 4-7 of a chunk), butterfly warp sum -- the summation order of decode_kernel.cu: gemv_units.
 template <int R>
-__device__ __forceinline__ void gemv_rows(const unsigned char* sm, const uint32_t (&w)[R], uint32_t xs, int nchunks, int lane, float (&r)[R]) {
+__device__ __forceinline__ void gemv_rows(const unsigned char* sm, const uint32_t (&w)[R], uint32_t xs, int c0, int nchunks, int lane, float (&r)[R]) {
     // plain shared-memory loads through the kernel's own array (the compiler may hoist and batch them)
     float a0[R], a1[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
-#pragma unroll 4
-    for (int ch = lane; ch < nchunks; ch += 32) {
+#pragma unroll 1
+    for (int ch = c0 + lane; ch < nchunks; ch += 32) {
         float x[8];
         unpack8(*reinterpret_cast<const uint4*>(sm + xs + (uint32_t)ch * 16u), x);
 #pragma unroll
@@ -717,7 +779,7 @@ __device__ __forceinline__ void build_desc(const DevModel& M, const CallArgs& A,
         if (kind == PH_QKV) aux = (unsigned long long)(fast ? M.fast_rope + (size_t)ph.depth_pos * kHeadDim : M.rope);
         if (kind == PH_HEAD) {
             aux = (unsigned long long)(fast ? M.depth_logits + (size_t)ph.depth_pos * M.codebook_size : M.token_logits);
-            nrep = 1;
+            nrep = 1;  // logits words are read by the sampler CTA only (greedy rows use the candidate words)
         }
         w[0] = (uint32_t)src; w[1] = (uint32_t)(src >> 32);
         w[2] = (uint32_t)(unsigned long long)nw; w[3] = (uint32_t)((unsigned long long)nw >> 32);
@@ -791,8 +853,12 @@ __device__ __noinline__ void prologue_embed(const DevModel& M, const CallArgs& A
     }
     if (src_kind == 2) {
         const int r = depth_pos;  // row of depth code depth_pos-1
-        const int code = token_word_get(M, r, epoch - (uint32_t)(p - sample_phase_index(M, r)));
-        if (lane == 0) s_nw[r] = code;
+        int code;
+        if (row_is_local(M, A, r)) code = s_nw[r];
+        else {
+            code = token_word_get(M, r, epoch - (uint32_t)(p - sample_phase_index(M, r)));
+            if (lane == 0) s_nw[r] = code;
+        }
         const uint16_t* row = emb_base + (size_t)code * (nch * 8);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -999,6 +1065,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
             csync();
             LL_TRACE(2);
 
+            uint32_t warp_cand = 0u;  // HEAD phases: this warp's best (logit, index)
             {
                 const uint4 d1 = lds_v4(dsc + 16u);
                 unsigned long long* out = reinterpret_cast<unsigned long long*>((unsigned long long)d1.x | ((unsigned long long)d1.y << 32));
@@ -1011,6 +1078,24 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                 const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
                 if (fast && kind == PH_HEAD && depth_pos == M.depth - 1) __threadfence();  // release side of the once-per-frame fence
 
+                // long rows (w2): the K slices of 128 chunks of a unit go to different warps, partial sums meet in
+                // shared memory and are added in slice order (the order decode_kernel.cu uses inside one warp)
+#ifndef LL_KSPLIT
+#define LL_KSPLIT 1
+#endif
+                const int n_slices = (nch + 127) >> 7;
+                const bool ksplit = LL_KSPLIT && !(A.repeat & 1);
+                if (ksplit && n_slices > 1) {
+#pragma unroll 1
+                    for (int t = warp; t < nu * n_slices; t += kLLWarps) {
+                        const int j = t / n_slices, sl = t - j * n_slices;
+                        const uint32_t w[2] = {wbase - sm0 + (uint32_t)(2 * j) * row_bytes, wbase - sm0 + (uint32_t)(2 * j + 1) * row_bytes};
+                        float r[2];
+                        gemv_rows<2>(smem_dyn, w, xs - sm0, sl * 128, min(nch, sl * 128 + 128), lane, r);
+                        if (lane == 0) { s_kpart[2 * t] = r[0]; s_kpart[2 * t + 1] = r[1]; }
+                    }
+                    csync();
+                }
 #pragma unroll 1
                 for (int j = warp; j < nu; j += kLLWarps) {
                     const int n0 = 2 * (u0 + j);
@@ -1029,13 +1114,28 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                         const uint32_t w[4] = {wbase - sm0 + (uint32_t)(2 * j) * row_bytes, wbase - sm0 + (uint32_t)(2 * j + 1) * row_bytes,
                                                wbase2 - sm0 + (uint32_t)(2 * j) * row_bytes, wbase2 - sm0 + (uint32_t)(2 * j + 1) * row_bytes};
                         float r[4];
-                        gemv_rows<4>(smem_dyn, w, xs - sm0, nch, lane, r);
-                        a0 = r[0]; a1 = r[1]; g0 = r[2]; g1 = r[3];
+                        gemv_rows<4>(smem_dyn, w, xs - sm0, 0, nch, lane, r);
+                        a0 = __fadd_rn(0.f, r[0]); a1 = __fadd_rn(0.f, r[1]); g0 = __fadd_rn(0.f, r[2]); g1 = __fadd_rn(0.f, r[3]);
+                    } else if (ksplit && n_slices > 1) {
+                        a0 = 0.f; a1 = 0.f;
+                        for (int sl = 0; sl < n_slices; ++sl) {
+                            a0 = __fadd_rn(a0, s_kpart[2 * (j * n_slices + sl)]);
+                            a1 = __fadd_rn(a1, s_kpart[2 * (j * n_slices + sl) + 1]);
+                        }
+                    } else if (n_slices > 1) {
+                        const uint32_t w[2] = {wbase - sm0 + (uint32_t)(2 * j) * row_bytes, wbase - sm0 + (uint32_t)(2 * j + 1) * row_bytes};
+                        a0 = 0.f; a1 = 0.f;
+#pragma unroll 1
+                        for (int sl = 0; sl < n_slices; ++sl) {
+                            float r[2];
+                            gemv_rows<2>(smem_dyn, w, xs - sm0, sl * 128, min(nch, sl * 128 + 128), lane, r);
+                            a0 = __fadd_rn(a0, r[0]); a1 = __fadd_rn(a1, r[1]);
+                        }
                     } else {
                         const uint32_t w[2] = {wbase - sm0 + (uint32_t)(2 * j) * row_bytes, wbase - sm0 + (uint32_t)(2 * j + 1) * row_bytes};
                         float r[2];
-                        gemv_rows<2>(smem_dyn, w, xs - sm0, nch, lane, r);
-                        a0 = r[0]; a1 = r[1];
+                        gemv_rows<2>(smem_dyn, w, xs - sm0, 0, nch, lane, r);
+                        a0 = __fadd_rn(0.f, r[0]); a1 = __fadd_rn(0.f, r[1]);
                     }
                     if (j == warp) LL_TRACE(4);
                     uint32_t word = 0u;
@@ -1059,6 +1159,8 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                         const float l0 = bf16_round(a0), l1 = bf16_round(a1);
                         *reinterpret_cast<float2*>(reinterpret_cast<float*>(aux) + n0) = make_float2(l0, l1);
                         word = pack_bf16(l0, l1);
+                        const uint32_t c0 = cand_pack(l0, n0), c1 = cand_pack(l1, n0 + 1);
+                        warp_cand = max(warp_cand, max(c0, c1));
                     } else {
                         // wo: h = x + wo(attn)  (P:499)      w2: x' = h + w2(act)  (P:500)
                         word = pack_bf16(__fadd_rn(bf_lo(pre), bf16_round(a0)), __fadd_rn(bf_hi(pre), bf16_round(a1)));
@@ -1070,13 +1172,32 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                     if (lane == 0 && kind == PH_QKV && !fast && n0 >= q_rows) kv_append(M, A, it, layer, n0, word);
                 }
             }
+            if (kind == PH_HEAD && M.force == nullptr && !(A.repeat & 2) && (fast ? A.s.fast_temp : A.s.temp) == 0.0f) {
+                // greedy row: the CTA's best (logit, index) goes out as one word per replica
+                if (lane == 0) s_cand[warp] = warp_cand;
+                csync();
+                if (warp == 0) {
+                    uint32_t best = lane < kLLWarps ? s_cand[lane] : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        best = ob > best ? ob : best;
+                    }
+                    const int r = fast ? 1 + depth_pos : 0;
+                    if (lane < kLLRep) st_relaxed_v2(M.ll_cand + ((size_t)r * kLLRep + lane) * kLLMaxCtas + blockIdx.x, best, epoch);
+                }
+            }
             // this warp is done with the stage(s): hand the ring space back to the producer
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(empty0 + 8u * (wseq % kStages));
                 if (n_parts == 2) mbar_arrive(empty0 + 8u * ((wseq + 1) % kStages));
             }
-            if (LL_END_SYNC) csync();
+            if (LL_END_SYNC && !(A.repeat & 4)) csync();
+            // A CTA that is done early would hammer L2 with polls for words that cannot be there yet, and that slows
+            // the very stores it is waiting for (measured: -14% frame time).  Hold off for a fraction of the hand-off
+            // latency before the next phase's first poll.  (option "repeat" >> 3 overrides the delay, in 64 ns units)
+            __nanosleep((A.repeat >> 3) ? (unsigned)(A.repeat >> 3) * 64u : 256u);
             LL_TRACE(6);
         }
         if (A.mode == 1) {  // prefill: a sequence still inside its prompt advances one position
@@ -1139,6 +1260,10 @@ size_t ll_smem_plan(const DevModel& M, int bt, int n_ctas, int* xs_bytes, int* r
     upd(per(M.finter / 2, 4L * M.fdim));
     upd(per(M.fdim / 2, 4L * M.finter));
     upd(per(M.codebook_size / 2, 4L * M.fdim));
+    {   // partial sums of the K slices of long rows live in a 64-float shared array
+        const int f = M.inter > M.finter ? M.inter : M.finter, d = M.dim > M.fdim ? M.dim : M.fdim;
+        if (((d / 2 + n_ctas - 1) / n_ctas) * ((f + 1023) / 1024) * 2 > 64) return 0;
+    }
     // the ring allocator is a pure function of the stage sizes (producer and consumers replay it
     // independently); it cannot stall forever as long as two of the largest stages fit
     if (fixed + 2 * need > budget) return 0;
