@@ -60,7 +60,7 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram bytes per launch of the decode kernel from the committed ncu capture, if any."""
+    """dram bytes per frame of the data-flow decode kernel from the committed ncu --set full capture (bs=1, 150m)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
@@ -340,7 +340,8 @@ def run_ours(args):
                 "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                 "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": kernel_ms_mean,
-                "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None,
+                "traffic": ((traffic or {}).get("dram_bytes_per_frame") * args.frames
+                            if traffic and dataflow and args.model == "smoltts_byte_150m" and args.batch == 1 else None),
             },
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
