@@ -1096,8 +1096,11 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                     }
                     csync();
                 }
+                // units go to warps 1, 2, .., 10, 0: the norm warp, which reaches the barrier last, gets a unit only when
+                // every other warp has one  (option "repeat" bit 3 switches the rotation off)
+                const int jw = (A.repeat & 8) ? warp : (warp + kLLWarps - 1) % kLLWarps;
 #pragma unroll 1
-                for (int j = warp; j < nu; j += kLLWarps) {
+                for (int j = jw; j < nu; j += kLLWarps) {
                     const int n0 = 2 * (u0 + j);
                     // operands of the epilogue that do not depend on the GEMV: issue their loads first
                     uint32_t pre = 0u;
@@ -1137,7 +1140,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                         gemv_rows<2>(smem_dyn, w, xs - sm0, 0, nch, lane, r);
                         a0 = __fadd_rn(0.f, r[0]); a1 = __fadd_rn(0.f, r[1]);
                     }
-                    if (j == warp) LL_TRACE(4);
+                    if (j == jw) LL_TRACE(4);
                     uint32_t word = 0u;
                     if (lane != 0) {
                         // lanes 1.. only help publishing
@@ -1168,7 +1171,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                     // one replica per lane: the copies leave in one store instruction
                     word = __shfl_sync(0xffffffffu, word, 0);
                     if (lane < nrep) st_relaxed_v2(out + j + (size_t)lane * len_out, word, epoch);
-                    if (j == warp) LL_TRACE(5);
+                    if (j == jw) LL_TRACE(5);
                     if (lane == 0 && kind == PH_QKV && !fast && n0 >= q_rows) kv_append(M, A, it, layer, n0, word);
                 }
             }
@@ -1197,7 +1200,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
             // A CTA that is done early would hammer L2 with polls for words that cannot be there yet, and that slows
             // the very stores it is waiting for (measured: -14% frame time).  Hold off for a fraction of the hand-off
             // latency before the next phase's first poll.  (option "repeat" >> 3 overrides the delay, in 64 ns units)
-            __nanosleep((A.repeat >> 3) ? (unsigned)(A.repeat >> 3) * 64u : 256u);
+            __nanosleep((A.repeat >> 8) ? (unsigned)(A.repeat >> 8) * 64u : 256u);
             LL_TRACE(6);
         }
         if (A.mode == 1) {  // prefill: a sequence still inside its prompt advances one position
@@ -1267,6 +1270,10 @@ size_t ll_smem_plan(const DevModel& M, int bt, int n_ctas, int* xs_bytes, int* r
     // the ring allocator is a pure function of the stage sizes (producer and consumers replay it
     // independently); it cannot stall forever as long as two of the largest stages fit
     if (fixed + 2 * need > budget) return 0;
+    {   // the gated MLP needs BOTH of its stages resident at once, possibly behind a wrap gap shorter than one stage
+        const size_t part = per(M.inter / 2, 4L * M.dim) > per(M.finter / 2, 4L * M.fdim) ? per(M.inter / 2, 4L * M.dim) : per(M.finter / 2, 4L * M.fdim);
+        if (fixed + 3 * part > budget) return 0;
+    }
     *ring_bytes = (int)((budget - fixed) / 128 * 128);
     return fixed + (size_t)*ring_bytes;
 }

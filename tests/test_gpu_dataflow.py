@@ -83,13 +83,78 @@ def test_dataflow_equals_barrier_kernel_sampled(size, B):
     _same(ref, got, f"{size} sampled B={B}")
 
 
-def test_dataflow_long_context_many_splits():
-    """Context past 64 * splits and across many KV pages: the combiner path with several splits."""
-    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=2, max_seq_len=2304)
-    prompts = [prompt_grid(byte_prompt(2100 - 400 * b, seed=70 + b), cfg) for b in range(2)]
+@pytest.mark.parametrize("size,n_prompt", [("smoltts_byte_tiny", 2100), ("smoltts_byte_70m", 2100), ("smoltts_byte_tiny", 700)])
+def test_dataflow_long_context_many_splits(size, n_prompt):
+    """Context past 64 * splits and across many KV pages: the combiner path with up to 32 splits per head; on 70m
+    (9 heads x 32 splits = 288 attention units) some CTAs run two units per phase."""
+    cfg, sd, model, orc = model_and_oracle(size, max_batch=1, max_seq_len=2304)
+    prompts = [prompt_grid(byte_prompt(n_prompt, seed=70), cfg)]
     ref = _run(model, 0, prompts, 6, 6, None)
     got = _run(model, 2, prompts, 6, 6, None)
-    _same(ref, got, "long context")
+    assert model.get_option("ll_ready") == 1
+    _same(ref, got, f"long context {size} {n_prompt}")
+
+
+def test_dataflow_depth7_without_duplicate_code_0():
+    """duplicate_code_0 = False (the kokoro_v1 data config): 7 depth steps, shifted embedding offsets."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=1, duplicate_code_0=False)
+    assert cfg.max_fast_seqlen == 7
+    prompts = [prompt_grid(byte_prompt(30, seed=75), cfg)]
+    ref = _run(model, 0, prompts, 10, 4, None)
+    got = _run(model, 2, prompts, 10, 4, None)
+    assert model.get_option("ll_ready") == 1
+    _same(ref, got, "depth 7")
+
+
+def test_dataflow_fewer_ctas_and_mixed_sampling():
+    """A grid smaller than the GPU (more units per CTA, two GEMV rounds per warp) and the mixed case: the slow id sampled
+    by CTA 0 (published per CTA), the depth codes greedy (resolved by every CTA from the candidate words)."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=1)
+    prompts = [prompt_grid(byte_prompt(40, seed=77), cfg)]
+    kw = dict(temp=0.9, fast_temp=0.0, top_k=30, top_p=0.95, seed=5)
+    ref = _run(model, 0, prompts, 12, 5, [9], **kw)
+    got = _run(model, 2, prompts, 12, 5, [9], **kw)
+    _same(ref, got, "mixed sampling")
+    model.set_option("n_ctas", 40)
+    try:
+        few = _run(model, 2, prompts, 12, 5, [9], **kw)
+        assert model.get_option("n_ctas") == 40
+    finally:
+        model.set_option("n_ctas", 0)
+    for k in ("codes", "tokens", "seq_len", "step"):
+        assert torch.equal(ref[k], few[k]), f"40 CTAs: {k} differ"
+
+
+def test_dataflow_stop_rule_single_sequence():
+    """<|im_end|> forced in frame 2 of a 6-frame schedule: the sequence must freeze (tokens, seq_len, step, codes) in the
+    middle of a multi-frame launch of the data-flow kernel exactly as in the barrier kernel."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=1)
+    R = cfg.n_rows
+    prompts = [prompt_grid(byte_prompt(14, seed=81), cfg)]
+    res = {}
+    for mode in (0, 2):
+        model.set_option("mode", mode)
+        padded, lens = pack_prompts(model, prompts)
+        batch = model.new_batch(1, max_positions=64, max_frames=8)
+        try:
+            model.prefill(batch, padded, lens)
+            s = model.sampling(audio_only=True)
+            model.decode_frames(batch, s, 1)
+            force = torch.zeros(1, R, dtype=torch.int32, device=model.device)
+            force[0, 0] = model.token_config.im_end_id
+            model.set_force(force)
+            model.decode_frames(batch, s, 3)   # the stop fires in the first of these three frames
+            model.set_force(None)
+            model.decode_frames(batch, s, 2)
+            torch.cuda.synchronize()
+            res[mode] = (batch.tokens.clone(), batch.seq_len.clone(), batch.step.clone(), batch.finished.clone(), batch.out_codes.clone())
+        finally:
+            model.set_force(None)
+            model.set_option("mode", 2)
+            batch.release()
+    assert res[0][3].tolist() == [1] and res[0][2].tolist() == [2]
+    for a, b in zip(res[0], res[2]):
+        assert torch.equal(a, b)
 
 
 def test_dataflow_stop_rule_and_force():
