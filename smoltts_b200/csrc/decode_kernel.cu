@@ -627,12 +627,11 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
     }
 }
 
+// Splits per (sequence, kv head): a function of the sequence's own length only (ceil(L / 64), at most kMaxSplits),
+// never of the batch size or the grid -- a sequence must decode to the same bits alone, in any batch and on any shard.
 __device__ int attn_splits(const DevModel& M, int batch, int n_ctas) {
-    const int pairs = batch * M.n_kv;
-    int s = (2 * n_ctas + pairs - 1) / pairs;
-    if (s < 1) s = 1;
-    if (s > kMaxSplits) s = kMaxSplits;
-    return s;
+    (void)M; (void)batch; (void)n_ctas;
+    return kMaxSplits;
 }
 
 __device__ void phase_attn(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {

@@ -430,10 +430,8 @@ __device__ __forceinline__ void fast_attention(const DevModel& M, int layer, int
 // positions from the paged pool; the result leaves as LL words: directly (one split) or as (m, l, o[64])
 // partials that the head's combiner CTA merges in split order.
 __device__ __forceinline__ int attn_splits(const DevModel& M, int n_ctas) {
-    int s = (2 * n_ctas + M.n_kv - 1) / M.n_kv;
-    if (s < 1) s = 1;
-    if (s > kMaxSplits) s = kMaxSplits;
-    return s;
+    (void)M; (void)n_ctas;
+    return kMaxSplits;  // splits depend on the sequence's length only (decode_kernel.cu: attn_splits)
 }
 __device__ __forceinline__ unsigned long long* partial_words(const DevModel& M, int layer, int hq, int s) {
     return M.ll_partial + (((size_t)(layer & 1) * M.n_head + hq) * kMaxSplits + s) * kPartialStride;
