@@ -108,7 +108,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("SMOLTTS_B200_LIB") or _build.LIB_PATH  # override: A/B runs of two builds on one GPU box
     if not os.path.exists(path):
         path = _build.build()
     lib = C.CDLL(path)

@@ -88,6 +88,10 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { sts_u32(a, __float_as_uint(v)); }
 
 // ---- LL words ------------------------------------------------------------------------------------
+// Polling loads: ld.relaxed.gpu (a strong load that always goes to L2).  ld.global.cv looks twice as fast in an isolated
+// exchange micro-benchmark (tools/micro/ll_atom.cu) but makes no difference inside this kernel (the L1 next to 227 KB of
+// shared memory is too small to matter); atomics as polls are slower.  Each 8-byte word {payload, epoch} is one aligned
+// access, so a reader sees a word entirely old or entirely new.
 __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
     uint4 v;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -570,9 +574,33 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, in
     // All of the head's partial words are polled in parallel into shared memory first (one L2 round trip).
     for (int hq = 0; hq < Hq; ++hq) {
         if ((n_units + hq) % n_ctas != cta) continue;
-        for (int i = tid; i < ns * kPartialStride; i += kCons) {
-            const int si = i / kPartialStride, k = i - si * kPartialStride;
-            sts_u32(scratch + (uint32_t)i * 4u, ll_get(partial_words(M, layer, hq, si) + k, epoch));
+        {   // all of the thread's words in flight before the first epoch is looked at (32 * 66 words / 352 threads = 6)
+            constexpr int kPer = (kMaxSplits * kPartialStride + kCons - 1) / kCons;
+            uint2 v[kPer];
+            const int n_words = ns * kPartialStride;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int i = tid + k * kCons;
+                v[k] = make_uint2(0u, epoch);
+                if (i < n_words) v[k] = ld_relaxed_v2(partial_words(M, layer, hq, i / kPartialStride) + i % kPartialStride);
+            }
+            uint32_t spins = 0;
+            for (;;) {
+                bool ready = true;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) {
+                    if (v[k].y != epoch) {
+                        const int i = tid + k * kCons;
+                        ready = false;
+                        v[k] = ld_relaxed_v2(partial_words(M, layer, hq, i / kPartialStride) + i % kPartialStride);
+                    }
+                }
+                if (ready) break;
+                LL_SPIN_GUARD(spins);
+            }
+#pragma unroll
+            for (int k = 0; k < kPer; ++k)
+                if (tid + k * kCons < n_words) sts_u32(scratch + (uint32_t)(tid + k * kCons) * 4u, v[k].x);
         }
         csync();
         if (tid < kHeadDim) {
@@ -695,22 +723,37 @@ __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, 
 // 0-3 / 4-7 of a chunk), butterfly warp sum -- the summation order of decode_kernel.cu: gemv_units.
 template <int R>
 __device__ __forceinline__ void gemv_rows(const unsigned char* sm, const uint32_t (&w)[R], uint32_t xs, int c0, int nchunks, int lane, float (&r)[R]) {
-    // plain shared-memory loads through the kernel's own array (the compiler may hoist and batch them)
+    // plain shared-memory loads through the kernel's own array (the compiler may batch them); kT chunks (lane, lane+32, ..)
+    // per trip so that their loads are in flight before the first FMA -- chunks are still accumulated in ascending order
+    constexpr int kT = R <= 2 ? 3 : 1;
     float a0[R], a1[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
 #pragma unroll 1
-    for (int ch = c0 + lane; ch < nchunks; ch += 32) {
-        float x[8];
-        unpack8(*reinterpret_cast<const uint4*>(sm + xs + (uint32_t)ch * 16u), x);
+    for (int ch = c0 + lane; ch < nchunks; ch += 32 * kT) {
+        uint4 xv[kT], wv[R][kT];
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(sm + w[i] + (uint32_t)ch * 16u), f);
-            a0[i] = fmaf(f[0], x[0], a0[i]); a1[i] = fmaf(f[4], x[4], a1[i]);
-            a0[i] = fmaf(f[1], x[1], a0[i]); a1[i] = fmaf(f[5], x[5], a1[i]);
-            a0[i] = fmaf(f[2], x[2], a0[i]); a1[i] = fmaf(f[6], x[6], a1[i]);
-            a0[i] = fmaf(f[3], x[3], a0[i]); a1[i] = fmaf(f[7], x[7], a1[i]);
+        for (int t = 0; t < kT; ++t) {
+            const int cc = min(ch + 32 * t, nchunks - 1);  // clamp: a chunk past the end is loaded but not used
+            xv[t] = *reinterpret_cast<const uint4*>(sm + xs + (uint32_t)cc * 16u);
+#pragma unroll
+            for (int i = 0; i < R; ++i) wv[i][t] = *reinterpret_cast<const uint4*>(sm + w[i] + (uint32_t)cc * 16u);
+        }
+#pragma unroll
+        for (int t = 0; t < kT; ++t) {
+            if (ch + 32 * t < nchunks) {
+                float x[8];
+                unpack8(xv[t], x);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    float f[8];
+                    unpack8(wv[i][t], f);
+                    a0[i] = fmaf(f[0], x[0], a0[i]); a1[i] = fmaf(f[4], x[4], a1[i]);
+                    a0[i] = fmaf(f[1], x[1], a0[i]); a1[i] = fmaf(f[5], x[5], a1[i]);
+                    a0[i] = fmaf(f[2], x[2], a0[i]); a1[i] = fmaf(f[6], x[6], a1[i]);
+                    a0[i] = fmaf(f[3], x[3], a0[i]); a1[i] = fmaf(f[7], x[7], a1[i]);
+                }
+            }
         }
     }
 #pragma unroll
@@ -937,10 +980,10 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
     }
 
     // cycle trace of the launch's last iteration (kTrace): CTA 0 and CTA n/2; thread 0 stamps 0 start, 1 input words
-    // arrived, 7 input row staged, 2 past the block barrier, 4 GEMV done, 5 result published, 6 end; lane 0 of the
-    // last consumer warp stamps 3 = weights seen
+    // arrived, 7 input row staged, 2 past the block barrier, 6 end; lane 0 of warp 1 (first GEMV unit of the CTA) stamps
+    // 3 GEMV start, 4 GEMV done, 5 result published
     unsigned long long* tr = nullptr;
-    if (kTrace && M.prof != nullptr && (tid == 0 || tid == (kLLWarps - 1) * 32) && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
+    if (kTrace && M.prof != nullptr && (tid == 0 || tid == 32) && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
         tr = M.prof + 2 * kMaxProg + 64 + (blockIdx.x == 0 ? 0 : 1) * kMaxProg * 8;
 #define LL_TRACE(i) do { if (kTrace && tr && tid == 0) { unsigned long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); tr[p * 8 + (i)] = c_; } } while (0)
 #define LL_TRACE_AUX(i) do { if (kTrace && tr && tid != 0) { unsigned long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); tr[p * 8 + (i)] = c_; } } while (0)
@@ -1057,7 +1100,6 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
             // the block barrier below passes that on to everyone
             if (warp == kLLWarps - 1) {
                 for (int i = 0; i < n_parts; ++i) mbar_wait(full0 + 8u * ((wseq + i) % kStages), ((wseq + i) / kStages) & 1u);
-                LL_TRACE_AUX(3);
             }
             LL_TRACE(7);
             csync();
@@ -1111,6 +1153,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                         pre = lds_u32(res + (uint32_t)n0 * 2u);
                     }
                     float a0, a1, g0 = 0.f, g1 = 0.f;
+                    if (j == jw) LL_TRACE_AUX(3);
                     if (kind == PH_W13) {
                         const uint32_t w[4] = {wbase - sm0 + (uint32_t)(2 * j) * row_bytes, wbase - sm0 + (uint32_t)(2 * j + 1) * row_bytes,
                                                wbase2 - sm0 + (uint32_t)(2 * j) * row_bytes, wbase2 - sm0 + (uint32_t)(2 * j + 1) * row_bytes};
@@ -1138,7 +1181,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                         gemv_rows<2>(smem_dyn, w, xs - sm0, 0, nch, lane, r);
                         a0 = __fadd_rn(0.f, r[0]); a1 = __fadd_rn(0.f, r[1]);
                     }
-                    if (j == jw) LL_TRACE(4);
+                    if (j == jw) LL_TRACE_AUX(4);
                     uint32_t word = 0u;
                     if (lane != 0) {
                         // lanes 1.. only help publishing
@@ -1169,7 +1212,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                     // one replica per lane: the copies leave in one store instruction
                     word = __shfl_sync(0xffffffffu, word, 0);
                     if (lane < nrep) st_relaxed_v2(out + j + (size_t)lane * len_out, word, epoch);
-                    if (j == jw) LL_TRACE(5);
+                    if (j == jw) LL_TRACE_AUX(5);
                     if (lane == 0 && kind == PH_QKV && !fast && n0 >= q_rows) kv_append(M, A, it, layer, n0, word);
                 }
             }
@@ -1194,11 +1237,13 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                 mbar_arrive(empty0 + 8u * (wseq % kStages));
                 if (n_parts == 2) mbar_arrive(empty0 + 8u * ((wseq + 1) % kStages));
             }
+            // A CTA that is done early would poll for words that cannot be there yet, and that slows the very stores it is
+            // waiting for -- also when only ONE warp polls (skipping either measure before the norm phases costs +15 %).
+            // So: a block barrier (idle warps cannot run ahead and poll) and a hold-off of a fraction of the hand-off
+            // latency before the next phase's first poll (-20 % and -14 % frame time).  Option "repeat": bit 2 drops the
+            // barrier, bits 8.. override the hold-off in units of 64 ns.
             if (LL_END_SYNC && !(A.repeat & 4)) csync();
-            // A CTA that is done early would hammer L2 with polls for words that cannot be there yet, and that slows
-            // the very stores it is waiting for (measured: -14% frame time).  Hold off for a fraction of the hand-off
-            // latency before the next phase's first poll.  (option "repeat" >> 3 overrides the delay, in 64 ns units)
-            __nanosleep((A.repeat >> 8) ? (unsigned)(A.repeat >> 8) * 64u : 256u);
+            if ((A.repeat >> 8) != 255) __nanosleep((A.repeat >> 8) ? (unsigned)(A.repeat >> 8) * 64u : 256u);
             LL_TRACE(6);
         }
         if (A.mode == 1) {  // prefill: a sequence still inside its prompt advances one position

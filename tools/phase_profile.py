@@ -89,7 +89,7 @@ def main():
             name = ("fast." if k >= 8 else "slow.") + KINDS[k % 8]
             print(f"  {name:12s} " + " ".join(f"{v / 1e3:8.1f}" for v in seg[k]))
     if trace.any():
-        names = ["poll", "norm/fill", "bar", "gemv", "publish", "release", "total", "wts@"]
+        names = ["poll", "norm/fill", "bar", "setup", "gemv", "publish", "release", "total"]
         print("cycle trace of the last frame (data-flow kernel), mean cycles per phase kind: " + " | ".join(names))
         for slot, label in ((0, "CTA 0"), (1, "CTA n/2")):
             acc = {}
@@ -99,18 +99,18 @@ def main():
                     continue
                 k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
                 if t[2] == 0:  # attention / sample: start and end only
-                    d = [0, 0, 0, 0, 0, 0, t[6] - t[0], 0]
+                    d = [0, 0, 0, 0, 0, 0, 0, t[6] - t[0]]
                 else:
-                    t5 = t[5] if t[5] else t[2]
-                    t4 = t[4] if t[4] else t[2]
-                    # wts@ = when the last consumer warp saw the weights, relative to the phase start of warp 0
-                    d = [t[1] - t[0], t[7] - t[1], t[2] - t[7], t4 - t[2], t5 - t4, t[6] - t5, t[6] - t[0], (t[3] - t[0]) if t[3] else 0]
+                    t3 = t[3] if t[3] else t[2]
+                    t4 = t[4] if t[4] else t3
+                    t5 = t[5] if t[5] else t4
+                    d = [t[1] - t[0], t[7] - t[1], t[2] - t[7], t3 - t[2], t4 - t3, t5 - t4, t[6] - t5, t[6] - t[0]]
                 a0, n0 = acc.get(k, ([0.0] * 8, 0))
                 acc[k] = ([x + y for x, y in zip(a0, d)], n0 + 1)
             tot = 0.0
             for k, (v, n) in acc.items():
                 print(f"  {label:8s} {k:12s} x{n:3d} " + " ".join(f"{x / n:8.0f}" for x in v))
-                tot += v[6]
+                tot += v[7]
             print(f"  {label}: {tot:.0f} cycles per frame in phases")
     if a.out:
         with open(a.out, "w") as f:
