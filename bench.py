@@ -178,7 +178,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_frames = args.cpu_frames or 16
+    n_frames = args.cpu_frames or 128  # ~3 s of CPU work per step
     per_step = []
     for i in range(args.warmup + args.steps):
         r = cpu_decode_rate(args, n_frames, batch=args.batch)
@@ -350,7 +350,7 @@ def run_ours(args):
             "check": codes_check,
         }
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = args.cpu_frames or 12
+            n_cpu = args.cpu_frames or 480  # ~10 s of CPU work at ~46 frames/s
             r = cpu_decode_rate(args, n_cpu, batch=args.batch)
             line["cpu_baseline"] = {
                 "value": r["frames_per_s"], "unit": "frames/s", "cores": r["threads"], "kind": "port",

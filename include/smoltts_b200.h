@@ -186,7 +186,8 @@ int smol_set_profile(SmolModel* m, uint64_t* d_phase_ns);
 /* Options: "mode" 2 (default) = data-flow persistent kernel (flag-carrying activation words, TMA
  * producer warp; whole frames / prefill at batch <= 8, larger batches fall back to mode 0),
  * 0 = persistent cooperative kernel with a grid barrier per phase, 1 = one launch per phase, a frame
- * captured in a CUDA graph;  "n_ctas" = grid size (default: one CTA per SM). */
+ * captured in a CUDA graph;  "n_ctas" = grid size (default: one CTA per SM);  "ll_flags" = A/B switches of the
+ * data-flow kernel used by tools/ll_ncu.py (0 = the shipped configuration). */
 int smol_set_option(SmolModel* m, const char* name, int64_t value);
 int64_t smol_get_option(const SmolModel* m, const char* name);
 

@@ -56,6 +56,7 @@ struct SmolModel {
     int ll_state[9] = {0};  // 0 unknown, 1 ready, -1 does not fit
     int mode = 2;
     int repeat = 0;
+    int ll_flags = 0;  // data-flow kernel: A/B switches and hold-off override (tools/ll_ncu.py)
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
     cudaGraphExec_t frame_graph = nullptr;
@@ -343,11 +344,12 @@ static int ensure_ll_tile(SmolModel* m, int bt) {
 static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_iters = false) {
     const int bt = smol::decode_batch_tile(A.batch);
     int rc;
-    A.repeat = m->repeat;  // barrier kernel: profiling repeat count; data-flow kernel: experiment switches
+    A.repeat = m->repeat;
     if (m->mode == 2 && whole_iters && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
         if ((rc = ensure_ll_tile(m, bt))) return rc;
         if (m->ll_state[bt] == 1) {
             if (A.n_iter == 0 && !A.finalize) return SMOL_OK;
+            A.repeat = m->ll_flags;  // the data-flow kernel reads its switches from this field
             CU(smol::ll_launch(m->dm, A, bt, m->n_ctas, m->ll_smem[bt], m->ll_xs[bt], m->ll_res[bt], m->ll_scratch[bt],
                                m->ll_ring[bt], stream));
             m->launches += 1;
@@ -560,6 +562,10 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
     if (!std::strcmp(name, "repeat")) {
         m->repeat = value > 0 ? (int)value : 0;
         m->frame_key_valid = false;
+        return SMOL_OK;
+    }
+    if (!std::strcmp(name, "ll_flags")) {
+        m->ll_flags = (int)value;
         return SMOL_OK;
     }
     if (!std::strcmp(name, "n_ctas")) {

@@ -28,6 +28,8 @@
 
 #define SMOL_BLOCK_SYNC() asm volatile("bar.sync 1, 352;" ::: "memory")  // the 11 consumer warps
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dev_model.h"
 #include "sampler.cuh"
@@ -94,12 +96,20 @@ __device__ __forceinline__ void sts_f32(uint32_t a, float v) { sts_u32(a, __floa
 // access, so a reader sees a word entirely old or entirely new.
 __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
     uint4 v;
+#ifdef LL_POLL_CV
+    asm volatile("ld.global.cv.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+#else
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ uint2 ld_relaxed_v2(const void* p) {
     uint2 v;
+#ifdef LL_POLL_CV
+    asm volatile("ld.global.cv.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+#else
     asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ void st_relaxed_v2(void* p, uint32_t a, uint32_t b) {
@@ -1096,6 +1106,33 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                     norm_store(raw, wv, nch, lane, M.eps, xs, kind != PH_HEAD ? res : 0u);
                 }
             }
+            // Everything the GEMV of this warp's first unit needs that does not depend on the staged row is worked out
+            // BEFORE the block barrier (the warps that do not stage the row are idle here): descriptor fields, the unit
+            // index, the RoPE pair / the residual pair (written two barriers ago).
+            const uint4 d1 = lds_v4(dsc + 16u);
+            unsigned long long* out = reinterpret_cast<unsigned long long*>((unsigned long long)d1.x | ((unsigned long long)d1.y << 32));
+            const unsigned long long aux = (unsigned long long)d1.z | ((unsigned long long)d1.w << 32);
+            const int len_out = (int)(d2.z & 0xffffu);
+            const int u0 = (int)(d2.w & 0xffffu), nu = (int)(d2.w >> 16);
+            const int nrep = (int)((d3.x >> 12) & 63u);
+            const uint32_t row_bytes = (uint32_t)nch * 16u;
+            const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
+            const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
+            // units go to warps 1, 2, .., 10, 0: the norm warp, which reaches the barrier last, gets a unit only when
+            // every other warp has one  (option "ll_flags" bit 3 switches the rotation off)
+            const int jw = (A.repeat & 8) ? warp : (warp + kLLWarps - 1) % kLLWarps;
+            uint32_t pre_first = 0u;
+            if (jw < nu) {
+                const int n0 = 2 * (u0 + jw);
+                if (kind == PH_QKV) {
+                    if (n0 < k_end) {
+                        const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)s_pos * kHeadDim);
+                        pre_first = __ldg(reinterpret_cast<const uint32_t*>(table + (n0 & (kHeadDim - 1))));
+                    }
+                } else if (kind == PH_WO || kind == PH_W2) {
+                    pre_first = lds_u32(res + (uint32_t)n0 * 2u);
+                }
+            }
             // the last consumer warp (never on the critical path of a prologue) makes sure the weights have landed;
             // the block barrier below passes that on to everyone
             if (warp == kLLWarps - 1) {
@@ -1107,15 +1144,6 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
 
             uint32_t warp_cand = 0u;  // HEAD phases: this warp's best (logit, index)
             {
-                const uint4 d1 = lds_v4(dsc + 16u);
-                unsigned long long* out = reinterpret_cast<unsigned long long*>((unsigned long long)d1.x | ((unsigned long long)d1.y << 32));
-                const unsigned long long aux = (unsigned long long)d1.z | ((unsigned long long)d1.w << 32);
-                const int len_out = (int)(d2.z & 0xffffu);
-                const int u0 = (int)(d2.w & 0xffffu), nu = (int)(d2.w >> 16);
-                const int nrep = (int)((d3.x >> 12) & 63u);
-                const uint32_t row_bytes = (uint32_t)nch * 16u;
-                const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
-                const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
                 if (fast && kind == PH_HEAD && depth_pos == M.depth - 1) __threadfence();  // release side of the once-per-frame fence
 
                 // long rows (w2): the K slices of 128 chunks of a unit go to different warps, partial sums meet in
@@ -1136,15 +1164,14 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                     }
                     csync();
                 }
-                // units go to warps 1, 2, .., 10, 0: the norm warp, which reaches the barrier last, gets a unit only when
-                // every other warp has one  (option "repeat" bit 3 switches the rotation off)
-                const int jw = (A.repeat & 8) ? warp : (warp + kLLWarps - 1) % kLLWarps;
 #pragma unroll 1
                 for (int j = jw; j < nu; j += kLLWarps) {
                     const int n0 = 2 * (u0 + j);
                     // operands of the epilogue that do not depend on the GEMV: issue their loads first
-                    uint32_t pre = 0u;
-                    if (kind == PH_QKV) {
+                    uint32_t pre = pre_first;
+                    if (j == jw) {
+                        // loaded before the barrier
+                    } else if (kind == PH_QKV) {
                         if (n0 < k_end) {
                             const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)s_pos * kHeadDim);
                             pre = __ldg(reinterpret_cast<const uint32_t*>(table + (n0 & (kHeadDim - 1))));
@@ -1240,8 +1267,8 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
             // A CTA that is done early would poll for words that cannot be there yet, and that slows the very stores it is
             // waiting for -- also when only ONE warp polls (skipping either measure before the norm phases costs +15 %).
             // So: a block barrier (idle warps cannot run ahead and poll) and a hold-off of a fraction of the hand-off
-            // latency before the next phase's first poll (-20 % and -14 % frame time).  Option "repeat": bit 2 drops the
-            // barrier, bits 8.. override the hold-off in units of 64 ns.
+            // latency before the next phase's first poll (-20 % and -14 % frame time).  Option "ll_flags" (CallArgs.repeat): bit 2
+            // drops the barrier, bits 8.. override the hold-off in units of 64 ns.
             if (LL_END_SYNC && !(A.repeat & 4)) csync();
             if ((A.repeat >> 8) != 255) __nanosleep((A.repeat >> 8) ? (unsigned)(A.repeat >> 8) * 64u : 256u);
             LL_TRACE(6);
@@ -1291,7 +1318,11 @@ size_t ll_smem_plan(const DevModel& M, int bt, int n_ctas, int* xs_bytes, int* r
     const size_t fq_bytes = (size_t)up((size_t)M.fdim * 2);
     const size_t fkv_bytes = (size_t)up((size_t)M.n_flayer * ll::kLLDepth * 2 * M.fn_kv * kHeadDim * 2);
     const size_t fixed = 2 * (size_t)*xs_bytes + 2 * (size_t)*res_bytes + (size_t)*scratch_bytes + desc_bytes + fq_bytes + fkv_bytes;
-    const size_t budget = 227 * 1024 - 2048;  // static shared (barriers, sampler scratch, state) stays below 2 KB
+    size_t budget = 227 * 1024 - 2048;  // static shared (barriers, sampler scratch, state) stays below 2 KB
+    if (const char* cap = getenv("SMOL_LL_SMEM_KB")) {  // experiment: leave more of the 256 KB to the L1
+        const size_t kb = (size_t)atoi(cap);
+        if (kb >= 64 && kb * 1024 < budget) budget = kb * 1024;
+    }
     // heaviest stage of one CTA
     auto per = [&](long units, long unit_bytes) { return (size_t)((units + n_ctas - 1) / n_ctas) * (size_t)unit_bytes; };
     size_t need = 0;

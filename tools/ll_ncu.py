@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--prompt-bytes", type=int, default=200)
     ap.add_argument("--mode", type=int, default=2)
     ap.add_argument("--n-ctas", type=int, default=0)
-    ap.add_argument("--flags", type=int, nargs="*", default=[0], help="experiment switches of the data-flow kernel (option \"repeat\")")
+    ap.add_argument("--flags", type=int, nargs="*", default=[0], help="A/B switches of the data-flow kernel (option \"ll_flags\": 1 no K split, 2 sampler CTA for greedy rows, 4 no end-of-phase barrier, 8 no unit rotation, n<<8 hold-off in 64 ns units, 255<<8 none)")
     a = ap.parse_args()
     cfg = named_config(a.model)
     need = a.prompt_bytes + 12 + 2 * a.frames + 16
@@ -41,7 +41,7 @@ def main():
     host_len0 = list(batch.host_len)
     for rnd in range(2 if len(a.flags) > 1 else 1):
         for fl in a.flags:
-            model.set_option("repeat", fl)
+            model.set_option("ll_flags", fl)
             batch.tokens.copy_(tokens0); batch.seq_len.copy_(len0); batch.step.zero_(); batch.host_len = list(host_len0)
             model.decode_frames(batch, s, a.frames)     # launch 1 (warm)
             torch.cuda.synchronize()
