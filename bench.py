@@ -198,7 +198,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -356,7 +356,7 @@ def run_ours(args):
                 "value": r["frames_per_s"], "unit": "frames/s", "cores": r["threads"], "kind": "port",
                 "sample": (f"{n_cpu} frames after a {n_prompt}-token prefill ({r['prefill_s']:.1f} s), bs={args.batch}, "
                            f"bf16 eager CPU oracle, {r['decode_s']:.1f} s of decode")}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
