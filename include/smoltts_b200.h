@@ -183,6 +183,11 @@ int32_t smol_phase_count(const SmolModel* m);
  * GEMV + epilogue, closing block barrier) of the weight phases.  NULL switches it off. */
 int smol_set_profile(SmolModel* m, uint64_t* d_phase_ns);
 
+/* Per-frame clock (the "p50 per-frame latency at bs=1" of BASELINE.json): d_frame_ns [capacity] uint64; after frame f of
+ * sequence 0 (f = its SmolBatch.step before the frame) the kernel stores %globaltimer (ns) in d_frame_ns[f].  Differences
+ * of consecutive entries are per-frame latencies measured on the device.  NULL switches it off. */
+int smol_set_frame_clock(SmolModel* m, uint64_t* d_frame_ns, int32_t capacity);
+
 /* Options: "mode" 2 (default) = data-flow persistent kernel (flag-carrying activation words, TMA
  * producer warp; whole frames / prefill at batch <= 8, larger batches fall back to mode 0),
  * 0 = persistent cooperative kernel with a grid barrier per phase, 1 = one launch per phase, a frame

@@ -80,6 +80,7 @@ PROTOTYPES = {
                                      C.c_void_p]),
     "smol_set_force": (C.c_int, [C.c_void_p, C.c_void_p]),
     "smol_set_profile": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "smol_set_frame_clock": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "smol_run_phases": (C.c_int, [C.c_void_p, C.POINTER(SmolBatch), C.c_int32, C.POINTER(SmolSampling), C.c_int32,
                                   C.c_int32, C.c_void_p]),
     "smol_phase_count": (C.c_int32, [C.c_void_p]),

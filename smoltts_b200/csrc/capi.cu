@@ -552,6 +552,15 @@ int smol_set_profile(SmolModel* m, uint64_t* d_phase_ns) {
     return SMOL_OK;
 }
 
+int smol_set_frame_clock(SmolModel* m, uint64_t* d_frame_ns, int32_t capacity) {
+    if (!m) return fail(SMOL_ERR_INVALID, "null model");
+    if (d_frame_ns && capacity <= 0) return fail(SMOL_ERR_INVALID, "smol_set_frame_clock: capacity must be positive");
+    m->dm.frame_ns = reinterpret_cast<unsigned long long*>(d_frame_ns);
+    m->dm.frame_ns_cap = d_frame_ns ? capacity : 0;
+    m->frame_key_valid = false;
+    return SMOL_OK;
+}
+
 int smol_set_option(SmolModel* m, const char* name, int64_t value) {
     if (!m || !name) return fail(SMOL_ERR_INVALID, "null argument");
     if (!std::strcmp(name, "mode")) {

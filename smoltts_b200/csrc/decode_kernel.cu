@@ -801,6 +801,7 @@ __device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c,
                             A.b.out_codes[((size_t)b * A.b.max_frames + st) * R + rr] = v;
                     }
                     if (A.b.step) A.b.step[b] = st + 1;
+                    if (b == 0 && M.frame_ns != nullptr && st < M.frame_ns_cap) M.frame_ns[st] = globaltimer_ns();
                     A.b.seq_len[b] = ldcg_i32(A.b.seq_len + b) + 1;
                     if (A.b.finished != nullptr && A.s.audio_only && !A.s.ignore_stop && slow == M.im_end)
                         A.b.finished[b] = 1;

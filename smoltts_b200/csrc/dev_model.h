@@ -83,6 +83,8 @@ struct DevModel {
     uint32_t prog[kMaxProg];   // the frame's phase program, packed (pack_phase), built on the host
     unsigned long long* prof;  // optional [2 * phases_per_frame] ns accumulators (CTA 0: work, barrier wait)
     const int32_t* force; // optional [B][n_rows] ids that override the sampled ones (teacher forcing)
+    unsigned long long* frame_ns;  // optional [frame_ns_cap]: %globaltimer at the end of every frame of sequence 0
+    int frame_ns_cap;
 
     // data-flow kernel: every phase publishes its output as 8-byte words {payload, epoch} that the
     // consumers poll ("LL" protocol: the flag travels with the data, no barrier, no fence)

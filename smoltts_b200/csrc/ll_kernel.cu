@@ -706,6 +706,7 @@ __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, 
                 if (A.b.out_codes != nullptr && st < A.b.max_frames) A.b.out_codes[(size_t)st * R + rr] = v;
             }
             if (A.b.step) A.b.step[0] = st + 1;
+            if (M.frame_ns != nullptr && st < M.frame_ns_cap) M.frame_ns[st] = globaltimer_ns();
             A.b.seq_len[0] = s_pos + 1;
             if (A.b.finished != nullptr && A.s.audio_only && !A.s.ignore_stop && slow == M.im_end) A.b.finished[0] = 1;
         }

@@ -327,6 +327,17 @@ class RQTransformer:
         _capi.check(self.lib.smol_set_profile(self._h, C.c_void_p(self._prof.data_ptr())))
         return self._prof
 
+    def set_frame_clock(self, capacity: int = 0) -> Optional[torch.Tensor]:
+        """Device-side per-frame clock: returns an int64 tensor [capacity]; entry f receives %globaltimer (ns) when
+        frame f of sequence 0 has been assembled.  capacity 0 switches it off."""
+        if capacity <= 0:
+            _capi.check(self.lib.smol_set_frame_clock(self._h, None, 0))
+            self._frame_ns = None
+            return None
+        self._frame_ns = torch.zeros(capacity, dtype=torch.int64, device=self.device)
+        _capi.check(self.lib.smol_set_frame_clock(self._h, C.c_void_p(self._frame_ns.data_ptr()), capacity))
+        return self._frame_ns
+
     def prefill(self, batch: DecodeBatch, prompts: torch.Tensor, lengths: torch.Tensor) -> None:
         """prompts [B, R, s_max] int32 (device), lengths [B] int32 (device).  Leaves every
         sequence with its first len-1 columns cached and the last column pending."""

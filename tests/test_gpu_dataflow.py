@@ -188,3 +188,21 @@ def test_dataflow_stop_rule_and_force():
     assert res[0][3].tolist() == [0, 1] and res[0][2].tolist() == [6, 2]
     for a, b in zip(res[0], res[2]):
         assert torch.equal(a, b)
+
+
+def test_frame_clock_is_monotonic_and_identical_ids():
+    """smol_set_frame_clock: one %globaltimer stamp per frame, strictly increasing inside a launch, and switching it on
+    does not change what is decoded."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=1)
+    prompts = [prompt_grid(byte_prompt(20, seed=90), cfg)]
+    ref = _run(model, 2, prompts, 16, 16, None)
+    clock = model.set_frame_clock(16)
+    try:
+        got = _run(model, 2, prompts, 16, 16, None)
+        torch.cuda.synchronize()
+        ns = clock.cpu().tolist()
+    finally:
+        model.set_frame_clock(0)
+    assert all(b > a > 0 for a, b in zip(ns, ns[1:])), ns
+    assert (ns[-1] - ns[0]) / 15 < 5e6, "more than 5 ms per frame on the tiny model"
+    assert torch.equal(ref["codes"], got["codes"])
