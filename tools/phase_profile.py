@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-phase time breakdown of the persistent decode kernel (in-kernel %globaltimer, CTA 0).
+"""Per-phase time breakdown of the persistent decode kernels: the barrier kernel accumulates %globaltimer per phase
+(CTA 0); the data-flow kernel (bs=1, default) records a %clock64 trace of the last frame (CTA 0 and CTA n/2).
 
 usage: python tools/phase_profile.py [--model smoltts_byte_150m] [--batch 1] [--frames 256] [--out profiles/x.json]
 """
@@ -76,18 +77,19 @@ def main():
         w, b, n = agg.get(k, (0.0, 0.0, 0))
         agg[k] = (w + ns[p, 0], b + ns[p, 1], n + 1)
     total = ns.sum()
-    print(f"{a.model} bs={a.batch} frames={a.frames}: {e0.elapsed_time(e1) * 1e3 / a.frames:.1f} us/frame by events, "
-          f"{total / 1e3:.1f} us/frame by in-kernel timers (CTA 0)")
-    print(f"{'phase':14s} {'count':>5s} {'work us':>9s} {'wait us':>9s} {'per-phase work':>15s} {'per-phase wait':>15s}")
+    print(f"{a.model} bs={a.batch} frames={a.frames}: {e0.elapsed_time(e1) * 1e3 / a.frames:.1f} us/frame by events"
+          + (f", {total / 1e3:.1f} us/frame by in-kernel timers (CTA 0)" if total > 0 else " (profiling build of the data-flow kernel)"))
     rows = {}
-    for k, (w, b, n) in sorted(agg.items(), key=lambda kv: -(kv[1][0] + kv[1][1])):
-        print(f"{k:14s} {n:5d} {w / 1e3:9.1f} {b / 1e3:9.1f} {w / n / 1e3:15.2f} {b / n / 1e3:15.2f}")
-        rows[k] = {"count": n, "work_us": w / 1e3, "wait_us": b / 1e3}
-    print("sub-phase segments of the weight phases, us per frame (CTA 0 thread 0): prologue | stage wait | gemv+epilogue | final sync")
-    for k in range(16):
-        if seg[k].sum() > 0:
-            name = ("fast." if k >= 8 else "slow.") + KINDS[k % 8]
-            print(f"  {name:12s} " + " ".join(f"{v / 1e3:8.1f}" for v in seg[k]))
+    if total > 0:  # barrier kernel: globaltimer accumulators (work, barrier wait) and sub-phase segments
+        print(f"{'phase':14s} {'count':>5s} {'work us':>9s} {'wait us':>9s} {'per-phase work':>15s} {'per-phase wait':>15s}")
+        for k, (w, b, n) in sorted(agg.items(), key=lambda kv: -(kv[1][0] + kv[1][1])):
+            print(f"{k:14s} {n:5d} {w / 1e3:9.1f} {b / 1e3:9.1f} {w / n / 1e3:15.2f} {b / n / 1e3:15.2f}")
+            rows[k] = {"count": n, "work_us": w / 1e3, "wait_us": b / 1e3}
+        print("sub-phase segments of the weight phases, us per frame (CTA 0 thread 0): prologue | stage wait | gemv+epilogue | final sync")
+        for k in range(16):
+            if seg[k].sum() > 0:
+                name = ("fast." if k >= 8 else "slow.") + KINDS[k % 8]
+                print(f"  {name:12s} " + " ".join(f"{v / 1e3:8.1f}" for v in seg[k]))
     if trace.any():
         names = ["poll", "norm/fill", "bar", "setup", "gemv", "publish", "release", "total"]
         print("cycle trace of the last frame (data-flow kernel), mean cycles per phase kind: " + " | ".join(names))
