@@ -166,6 +166,8 @@ __shared__ int s_tok[kMaxRows];        // pending input column
 __shared__ int s_nw[kMaxRows];         // ids sampled in the current frame
 __shared__ int s_spf, s_wodd;          // ring stages per iteration / (weight phases per iteration) & 1
 __shared__ uint32_t s_epoch0;          // phases executed by earlier launches
+constexpr int kBtabCache = 256;
+__shared__ int s_btab[kBtabCache];     // the sequence's block table (constant during a launch): saves an L2 round trip per KV access
 
 struct SmemPlan {
     int xs_bytes;       // one activation buffer
@@ -475,21 +477,43 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, in
             const bool newest = valid && (pp == pos_new);
             uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
             if (valid && !newest) {  // cached position: issue the pool loads before waiting for q
-                const int page = ldcg_i32(A.b.block_table + pp / ps);
+                const int pg = pp / ps;
+                const int page = pg < kBtabCache ? s_btab[pg] : ldcg_i32(A.b.block_table + pg);
                 const uint16_t* kp = M.kv_pool + ((((size_t)page * M.n_layer + layer) * 2) * Hkv + kvh) * head_stride
                                      + (size_t)(pp % ps) * kHeadDim + dch * 8;
                 kk = ldcg_v4(kp);
                 vv = ldcg_v4(kp + (size_t)Hkv * head_stride);
             }
-            if (!have_q) {
-                unpack8(ll_get8(qkv + hq * 32 + dch * 4, epoch - 1), qf);
+            {
+                // the polls of this step -- q (first step only) and, for the lane group that owns the newest position, its
+                // K/V from the QKV phase's words -- are in flight together
+                const unsigned long long* qp = qkv + hq * 32 + dch * 4;
+                const unsigned long long* kp2 = qkv + q_words + kvh * 32 + dch * 4;
+                const unsigned long long* vp2 = qkv + k_end_words + kvh * 32 + dch * 4;
+                const uint32_t e = epoch - 1;
+                const bool need_q = !have_q;
+                uint4 q0 = make_uint4(0u, e, 0u, e), q1 = q0, k0 = q0, k1 = q0, v0 = q0, v1 = q0;
+                if (need_q) { q0 = ld_relaxed_v4(qp); q1 = ld_relaxed_v4(qp + 2); }
+                if (newest) { k0 = ld_relaxed_v4(kp2); k1 = ld_relaxed_v4(kp2 + 2); v0 = ld_relaxed_v4(vp2); v1 = ld_relaxed_v4(vp2 + 2); }
+                uint32_t spins = 0;
+                for (;;) {
+                    bool ready = true;
+                    if (q0.y != e || q0.w != e) { ready = false; q0 = ld_relaxed_v4(qp); }
+                    if (q1.y != e || q1.w != e) { ready = false; q1 = ld_relaxed_v4(qp + 2); }
+                    if (k0.y != e || k0.w != e) { ready = false; k0 = ld_relaxed_v4(kp2); }
+                    if (k1.y != e || k1.w != e) { ready = false; k1 = ld_relaxed_v4(kp2 + 2); }
+                    if (v0.y != e || v0.w != e) { ready = false; v0 = ld_relaxed_v4(vp2); }
+                    if (v1.y != e || v1.w != e) { ready = false; v1 = ld_relaxed_v4(vp2 + 2); }
+                    if (ready) break;
+                    LL_SPIN_GUARD(spins);
+                }
+                if (need_q) {
+                    unpack8(make_uint4(q0.x, q0.z, q1.x, q1.z), qf);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) qf[e] *= 0.125f;  // 1/sqrt(64), exact
-                have_q = true;
-            }
-            if (newest) {
-                kk = ll_get8(qkv + q_words + kvh * 32 + dch * 4, epoch - 1);
-                vv = ll_get8(qkv + k_end_words + kvh * 32 + dch * 4, epoch - 1);
+                    for (int i = 0; i < 8; ++i) qf[i] *= 0.125f;  // 1/sqrt(64), exact
+                    have_q = true;
+                }
+                if (newest) { kk = make_uint4(k0.x, k0.z, k1.x, k1.z); vv = make_uint4(v0.x, v0.z, v1.x, v1.z); }
             }
             float kf[8], vf[8];
             unpack8(kk, kf);
@@ -916,7 +940,8 @@ __device__ __noinline__ void kv_append(const DevModel& M, const CallArgs& A, int
     if (pos >= A.b.max_pages * ps) return;
     const bool active = (A.mode == 1) ? (it + A.iter_base < ldcg_i32(A.prompt_len) - 1) : (s_fin == 0);
     if (!active) return;
-    const int page = ldcg_i32(A.b.block_table + pos / ps);
+    const int pg = pos / ps;
+    const int page = pg < kBtabCache ? s_btab[pg] : ldcg_i32(A.b.block_table + pg);
     const int is_v = n0 >= k_end ? 1 : 0;
     const int n1 = n0 - (is_v ? k_end : q_rows);
     const int kvh = n1 / kHeadDim, d = n1 & (kHeadDim - 1);
@@ -950,6 +975,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
     }
     if (A.mode == 0 && tid < M.n_rows) { s_tok[tid] = ldcg_i32(A.b.tokens + tid); s_nw[tid] = 0; }
     for (int p = tid; p < per_iter; p += kLLThreads) build_desc(M, A, p, LL_DSC0 + (uint32_t)p * (kDescWords * 4u));
+    for (int i = tid; i < kBtabCache && i < A.b.max_pages; i += kLLThreads) s_btab[i] = ldcg_i32(A.b.block_table + i);
     __syncthreads();
     if (tid == 0) {  // sequential pass: ring layout of one iteration, stage ordinals, activation buffer parity
         uint32_t head = 0, stage = 0, wph = 0;
