@@ -1007,6 +1007,10 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
     unsigned long long* tr = nullptr;
     if (kTrace && M.prof != nullptr && (tid == 0 || tid == 32) && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
         tr = M.prof + 2 * kMaxProg + 64 + (blockIdx.x == 0 ? 0 : 1) * kMaxProg * 8;
+    // skew trace (kTrace): EVERY CTA, thread 0, %globaltimer when its input words have arrived and at the end of the phase
+    unsigned long long* trg = nullptr;
+    if (kTrace && M.prof != nullptr && tid == 0) trg = M.prof + 2 * kMaxProg + 64 + 2 * kMaxProg * 8 + (size_t)blockIdx.x * (kMaxProg * 2);
+#define LL_SKEW(i) do { if (kTrace && trg) trg[p * 2 + (i)] = globaltimer_ns(); } while (0)
 #define LL_TRACE(i) do { if (kTrace && tr && tid == 0) { unsigned long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); tr[p * 8 + (i)] = c_; } } while (0)
 #define LL_TRACE_AUX(i) do { if (kTrace && tr && tid != 0) { unsigned long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); tr[p * 8 + (i)] = c_; } } while (0)
     // the only loop-carried state of a consumer thread is (it, p): everything else comes from the descriptors
@@ -1115,6 +1119,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                     for (int i = 0; i < 3; ++i)
                         if (lane + 32 * i < nch) raw[i] = make_uint4(a[i].x, a[i].z, b[i].x, b[i].z);
                     LL_TRACE(1);
+                    LL_SKEW(0);
                     norm_store(raw, wv, nch, lane, M.eps, xs, kind != PH_HEAD ? res : 0u);
                 }
             }
@@ -1281,6 +1286,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
             if (!(A.repeat & 4)) csync();
             if ((A.repeat >> 8) != 255) __nanosleep((A.repeat >> 8) ? (unsigned)(A.repeat >> 8) * 64u : 256u);
             LL_TRACE(6);
+            LL_SKEW(1);
         }
         if (A.mode == 1) {  // prefill: a sequence still inside its prompt advances one position
             csync();

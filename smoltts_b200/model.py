@@ -323,7 +323,7 @@ class RQTransformer:
             self._prof = None
             return None
         # [0 : 2*512] per-phase (work, wait) pairs, then 16 x 4 sub-phase segments of the weight phases
-        self._prof = torch.zeros(2 * 512 + 64 + 2 * 512 * 8, dtype=torch.int64, device=self.device)  # + cycle trace (data-flow kernel)
+        self._prof = torch.zeros(2 * 512 + 64 + 2 * 512 * 8 + 256 * 512 * 2, dtype=torch.int64, device=self.device)  # + cycle trace, + per-CTA skew trace (data-flow kernel)
         _capi.check(self.lib.smol_set_profile(self._h, C.c_void_p(self._prof.data_ptr())))
         return self._prof
 

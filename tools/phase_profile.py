@@ -7,12 +7,14 @@ usage: python tools/phase_profile.py [--model smoltts_byte_150m] [--batch 1] [--
 from __future__ import annotations
 
 import argparse
+import collections
 import json
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from smoltts_b200 import RQTransformer, named_config  # noqa: E402
@@ -70,7 +72,8 @@ def main():
     raw = prof.cpu().numpy().astype(float) / a.frames  # per frame
     ns = raw[: 2 * model.phase_count].reshape(-1, 2)
     seg = raw[2 * 512: 2 * 512 + 64].reshape(16, 4)
-    trace = prof.cpu().numpy()[2 * 512 + 64:].reshape(2, 512, 8)
+    trace = prof.cpu().numpy()[2 * 512 + 64: 2 * 512 + 64 + 2 * 512 * 8].reshape(2, 512, 8)
+    skew = prof.cpu().numpy()[2 * 512 + 64 + 2 * 512 * 8:].reshape(256, 512, 2).astype(float)
     agg = {}
     for p in range(ns.shape[0]):
         k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
@@ -114,6 +117,28 @@ def main():
                 print(f"  {label:8s} {k:12s} x{n:3d} " + " ".join(f"{x / n:8.0f}" for x in v))
                 tot += v[7]
             print(f"  {label}: {tot:.0f} cycles per frame in phases")
+    n_ctas = int((skew[:, 0, 1] > 0).sum())
+    if n_ctas > 1:
+        # per phase kind (norm-type phases stamp 'inputs arrived'): spread of the CTAs' phase ends, and the gap between the
+        # LAST CTA finishing phase p and the inputs of phase p+1 arriving at the median CTA
+        print(f"skew trace of the last frame over {n_ctas} CTAs (ns): phase-end spread p50/max | last end -> median arrival in the next norm phase")
+        acc = {}
+        P = model.phase_count
+        for p in range(P - 1):
+            end = skew[:n_ctas, p, 1]
+            if (end <= 0).any():
+                continue
+            k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
+            spread = end.max() - np.median(end)
+            arr = skew[:n_ctas, p + 1, 0]
+            gap = (np.median(arr[arr > 0]) - end.max()) if (arr > 0).any() else float("nan")
+            late = int(end.argmax())
+            a0 = acc.setdefault(k, [[], [], []])
+            a0[0].append(spread); a0[1].append(gap); a0[2].append(late)
+        for k, (sp, gp, late) in acc.items():
+            gp2 = [g for g in gp if g == g]
+            print(f"  {k:12s} end(max-median) mean {np.mean(sp):7.0f} max {np.max(sp):7.0f} | last-end -> next arrival "
+                  f"{(np.mean(gp2) if gp2 else float('nan')):7.0f} | most often last: {collections.Counter(late).most_common(5)}")
     if a.out:
         with open(a.out, "w") as f:
             json.dump({"model": a.model, "batch": a.batch, "frames": a.frames,
