@@ -56,6 +56,7 @@ struct SmolModel {
     int ll_state[9] = {0};  // 0 unknown, 1 ready, -1 does not fit
     int mode = 2;
     int repeat = 0;
+    int prefill_tile = 0;  // option: cap of prompt positions per prefill iteration (0 = as many as fit, up to 8)
     int ll_flags = 0;  // data-flow kernel: A/B switches and hold-off override (tools/ll_ncu.py)
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
@@ -111,7 +112,8 @@ static size_t ll_regions(const SmolConfig& c, int depth, int bl, uint32_t* off, 
 
 static WsLayout ws_layout(const SmolConfig& c, int depth) {
     WsLayout L;
-    const size_t B = (size_t)c.max_batch;
+    // rows: the batch, or one prefill tile of kBatchTile prompt positions when the batch is smaller
+    const size_t B = (size_t)(c.max_batch > smol::kBatchTile ? c.max_batch : smol::kBatchTile);
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -378,7 +380,7 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
         for (int p = begin; p < end; ++p) {
             const bool last = (it == n_iter - 1) && (p == end - 1);
             A.n_iter = 1;
-            A.iter_base = base + it;
+            A.iter_base = base + it * (A.tile_t > 1 ? A.tile_t : 1);
             A.phase_begin = p;
             A.phase_end = p + 1;
             A.finalize = last ? finalize : 0;
@@ -397,6 +399,8 @@ static CallArgs base_args(const SmolBatch* b, int batch, const SmolSampling* s) 
     if (s) A.s = *s;
     else { A.s.temp = 0.f; A.s.fast_temp = 0.f; A.s.top_p = 1.f; A.s.ignore_stop = 1; }
     A.batch = batch;
+    A.real_batch = batch;
+    A.tile_t = 1;
     A.n_iter = 1;
     return A;
 }
@@ -412,14 +416,23 @@ int smol_prefill(SmolModel* m, const SmolBatch* b, int32_t batch, const int32_t*
     if (!d_prompt || !d_prompt_len || s_max < 1) return fail(SMOL_ERR_INVALID, "smol_prefill: bad prompt");
     CallArgs A = base_args(b, batch, nullptr);
     A.mode = 1;
-    A.n_iter = s_max - 1;
+    // tile_t prompt positions per iteration share one pass over the weights (rows = batch * tile_t fit the workspace)
+    const int rows_cap = m->cfg.max_batch > smol::kBatchTile ? m->cfg.max_batch : smol::kBatchTile;
+    int T = rows_cap / batch;
+    if (T > smol::kBatchTile) T = smol::kBatchTile;
+    if (T < 1) T = 1;
+    if (m->prefill_tile > 0 && m->prefill_tile < T) T = m->prefill_tile;
+    A.tile_t = T;
+    A.real_batch = batch;
+    A.batch = batch * T;
+    A.n_iter = (s_max - 1 + T - 1) / T;
     A.finalize = 1;
     A.phase_begin = 0;
     A.phase_end = smol::phases_per_prefill_step(m->dm.n_layer);
     A.prompt = d_prompt;
     A.prompt_len = d_prompt_len;
     A.s_max = s_max;
-    return enqueue(m, A, (cudaStream_t)stream, true);
+    return enqueue(m, A, (cudaStream_t)stream, T == 1);  // tiled prefill runs on the barrier kernel
 }
 
 int smol_slow_step(SmolModel* m, const SmolBatch* b, int32_t batch, int32_t advance, void* stream) {
@@ -571,6 +584,10 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
     if (!std::strcmp(name, "repeat")) {
         m->repeat = value > 0 ? (int)value : 0;
         m->frame_key_valid = false;
+        return SMOL_OK;
+    }
+    if (!std::strcmp(name, "prefill_tile")) {
+        m->prefill_tile = value > 0 ? (int)value : 0;
         return SMOL_OK;
     }
     if (!std::strcmp(name, "ll_flags")) {

@@ -335,18 +335,26 @@ __device__ __forceinline__ void stage_wait(const Ctx& c, int n_units, uint32_t& 
 // ------------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------------
+// Prefill runs `tile_t` consecutive prompt positions of every sequence as rows of one iteration (they share the pass over
+// the weights; causality comes from each row's own context length): row bg = sequence bg / tile_t, offset bg % tile_t.
+__device__ __forceinline__ int row_seq(const CallArgs& A, int bg) { return A.tile_t > 1 ? bg / A.tile_t : bg; }
+__device__ __forceinline__ int row_off(const CallArgs& A, int bg) { return A.tile_t > 1 ? bg % A.tile_t : 0; }
+__device__ __forceinline__ int prefill_t(const CallArgs& A, const Ctx& c, int bg) {
+    return A.iter_base + c.iter * (A.tile_t > 1 ? A.tile_t : 1) + row_off(A, bg);
+}
 __device__ __forceinline__ bool seq_active(const DevModel& M, const CallArgs& A, const Ctx& c, int bg) {
-    if (A.mode == 1) return c.iter + A.iter_base < ldcg_i32(A.prompt_len + bg) - 1;
+    if (A.mode == 1) return prefill_t(A, c, bg) < ldcg_i32(A.prompt_len + row_seq(A, bg)) - 1;
     return A.b.finished == nullptr || __ldcg(A.b.finished + bg) == 0;
 }
 
 // id of grid row r of sequence bg for the slow embedding
 __device__ __forceinline__ int input_token(const DevModel& M, const CallArgs& A, const Ctx& c, int bg, int r) {
     if (A.mode == 1) {
-        int t = c.iter + A.iter_base;
-        const int len = ldcg_i32(A.prompt_len + bg);
+        int t = prefill_t(A, c, bg);
+        const int b = row_seq(A, bg);
+        const int len = ldcg_i32(A.prompt_len + b);
         if (t > len - 1) t = len - 1;
-        return ldcg_i32(A.prompt + ((size_t)bg * M.n_rows + r) * A.s_max + t);
+        return ldcg_i32(A.prompt + ((size_t)b * M.n_rows + r) * A.s_max + t);
     }
     return ldcg_i32(A.b.tokens + (size_t)bg * M.n_rows + r);
 }
@@ -481,7 +489,8 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
     const int n_units = A.batch * Hkv * s_max;
     for (int u = c.cta; u < n_units; u += c.n_ctas) {
         const int s = u % s_max, kvh = (u / s_max) % Hkv, b = u / (s_max * Hkv);
-        int Lb = ldcg_i32(A.b.seq_len + b) + 1;
+        const int bs = row_seq(A, b);  // the sequence whose cache this row reads (prefill tiles: several rows per sequence)
+        int Lb = ldcg_i32(A.b.seq_len + bs) + row_off(A, b) + 1;
         const int cap = A.b.max_pages * ps;
         if (Lb > cap) Lb = cap;
         int ns = (Lb + kSplitMin - 1) / kSplitMin;
@@ -507,7 +516,7 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
         }
-        const int32_t* bt = A.b.block_table + (size_t)b * A.b.max_pages;
+        const int32_t* bt = A.b.block_table + (size_t)bs * A.b.max_pages;
         const size_t head_stride = (size_t)ps * kHeadDim;
         for (int pb = p0 + c.warp * 4; pb < p1; pb += kWarps * 4) {
             const int p = pb + psub;
@@ -664,7 +673,8 @@ __device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, c
     for (int rep = 0; rep <= A.repeat; ++rep)
     for (int b0 = 0; b0 < A.batch; b0 += BT) {
         const int nb = min(BT, A.batch - b0);
-        if (kind == PH_QKV && c.tid < nb) g_pos[c.tid] = fast ? ph.depth_pos : ldcg_i32(A.b.seq_len + b0 + c.tid);
+        if (kind == PH_QKV && c.tid < nb)
+            g_pos[c.tid] = fast ? ph.depth_pos : ldcg_i32(A.b.seq_len + row_seq(A, b0 + c.tid)) + row_off(A, b0 + c.tid);
         if (normed) {
             // where the row of sequence b comes from: 0 token embedding (P:205-221), 1 slow hidden state,
             // 2 embedding of the previous depth code (G:136-140), 3 a stream buffer
@@ -738,7 +748,7 @@ __device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, c
                     if (!seq_active(M, A, c, bg)) return;
                     const int ps = M.page_size;
                     if (pos >= A.b.max_pages * ps) return;
-                    const int page = ldcg_i32(A.b.block_table + (size_t)bg * A.b.max_pages + pos / ps);
+                    const int page = ldcg_i32(A.b.block_table + (size_t)row_seq(A, bg) * A.b.max_pages + pos / ps);
                     uint16_t* dst = M.kv_pool + ((((size_t)page * M.n_layer + ph.layer) * 2 + is_v) * Hkv + kvh) * ((size_t)ps * kHeadDim)
                                     + (size_t)(pos % ps) * kHeadDim + d;
                     *reinterpret_cast<uint32_t*>(dst) = packed;
@@ -873,9 +883,13 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
                 if (prof) t1 = globaltimer_ns();
             }
             if (c.cta == 0 && p == per_iter - 1 && A.mode == 1) {
-                // prefill bookkeeping: sequences still inside their prompt advance one position
-                for (int b = c.tid; b < A.batch; b += kThreads)
-                    if (seq_active(M, A, c, b)) A.b.seq_len[b] = ldcg_i32(A.b.seq_len + b) + 1;
+                // prefill bookkeeping: every sequence advances by the positions of this tile that lie inside its prompt
+                const int T = A.tile_t > 1 ? A.tile_t : 1;
+                for (int b = c.tid; b < A.real_batch; b += kThreads) {
+                    int n_act = ldcg_i32(A.prompt_len + b) - 1 - (A.iter_base + c.iter * T);
+                    n_act = n_act < 0 ? 0 : (n_act > T ? T : n_act);
+                    if (n_act) A.b.seq_len[b] = ldcg_i32(A.b.seq_len + b) + n_act;
+                }
             }
             if (c.cta == 0 && A.mode == 0 && A.advance && p == A.phase_end - 1) {
                 for (int b = c.tid; b < A.batch; b += kThreads) A.b.seq_len[b] = ldcg_i32(A.b.seq_len + b) + 1;
@@ -902,7 +916,7 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
     }
     if (A.mode == 1 && A.finalize && c.cta == 0) {
         // leave the last prompt column as the pending input of the first decode frame (G:66-73)
-        for (int i = c.tid; i < A.batch * M.n_rows; i += kThreads) {
+        for (int i = c.tid; i < A.real_batch * M.n_rows; i += kThreads) {
             const int b = i / M.n_rows, r = i - b * M.n_rows;
             const int len = ldcg_i32(A.prompt_len + b);
             A.b.tokens[i] = ldcg_i32(A.prompt + ((size_t)b * M.n_rows + r) * A.s_max + (len - 1));

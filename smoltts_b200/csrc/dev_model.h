@@ -130,6 +130,8 @@ struct CallArgs {
     int advance;      // slow-only launches: bump seq_len after the last phase
     int fast_from_xf; // depth-step launches: layer 0 reads the caller-filled xf buffer
     int repeat;       // profiling only: run the body of every weight phase 1 + repeat times
+    int tile_t;       // prefill: prompt positions handled per iteration (rows = real_batch * tile_t share the weight pass)
+    int real_batch;   // prefill: sequences (rows / tile_t)
     const int32_t* prompt;      // prefill: [B][n_rows][s_max]
     const int32_t* prompt_len;  // prefill: [B]
     int s_max;

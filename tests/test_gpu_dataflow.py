@@ -206,3 +206,36 @@ def test_frame_clock_is_monotonic_and_identical_ids():
     assert all(b > a > 0 for a, b in zip(ns, ns[1:])), ns
     assert (ns[-1] - ns[0]) / 15 < 5e6, "more than 5 ms per frame on the tiny model"
     assert torch.equal(ref["codes"], got["codes"])
+
+
+@pytest.mark.parametrize("size,lens", [("smoltts_byte_tiny", [45]), ("smoltts_byte_70m", [70]), ("smoltts_byte_tiny", [33, 9, 58])])
+def test_prefill_tiles_and_kernels_write_identical_kv(size, lens):
+    """Prefill three ways -- 8 prompt positions per iteration on the barrier kernel (default), one position per iteration
+    on the barrier kernel, one position per iteration on the data-flow kernel (bs=1) -- must leave bit-identical K/V,
+    seq_len and pending tokens, also for ragged prompt lengths (rows of a tile past the end of a prompt are inert)."""
+    cfg, sd, model, orc = model_and_oracle(size)
+    B = len(lens)
+    prompts = [prompt_grid(byte_prompt(n, seed=110 + b), cfg) for b, n in enumerate(lens)]
+    variants = [(0, 0), (0, 1)] + ([(2, 1)] if B == 1 else []) + [(0, 3)]
+    got = []
+    for mode, tile in variants:
+        model.set_option("mode", mode)
+        model.set_option("prefill_tile", tile)
+        padded, lens_t = pack_prompts(model, prompts)
+        batch = model.new_batch(B, max_positions=128, max_frames=4)
+        try:
+            pages = torch.tensor(batch.pages, device=model.device)
+            model.kv_view()[pages] = 0
+            model.prefill(batch, padded, lens_t)
+            model.decode_frames(batch, model.sampling(ignore_stop=True), 2)
+            torch.cuda.synchronize()
+            got.append((model.kv_view()[pages].clone(), batch.seq_len.clone(), batch.tokens.clone(), batch.out_codes.clone()))
+        finally:
+            model.set_option("mode", 2)
+            model.set_option("prefill_tile", 0)
+            batch.release()
+    assert got[0][1].tolist() == [n + 12 - 1 + 2 for n in lens]
+    for (mode, tile), g in zip(variants[1:], got[1:]):
+        assert torch.equal(g[0].view(torch.int16), got[0][0].view(torch.int16)), f"KV differs (mode {mode}, tile {tile})"
+        for a, b in zip(g[1:], got[0][1:]):
+            assert torch.equal(a, b), f"state differs (mode {mode}, tile {tile})"
