@@ -1,0 +1,271 @@
+// tcgen05 / TMEM building blocks for the batched decode path (sm_100a only).
+//
+// One output tile = 128 sequences (TMEM lanes) x n_blk weight rows (TMEM columns, fp32), accumulated by
+// tcgen05.mma.cta_group::1.kind::f16 over K in ring stages of 64 elements.  Both operands are K-major
+// (activations [row][K], weights [out][K] -- the checkpoint's own layout), staged in shared memory in the
+// canonical no-swizzle layout of the UMMA shared-memory descriptor:
+//
+//     byte offset of element (row r, k) inside a stage = (k / 8) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 8) * 2
+//
+// i.e. 8-row x 16-byte core matrices, SBO = 128 B between 8-row groups, LBO = rows * 16 B between the
+// 16-byte K chunks.  Global -> shared goes through per-thread 16-byte cp.async copies (three stages in
+// flight), an optional in-place transform of the thread's own pieces (RMSNorm), fence.proxy.async and a
+// block barrier; ONE thread issues the four K=16 MMAs of the stage and commits them to the stage's
+// mbarrier, which is what frees the stage for re-use.  The accumulator is read back with
+// tcgen05.ld.32x32b (thread = one sequence, 8 consecutive columns per load).
+#pragma once
+
+#include <stdint.h>
+
+namespace smol {
+namespace umma {
+
+constexpr int kM = 128;                      // sequences per tile (TMEM lanes)
+constexpr int kBK = 64;                      // K elements per ring stage (4 MMAs of K = 16)
+constexpr int kMaxN = 96;                    // widest tile (w1|w3: 48 + 48 rows)
+constexpr int kStages = 5;
+constexpr int kAhead = 3;                    // stages in flight ahead of the MMA
+constexpr int kStageA = kM * kBK * 2;        // 16 KB
+constexpr int kStageB = kMaxN * kBK * 2;     // 12 KB
+constexpr int kStageBytes = kStageA + kStageB;
+constexpr int kRingBytes = kStages * kStageBytes;  // 140 KB
+constexpr int kTmemCols = 128;               // allocation (power of two >= kMaxN)
+
+struct Bars {
+    uint64_t free_[kStages];  // stage consumed by its MMAs (tcgen05.commit)
+    uint64_t done;            // accumulator of the tile complete
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+// Running counters (uniform across the CTA): ring stages used and tiles finished since the barriers were initialised.
+struct Pipe {
+    uint32_t chunk;
+    uint32_t tile;
+};
+
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(bar)), "r"(count) : "memory");
+}
+// Bounded wait: a barrier that never completes is a protocol bug -- trap instead of hanging the GPU.
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = s2u(bar);
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(dst_smem)), "r"((uint32_t)kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t base) {  // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"((uint32_t)kTmemCols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, no swizzle (layout type 0), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// D fp32, A/B bf16, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+}
+// 8 consecutive fp32 columns of this thread's lane (lane quadrant = warp % 4).
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Called once per kernel by all threads (before any tile): barriers + TMEM allocation by warp 0.
+__device__ __forceinline__ void setup(Bars* bars, Pipe& pipe) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) bar_init(&bars->free_[s], 1u);
+        bar_init(&bars->done, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 0) tmem_alloc(&bars->tmem_base);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    pipe.chunk = 0;
+    pipe.tile = 0;
+}
+__device__ __forceinline__ void teardown(Bars* bars) {
+    fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tmem_free(bars->tmem_base);
+}
+
+// Copies of ring chunk `kc` of the tile into stage `s`: A = 128 rows x 64 k, B = n_blk rows x 64 k.
+// Piece p of a warp's 32: 4 consecutive 16-byte pieces of 8 consecutive rows (64 contiguous global bytes per
+// row; the 8 rows of one K chunk are 128 contiguous shared-memory bytes: conflict-free stores).
+template <int NT, class RowA, class RowB>
+__device__ __forceinline__ void issue_chunk(unsigned char* ring, int s, int kc, int n_blk, RowA row_a, RowB row_b) {
+    const uint32_t a0 = s2u(ring + (size_t)s * kStageBytes), b0 = a0 + kStageA;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < (kM * 8 + NT - 1) / NT; ++j) {
+        const int p = tid + NT * j;
+        if (p < kM * 8) {
+            const int lane = p & 31, w = p >> 5;
+            const int c8 = ((w & 1) << 2) | (lane & 3), row = ((w >> 1) << 3) | (lane >> 2);
+            const uint16_t* src = row_a(row);
+            const uint32_t dst = a0 + c8 * (kM * 16) + row * 16;
+            // rows past the batch: zero fill (src-size 0; the address only has to be a valid global one)
+            if (src) cp_async16(dst, src + kc * kBK + c8 * 8, 16u);
+            else cp_async16(dst, row_b(0), 0u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < (kMaxN * 8 + NT - 1) / NT; ++j) {
+        const int p = tid + NT * j;
+        if (p < n_blk * 8) {
+            const int lane = p & 31, w = p >> 5;
+            const int c8 = ((w & 1) << 2) | (lane & 3), row = ((w >> 1) << 3) | (lane >> 2);
+            const uint16_t* src = row_b(row);
+            const uint32_t dst = b0 + c8 * (n_blk * 16) + row * 16;
+            cp_async16(dst, src + kc * kBK + c8 * 8, 16u);
+        }
+    }
+}
+
+// acc[128][n_blk] (TMEM) = A[128][K] * B[n_blk][K]^T.  All NT threads of the CTA call this (uniform arguments).
+// row_a(r) -> pointer to the K bf16 of tile row r (nullptr: zero row); row_b(j) -> weight row j;
+// xform(r, k0, uint4&) rewrites the 8 elements [k0, k0 + 8) of row r in place before the MMA sees them (or no-op).
+// On return the accumulator is complete and visible to tcgen05.ld of every thread.
+template <int NT, bool XFORM, class RowA, class RowB, class Xform>
+__device__ __forceinline__ void tile_mma(unsigned char* ring, Bars* bars, Pipe& pipe, int K, int n_blk, RowA row_a, RowB row_b,
+                                         Xform xform, bool swap_strides = false) {
+    const int nk = K / kBK;
+    const int tid = threadIdx.x;
+    const uint32_t idesc = instr_desc(n_blk);
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t g0 = pipe.chunk;
+    auto acquire_and_issue = [&](int kc) {
+        if (kc < nk) {
+            const uint32_t g = g0 + (uint32_t)kc;
+            const int s = (int)(g % kStages);
+            if (g >= (uint32_t)kStages) bar_wait(&bars->free_[s], (g / kStages - 1u) & 1u);
+            issue_chunk<NT>(ring, s, kc, n_blk, row_a, row_b);
+        }
+        cp_async_commit();
+    };
+    for (int kc = 0; kc < kAhead; ++kc) acquire_and_issue(kc);
+    for (int kc = 0; kc < nk; ++kc) {
+        const uint32_t g = g0 + (uint32_t)kc;
+        const int s = (int)(g % kStages);
+        unsigned char* stage = ring + (size_t)s * kStageBytes;
+        cp_async_wait<kAhead - 1>();
+        if (XFORM) {
+#pragma unroll
+            for (int j = 0; j < (kM * 8 + NT - 1) / NT; ++j) {
+                const int p = tid + NT * j;
+                if (p < kM * 8) {
+                    const int lane = p & 31, w = p >> 5;
+                    const int c8 = ((w & 1) << 2) | (lane & 3), row = ((w >> 1) << 3) | (lane >> 2);
+                    uint4* q = reinterpret_cast<uint4*>(stage + c8 * (kM * 16) + row * 16);
+                    uint4 v = *q;
+                    xform(row, kc * kBK + c8 * 8, v);
+                    *q = v;
+                }
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t a0 = s2u(stage), b0 = a0 + kStageA;
+            const uint32_t lbo_a = kM * 16, lbo_b = (uint32_t)n_blk * 16, sbo = 128;
+#pragma unroll
+            for (int j = 0; j < kBK / 16; ++j) {
+                const uint64_t ad = swap_strides ? smem_desc(a0 + 2 * j * lbo_a, sbo, lbo_a) : smem_desc(a0 + 2 * j * lbo_a, lbo_a, sbo);
+                const uint64_t bd = swap_strides ? smem_desc(b0 + 2 * j * lbo_b, sbo, lbo_b) : smem_desc(b0 + 2 * j * lbo_b, lbo_b, sbo);
+                mma_bf16(tmem, ad, bd, idesc, (kc | j) ? 1u : 0u);
+            }
+            commit(&bars->free_[s]);
+            if (kc == nk - 1) commit(&bars->done);
+        }
+        __syncwarp();
+        acquire_and_issue(kc + kAhead);
+    }
+    cp_async_wait<0>();
+    pipe.chunk = g0 + (uint32_t)nk;
+    bar_wait(&bars->done, pipe.tile & 1u);
+    pipe.tile += 1;
+    fence_after_sync();
+}
+
+// Hands 8 consecutive accumulator columns of one sequence to epi(row, col0, v[8]); with `paired` the thread also gets the
+// columns half a tile further (w1 | w3 halves): epi2(row, col0, gate[8], up[8]).  Ends with the fences + block barrier
+// that let the next tile overwrite the accumulator.
+template <class Epi>
+__device__ __forceinline__ void tile_epilogue(Bars* bars, int n_cols, Epi epi) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = ((w & 3) << 5) | lane;
+    const uint32_t base = bars->tmem_base + ((uint32_t)((w & 3) << 5) << 16);
+    const int n_warps = blockDim.x >> 5;
+    for (int cg = w >> 2; cg * 8 < n_cols; cg += n_warps >> 2) {
+        float v[8];
+        tmem_ld8(base + (uint32_t)(cg * 8), v);
+        epi(row, cg * 8, v);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+}
+template <class Epi2>
+__device__ __forceinline__ void tile_epilogue_paired(Bars* bars, int half_cols, Epi2 epi2) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = ((w & 3) << 5) | lane;
+    const uint32_t base = bars->tmem_base + ((uint32_t)((w & 3) << 5) << 16);
+    const int n_warps = blockDim.x >> 5;
+    for (int cg = w >> 2; cg * 8 < half_cols; cg += n_warps >> 2) {
+        float a[8], b[8];
+        tmem_ld8(base + (uint32_t)(cg * 8), a);
+        tmem_ld8(base + (uint32_t)(half_cols + cg * 8), b);
+        epi2(row, cg * 8, a, b);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+}
+
+}  // namespace umma
+}  // namespace smol

@@ -1,0 +1,120 @@
+// Stand-alone check of csrc/umma.cuh on the GPU: C[128][2n] = A[128][K] * B[2n][K]^T as two consecutive tiles of one
+// CTA (ring / barrier parities carry over), bf16 inputs, fp32 accumulators, against a CPU fp64 reference.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/micro/umma_test tools/micro/umma_test.cu
+//   tools/micro/umma_test            # all shapes; exit code 0 iff every tile matches
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../smoltts_b200/csrc/umma.cuh"
+
+using namespace smol;
+
+constexpr int NT = 512;
+
+__global__ void __launch_bounds__(NT, 1)
+umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_blk, int m_valid, int swap, int xf, int paired) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) umma::Bars bars;
+    umma::Pipe pipe;
+    umma::setup(&bars, pipe);
+    for (int t = 0; t < 2; ++t) {
+        auto row_a = [&](int r) { return r < m_valid ? A + (size_t)r * K : (const uint16_t*)nullptr; };
+        auto row_b = [&](int j) { return B + (size_t)(t * n_blk + j) * K; };
+        auto xform = [&](int r, int k0, uint4& v) {  // doubles every element (exact in bf16)
+            uint16_t* e = reinterpret_cast<uint16_t*>(&v);
+            for (int i = 0; i < 8; ++i) {
+                float f = __uint_as_float(((uint32_t)e[i]) << 16) * 2.0f;
+                e[i] = (uint16_t)(__float_as_uint(f) >> 16);
+            }
+            (void)r; (void)k0;
+        };
+        if (xf) umma::tile_mma<NT, true>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform, swap != 0);
+        else umma::tile_mma<NT, false>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform, swap != 0);
+        if (paired) {
+            umma::tile_epilogue_paired(&bars, n_blk / 2, [&](int row, int c0, const float (&a)[8], const float (&b)[8]) {
+                for (int i = 0; i < 8; ++i) {
+                    C[(size_t)row * 2 * n_blk + t * n_blk + c0 + i] = a[i];
+                    C[(size_t)row * 2 * n_blk + t * n_blk + n_blk / 2 + c0 + i] = b[i];
+                }
+            });
+        } else {
+            umma::tile_epilogue(&bars, n_blk, [&](int row, int c0, const float (&v)[8]) {
+                for (int i = 0; i < 8; ++i) C[(size_t)row * 2 * n_blk + t * n_blk + c0 + i] = v[i];
+            });
+        }
+    }
+    umma::teardown(&bars);
+}
+
+static uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7FFF + ((u >> 16) & 1);
+    return (uint16_t)(u >> 16);
+}
+static float bf2f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+static double run(int K, int n, int m_valid, int swap, int xf, int paired, int ctas) {
+    std::vector<uint16_t> hA((size_t)128 * K), hB((size_t)2 * n * K);
+    srand(K * 131 + n);
+    for (auto& v : hA) v = f2bf((rand() % 2001 - 1000) / 1000.0f);
+    for (auto& v : hB) v = f2bf((rand() % 2001 - 1000) / 1000.0f);
+    uint16_t *dA, *dB;
+    float* dC;
+    cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dC, (size_t)128 * 2 * n * 4);
+    cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemset(dC, 0xFF, (size_t)128 * 2 * n * 4);
+    cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::kRingBytes);
+    umma_test_kernel<<<ctas, NT, umma::kRingBytes>>>(dA, dB, dC, K, n, m_valid, swap, xf, paired);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(3); }
+    std::vector<float> hC((size_t)128 * 2 * n);
+    cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost);
+    double worst = 0;
+    for (int r = 0; r < m_valid; ++r)
+        for (int j = 0; j < 2 * n; ++j) {
+            double acc = 0;
+            for (int k = 0; k < K; ++k) acc += (double)bf2f(hA[(size_t)r * K + k]) * bf2f(hB[(size_t)j * K + k]);
+            if (xf) acc *= 2;
+            double d = fabs(acc - hC[(size_t)r * 2 * n + j]);
+            if (!(d <= worst)) worst = d;  // NaN-safe
+        }
+    for (int r = m_valid; r < 128; ++r)
+        for (int j = 0; j < 2 * n; ++j)
+            if (hC[(size_t)r * 2 * n + j] != 0.0f) worst = fmax(worst, 1e9);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return worst;
+}
+
+int main() {
+    int bad = 0;
+    const int Ks[] = {64, 320, 768, 3072};
+    const int Ns[] = {16, 32, 64, 96};
+    {   // the LBO / SBO convention of umma.cuh (the swapped one addresses shared memory out of range and faults)
+        double w = run(768, 32, 128, 0, 0, 0, 1);
+        printf("stride convention: max |err| = %.3g (K=768 n=32)\n", w);
+        if (!(w < 1e-2)) { printf("FAIL: stride convention is wrong\n"); return 1; }
+    }
+    for (int K : Ks)
+        for (int n : Ns)
+            for (int variant = 0; variant < 3; ++variant) {
+                const int m_valid = variant == 1 ? 77 : 128, xf = variant == 1, paired = variant == 2;
+                double w = run(K, n, m_valid, 0, xf, paired, variant == 2 ? 148 : 1);
+                const double tol = 1e-3 * sqrt((double)K) * (xf ? 2 : 1);
+                printf("K=%4d n=%3d rows=%3d xform=%d paired=%d: max |err| = %.3g %s\n", K, n, m_valid, xf, paired, w, w < tol ? "ok" : "FAIL");
+                if (!(w < tol)) bad = 1;
+            }
+    printf(bad ? "FAIL\n" : "PASS\n");
+    return bad;
+}
