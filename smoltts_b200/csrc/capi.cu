@@ -56,7 +56,8 @@ struct SmolModel {
     int ll_state[9] = {0};  // 0 unknown, 1 ready, -1 does not fit
     int mode = 2;
     int repeat = 0;
-    int prefill_tile = 0;  // option: cap of prompt positions per prefill iteration (0 = as many as fit, up to 8)
+    int prefill_tile = 0;  // option: cap of prompt positions per prefill iteration (0 = as many as fit)
+    int tc_min_batch = 16; // rows (sequences, or prompt positions of a prefill tile) from which the tcgen05 variant runs
     int ll_flags = 0;  // data-flow kernel: A/B switches and hold-off override (tools/ll_ncu.py)
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
@@ -64,6 +65,7 @@ struct SmolModel {
     cudaStream_t capture_stream = nullptr;  // the caller's stream may be the legacy default stream, which cannot capture
     GraphKey frame_key;
     bool frame_key_valid = false;
+    int64_t frame_graph_launches = 0;
 };
 
 static thread_local std::string g_err;
@@ -110,10 +112,14 @@ static size_t ll_regions(const SmolConfig& c, int depth, int bl, uint32_t* off, 
     return words;
 }
 
+// Rows of the activation workspace: a prefill iteration carries up to this many prompt positions (one tensor-core tile).
+constexpr int kPrefillRows = 128;
+static int ws_rows(const SmolConfig& c) { return c.max_batch > kPrefillRows ? c.max_batch : kPrefillRows; }
+
 static WsLayout ws_layout(const SmolConfig& c, int depth) {
     WsLayout L;
-    // rows: the batch, or one prefill tile of kBatchTile prompt positions when the batch is smaller
-    const size_t B = (size_t)(c.max_batch > smol::kBatchTile ? c.max_batch : smol::kBatchTile);
+    // rows: the batch, or one prefill tile of kPrefillRows prompt positions when the batch is smaller
+    const size_t B = (size_t)ws_rows(c);
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -309,7 +315,7 @@ static int ensure_configured(SmolModel* m) {
 static int ensure_tile(SmolModel* m, int bt) {
     if (m->tile_ready[bt]) return SMOL_OK;
     m->xs_bytes[bt] = smol::decode_xs_bytes(m->dm, bt);
-    m->smem[bt] = m->xs_bytes[bt] + smol::decode_stage_bytes(m->dm, m->n_ctas);
+    m->smem[bt] = m->xs_bytes[bt] + (bt == 0 ? 0 : smol::decode_stage_bytes(m->dm, m->n_ctas));  // bt 0: tensor-core variant, ring only
     if (m->smem[bt] > 227 * 1024)
         return fail(SMOL_ERR_UNSUPPORTED, "activation tile + weight stage exceed 227 KB of shared memory");
     CU(smol::decode_configure(bt, m->smem[bt]));
@@ -343,8 +349,13 @@ static int ensure_ll_tile(SmolModel* m, int bt) {
 }
 
 // whole_iters: the call runs complete frames / complete prefill positions (what the data-flow kernel carries).
+static bool use_tc(const SmolModel* m, int rows) {
+    return m->tc_min_batch > 0 && rows >= m->tc_min_batch && (m->cfg.dim % 64) == 0 &&
+           (m->cfg.intermediate_size % 64) == 0 && (m->cfg.fast_intermediate_size % 64) == 0;
+}
+
 static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_iters = false) {
-    const int bt = smol::decode_batch_tile(A.batch);
+    const int bt = use_tc(m, A.batch) ? 0 : smol::decode_batch_tile(A.batch);
     int rc;
     A.repeat = m->repeat;
     if (m->mode == 2 && whole_iters && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
@@ -383,6 +394,15 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
             A.iter_base = base + it * (A.tile_t > 1 ? A.tile_t : 1);
             A.phase_begin = p;
             A.phase_end = p + 1;
+            A.finalize = 0;
+            A.advance = 0;
+            A.tc_part = 0;
+            if (bt == 0 && smol::tc_has_prestep(smol::unpack_phase(m->dm.prog[p]))) {
+                A.tc_part = 1;  // the grid barrier between pre-step and tiles becomes a launch boundary
+                CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
+                m->launches += 1;
+                A.tc_part = 2;
+            }
             A.finalize = last ? finalize : 0;
             A.advance = (p == end - 1) ? advance : 0;
             CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
@@ -417,11 +437,14 @@ int smol_prefill(SmolModel* m, const SmolBatch* b, int32_t batch, const int32_t*
     CallArgs A = base_args(b, batch, nullptr);
     A.mode = 1;
     // tile_t prompt positions per iteration share one pass over the weights (rows = batch * tile_t fit the workspace)
-    const int rows_cap = m->cfg.max_batch > smol::kBatchTile ? m->cfg.max_batch : smol::kBatchTile;
+    // -- up to one 128-row tensor-core tile; 8 positions on the CUDA-core variants
+    const int rows_cap = ws_rows(m->cfg);
     int T = rows_cap / batch;
-    if (T > smol::kBatchTile) T = smol::kBatchTile;
+    if (T > kPrefillRows) T = kPrefillRows;
+    if (T > s_max - 1) T = s_max - 1;
     if (T < 1) T = 1;
     if (m->prefill_tile > 0 && m->prefill_tile < T) T = m->prefill_tile;
+    if (!use_tc(m, batch * T) && T > smol::kBatchTile) T = smol::kBatchTile;
     A.tile_t = T;
     A.real_batch = batch;
     A.batch = batch * T;
@@ -533,6 +556,7 @@ int smol_decode_frames(SmolModel* m, const SmolBatch* b, int32_t batch, const Sm
         A.n_iter = 1;
         const int64_t before = m->launches;
         rc = enqueue(m, A, m->capture_stream);
+        m->frame_graph_launches = m->launches - before;
         m->launches = before;
         cudaError_t e = cudaStreamEndCapture(m->capture_stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
@@ -544,7 +568,7 @@ int smol_decode_frames(SmolModel* m, const SmolBatch* b, int32_t batch, const Sm
         m->frame_key_valid = true;
     }
     for (int f = 0; f < n_frames; ++f) CU(cudaGraphLaunch(m->frame_graph, stream));
-    m->launches += (int64_t)n_frames * A.phase_end;
+    m->launches += (int64_t)n_frames * m->frame_graph_launches;
     return SMOL_OK;
 }
 
@@ -590,6 +614,10 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
         m->prefill_tile = value > 0 ? (int)value : 0;
         return SMOL_OK;
     }
+    if (!std::strcmp(name, "tc_min_batch")) {  // 0 disables the tensor-core variant
+        m->tc_min_batch = value > 0 ? (int)value : 0;
+        return SMOL_OK;
+    }
     if (!std::strcmp(name, "ll_flags")) {
         m->ll_flags = (int)value;
         return SMOL_OK;
@@ -610,6 +638,8 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!std::strcmp(name, "n_ctas")) return m->n_ctas;
     if (!std::strcmp(name, "n_sms")) return m->n_sms;
     if (!std::strcmp(name, "smem_bytes")) return (int64_t)m->smem[1];
+    if (!std::strcmp(name, "tc_min_batch")) return m->tc_min_batch;
+    if (!std::strcmp(name, "tc_ready")) return m->tile_ready[0] ? 1 : 0;
     if (!std::strcmp(name, "ll_smem_bytes")) return (int64_t)m->ll_smem[1];
     if (!std::strcmp(name, "ll_ring_bytes")) return (int64_t)m->ll_ring[1];
     if (!std::strcmp(name, "ll_ready")) return (int64_t)m->ll_state[1];

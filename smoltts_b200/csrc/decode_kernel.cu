@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "dev_model.h"
 #include "sampler.cuh"
+#include "umma.cuh"
 
 namespace smol {
 
@@ -647,6 +648,12 @@ __device__ void phase_attn(const DevModel& M, const CallArgs& A, const Ctx& c, c
     phase_attn_g(M, A, c, ph, attn_splits(M, A.batch, c.n_ctas));
 }
 
+}  // namespace smol
+#include "tc_phases.cuh"
+namespace smol {
+
+__shared__ __align__(8) umma::Bars g_tc_bars;
+
 // Every phase that streams weights: [gather / RMSNorm / fast attention] -> staged-weight GEMV ->
 // epilogue.  One function so that each building block is instantiated exactly once (code size is what
 // the instruction cache sees: every phase runs once per frame).
@@ -822,12 +829,19 @@ __device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c,
     }
 }
 
+// BT == 0: the tensor-core variant (tc_phases.cuh) -- 128-row tiles, batch attention, cooperative launches only.
 template <int BT>
 __device__ __forceinline__ void run_phase(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph,
-                                          uint32_t& parity) {
+                                          uint32_t& parity, umma::Pipe& pipe, uint32_t& target) {
+    if (BT == 0) {
+        if (ph.kind == PH_ATTN) phase_attn_batch(M, A, c, ph);
+        else if (ph.kind == PH_SAMPLE) phase_sample(M, A, c, ph);
+        else phase_gemm_tc(M, A, c, ph, &g_tc_bars, pipe, target);
+        return;
+    }
     if (ph.kind == PH_ATTN) phase_attn(M, A, c, ph);
     else if (ph.kind == PH_SAMPLE) phase_sample(M, A, c, ph);
-    else phase_gemv<BT>(M, A, c, ph, parity);
+    else phase_gemv<(BT > 0 ? BT : 1)>(M, A, c, ph, parity);
 }
 
 // Flat index (iteration, phase) of the next phase of this launch that streams weights, or -1.
@@ -861,6 +875,9 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
     uint32_t target = 0;
     if (A.cooperative) target = ldcg_u32(M.barrier + 1);
     uint32_t parity = 0;
+    umma::Pipe pipe;
+    pipe.chunk = 0; pipe.tile = 0;
+    if (BT == 0) umma::setup(&g_tc_bars, pipe);
     const int per_iter = (A.mode == 1) ? phases_per_prefill_step(M.n_layer)
                                        : phases_per_frame(M.n_layer, M.n_flayer, M.depth);
     const bool prof_cta = (M.prof != nullptr) && c.cta == 0;  // CTA-uniform
@@ -871,13 +888,13 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
         c.iter = it;
         for (int p = A.phase_begin; p < A.phase_end; ++p) {
             const Phase ph = unpack_phase(M.prog[p]);
-            const bool has_w = ph.kind != PH_ATTN && ph.kind != PH_SAMPLE;
+            const bool has_w = BT != 0 && ph.kind != PH_ATTN && ph.kind != PH_SAMPLE;  // weights staged a phase ahead (GEMV variants)
             if (prof) t0 = globaltimer_ns();
             if (has_w && !(st_it == it && st_p == p)) {  // cold start of a launch
                 stage_issue(c, phase_plan(M, ph));
                 st_it = it; st_p = p;
             }
-            run_phase<BT>(M, A, c, ph, parity);
+            run_phase<BT>(M, A, c, ph, parity, pipe, target);
             if (prof_cta) {
                 __syncthreads();
                 if (prof) t1 = globaltimer_ns();
@@ -923,6 +940,7 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
         }
     }
     if (A.cooperative && c.cta == 0 && c.tid == 0) M.barrier[1] = target;
+    if (BT == 0) umma::teardown(&g_tc_bars);
 }
 
 // Stand-alone sampler on caller-provided logits [B][n] (smol_sample): one CTA per sequence.
@@ -968,6 +986,7 @@ cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int 
 // Activation region: the batch tile's rows in fp32 (also the attention merge scratch and the
 // sampler's logits row).  Sized for the batch the model was created for.
 size_t decode_xs_bytes(const DevModel& M, int bt) {
+    if (bt == 0) return (size_t)umma::kRingBytes + 3 * kTcRows * 4;  // ring + rstd / pos / erow of the tile's rows
     int kmax = M.dim;
     if (M.inter > kmax) kmax = M.inter;
     if (M.fdim > kmax) kmax = M.fdim;
@@ -1000,9 +1019,10 @@ size_t decode_stage_bytes(const DevModel& M, int n_ctas) {
 }
 
 // Kernel variant by batch tile (sequences whose activations share one pass over the weights).
-static int tile_index(int bt) { return bt <= 1 ? 0 : bt <= 2 ? 1 : bt <= 4 ? 2 : 3; }
+static int tile_index(int bt) { return bt <= 0 ? 4 : bt <= 1 ? 0 : bt <= 2 ? 1 : bt <= 4 ? 2 : 3; }  // bt 0: tensor-core variant
 static const void* decode_fn(int bt) {
     switch (tile_index(bt)) {
+        case 4: return (const void*)smol_decode_kernel<0>;
         case 0: return (const void*)smol_decode_kernel<1>;
         case 1: return (const void*)smol_decode_kernel<2>;
         case 2: return (const void*)smol_decode_kernel<4>;
@@ -1012,7 +1032,7 @@ static const void* decode_fn(int bt) {
 int decode_batch_tile(int batch) { return batch <= 1 ? 1 : batch <= 2 ? 2 : batch <= 4 ? 4 : 8; }
 
 // The attribute is per function, not per model: it only ever grows (several models may coexist).
-static size_t g_smem_configured[4] = {0, 0, 0, 0};
+static size_t g_smem_configured[5] = {0, 0, 0, 0, 0};
 cudaError_t decode_configure(int bt, size_t smem) {
     size_t& cur = g_smem_configured[tile_index(bt)];
     if (smem <= cur) return cudaSuccess;

@@ -132,6 +132,7 @@ struct CallArgs {
     int repeat;       // profiling only: run the body of every weight phase 1 + repeat times
     int tile_t;       // prefill: prompt positions handled per iteration (rows = real_batch * tile_t share the weight pass)
     int real_batch;   // prefill: sequences (rows / tile_t)
+    int tc_part;      // tensor-core variant, one phase per launch: 1 = only the phase's distributed pre-step, 2 = only its tiles
     const int32_t* prompt;      // prefill: [B][n_rows][s_max]
     const int32_t* prompt_len;  // prefill: [B]
     int s_max;
@@ -186,6 +187,11 @@ __host__ __device__ inline Phase decode_phase(int p, int n_layer, int n_flayer) 
         ph.kind = PH_SAMPLE;
     }
     return ph;
+}
+
+// Tensor-core variant: phases that start with a grid-wide pre-step (token embedding / depth attention).
+__host__ __device__ inline bool tc_has_prestep(const Phase& ph) {
+    return (ph.kind == PH_QKV && !ph.fast && ph.layer == 0) || (ph.kind == PH_WO && ph.fast);
 }
 
 __host__ __device__ inline uint32_t pack_phase(const Phase& ph) {

@@ -1,0 +1,489 @@
+// Batched decode on the tensor cores: the weight phases of decode_kernel.cu as tcgen05 tiles (umma.cuh) for batches of
+// 16+ rows (sequences, or prompt positions of a prefill tile), plus the batch forms of the two attentions.
+// Included by decode_kernel.cu (uses its Ctx, grid barrier, embedding and row bookkeeping helpers).
+//
+// A weight phase Y[rows][n_out] = f(X)[rows][K] * W[n_out][K]^T is cut into units (128-row tile, block of `blk` weight
+// rows); blk is the smallest multiple of 16 that gives every CTA at most one unit.  A unit streams its 128 x K activation
+// tile and blk x K weight rows through the cp.async ring in 64-element stages; RMSNorm is applied to the activation
+// pieces in shared memory (row statistics from a first pass over the rows), the epilogues (RoPE + KV append, residual
+// add, silu * up, logits) read the fp32 accumulator from TMEM -- same rounding points as the GEMV kernels (bf16 after
+// every Linear / norm stage / RoPE / silu / product / residual add), only the summation order inside a dot product is
+// the tensor core's.
+#pragma once
+
+namespace smol {
+
+constexpr int kTcRows = umma::kM;
+constexpr int kTcSplit = 256;  // cached positions per attention split of the batch attention
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]); v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
+    return v;
+}
+
+// BaseTransformer.embed (P:205-221) of every row into the slow residual stream, spread over all warps of the grid.
+__device__ void tc_embed_rows(const DevModel& M, const CallArgs& A, const Ctx& c) {
+    const int D = M.dim, nch = D >> 3;
+    for (int bg = c.cta * kWarps + c.warp; bg < A.batch; bg += c.n_ctas * kWarps) {
+        for (int ch = c.lane; ch < nch; ch += 32) {
+            float f[8];
+            embed_chunk(M, A, c, bg, ch, f);
+            *reinterpret_cast<uint4*>(M.x + (size_t)bg * D + ch * 8) = pack8(f);
+        }
+    }
+}
+
+// rstd[r] = 1 / sqrt(mean(x_r^2) + eps) for the tile's rows (RMSNorm.forward P:607-609, fp32).  One warp per row,
+// four rows in flight.
+template <class RowPtr>
+__device__ __forceinline__ void tc_row_stats(const Ctx& c, int K, float eps, float* rstd, RowPtr rowptr) {
+    const int nch = K >> 3;
+    for (int r0 = c.warp * 4; r0 < kTcRows; r0 += kWarps * 4) {
+        uint4 v[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint16_t* src = rowptr(r0 + i);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int ch = c.lane + 32 * j;
+                v[i][j] = (src != nullptr && ch < nch) ? ldcg_v4(src + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float x[8];
+                unpack8(v[i][j], x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+            }
+            ss = warp_sum(ss);
+            if (c.lane == 0) {
+                const float mean = __fdiv_rn(ss, (float)K);
+                rstd[r0 + i] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+            }
+        }
+    }
+}
+
+// Attention of the fast transformer for every (row, head) of the batch, one warp per pair, spread over the grid; the
+// result goes to M.attn (the wo tiles read it after a grid barrier).  Same arithmetic as fast_attention_rows.
+__device__ void tc_fast_attention(const DevModel& M, const CallArgs& A, const Ctx& c, int layer, int depth_pos) {
+    const int Hq = M.fn_head, Hkv = M.fn_kv, G = Hq / Hkv, D = M.fdim;
+    const int kvw = Hkv * kHeadDim;
+    const int jl = c.lane >> 2, part = c.lane & 3;
+    for (int pair = c.cta * kWarps + c.warp; pair < A.batch * Hq; pair += c.n_ctas * kWarps) {
+        const int bg = pair / Hq, hq = pair - bg * Hq, kvh = hq / G;
+        const uint16_t* qp = M.q + (size_t)bg * Hq * kHeadDim + hq * kHeadDim + part * 16;
+        const uint16_t* kb = M.fkv + ((size_t)(bg * M.n_flayer + layer) * 2) * M.depth * kvw + kvh * kHeadDim;
+        const uint16_t* vb = kb + (size_t)M.depth * kvw;
+        float qf[16];
+        {
+            float t0[8], t1[8];
+            unpack8(ldcg_v4(qp), t0);
+            unpack8(ldcg_v4(qp + 8), t1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { qf[e] = t0[e]; qf[8 + e] = t1[e]; }
+        }
+        float sc[2];
+        bool ok[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = jl + 8 * h2;
+            ok[h2] = j <= depth_pos;
+            sc[h2] = -INFINITY;
+            float s = 0.f;
+            if (ok[h2]) {
+                float k0[8], k1[8];
+                unpack8(ldcg_v4(kb + (size_t)j * kvw + part * 16), k0);
+                unpack8(ldcg_v4(kb + (size_t)j * kvw + part * 16 + 8), k1);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s = fmaf(qf[e], k0[e], s);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s = fmaf(qf[8 + e], k1[e], s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (ok[h2]) sc[h2] = s * 0.125f;
+        }
+        float m = fmaxf(sc[0], sc[1]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        const float pe0 = ok[0] ? expf(sc[0] - m) : 0.f;
+        const float pe1 = ok[1] ? expf(sc[1] - m) : 0.f;
+        float l = pe0 + pe1;
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        const float pb0 = bf16_round(pe0), pb1 = bf16_round(pe1);
+        float o0 = 0.f, o1 = 0.f;  // lane owns dims 2*lane, 2*lane+1
+        for (int j = 0; j < kMaxDepth; ++j) {
+            const float p = __shfl_sync(0xffffffffu, j < 8 ? pb0 : pb1, (j & 7) * 4);
+            if (j <= depth_pos) {
+                const uint32_t v = ldcg_u32(vb + (size_t)j * kvw + 2 * c.lane);
+                o0 = fmaf(p, bf_lo(v), o0);
+                o1 = fmaf(p, bf_hi(v), o1);
+            }
+        }
+        const float inv = 1.0f / l;
+        *reinterpret_cast<uint32_t*>(M.attn + (size_t)bg * D + hq * kHeadDim + 2 * c.lane) = pack_bf16(o0 * inv, o1 * inv);
+    }
+}
+
+// Decode attention over the paged cache for a batch: one WARP per (row, kv head, split of kTcSplit positions); each
+// 8-lane group owns one cached position per step, four steps (16 positions, their K and V) in flight per iteration.
+// Splits of a long row meet through M.partial / M.split_count; the last arriver combines them in split order.
+__device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
+    constexpr int GM = kMaxGroup;
+    const int Hq = M.n_head, Hkv = M.n_kv, ps = M.page_size, G = Hq / Hkv;
+    const int dch = c.lane & 7, psub = c.lane >> 3;
+    const int cap = A.b.max_pages * ps;
+    int s_cap = (cap + kTcSplit - 1) / kTcSplit;
+    if (s_cap > kMaxSplits) s_cap = kMaxSplits;
+    if (s_cap < 1) s_cap = 1;
+    const int n_tasks = A.batch * Hkv * s_cap;
+    const size_t head_stride = (size_t)ps * kHeadDim;
+    for (int t = c.cta * kWarps + c.warp; t < n_tasks; t += c.n_ctas * kWarps) {
+        const int s = t % s_cap, kvh = (t / s_cap) % Hkv, b = t / (s_cap * Hkv);
+        const int bs = row_seq(A, b);
+        int Lb = ldcg_i32(A.b.seq_len + bs) + row_off(A, b) + 1;
+        if (Lb > cap) Lb = cap;
+        int ns = (Lb + kTcSplit - 1) / kTcSplit;
+        if (ns > s_cap) ns = s_cap;
+        if (s >= ns) continue;
+        int chunk = (Lb + ns - 1) / ns;
+        chunk = (chunk + 15) & ~15;
+        const int p0 = s * chunk, p1 = min(Lb, p0 + chunk);
+
+        float qf[GM][8];
+#pragma unroll
+        for (int g = 0; g < GM; ++g) {
+            if (g >= G) continue;
+            unpack8(ldcg_v4(M.q + (size_t)b * Hq * kHeadDim + (kvh * G + g) * kHeadDim + dch * 8), qf[g]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) qf[g][e] *= 0.125f;
+        }
+        float m[GM], l[GM], acc[GM][8];
+#pragma unroll
+        for (int g = 0; g < GM; ++g) {
+            m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
+        }
+        const int32_t* bt = A.b.block_table + (size_t)bs * A.b.max_pages;
+        const size_t layer_off = ((size_t)ph.layer * 2 * Hkv + kvh) * head_stride + (size_t)dch * 8;
+        const size_t page_stride = (size_t)M.n_layer * 2 * Hkv * head_stride;
+        int page[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = p0 + j * 4 + psub;
+            page[j] = p < p1 ? ldcg_i32(bt + p / ps) : 0;
+        }
+        for (int pb = p0; pb < p1; pb += 16) {
+            uint4 kk[4], vv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int p = pb + j * 4 + psub;
+                kk[j] = make_uint4(0u, 0u, 0u, 0u); vv[j] = kk[j];
+                if (p < p1) {
+                    const uint16_t* kp = M.kv_pool + (size_t)page[j] * page_stride + layer_off + (size_t)(p % ps) * kHeadDim;
+                    kk[j] = ldcg_v4(kp);
+                    vv[j] = ldcg_v4(kp + (size_t)Hkv * head_stride);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // page ids of the next iteration travel with this one's K/V
+                const int p = pb + 16 + j * 4 + psub;
+                page[j] = p < p1 ? ldcg_i32(bt + p / ps) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool valid = pb + j * 4 + psub < p1;
+                float kf[8], vf[8];
+                unpack8(kk[j], kf);
+                unpack8(vv[j], vf);
+#pragma unroll
+                for (int g = 0; g < GM; ++g) {
+                    if (g >= G) continue;
+                    float sc = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sc = fmaf(qf[g][e], kf[e], sc);
+                    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+                    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+                    if (valid) {
+                        const float mn = fmaxf(m[g], sc);
+                        const float corr = (m[g] == -INFINITY) ? 0.f : expf(m[g] - mn);
+                        const float pe = expf(sc - mn);
+                        l[g] = fmaf(l[g], corr, pe);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(acc[g][e], corr, pe * vf[e]);
+                        m[g] = mn;
+                    }
+                }
+            }
+        }
+        // merge the four position groups of the warp
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                if (g >= G) continue;
+                const float mo = __shfl_xor_sync(0xffffffffu, m[g], o);
+                const float lo = __shfl_xor_sync(0xffffffffu, l[g], o);
+                const float mn = fmaxf(m[g], mo);
+                const float c1 = (m[g] == -INFINITY) ? 0.f : expf(m[g] - mn);
+                const float c2 = (mo == -INFINITY) ? 0.f : expf(mo - mn);
+                l[g] = fmaf(l[g], c1, __fmul_rn(lo, c2));
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float ao = __shfl_xor_sync(0xffffffffu, acc[g][e], o);
+                    acc[g][e] = fmaf(acc[g][e], c1, __fmul_rn(ao, c2));
+                }
+                m[g] = mn;
+            }
+        }
+        if (ns == 1) {
+            if (psub == 0) {
+#pragma unroll
+                for (int g = 0; g < GM; ++g) {
+                    if (g >= G) continue;
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = acc[g][e] / l[g];
+                    *reinterpret_cast<uint4*>(M.attn + (size_t)b * Hq * kHeadDim + (kvh * G + g) * kHeadDim + dch * 8) = pack8(o);
+                }
+            }
+            continue;
+        }
+        if (psub == 0) {
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                if (g >= G) continue;
+                float* dst = M.partial + (((size_t)b * Hq + kvh * G + g) * kMaxSplits + s) * kPartialStride;
+                if (dch == 0) { dst[0] = m[g]; dst[1] = l[g]; }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dst[2 + dch * 8 + e] = acc[g][e];
+            }
+        }
+        __threadfence();
+        __syncwarp();
+        uint32_t old = 0;
+        if (c.lane == 0) old = atomicAdd(M.split_count + (size_t)b * Hkv + kvh, 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != (uint32_t)(ns - 1)) continue;
+        __threadfence();  // last split of this (row, kv head): combine all splits in split order
+        for (int g = 0; g < G; ++g) {
+            const int hq = kvh * G + g;
+            const float* base = M.partial + ((size_t)b * Hq + hq) * kMaxSplits * kPartialStride;
+            float Mg = -INFINITY;
+            for (int si = 0; si < ns; ++si) Mg = fmaxf(Mg, ldcg_f32(base + si * kPartialStride));
+            float Lg = 0.f, O0 = 0.f, O1 = 0.f;
+            for (int si = 0; si < ns; ++si) {
+                const float* src = base + si * kPartialStride;
+                const float ms = ldcg_f32(src);
+                if (ms == -INFINITY) continue;
+                const float sc = expf(ms - Mg);
+                Lg = fmaf(ldcg_f32(src + 1), sc, Lg);
+                O0 = fmaf(ldcg_f32(src + 2 + 2 * c.lane), sc, O0);
+                O1 = fmaf(ldcg_f32(src + 3 + 2 * c.lane), sc, O1);
+            }
+            *reinterpret_cast<uint32_t*>(M.attn + (size_t)b * Hq * kHeadDim + hq * kHeadDim + 2 * c.lane) = pack_bf16(O0 / Lg, O1 / Lg);
+        }
+        if (c.lane == 0) M.split_count[(size_t)b * Hkv + kvh] = 0u;
+    }
+}
+
+// One weight phase on the tensor cores.  `target` is the grid barrier's running count: two phases have a distributed
+// pre-step (token embedding before the first slow QKV, the depth attention before a fast wo) followed by an extra grid
+// barrier; one-phase-per-launch mode runs the pre-step and the tiles as two launches instead (A.tc_part).
+__device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, umma::Bars* bars,
+                              umma::Pipe& pipe, uint32_t& target) {
+    const bool fast = ph.fast != 0;
+    const int kind = ph.kind;
+    const int D = fast ? M.fdim : M.dim, F = fast ? M.finter : M.inter;
+    const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
+    const DevLayer& L = fast ? M.fast_layers[ph.layer] : M.layers[ph.layer];
+    const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
+    const int n_head_rows = fast ? M.codebook_size : M.vocab;
+    const int K = (kind == PH_W2) ? F : D;
+    const int n_out = kind == PH_QKV ? (Hq + 2 * Hkv) * kHeadDim : kind == PH_W13 ? F : kind == PH_HEAD ? n_head_rows : D;
+    const bool normed = kind == PH_QKV || kind == PH_W13 || kind == PH_HEAD;
+    const uint16_t* norm_w = kind == PH_QKV ? L.attention_norm : kind == PH_W13 ? L.ffn_norm : (fast ? M.fast_norm : M.norm);
+    const uint16_t* table = fast ? M.fast_rope : M.rope;
+    uint16_t* stream = fast ? M.xf : M.x;
+    const uint16_t* w0 = kind == PH_QKV ? L.wqkv : kind == PH_WO ? L.wo : kind == PH_W13 ? L.w1 : kind == PH_W2 ? L.w2
+                         : (fast ? M.fast_output + (M.depthwise_output ? (size_t)ph.depth_pos * n_head_rows * D : 0) : M.head);
+    const uint16_t* w1 = kind == PH_W13 ? L.w3 : nullptr;
+    unsigned char* ring = reinterpret_cast<unsigned char*>(c.xs);
+    float* rstd = reinterpret_cast<float*>(ring + umma::kRingBytes);
+    int* pos = reinterpret_cast<int*>(rstd + kTcRows);
+    int* erow = pos + kTcRows;  // depth steps > 0: row of fast_embeddings that holds the previous code's embedding
+
+    // sub-phase timers of CTA 0 (tools/phase_profile.py): pre-step + barrier | row statistics | ring + MMA | epilogue
+    const bool prof = (M.prof != nullptr) && c.cta == 0 && c.tid == 0;
+    unsigned long long* seg = M.prof + 2 * kMaxProg + (size_t)(kind + (fast ? 8 : 0)) * 4;
+    unsigned long long ts = 0;
+    if (prof) ts = globaltimer_ns();
+
+    // ---- distributed pre-steps ----
+    int src_kind = 3;  // 0 slow stream written by the embedding pre-step, 1 slow hidden state, 2 embedding of the previous depth code, 3 a stream buffer
+    if (kind == PH_QKV && ph.layer == 0 && fast && !A.fast_from_xf) src_kind = ph.depth_pos == 0 ? 1 : 2;
+    if (tc_has_prestep(ph)) {
+        if (A.tc_part != 2) {
+            if (kind == PH_QKV) tc_embed_rows(M, A, c);
+            else tc_fast_attention(M, A, c, ph.layer, ph.depth_pos);
+        }
+        if (A.cooperative) {
+            grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
+            grid_wait(M.barrier, target);
+        }
+        if (A.tc_part == 1) return;
+    }
+
+    if (prof) { const unsigned long long t = globaltimer_ns(); seg[0] += t - ts; ts = t; }
+    const int m_tiles = (A.batch + kTcRows - 1) / kTcRows;
+    const int blk_cap = kind == PH_W13 ? umma::kMaxN / 2 : umma::kMaxN;
+    int blk = 16;
+    while (blk < blk_cap && m_tiles * ((n_out + blk - 1) / blk) > c.n_ctas) blk += 16;
+    const int n_blocks = (n_out + blk - 1) / blk;
+    const int n_units = m_tiles * n_blocks;
+    const uint16_t* in_base = kind == PH_W13 ? M.h : kind == PH_WO ? M.attn : kind == PH_W2 ? M.act : stream;
+
+    for (int u = c.cta; u < n_units; u += c.n_ctas) {
+        const int mt = u / n_blocks, nb = u - mt * n_blocks;
+        const int m0 = mt * kTcRows, n0 = nb * blk;
+        auto row_a = [&](int r) -> const uint16_t* {
+            const int bg = m0 + r;
+            if (bg >= A.batch) return nullptr;
+            if (src_kind == 1) return M.x + (size_t)bg * D;
+            if (src_kind == 2) return M.fast_embeddings + (size_t)erow[r] * D;
+            return in_base + (size_t)bg * K;
+        };
+        auto row_b = [&](int j) -> const uint16_t* {
+            if (w1 != nullptr) {
+                const int half = blk, jj = j < half ? j : j - half;
+                const int n = min(n0 + jj, n_out - 1);
+                return (j < half ? w0 : w1) + (size_t)n * K;
+            }
+            return w0 + (size_t)min(n0 + j, n_out - 1) * K;
+        };
+        if (kind == PH_QKV && c.tid < kTcRows) {
+            const int bg = min(m0 + c.tid, A.batch - 1);
+            pos[c.tid] = fast ? ph.depth_pos : ldcg_i32(A.b.seq_len + row_seq(A, bg)) + row_off(A, bg);
+        }
+        if (src_kind == 2 && c.tid < kTcRows) {  // G:136-140
+            const int bg = min(m0 + c.tid, A.batch - 1);
+            const int code = ldcg_i32(M.frame_tokens + (size_t)bg * M.n_rows + ph.depth_pos);
+            erow[c.tid] = code + (M.depthwise_wte ? (M.dup0 ? ph.depth_pos - 1 : ph.depth_pos) * M.codebook_size : 0);
+        }
+        __syncthreads();
+        if (src_kind != 3) {
+            // the depth transformer's input row becomes its residual stream: the units of a tile share the copy
+            for (int r = nb * kWarps + c.warp; r < kTcRows; r += n_blocks * kWarps) {
+                const uint16_t* src = row_a(r);
+                if (src == nullptr) continue;
+                for (int ch = c.lane; ch < (D >> 3); ch += 32)
+                    *reinterpret_cast<uint4*>(M.xf + (size_t)(m0 + r) * D + ch * 8) = ldcg_v4(src + ch * 8);
+            }
+        }
+        if (normed) tc_row_stats(c, K, M.eps, rstd, row_a);
+        __syncthreads();
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[1] += t - ts; ts = t; }
+        auto xform = [&](int r, int k0, uint4& v) {
+            const float rs = rstd[r];
+            float x[8], wf[8], o[8];
+            unpack8(v, x);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(norm_w + k0)), wf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(x[e], rs)), wf[e]);
+            v = pack8(o);
+        };
+        const int n_tile = w1 != nullptr ? 2 * blk : blk;
+        if (normed) umma::tile_mma<kThreads, true>(ring, bars, pipe, K, n_tile, row_a, row_b, xform);
+        else umma::tile_mma<kThreads, false>(ring, bars, pipe, K, n_tile, row_a, row_b, xform);
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[2] += t - ts; ts = t; }
+
+        if (kind == PH_W13) {
+            umma::tile_epilogue_paired(bars, blk, [&](int row, int c0, const float (&ga)[8], const float (&up)[8]) {
+                const int bg = m0 + row, u0 = n0 + c0;
+                if (bg >= A.batch || u0 >= n_out) return;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float a = bf16_round(ga[e]), g = bf16_round(up[e]);
+                    const float sg = bf16_round(__fdiv_rn(a, __fadd_rn(1.0f, expf(-a))));
+                    o[e] = __fmul_rn(sg, g);
+                }
+                *reinterpret_cast<uint4*>(M.act + (size_t)bg * F + u0) = pack8(o);
+            });
+        } else {
+            umma::tile_epilogue(bars, blk, [&](int row, int c0, const float (&acc)[8]) {
+                const int bg = m0 + row, u0 = n0 + c0;
+                if (bg >= A.batch || u0 >= n_out) return;
+                if (kind == PH_HEAD) {
+                    float* out = fast ? M.depth_logits + ((size_t)bg * M.depth + ph.depth_pos) * n_head_rows
+                                      : M.token_logits + (size_t)bg * n_head_rows;
+                    *reinterpret_cast<float4*>(out + u0) = make_float4(bf16_round(acc[0]), bf16_round(acc[1]), bf16_round(acc[2]), bf16_round(acc[3]));
+                    *reinterpret_cast<float4*>(out + u0 + 4) = make_float4(bf16_round(acc[4]), bf16_round(acc[5]), bf16_round(acc[6]), bf16_round(acc[7]));
+                    return;
+                }
+                if (kind != PH_QKV) {
+                    // wo: h = stream + wo(attn)   (P:499)      w2: stream = h + w2(act)   (P:500)
+                    const uint16_t* res = kind == PH_WO ? stream : M.h;
+                    uint16_t* dst = kind == PH_WO ? M.h : stream;
+                    const size_t o = (size_t)bg * D + u0;
+                    float rf[8], of[8];
+                    unpack8(ldcg_v4(res + o), rf);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) of[e] = __fadd_rn(rf[e], bf16_round(acc[e]));
+                    *reinterpret_cast<uint4*>(dst + o) = pack8(of);
+                    return;
+                }
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = bf16_round(acc[e]);
+                const int p = pos[row];
+                if (u0 < k_end) {  // q and k rows: interleaved-pair RoPE with the bf16 table (P:616-640)
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const int j = ((u0 + e) & (kHeadDim - 1)) >> 1;
+                        const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + ((size_t)p * (kHeadDim / 2) + j) * 2));
+                        const float co = bf_lo(cs), si = bf_hi(cs);
+                        const float r0 = bf16_round(__fsub_rn(__fmul_rn(v[e], co), __fmul_rn(v[e + 1], si)));
+                        const float r1 = bf16_round(__fadd_rn(__fmul_rn(v[e + 1], co), __fmul_rn(v[e], si)));
+                        v[e] = r0; v[e + 1] = r1;
+                    }
+                }
+                const uint4 packed = pack8(v);
+                if (u0 < q_rows) {
+                    *reinterpret_cast<uint4*>(M.q + (size_t)bg * q_rows + u0) = packed;
+                    return;
+                }
+                const int is_v = u0 >= k_end ? 1 : 0;
+                const int n1 = u0 - (is_v ? k_end : q_rows);
+                const int kvh = n1 / kHeadDim, d = n1 & (kHeadDim - 1);
+                if (fast) {
+                    uint16_t* dst = M.fkv + (((size_t)(bg * M.n_flayer + ph.layer) * 2 + is_v) * M.depth + ph.depth_pos) * (Hkv * kHeadDim)
+                                    + kvh * kHeadDim + d;
+                    *reinterpret_cast<uint4*>(dst) = packed;
+                } else {
+                    if (!seq_active(M, A, c, bg)) return;
+                    const int ps = M.page_size;
+                    if (p >= A.b.max_pages * ps) return;
+                    const int page = ldcg_i32(A.b.block_table + (size_t)row_seq(A, bg) * A.b.max_pages + p / ps);
+                    uint16_t* dst = M.kv_pool + ((((size_t)page * M.n_layer + ph.layer) * 2 + is_v) * Hkv + kvh) * ((size_t)ps * kHeadDim)
+                                    + (size_t)(p % ps) * kHeadDim + d;
+                    *reinterpret_cast<uint4*>(dst) = packed;
+                }
+            });
+        }
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[3] += t - ts; ts = t; }
+    }
+}
+
+}  // namespace smol

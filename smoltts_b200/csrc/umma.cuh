@@ -171,8 +171,8 @@ __device__ __forceinline__ void issue_chunk(unsigned char* ring, int s, int kc, 
 // xform(r, k0, uint4&) rewrites the 8 elements [k0, k0 + 8) of row r in place before the MMA sees them (or no-op).
 // On return the accumulator is complete and visible to tcgen05.ld of every thread.
 template <int NT, bool XFORM, class RowA, class RowB, class Xform>
-__device__ __forceinline__ void tile_mma(unsigned char* ring, Bars* bars, Pipe& pipe, int K, int n_blk, RowA row_a, RowB row_b,
-                                         Xform xform, bool swap_strides = false) {
+__device__ __forceinline__ void tile_mma_cpasync(unsigned char* ring, Bars* bars, Pipe& pipe, int K, int n_blk, RowA row_a, RowB row_b,
+                                                 Xform xform, bool swap_strides = false) {
     const int nk = K / kBK;
     const int tid = threadIdx.x;
     const uint32_t idesc = instr_desc(n_blk);
@@ -226,6 +226,105 @@ __device__ __forceinline__ void tile_mma(unsigned char* ring, Bars* bars, Pipe& 
         acquire_and_issue(kc + kAhead);
     }
     cp_async_wait<0>();
+    pipe.chunk = g0 + (uint32_t)nk;
+    bar_wait(&bars->done, pipe.tile & 1u);
+    pipe.tile += 1;
+    fence_after_sync();
+}
+
+// Register-staged form of the same tile (the one the decode kernel uses): every thread keeps its pieces of the next
+// kPre stages in registers (ld.global.cg issued kPre stages ahead), applies the transform there, stores them to the
+// stage with st.shared and fences.  Unlike the cp.async form no asynchronous shared-memory write is in flight when
+// fence.proxy.async executes -- measured on B200: the fence waits for the thread's outstanding cp.async groups, which
+// serialises that pipeline at one L2 round trip per stage.
+constexpr int kPre = 2;
+template <int NT, bool XFORM, class RowA, class RowB, class Xform>
+__device__ __forceinline__ void tile_mma(unsigned char* ring, Bars* bars, Pipe& pipe, int K, int n_blk, RowA row_a, RowB row_b,
+                                         Xform xform) {
+    constexpr int PA = (kM * 8 + NT - 1) / NT, PB = (kMaxN * 8 + NT - 1) / NT;
+    const int nk = K / kBK;
+    const int tid = threadIdx.x;
+    const uint32_t idesc = instr_desc(n_blk);
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t g0 = pipe.chunk;
+    // piece i of this thread: rows / K chunks are a function of (tid, i) only, so one pointer per piece is all the state
+    const uint16_t* src_a[PA];
+    const uint16_t* src_b[PB];
+    auto piece = [&](int i, int& c8, int& row) {
+        const int p = tid + NT * i, lane = p & 31, w = p >> 5;
+        c8 = ((w & 1) << 2) | (lane & 3);
+        row = ((w >> 1) << 3) | (lane >> 2);
+    };
+#pragma unroll
+    for (int i = 0; i < PA; ++i) {
+        int c8, row;
+        piece(i, c8, row);
+        const uint16_t* r = tid + NT * i < kM * 8 ? row_a(row) : nullptr;
+        src_a[i] = r ? r + c8 * 8 : nullptr;
+    }
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+        int c8, row;
+        piece(i, c8, row);
+        src_b[i] = tid + NT * i < n_blk * 8 ? row_b(row) + c8 * 8 : nullptr;
+    }
+    uint4 ra[kPre][PA], rb[kPre][PB];
+    auto load = [&](uint4 (&va)[PA], uint4 (&vb)[PB], int kc) {
+        if (kc >= nk) return;
+#pragma unroll
+        for (int i = 0; i < PA; ++i)
+            va[i] = src_a[i] ? __ldcg(reinterpret_cast<const uint4*>(src_a[i] + kc * kBK)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < PB; ++i)
+            if (src_b[i]) vb[i] = __ldcg(reinterpret_cast<const uint4*>(src_b[i] + kc * kBK));
+    };
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) load(ra[j], rb[j], j);
+    for (int kc0 = 0; kc0 < nk; kc0 += kPre) {
+#pragma unroll
+        for (int j = 0; j < kPre; ++j) {
+            const int kc = kc0 + j;
+            if (kc < nk) {
+                const uint32_t g = g0 + (uint32_t)kc;
+                const int s = (int)(g % kStages);
+                unsigned char* stage = ring + (size_t)s * kStageBytes;
+                if (g >= (uint32_t)kStages) bar_wait(&bars->free_[s], (g / kStages - 1u) & 1u);
+#pragma unroll
+                for (int i = 0; i < PA; ++i) {
+                    if (tid + NT * i < kM * 8) {
+                        int c8, row;
+                        piece(i, c8, row);
+                        uint4 v = ra[j][i];
+                        if (XFORM) xform(row, kc * kBK + c8 * 8, v);
+                        *reinterpret_cast<uint4*>(stage + c8 * (kM * 16) + row * 16) = v;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < PB; ++i) {
+                    if (src_b[i]) {
+                        int c8, row;
+                        piece(i, c8, row);
+                        *reinterpret_cast<uint4*>(stage + kStageA + c8 * (n_blk * 16) + row * 16) = rb[j][i];
+                    }
+                }
+                load(ra[j], rb[j], kc + kPre);
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    fence_after_sync();
+                    const uint32_t a0 = s2u(stage), b0 = a0 + kStageA;
+                    const uint32_t lbo_a = kM * 16, lbo_b = (uint32_t)n_blk * 16, sbo = 128;
+#pragma unroll
+                    for (int q = 0; q < kBK / 16; ++q)
+                        mma_bf16(tmem, smem_desc(a0 + 2 * q * lbo_a, lbo_a, sbo), smem_desc(b0 + 2 * q * lbo_b, lbo_b, sbo), idesc,
+                                 (kc | q) ? 1u : 0u);
+                    commit(&bars->free_[s]);
+                    if (kc == nk - 1) commit(&bars->done);
+                }
+                __syncwarp();
+            }
+        }
+    }
     pipe.chunk = g0 + (uint32_t)nk;
     bar_wait(&bars->done, pipe.tile & 1u);
     pipe.tile += 1;

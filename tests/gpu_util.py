@@ -36,7 +36,10 @@ def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return (a - b).abs() / ulp
 
 
-def close_report(name: str, got: torch.Tensor, want: torch.Tensor, max_ulp: float = 2.0, min_exact: float = 0.98):
+def close_report(name: str, got: torch.Tensor, want: torch.Tensor, max_ulp: float = 2.0, min_exact: float = 0.98,
+                 outlier_frac: float = 0.0):
+    """outlier_frac: share of elements that may miss the ulp bar as long as they stay within one bf16 ulp of the tensor's
+    LARGEST value -- a one-ulp flip of an intermediate (pre-RoPE value, residual operand) seen after cancellation."""
     got = got.float().cpu()
     want = want.float().cpu()
     assert got.shape == want.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
@@ -47,6 +50,9 @@ def close_report(name: str, got: torch.Tensor, want: torch.Tensor, max_ulp: floa
     # an absolute slack of one ulp of the tensor's typical magnitude
     scale = want.abs().mean().item() + 1e-12
     bad = (ulps > max_ulp) & ((got - want).abs() > scale * 2.0 ** -7)
+    if outlier_frac > 0 and 0 < int(bad.sum()) <= max(1, int(outlier_frac * got.numel())):
+        big = want.abs().max().item()
+        bad = bad & ((got - want).abs() > 2.0 ** (np.floor(np.log2(max(big, 1e-30))) - 7) * 1.5)
     if bad.any():
         idx = bad.nonzero()[:6].tolist()
         detail = "; ".join(f"{tuple(i)}: got {got[tuple(i)].item():.6g} want {want[tuple(i)].item():.6g}" for i in idx)

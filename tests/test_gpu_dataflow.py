@@ -210,13 +210,13 @@ def test_frame_clock_is_monotonic_and_identical_ids():
 
 @pytest.mark.parametrize("size,lens", [("smoltts_byte_tiny", [45]), ("smoltts_byte_70m", [70]), ("smoltts_byte_tiny", [33, 9, 58])])
 def test_prefill_tiles_and_kernels_write_identical_kv(size, lens):
-    """Prefill three ways -- 8 prompt positions per iteration on the barrier kernel (default), one position per iteration
+    """Prefill three ways -- 8 prompt positions per iteration on the barrier kernel, one position per iteration
     on the barrier kernel, one position per iteration on the data-flow kernel (bs=1) -- must leave bit-identical K/V,
     seq_len and pending tokens, also for ragged prompt lengths (rows of a tile past the end of a prompt are inert)."""
     cfg, sd, model, orc = model_and_oracle(size)
     B = len(lens)
     prompts = [prompt_grid(byte_prompt(n, seed=110 + b), cfg) for b, n in enumerate(lens)]
-    variants = [(0, 0), (0, 1)] + ([(2, 1)] if B == 1 else []) + [(0, 3)]
+    variants = [(0, 8 // B), (0, 1)] + ([(2, 1)] if B == 1 else []) + [(0, 3)]   # all below 16 rows: the CUDA-core variants
     got = []
     for mode, tile in variants:
         model.set_option("mode", mode)

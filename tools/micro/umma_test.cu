@@ -17,12 +17,13 @@ using namespace smol;
 constexpr int NT = 512;
 
 __global__ void __launch_bounds__(NT, 1)
-umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_blk, int m_valid, int swap, int xf, int paired) {
+umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_blk, int m_valid, int variant, int xf, int paired, int tiles) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) umma::Bars bars;
     umma::Pipe pipe;
     umma::setup(&bars, pipe);
-    for (int t = 0; t < 2; ++t) {
+    for (int tt = 0; tt < tiles; ++tt) {
+        const int t = tt & 1;
         auto row_a = [&](int r) { return r < m_valid ? A + (size_t)r * K : (const uint16_t*)nullptr; };
         auto row_b = [&](int j) { return B + (size_t)(t * n_blk + j) * K; };
         auto xform = [&](int r, int k0, uint4& v) {  // doubles every element (exact in bf16)
@@ -33,8 +34,13 @@ umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_bl
             }
             (void)r; (void)k0;
         };
-        if (xf) umma::tile_mma<NT, true>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform, swap != 0);
-        else umma::tile_mma<NT, false>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform, swap != 0);
+        if (variant == 1) {  // cp.async staging (kept for the A/B timing)
+            if (xf) umma::tile_mma_cpasync<NT, true>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
+            else umma::tile_mma_cpasync<NT, false>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
+        } else {
+            if (xf) umma::tile_mma<NT, true>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
+            else umma::tile_mma<NT, false>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
+        }
         if (paired) {
             umma::tile_epilogue_paired(&bars, n_blk / 2, [&](int row, int c0, const float (&a)[8], const float (&b)[8]) {
                 for (int i = 0; i < 8; ++i) {
@@ -64,7 +70,7 @@ static float bf2f(uint16_t h) {
     return f;
 }
 
-static double run(int K, int n, int m_valid, int swap, int xf, int paired, int ctas) {
+static double run(int K, int n, int m_valid, int variant, int xf, int paired, int ctas, int tiles = 2, float* us_per_tile = nullptr) {
     std::vector<uint16_t> hA((size_t)128 * K), hB((size_t)2 * n * K);
     srand(K * 131 + n);
     for (auto& v : hA) v = f2bf((rand() % 2001 - 1000) / 1000.0f);
@@ -76,8 +82,19 @@ static double run(int K, int n, int m_valid, int swap, int xf, int paired, int c
     cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
     cudaMemset(dC, 0xFF, (size_t)128 * 2 * n * 4);
     cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::kRingBytes);
-    umma_test_kernel<<<ctas, NT, umma::kRingBytes>>>(dA, dB, dC, K, n, m_valid, swap, xf, paired);
+    umma_test_kernel<<<ctas, NT, umma::kRingBytes>>>(dA, dB, dC, K, n, m_valid, variant, xf, paired, tiles);
     cudaError_t e = cudaDeviceSynchronize();
+    if (us_per_tile && e == cudaSuccess) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int r = 0; r < 5; ++r) umma_test_kernel<<<ctas, NT, umma::kRingBytes>>>(dA, dB, dC, K, n, m_valid, variant, xf, paired, tiles);
+        cudaEventRecord(e1);
+        e = cudaDeviceSynchronize();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *us_per_tile = ms * 1e3f / 5 / tiles;
+    }
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(3); }
     std::vector<float> hC((size_t)128 * 2 * n);
     cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost);
@@ -103,6 +120,7 @@ int main() {
     const int Ns[] = {16, 32, 64, 96};
     {   // the LBO / SBO convention of umma.cuh (the swapped one addresses shared memory out of range and faults)
         double w = run(768, 32, 128, 0, 0, 0, 1);
+        if (w < 1e-2) w = run(768, 32, 128, 1, 0, 0, 1);  // and the cp.async form
         printf("stride convention: max |err| = %.3g (K=768 n=32)\n", w);
         if (!(w < 1e-2)) { printf("FAIL: stride convention is wrong\n"); return 1; }
     }
@@ -115,6 +133,16 @@ int main() {
                 printf("K=%4d n=%3d rows=%3d xform=%d paired=%d: max |err| = %.3g %s\n", K, n, m_valid, xf, paired, w, w < tol ? "ok" : "FAIL");
                 if (!(w < tol)) bad = 1;
             }
+    // time per tile (all CTAs compute the same tile: the activation rows are shared the way the units of a phase share them)
+    for (int variant = 0; variant < 2; ++variant)
+        for (int K : {768, 3072})
+            for (int ctas : {1, 48, 148})
+                for (int xf = 0; xf < 2; ++xf) {
+                    float us = 0;
+                    run(K, 32, 128, variant, xf, 0, ctas, 40, &us);
+                    printf("%s staging K=%4d n=32 xform=%d ctas=%3d: %.2f us per tile (%.0f ns per 64-element stage)\n",
+                           variant ? "cp.async " : "registers", K, xf, ctas, us, us * 1e3 / (K / 64));
+                }
     printf(bad ? "FAIL\n" : "PASS\n");
     return bad;
 }
