@@ -12,6 +12,7 @@
 
 #include "../../include/smoltts_b200.h"
 #include "dev_model.h"
+#include "tmap_host.h"
 
 namespace smol {
 size_t decode_xs_bytes(const DevModel& M, int bt);
@@ -66,6 +67,7 @@ struct SmolModel {
     GraphKey frame_key;
     bool frame_key_valid = false;
     int64_t frame_graph_launches = 0;
+    bool tmaps_ready = false;  // tensor maps of the tcgen05 variant (rebuilt after a weight / workspace bind)
 };
 
 static thread_local std::string g_err;
@@ -89,7 +91,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int imax(int a, int b) { return a > b ? a : b; }
 
 struct WsLayout {
-    size_t x, h, xf, q, attn, act, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
+    size_t x, h, xf, q, attn, act, xn, tmaps, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
     size_t ll, ll_partial, ll_tok, ll_cand, ll_epoch, total;
 };
 
@@ -133,6 +135,8 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.q = take(B * imax(c.n_head, c.fast_n_head) * 64 * 2);
     L.attn = take(B * dmax * 2);
     L.act = take(B * imax(c.intermediate_size, c.fast_intermediate_size) * 2);
+    L.xn = take(B * dmax * 2);
+    L.tmaps = take((size_t)(smol::TM_LAYERS + (SMOL_MAX_LAYERS + SMOL_MAX_FAST_LAYERS) * 5) * smol::kTensorMapBytes);
     L.fkv = take(B * c.n_fast_layer * 2 * depth * c.fast_n_local_heads * 64 * 2);
     L.token_logits = take(B * c.vocab_size * 4);
     L.depth_logits = take(B * depth * c.codebook_size * 4);
@@ -242,6 +246,7 @@ int smol_bind_weights(SmolModel* m, const SmolWeights* w) {
     for (int l = 0; l < c.n_fast_layer; ++l)
         if (!bind_layer(w->fast_layers[l], d.fast_layers[l], "fast_layers[*]")) return SMOL_ERR_INVALID;
     m->weights_bound = true;
+    m->tmaps_ready = false;
     m->frame_key_valid = false;
     return SMOL_OK;
 }
@@ -261,6 +266,8 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     d.x = (uint16_t*)(base + L.x); d.h = (uint16_t*)(base + L.h); d.xf = (uint16_t*)(base + L.xf);
     d.q = (uint16_t*)(base + L.q); d.attn = (uint16_t*)(base + L.attn); d.act = (uint16_t*)(base + L.act);
     d.fkv = (uint16_t*)(base + L.fkv);
+    d.xn = (uint16_t*)(base + L.xn); d.tmaps = (const unsigned char*)(base + L.tmaps);
+    m->tmaps_ready = false;
     d.token_logits = (float*)(base + L.token_logits); d.depth_logits = (float*)(base + L.depth_logits);
     d.frame_tokens = (int32_t*)(base + L.frame_tokens);
     d.partial = (float*)(base + L.partial); d.split_count = (uint32_t*)(base + L.split_count);
@@ -311,8 +318,52 @@ static int ensure_configured(SmolModel* m) {
     return SMOL_OK;
 }
 
+// TMA tensor maps of the tcgen05 variant: encoded on the host and copied into the workspace once per bind (setup-time,
+// synchronous; compute calls never come here again).
+static int ensure_tmaps(SmolModel* m) {
+    if (m->tmaps_ready) return SMOL_OK;
+    const SmolConfig& c = m->cfg;
+    const DevModel& d = m->dm;
+    const int n_slots = smol::TM_LAYERS + (c.n_layer + c.n_fast_layer) * 5;
+    std::vector<CUtensorMap> maps((size_t)n_slots);
+    static_assert(sizeof(CUtensorMap) == smol::kTensorMapBytes, "tensor map size");
+    const uint64_t rows = (uint64_t)ws_rows(c);
+    const int dmax = imax(c.dim, c.fast_dim), fmax = imax(c.intermediate_size, c.fast_intermediate_size);
+    bool ok = true;
+    auto act = [&](int slot, const void* p, int K, int pitch) { ok = ok && smol::make_tensor_map_2d(&maps[slot], p, rows, K, pitch, 128); };
+    auto wgt = [&](int slot, const void* p, uint64_t n, int K) { ok = ok && smol::make_tensor_map_2d(&maps[slot], p, n, K, K, 16); };
+    act(smol::TM_XN_S, d.xn, c.dim, dmax);
+    act(smol::TM_XN_F, d.xn, c.fast_dim, dmax);
+    act(smol::TM_ATTN_S, d.attn, c.dim, dmax);
+    act(smol::TM_ATTN_F, d.attn, c.fast_dim, dmax);
+    act(smol::TM_ACT_S, d.act, c.intermediate_size, fmax);
+    act(smol::TM_ACT_F, d.act, c.fast_intermediate_size, fmax);
+    wgt(smol::TM_HEAD, d.head, c.vocab_size, c.dim);
+    wgt(smol::TM_FAST_OUT, d.fast_output, (uint64_t)c.codebook_size * (c.depthwise_output ? d.depth : 1), c.fast_dim);
+    for (int f = 0; f < 2; ++f) {
+        const int nl = f ? c.n_fast_layer : c.n_layer, D = f ? c.fast_dim : c.dim, F = f ? c.fast_intermediate_size : c.intermediate_size;
+        const int qkv = ((f ? c.fast_n_head : c.n_head) + 2 * (f ? c.fast_n_local_heads : c.n_local_heads)) * 64;
+        for (int l = 0; l < nl; ++l) {
+            const smol::DevLayer& L = f ? d.fast_layers[l] : d.layers[l];
+            wgt(smol::tm_layer_slot(c.n_layer, f, l, 0), L.wqkv, qkv, D);
+            wgt(smol::tm_layer_slot(c.n_layer, f, l, 1), L.wo, D, D);
+            wgt(smol::tm_layer_slot(c.n_layer, f, l, 2), L.w1, F, D);
+            wgt(smol::tm_layer_slot(c.n_layer, f, l, 3), L.w3, F, D);
+            wgt(smol::tm_layer_slot(c.n_layer, f, l, 4), L.w2, D, F);
+        }
+    }
+    if (!ok) return fail(SMOL_ERR_CUDA, "cuTensorMapEncodeTiled failed for the tensor-core variant's operands");
+    CU(cudaMemcpy(const_cast<unsigned char*>(d.tmaps), maps.data(), (size_t)n_slots * smol::kTensorMapBytes, cudaMemcpyHostToDevice));
+    m->tmaps_ready = true;
+    return SMOL_OK;
+}
+
 // Shared-memory budget and function attributes of the kernel variant for this batch tile.
 static int ensure_tile(SmolModel* m, int bt) {
+    if (bt == 0) {
+        const int rc = ensure_tmaps(m);
+        if (rc) return rc;
+    }
     if (m->tile_ready[bt]) return SMOL_OK;
     m->xs_bytes[bt] = smol::decode_xs_bytes(m->dm, bt);
     m->smem[bt] = m->xs_bytes[bt] + (bt == 0 ? 0 : smol::decode_stage_bytes(m->dm, m->n_ctas));  // bt 0: tensor-core variant, ring only

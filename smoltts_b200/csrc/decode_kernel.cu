@@ -120,6 +120,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Generic-proxy writes (st.global of activations) <-> async-proxy reads (TMA tensor loads of the same buffers by other
+// CTAs): fenced on both sides of the grid barrier in the tensor-core variant.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct Ctx {
     int cta, n_ctas, warp, lane, tid;
@@ -913,7 +916,10 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
             }
             const bool last = (it == A.n_iter - 1) && (p == A.phase_end - 1);
             const bool sync = A.cooperative && !last;
-            if (sync) grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
+            if (sync) {
+                if (BT == 0) fence_proxy_async_all();
+                grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
+            }
             if (has_w) {
                 // Every warp is past its last read of the stage buffer (phases end with a block barrier):
                 // stream the next weight phase in while the other CTAs arrive at the grid barrier.
@@ -923,7 +929,10 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
                     st_it = nit; st_p = np;
                 }
             }
-            if (sync) grid_wait(M.barrier, target);
+            if (sync) {
+                grid_wait(M.barrier, target);
+                if (BT == 0) fence_proxy_async_all();
+            }
             if (prof) {  // [2p] CTA 0's own time in the phase, [2p+1] its wait at the barrier that follows
                 const unsigned long long t2 = globaltimer_ns();
                 M.prof[2 * p] += t1 - t0;
@@ -986,7 +995,7 @@ cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int 
 // Activation region: the batch tile's rows in fp32 (also the attention merge scratch and the
 // sampler's logits row).  Sized for the batch the model was created for.
 size_t decode_xs_bytes(const DevModel& M, int bt) {
-    if (bt == 0) return (size_t)umma::kRingBytes + 3 * kTcRows * 4;  // ring + rstd / pos / erow of the tile's rows
+    if (bt == 0) return (size_t)umma::kRingBytes + 2048 + kTcRows * 4;  // 1024-aligned ring + RoPE positions of the tile's rows
     int kmax = M.dim;
     if (M.inter > kmax) kmax = M.inter;
     if (M.fdim > kmax) kmax = M.fdim;

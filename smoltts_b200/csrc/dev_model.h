@@ -73,6 +73,8 @@ struct DevModel {
     uint16_t* q;        // rotated queries                 [B][max(n_head,fn_head)*64]
     uint16_t* attn;     // attention output                [B][max(dim,fdim)]
     uint16_t* act;      // silu(w1 x) * w3 x               [B][max(inter,finter)]
+    uint16_t* xn;       // tensor-core variant: RMSNorm output feeding the next weight phase  [B][max(dim,fdim)]
+    const unsigned char* tmaps;  // tensor-core variant: TMA tensor maps (128 B each, TensorMapSlot), in the workspace
     uint16_t* fkv;      // fast KV  [B][n_flayer][2][depth][fn_kv*64]
     float* token_logits;  // [B][vocab]           (bf16-rounded values)
     float* depth_logits;  // [B][depth][codebook] (bf16-rounded values)
@@ -189,10 +191,22 @@ __host__ __device__ inline Phase decode_phase(int p, int n_layer, int n_flayer) 
     return ph;
 }
 
-// Tensor-core variant: phases that start with a grid-wide pre-step (token embedding / depth attention).
+// Tensor-core variant: phases that start with a grid-wide pre-step (embedding / input gather + RMSNorm into xn, or the
+// depth attention) -- every weight phase except the slow wo and the w2's, whose inputs the previous phase left in place.
 __host__ __device__ inline bool tc_has_prestep(const Phase& ph) {
-    return (ph.kind == PH_QKV && !ph.fast && ph.layer == 0) || (ph.kind == PH_WO && ph.fast);
+    if (ph.kind == PH_ATTN || ph.kind == PH_SAMPLE) return false;
+    return !(ph.kind == PH_W2 || (ph.kind == PH_WO && !ph.fast));
 }
+
+// Slots of the tensor-map table (DevModel.tmaps).  Activations: 128-row boxes; weights: 16-row boxes.
+enum TensorMapSlot {
+    TM_XN_S = 0, TM_XN_F, TM_ATTN_S, TM_ATTN_F, TM_ACT_S, TM_ACT_F, TM_HEAD, TM_FAST_OUT,
+    TM_LAYERS = 8  // then 5 per layer (wqkv, wo, w1, w3, w2): slow layers first, fast layers after them
+};
+__host__ __device__ inline int tm_layer_slot(int n_layer, int fast, int layer, int which) {
+    return TM_LAYERS + ((fast ? n_layer : 0) + layer) * 5 + which;
+}
+constexpr int kTensorMapBytes = 128;
 
 __host__ __device__ inline uint32_t pack_phase(const Phase& ph) {
     return (uint32_t)ph.kind | ((uint32_t)ph.fast << 4) | ((uint32_t)ph.layer << 8) | ((uint32_t)ph.depth_pos << 16);

@@ -14,7 +14,7 @@
 namespace smol {
 
 constexpr int kTcRows = umma::kM;
-constexpr int kTcSplit = 256;  // cached positions per attention split of the batch attention
+constexpr int kTcSplit = kSplitMin;  // cached positions per attention split (ceil(L / 64) splits, at most kMaxSplits: the rule of every variant)
 
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     uint4 v;
@@ -22,48 +22,48 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return v;
 }
 
-// BaseTransformer.embed (P:205-221) of every row into the slow residual stream, spread over all warps of the grid.
-__device__ void tc_embed_rows(const DevModel& M, const CallArgs& A, const Ctx& c) {
-    const int D = M.dim, nch = D >> 3;
+// Input pre-step of a normed weight phase, one warp per row over the whole grid: gather the row (token embedding
+// P:205-221, the slow hidden state or the previous depth code's embedding G:136-140, or a residual stream), keep the raw
+// row as the residual stream where the phase starts one (`spill`), and write RMSNorm(row) (P:601-613: fp32 normalise,
+// round to bf16, multiply by the bf16 weight, round again) to M.xn, which the phase's tiles read through TMA.
+// src_kind: 0 token embedding, 1 slow hidden state, 2 embedding of the previous depth code, 3 `base` rows.
+__device__ void tc_norm_rows(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, int src_kind,
+                             const uint16_t* base, uint16_t* spill, const uint16_t* norm_w, int D) {
+    const int nch = D >> 3;
     for (int bg = c.cta * kWarps + c.warp; bg < A.batch; bg += c.n_ctas * kWarps) {
-        for (int ch = c.lane; ch < nch; ch += 32) {
-            float f[8];
-            embed_chunk(M, A, c, bg, ch, f);
-            *reinterpret_cast<uint4*>(M.x + (size_t)bg * D + ch * 8) = pack8(f);
+        const uint16_t* src = base + (size_t)bg * D;
+        if (src_kind == 1) {
+            src = M.x + (size_t)bg * D;
+        } else if (src_kind == 2) {
+            const int code = ldcg_i32(M.frame_tokens + (size_t)bg * M.n_rows + ph.depth_pos);
+            const int off = M.depthwise_wte ? (M.dup0 ? ph.depth_pos - 1 : ph.depth_pos) * M.codebook_size : 0;
+            src = M.fast_embeddings + (size_t)(code + off) * D;
         }
-    }
-}
-
-// rstd[r] = 1 / sqrt(mean(x_r^2) + eps) for the tile's rows (RMSNorm.forward P:607-609, fp32).  One warp per row,
-// four rows in flight.
-template <class RowPtr>
-__device__ __forceinline__ void tc_row_stats(const Ctx& c, int K, float eps, float* rstd, RowPtr rowptr) {
-    const int nch = K >> 3;
-    for (int r0 = c.warp * 4; r0 < kTcRows; r0 += kWarps * 4) {
-        uint4 v[4][3];
+        float x[3][8];
+        float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint16_t* src = rowptr(r0 + i);
+        for (int j = 0; j < 3; ++j) {
+            const int ch = c.lane + 32 * j;
+            if (ch < nch) {
+                if (src_kind == 0) embed_chunk(M, A, c, bg, ch, x[j]);
+                else unpack8(ldcg_v4(src + ch * 8), x[j]);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int ch = c.lane + 32 * j;
-                v[i][j] = (src != nullptr && ch < nch) ? ldcg_v4(src + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+                for (int e = 0; e < 8; ++e) ss = fmaf(x[j][e], x[j][e], ss);
             }
         }
+        ss = warp_sum(ss);
+        const float mean = __fdiv_rn(ss, (float)D);
+        const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float ss = 0.f;
+        for (int j = 0; j < 3; ++j) {
+            const int ch = c.lane + 32 * j;
+            if (ch < nch) {
+                if (spill != nullptr) *reinterpret_cast<uint4*>(spill + (size_t)bg * D + ch * 8) = pack8(x[j]);
+                float wf[8], o[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(norm_w + ch * 8)), wf);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                float x[8];
-                unpack8(v[i][j], x);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
-            }
-            ss = warp_sum(ss);
-            if (c.lane == 0) {
-                const float mean = __fdiv_rn(ss, (float)K);
-                rstd[r0 + i] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+                for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(x[j][e], r)), wf[e]);
+                *reinterpret_cast<uint4*>(M.xn + (size_t)bg * D + ch * 8) = pack8(o);
             }
         }
     }
@@ -80,31 +80,33 @@ __device__ void tc_fast_attention(const DevModel& M, const CallArgs& A, const Ct
         const uint16_t* qp = M.q + (size_t)bg * Hq * kHeadDim + hq * kHeadDim + part * 16;
         const uint16_t* kb = M.fkv + ((size_t)(bg * M.n_flayer + layer) * 2) * M.depth * kvw + kvh * kHeadDim;
         const uint16_t* vb = kb + (size_t)M.depth * kvw;
-        float qf[16];
-        {
-            float t0[8], t1[8];
-            unpack8(ldcg_v4(qp), t0);
-            unpack8(ldcg_v4(qp + 8), t1);
+        // every load of the pair is issued before the first use: q (16 dims per lane), the lane group's K rows, all V
+        const bool ok0 = jl <= depth_pos, ok1 = jl + 8 <= depth_pos;
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 q0 = ldcg_v4(qp), q1 = ldcg_v4(qp + 8);
+        const uint4 ka0 = ok0 ? ldcg_v4(kb + (size_t)jl * kvw + part * 16) : zero4;
+        const uint4 ka1 = ok0 ? ldcg_v4(kb + (size_t)jl * kvw + part * 16 + 8) : zero4;
+        const uint4 kb0 = ok1 ? ldcg_v4(kb + (size_t)(jl + 8) * kvw + part * 16) : zero4;
+        const uint4 kb1 = ok1 ? ldcg_v4(kb + (size_t)(jl + 8) * kvw + part * 16 + 8) : zero4;
+        uint32_t vv[kMaxDepth];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { qf[e] = t0[e]; qf[8 + e] = t1[e]; }
-        }
+        for (int j = 0; j < kMaxDepth; ++j) vv[j] = j <= depth_pos ? ldcg_u32(vb + (size_t)j * kvw + 2 * c.lane) : 0u;
+        float qf[16];
+        unpack8(q0, *reinterpret_cast<float(*)[8]>(qf));
+        unpack8(q1, *reinterpret_cast<float(*)[8]>(qf + 8));
         float sc[2];
-        bool ok[2];
+        const bool ok[2] = {ok0, ok1};
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            const int j = jl + 8 * h2;
-            ok[h2] = j <= depth_pos;
             sc[h2] = -INFINITY;
+            float k0[8], k1[8];
+            unpack8(h2 ? kb0 : ka0, k0);
+            unpack8(h2 ? kb1 : ka1, k1);
             float s = 0.f;
-            if (ok[h2]) {
-                float k0[8], k1[8];
-                unpack8(ldcg_v4(kb + (size_t)j * kvw + part * 16), k0);
-                unpack8(ldcg_v4(kb + (size_t)j * kvw + part * 16 + 8), k1);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) s = fmaf(qf[e], k0[e], s);
+            for (int e = 0; e < 8; ++e) s = fmaf(qf[e], k0[e], s);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) s = fmaf(qf[8 + e], k1[e], s);
-            }
+            for (int e = 0; e < 8; ++e) s = fmaf(qf[8 + e], k1[e], s);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             if (ok[h2]) sc[h2] = s * 0.125f;
@@ -121,13 +123,11 @@ __device__ void tc_fast_attention(const DevModel& M, const CallArgs& A, const Ct
         l += __shfl_xor_sync(0xffffffffu, l, 16);
         const float pb0 = bf16_round(pe0), pb1 = bf16_round(pe1);
         float o0 = 0.f, o1 = 0.f;  // lane owns dims 2*lane, 2*lane+1
+#pragma unroll
         for (int j = 0; j < kMaxDepth; ++j) {
             const float p = __shfl_sync(0xffffffffu, j < 8 ? pb0 : pb1, (j & 7) * 4);
-            if (j <= depth_pos) {
-                const uint32_t v = ldcg_u32(vb + (size_t)j * kvw + 2 * c.lane);
-                o0 = fmaf(p, bf_lo(v), o0);
-                o1 = fmaf(p, bf_hi(v), o1);
-            }
+            o0 = fmaf(p, bf_lo(vv[j]), o0);   // positions past depth_pos: p = 0, v = 0
+            o1 = fmaf(p, bf_hi(vv[j]), o1);
         }
         const float inv = 1.0f / l;
         *reinterpret_cast<uint32_t*>(M.attn + (size_t)bg * D + hq * kHeadDim + 2 * c.lane) = pack_bf16(o0 * inv, o1 * inv);
@@ -142,7 +142,21 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
     const int Hq = M.n_head, Hkv = M.n_kv, ps = M.page_size, G = Hq / Hkv;
     const int dch = c.lane & 7, psub = c.lane >> 3;
     const int cap = A.b.max_pages * ps;
-    int s_cap = (cap + kTcSplit - 1) / kTcSplit;
+    // splits to enumerate: enough for the longest row of the batch (one pass over seq_len; rows with fewer splits skip)
+    if (c.tid == 0) g_flag = 1;
+    __syncthreads();
+    {
+        int lmax = 1;
+        for (int b = c.tid; b < A.batch; b += kThreads) lmax = max(lmax, ldcg_i32(A.b.seq_len + row_seq(A, b)) + row_off(A, b) + 1);
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, 16));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, 8));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, 4));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, 2));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, 1));
+        if (c.lane == 0) atomicMax(&g_flag, lmax);
+    }
+    __syncthreads();
+    int s_cap = (min(g_flag, cap) + kTcSplit - 1) / kTcSplit;
     if (s_cap > kMaxSplits) s_cap = kMaxSplits;
     if (s_cap < 1) s_cap = 1;
     const int n_tasks = A.batch * Hkv * s_cap;
@@ -152,8 +166,8 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
         const int bs = row_seq(A, b);
         int Lb = ldcg_i32(A.b.seq_len + bs) + row_off(A, b) + 1;
         if (Lb > cap) Lb = cap;
-        int ns = (Lb + kTcSplit - 1) / kTcSplit;
-        if (ns > s_cap) ns = s_cap;
+        int ns = (Lb + kTcSplit - 1) / kTcSplit;   // a function of the row's own length only
+        if (ns > kMaxSplits) ns = kMaxSplits;
         if (s >= ns) continue;
         int chunk = (Lb + ns - 1) / ns;
         chunk = (chunk + 15) & ~15;
@@ -177,28 +191,28 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
         const int32_t* bt = A.b.block_table + (size_t)bs * A.b.max_pages;
         const size_t layer_off = ((size_t)ph.layer * 2 * Hkv + kvh) * head_stride + (size_t)dch * 8;
         const size_t page_stride = (size_t)M.n_layer * 2 * Hkv * head_stride;
-        int page[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = p0 + j * 4 + psub;
-            page[j] = p < p1 ? ldcg_i32(bt + p / ps) : 0;
-        }
+        // page ids of the split: lane i holds the id of the i-th page the split touches (one coalesced load; longer
+        // splits -- contexts beyond 32 x 64 positions -- reload every 32 pages)
+        const int pg0 = p0 / ps;
+        int pg_base = pg0;
+        int my_page = (pg_base + c.lane) * ps < p1 ? ldcg_i32(bt + pg_base + c.lane) : 0;
         for (int pb = p0; pb < p1; pb += 16) {
             uint4 kk[4], vv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int p = pb + j * 4 + psub;
+                const int pg = min(p, p1 - 1) / ps;
+                const int page = __shfl_sync(0xffffffffu, my_page, (pg - pg_base) & 31);
                 kk[j] = make_uint4(0u, 0u, 0u, 0u); vv[j] = kk[j];
                 if (p < p1) {
-                    const uint16_t* kp = M.kv_pool + (size_t)page[j] * page_stride + layer_off + (size_t)(p % ps) * kHeadDim;
+                    const uint16_t* kp = M.kv_pool + (size_t)page * page_stride + layer_off + (size_t)(p % ps) * kHeadDim;
                     kk[j] = ldcg_v4(kp);
                     vv[j] = ldcg_v4(kp + (size_t)Hkv * head_stride);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {  // page ids of the next iteration travel with this one's K/V
-                const int p = pb + 16 + j * 4 + psub;
-                page[j] = p < p1 ? ldcg_i32(bt + p / ps) : 0;
+            if ((pb + 16) / ps - pg_base >= 31 && pb + 16 < p1) {  // next group may leave the window of 32 cached page ids
+                pg_base = (pb + 16) / ps;
+                my_page = (pg_base + c.lane) * ps < p1 ? ldcg_i32(bt + pg_base + c.lane) : 0;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -298,9 +312,9 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
     }
 }
 
-// One weight phase on the tensor cores.  `target` is the grid barrier's running count: two phases have a distributed
-// pre-step (token embedding before the first slow QKV, the depth attention before a fast wo) followed by an extra grid
-// barrier; one-phase-per-launch mode runs the pre-step and the tiles as two launches instead (A.tc_part).
+// One weight phase on the tensor cores.  `target` is the grid barrier's running count: most phases start with a
+// distributed pre-step (tc_norm_rows, or the depth attention before a fast wo) followed by an extra grid barrier;
+// one-phase-per-launch mode runs the pre-step and the tiles as two launches instead (A.tc_part).
 __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, umma::Bars* bars,
                               umma::Pipe& pipe, uint32_t& target) {
     const bool fast = ph.fast != 0;
@@ -312,100 +326,73 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
     const int n_head_rows = fast ? M.codebook_size : M.vocab;
     const int K = (kind == PH_W2) ? F : D;
     const int n_out = kind == PH_QKV ? (Hq + 2 * Hkv) * kHeadDim : kind == PH_W13 ? F : kind == PH_HEAD ? n_head_rows : D;
-    const bool normed = kind == PH_QKV || kind == PH_W13 || kind == PH_HEAD;
-    const uint16_t* norm_w = kind == PH_QKV ? L.attention_norm : kind == PH_W13 ? L.ffn_norm : (fast ? M.fast_norm : M.norm);
     const uint16_t* table = fast ? M.fast_rope : M.rope;
     uint16_t* stream = fast ? M.xf : M.x;
-    const uint16_t* w0 = kind == PH_QKV ? L.wqkv : kind == PH_WO ? L.wo : kind == PH_W13 ? L.w1 : kind == PH_W2 ? L.w2
-                         : (fast ? M.fast_output + (M.depthwise_output ? (size_t)ph.depth_pos * n_head_rows * D : 0) : M.head);
-    const uint16_t* w1 = kind == PH_W13 ? L.w3 : nullptr;
-    unsigned char* ring = reinterpret_cast<unsigned char*>(c.xs);
-    float* rstd = reinterpret_cast<float*>(ring + umma::kRingBytes);
-    int* pos = reinterpret_cast<int*>(rstd + kTcRows);
-    int* erow = pos + kTcRows;  // depth steps > 0: row of fast_embeddings that holds the previous code's embedding
-
-    // sub-phase timers of CTA 0 (tools/phase_profile.py): pre-step + barrier | row statistics | ring + MMA | epilogue
+    unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)c.xs + 1023) & ~(uintptr_t)1023);
+    int* pos = reinterpret_cast<int*>(ring + umma::kRingBytes);
+    // sub-phase timers of CTA 0 (tools/phase_profile.py): pre-step + barrier | tile setup | ring + MMA | epilogue
     const bool prof = (M.prof != nullptr) && c.cta == 0 && c.tid == 0;
     unsigned long long* seg = M.prof + 2 * kMaxProg + (size_t)(kind + (fast ? 8 : 0)) * 4;
     unsigned long long ts = 0;
     if (prof) ts = globaltimer_ns();
 
-    // ---- distributed pre-steps ----
-    int src_kind = 3;  // 0 slow stream written by the embedding pre-step, 1 slow hidden state, 2 embedding of the previous depth code, 3 a stream buffer
-    if (kind == PH_QKV && ph.layer == 0 && fast && !A.fast_from_xf) src_kind = ph.depth_pos == 0 ? 1 : 2;
+    // ---- distributed pre-step ----
     if (tc_has_prestep(ph)) {
         if (A.tc_part != 2) {
-            if (kind == PH_QKV) tc_embed_rows(M, A, c);
-            else tc_fast_attention(M, A, c, ph.layer, ph.depth_pos);
+            if (kind == PH_WO) {
+                tc_fast_attention(M, A, c, ph.layer, ph.depth_pos);
+            } else {
+                int src_kind = 3;
+                const uint16_t* base = kind == PH_W13 ? M.h : stream;
+                uint16_t* spill = nullptr;
+                if (kind == PH_QKV && ph.layer == 0) {
+                    if (!fast) { src_kind = 0; spill = M.x; }
+                    else if (!A.fast_from_xf) { src_kind = ph.depth_pos == 0 ? 1 : 2; spill = M.xf; }
+                }
+                const uint16_t* norm_w = kind == PH_QKV ? L.attention_norm : kind == PH_W13 ? L.ffn_norm : (fast ? M.fast_norm : M.norm);
+                tc_norm_rows(M, A, c, ph, src_kind, base, spill, norm_w, D);
+            }
         }
         if (A.cooperative) {
+            fence_proxy_async_all();
             grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
             grid_wait(M.barrier, target);
+            fence_proxy_async_all();
         }
         if (A.tc_part == 1) return;
     }
-
     if (prof) { const unsigned long long t = globaltimer_ns(); seg[0] += t - ts; ts = t; }
+
+    // ---- operands: activation tile and weight rows through TMA ----
+    const unsigned char* tm = M.tmaps;
+    const void* tm_a = tm + (size_t)kTensorMapBytes * (kind == PH_WO ? (fast ? TM_ATTN_F : TM_ATTN_S)
+                                                       : kind == PH_W2 ? (fast ? TM_ACT_F : TM_ACT_S) : (fast ? TM_XN_F : TM_XN_S));
+    const int which = kind == PH_QKV ? 0 : kind == PH_WO ? 1 : kind == PH_W13 ? 2 : 4;
+    const void* tm_w0 = kind == PH_HEAD ? tm + (size_t)kTensorMapBytes * (fast ? TM_FAST_OUT : TM_HEAD)
+                                        : tm + (size_t)kTensorMapBytes * tm_layer_slot(M.n_layer, fast ? 1 : 0, ph.layer, which);
+    const void* tm_w1 = kind == PH_W13 ? tm + (size_t)kTensorMapBytes * tm_layer_slot(M.n_layer, fast ? 1 : 0, ph.layer, 3) : nullptr;
+    const int w_row_base = (kind == PH_HEAD && fast && M.depthwise_output) ? ph.depth_pos * n_head_rows : 0;
+
     const int m_tiles = (A.batch + kTcRows - 1) / kTcRows;
     const int blk_cap = kind == PH_W13 ? umma::kMaxN / 2 : umma::kMaxN;
     int blk = 16;
     while (blk < blk_cap && m_tiles * ((n_out + blk - 1) / blk) > c.n_ctas) blk += 16;
     const int n_blocks = (n_out + blk - 1) / blk;
     const int n_units = m_tiles * n_blocks;
-    const uint16_t* in_base = kind == PH_W13 ? M.h : kind == PH_WO ? M.attn : kind == PH_W2 ? M.act : stream;
 
     for (int u = c.cta; u < n_units; u += c.n_ctas) {
         const int mt = u / n_blocks, nb = u - mt * n_blocks;
         const int m0 = mt * kTcRows, n0 = nb * blk;
-        auto row_a = [&](int r) -> const uint16_t* {
-            const int bg = m0 + r;
-            if (bg >= A.batch) return nullptr;
-            if (src_kind == 1) return M.x + (size_t)bg * D;
-            if (src_kind == 2) return M.fast_embeddings + (size_t)erow[r] * D;
-            return in_base + (size_t)bg * K;
-        };
-        auto row_b = [&](int j) -> const uint16_t* {
-            if (w1 != nullptr) {
-                const int half = blk, jj = j < half ? j : j - half;
-                const int n = min(n0 + jj, n_out - 1);
-                return (j < half ? w0 : w1) + (size_t)n * K;
-            }
-            return w0 + (size_t)min(n0 + j, n_out - 1) * K;
-        };
         if (kind == PH_QKV && c.tid < kTcRows) {
             const int bg = min(m0 + c.tid, A.batch - 1);
             pos[c.tid] = fast ? ph.depth_pos : ldcg_i32(A.b.seq_len + row_seq(A, bg)) + row_off(A, bg);
         }
-        if (src_kind == 2 && c.tid < kTcRows) {  // G:136-140
-            const int bg = min(m0 + c.tid, A.batch - 1);
-            const int code = ldcg_i32(M.frame_tokens + (size_t)bg * M.n_rows + ph.depth_pos);
-            erow[c.tid] = code + (M.depthwise_wte ? (M.dup0 ? ph.depth_pos - 1 : ph.depth_pos) * M.codebook_size : 0);
-        }
-        __syncthreads();
-        if (src_kind != 3) {
-            // the depth transformer's input row becomes its residual stream: the units of a tile share the copy
-            for (int r = nb * kWarps + c.warp; r < kTcRows; r += n_blocks * kWarps) {
-                const uint16_t* src = row_a(r);
-                if (src == nullptr) continue;
-                for (int ch = c.lane; ch < (D >> 3); ch += 32)
-                    *reinterpret_cast<uint4*>(M.xf + (size_t)(m0 + r) * D + ch * 8) = ldcg_v4(src + ch * 8);
-            }
-        }
-        if (normed) tc_row_stats(c, K, M.eps, rstd, row_a);
         __syncthreads();
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[1] += t - ts; ts = t; }
-        auto xform = [&](int r, int k0, uint4& v) {
-            const float rs = rstd[r];
-            float x[8], wf[8], o[8];
-            unpack8(v, x);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(norm_w + k0)), wf);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(x[e], rs)), wf[e]);
-            v = pack8(o);
-        };
-        const int n_tile = w1 != nullptr ? 2 * blk : blk;
-        if (normed) umma::tile_mma<kThreads, true>(ring, bars, pipe, K, n_tile, row_a, row_b, xform);
-        else umma::tile_mma<kThreads, false>(ring, bars, pipe, K, n_tile, row_a, row_b, xform);
+        umma::BSrc b0, b1;
+        b0.tm = tm_w0; b0.row0 = w_row_base + n0; b0.n = blk;
+        b1.tm = tm_w1; b1.row0 = n0; b1.n = tm_w1 != nullptr ? blk : 0;
+        umma::tile_mma_tma<kThreads, false>(ring, bars, pipe, K, tm_a, m0, b0, b1, [](int, int, uint4&) {});
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[2] += t - ts; ts = t; }
 
         if (kind == PH_W13) {

@@ -23,7 +23,10 @@ namespace umma {
 constexpr int kM = 128;                      // sequences per tile (TMEM lanes)
 constexpr int kBK = 64;                      // K elements per ring stage (4 MMAs of K = 16)
 constexpr int kMaxN = 96;                    // widest tile (w1|w3: 48 + 48 rows)
-constexpr int kStages = 5;
+#ifndef UMMA_STAGES
+#define UMMA_STAGES 5
+#endif
+constexpr int kStages = UMMA_STAGES;
 constexpr int kAhead = 3;                    // stages in flight ahead of the MMA
 constexpr int kStageA = kM * kBK * 2;        // 16 KB
 constexpr int kStageB = kMaxN * kBK * 2;     // 12 KB
@@ -33,6 +36,7 @@ constexpr int kTmemCols = 128;               // allocation (power of two >= kMax
 
 struct Bars {
     uint64_t free_[kStages];  // stage consumed by its MMAs (tcgen05.commit)
+    uint64_t full_[kStages];  // TMA form: the stage's bytes have landed (complete_tx)
     uint64_t done;            // accumulator of the tile complete
     uint32_t tmem_base;
     uint32_t pad;
@@ -116,7 +120,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Called once per kernel by all threads (before any tile): barriers + TMEM allocation by warp 0.
 __device__ __forceinline__ void setup(Bars* bars, Pipe& pipe) {
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) bar_init(&bars->free_[s], 1u);
+        for (int s = 0; s < kStages; ++s) { bar_init(&bars->free_[s], 1u); bar_init(&bars->full_[s], 1u); }
         bar_init(&bars->done, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -323,6 +327,124 @@ __device__ __forceinline__ void tile_mma(unsigned char* ring, Bars* bars, Pipe& 
                 }
                 __syncwarp();
             }
+        }
+    }
+    pipe.chunk = g0 + (uint32_t)nk;
+    bar_wait(&bars->done, pipe.tile & 1u);
+    pipe.tile += 1;
+    fence_after_sync();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA form (the one the decode kernel uses).  Both operands are row-major [rows][K] bf16 buffers described by 2-D tensor
+// maps with a 64-element x R-row box and the 128-byte swizzle, so a stage is rows of 128 bytes whose 16-byte chunks are
+// XOR-ed with (row % 8) -- the canonical SWIZZLE_128B K-major layout of the UMMA descriptor (8-row groups 1024 B apart,
+// K advanced by adding 32 B to the start address).  One thread issues the copies of a stage (activation box of 128 rows,
+// weight boxes of 16 rows), the bytes complete on the stage's `full` mbarrier, one thread issues the MMAs; nothing else
+// touches the operands unless a transform (RMSNorm) has to rewrite the activation pieces in shared memory.
+// Measured on B200 (tools/micro/umma_test): per-thread 16-byte loads (cp.async or registers) cost 0.7-1.0 us per stage --
+// 8 cache lines per warp instruction through the L1 pipe -- which is what this form removes.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBoxRowsB = 16;   // weight rows per TMA box
+
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(s2u(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128-byte swizzle (layout type 2), 8-row groups 1024 B apart, descriptor version 1.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// One weight operand: rows [row0, row0 + n) of tensor map `tm` (n a multiple of 16).
+struct BSrc {
+    const void* tm;
+    int row0, n;
+};
+
+// acc[128][b0.n + b1.n] (TMEM) = A[rows a_row0.. +128][K] * [B0 rows | B1 rows]^T.  All NT threads call this with uniform
+// arguments; `ring` is 1024-byte aligned.  xform(r, k0, uint4&) rewrites elements [k0, k0 + 8) of tile row r (XFORM only).
+// SKIP (micro-benchmark only): 1 = no copies (the producer only arrives on `full`), 2 = no MMAs (plain arrives on `free`).
+template <int NT, bool XFORM, class Xform, int SKIP = 0>
+__device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pipe& pipe, int K, const void* tm_a, int a_row0,
+                                             BSrc b0, BSrc b1, Xform xform) {
+    const int nk = K / kBK;
+    const int tid = threadIdx.x;
+    const int n_blk = b0.n + b1.n;
+    const uint32_t idesc = instr_desc(n_blk);
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t g0 = pipe.chunk;
+    const uint32_t stage_tx = (uint32_t)(kStageA + n_blk * kBK * 2);
+    auto produce = [&](int kc) {  // one thread
+        const uint32_t g = g0 + (uint32_t)kc;
+        const int s = (int)(g % kStages);
+        if (g >= (uint32_t)kStages) bar_wait(&bars->free_[s], (g / kStages - 1u) & 1u);
+        const uint32_t a = s2u(ring + (size_t)s * kStageBytes), b = a + kStageA;
+        if (SKIP == 1) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&bars->full_[s])) : "memory");
+            return;
+        }
+        bar_expect_tx(&bars->full_[s], stage_tx);
+        tma_load_2d(a, tm_a, kc * kBK, a_row0, &bars->full_[s]);
+        for (int j = 0; j < b0.n; j += kBoxRowsB) tma_load_2d(b + j * (kBK * 2), b0.tm, kc * kBK, b0.row0 + j, &bars->full_[s]);
+        for (int j = 0; j < b1.n; j += kBoxRowsB)
+            tma_load_2d(b + (b0.n + j) * (kBK * 2), b1.tm, kc * kBK, b1.row0 + j, &bars->full_[s]);
+    };
+    auto issue_mma = [&](int kc) {  // one thread
+        const uint32_t g = g0 + (uint32_t)kc;
+        const int s = (int)(g % kStages);
+        const uint32_t a = s2u(ring + (size_t)s * kStageBytes), b = a + kStageA;
+        if (SKIP == 2) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&bars->free_[s])) : "memory");
+            if (kc == nk - 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&bars->done)) : "memory");
+            return;
+        }
+        fence_after_sync();
+#pragma unroll
+        for (int q = 0; q < kBK / 16; ++q)
+            mma_bf16(tmem, smem_desc_sw128(a + q * 32), smem_desc_sw128(b + q * 32), idesc, (kc | q) ? 1u : 0u);
+        commit(&bars->free_[s]);
+        if (kc == nk - 1) commit(&bars->done);
+    };
+    if (!XFORM) {
+        if (tid == 32) {
+            for (int kc = 0; kc < nk; ++kc) produce(kc);
+        } else if (tid == 0) {
+            for (int kc = 0; kc < nk; ++kc) {
+                const uint32_t g = g0 + (uint32_t)kc;
+                bar_wait(&bars->full_[g % kStages], (g / kStages) & 1u);
+                issue_mma(kc);
+            }
+        }
+        __syncwarp();
+    } else {
+        if (tid == 32)
+            for (int kc = 0; kc < kStages - 1 && kc < nk; ++kc) produce(kc);
+        __syncwarp();
+        for (int kc = 0; kc < nk; ++kc) {
+            const uint32_t g = g0 + (uint32_t)kc;
+            const int s = (int)(g % kStages);
+            unsigned char* stage = ring + (size_t)s * kStageBytes;
+            bar_wait(&bars->full_[s], (g / kStages) & 1u);
+#pragma unroll
+            for (int i = 0; i < (kM * 8 + NT - 1) / NT; ++i) {
+                const int p = tid + NT * i;
+                if (p < kM * 8) {
+                    const int row = p >> 3, phys = p & 7, c8 = phys ^ (row & 7);
+                    uint4* q = reinterpret_cast<uint4*>(stage + row * 128 + phys * 16);
+                    uint4 v = *q;
+                    xform(row, kc * kBK + c8 * 8, v);
+                    *q = v;
+                }
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) issue_mma(kc);
+            if (tid == 32 && kc + kStages - 1 < nk) produce(kc + kStages - 1);
+            __syncwarp();
         }
     }
     pipe.chunk = g0 + (uint32_t)nk;

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "../../smoltts_b200/csrc/tmap_host.h"
 #include "../../smoltts_b200/csrc/umma.cuh"
 
 using namespace smol;
@@ -17,8 +18,10 @@ using namespace smol;
 constexpr int NT = 512;
 
 __global__ void __launch_bounds__(NT, 1)
-umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_blk, int m_valid, int variant, int xf, int paired, int tiles) {
-    extern __shared__ __align__(128) unsigned char ring[];
+umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_blk, int m_valid, int variant, int xf, int paired, int tiles,
+                 const CUtensorMap* maps) {
+    extern __shared__ __align__(1024) unsigned char ring_raw[];
+    unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)ring_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) umma::Bars bars;
     umma::Pipe pipe;
     umma::setup(&bars, pipe);
@@ -34,7 +37,15 @@ umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_bl
             }
             (void)r; (void)k0;
         };
-        if (variant == 1) {  // cp.async staging (kept for the A/B timing)
+        if (variant >= 2) {  // TMA staging (what the decode kernel uses): maps[0] = A (rows past m_valid are outside the map: zero)
+            umma::BSrc b0, b1;
+            b0.tm = maps + 1; b0.row0 = t * n_blk; b0.n = paired ? n_blk / 2 : n_blk;
+            b1.tm = maps + 1; b1.row0 = t * n_blk + n_blk / 2; b1.n = paired ? n_blk / 2 : 0;
+            if (variant == 3) umma::tile_mma_tma<NT, false, decltype(xform), 1>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (variant == 4) umma::tile_mma_tma<NT, false, decltype(xform), 2>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (xf) umma::tile_mma_tma<NT, true>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else umma::tile_mma_tma<NT, false>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+        } else if (variant == 1) {  // cp.async staging (kept for the A/B timing)
             if (xf) umma::tile_mma_cpasync<NT, true>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
             else umma::tile_mma_cpasync<NT, false>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
         } else {
@@ -81,14 +92,23 @@ static double run(int K, int n, int m_valid, int variant, int xf, int paired, in
     cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
     cudaMemset(dC, 0xFF, (size_t)128 * 2 * n * 4);
-    cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::kRingBytes);
-    umma_test_kernel<<<ctas, NT, umma::kRingBytes>>>(dA, dB, dC, K, n, m_valid, variant, xf, paired, tiles);
+    const int smem = umma::kRingBytes + 1024;
+    cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    CUtensorMap hmaps[2];
+    CUtensorMap* dmaps;
+    if (!smol::make_tensor_map_2d(&hmaps[0], dA, m_valid, K, K, 128) || !smol::make_tensor_map_2d(&hmaps[1], dB, 2 * n, K, K, 16)) {
+        printf("tensor map encode failed\n");
+        exit(4);
+    }
+    cudaMalloc(&dmaps, sizeof(hmaps));
+    cudaMemcpy(dmaps, hmaps, sizeof(hmaps), cudaMemcpyHostToDevice);
+    umma_test_kernel<<<ctas, NT, smem>>>(dA, dB, dC, K, n, m_valid, variant, xf, paired, tiles, dmaps);
     cudaError_t e = cudaDeviceSynchronize();
     if (us_per_tile && e == cudaSuccess) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        for (int r = 0; r < 5; ++r) umma_test_kernel<<<ctas, NT, umma::kRingBytes>>>(dA, dB, dC, K, n, m_valid, variant, xf, paired, tiles);
+        for (int r = 0; r < 5; ++r) umma_test_kernel<<<ctas, NT, smem>>>(dA, dB, dC, K, n, m_valid, variant, xf, paired, tiles, dmaps);
         cudaEventRecord(e1);
         e = cudaDeviceSynchronize();
         float ms = 0;
@@ -110,17 +130,30 @@ static double run(int K, int n, int m_valid, int variant, int xf, int paired, in
     for (int r = m_valid; r < 128; ++r)
         for (int j = 0; j < 2 * n; ++j)
             if (hC[(size_t)r * 2 * n + j] != 0.0f) worst = fmax(worst, 1e9);
-    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dmaps);
     return worst;
 }
 
-int main() {
+int main(int argc, char** argv) {
     int bad = 0;
+    if (argc > 1) {  // timing of the TMA form only (ring depth experiments: -DUMMA_STAGES=n)
+        for (int variant : {2, 3, 4})
+            for (int n : {16, 32, 96})
+                for (int ctas : {1, 148}) {
+                    float us = 0;
+                    run(3072, n, 128, variant, 0, 0, ctas, 40, &us);
+                    printf("%s stages=%d K=3072 n=%2d ctas=%3d: %.2f us per tile (%.0f ns per stage)\n",
+                           variant == 2 ? "TMA+MMA " : variant == 3 ? "MMA only" : "TMA only", umma::kStages, n, ctas, us, us * 1e3 / 48);
+                }
+        return 0;
+    }
     const int Ks[] = {64, 320, 768, 3072};
     const int Ns[] = {16, 32, 64, 96};
     {   // the LBO / SBO convention of umma.cuh (the swapped one addresses shared memory out of range and faults)
         double w = run(768, 32, 128, 0, 0, 0, 1);
         if (w < 1e-2) w = run(768, 32, 128, 1, 0, 0, 1);  // and the cp.async form
+        printf("no-swizzle forms: max |err| = %.3g\n", w);
+        if (w < 1e-2) w = run(768, 32, 128, 2, 0, 0, 1);  // TMA + 128-byte swizzle
         printf("stride convention: max |err| = %.3g (K=768 n=32)\n", w);
         if (!(w < 1e-2)) { printf("FAIL: stride convention is wrong\n"); return 1; }
     }
@@ -128,20 +161,22 @@ int main() {
         for (int n : Ns)
             for (int variant = 0; variant < 3; ++variant) {
                 const int m_valid = variant == 1 ? 77 : 128, xf = variant == 1, paired = variant == 2;
-                double w = run(K, n, m_valid, 0, xf, paired, variant == 2 ? 148 : 1);
+                if (paired && n < 32) continue;  // halves are whole 16-row weight boxes
+                double w = run(K, n, m_valid, 2, xf, paired, variant == 2 ? 148 : 1);
+                if (w < 1e-3 * sqrt((double)K) * (xf ? 2 : 1)) w = run(K, n, m_valid, 0, xf, paired, 1);
                 const double tol = 1e-3 * sqrt((double)K) * (xf ? 2 : 1);
                 printf("K=%4d n=%3d rows=%3d xform=%d paired=%d: max |err| = %.3g %s\n", K, n, m_valid, xf, paired, w, w < tol ? "ok" : "FAIL");
                 if (!(w < tol)) bad = 1;
             }
     // time per tile (all CTAs compute the same tile: the activation rows are shared the way the units of a phase share them)
-    for (int variant = 0; variant < 2; ++variant)
+    for (int variant = 0; variant < 3; ++variant)
         for (int K : {768, 3072})
             for (int ctas : {1, 48, 148})
                 for (int xf = 0; xf < 2; ++xf) {
                     float us = 0;
                     run(K, 32, 128, variant, xf, 0, ctas, 40, &us);
                     printf("%s staging K=%4d n=32 xform=%d ctas=%3d: %.2f us per tile (%.0f ns per 64-element stage)\n",
-                           variant ? "cp.async " : "registers", K, xf, ctas, us, us * 1e3 / (K / 64));
+                           variant == 2 ? "TMA sw128" : variant ? "cp.async " : "registers", K, xf, ctas, us, us * 1e3 / (K / 64));
                 }
     printf(bad ? "FAIL\n" : "PASS\n");
     return bad;
