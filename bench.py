@@ -59,6 +59,17 @@ def load_peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    """Dense bf16 TFLOP/s: the sustained cuBLAS figure of MEASURED_PEAKS.json (the kernel is timed inside a long step)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+    return 2250.0, "nominal dense bf16 (B200_PROFILING.md fallback)"
+
+
 def load_traffic():
     """dram bytes per frame of the data-flow decode kernel from the committed ncu --set full capture (bs=1, 150m)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
@@ -329,11 +340,19 @@ def run_ours(args):
         bytes_per_launch = bytes_per_frame * args.frames
         achieved = bytes_per_launch / (kernel_ms_mean * 1e-3) / 1e9
         traffic = load_traffic()
-        dataflow = args.mode == 2 and args.batch <= 8
-        kernel_name = "smol_ll_kernel" if dataflow else "smol_decode_kernel"
+        dataflow = args.mode == 2 and args.batch <= 1
+        tensor = not dataflow and args.batch >= model.get_option("tc_min_batch") > 0
+        kernel_name = ("smol_ll_kernel" if dataflow else "smol_decode_kernel<0> (tcgen05 tiles, TMA operand ring)" if tensor
+                       else "smol_decode_kernel")
         launch_mode = ("data-flow persistent kernel (LL flag words, TMA producer warp), one launch per step" if dataflow
                        else "persistent cooperative kernel with grid barriers" if args.mode != 1
                        else "per-phase launches in a CUDA graph")
+        # which roof binds: bytes over HBM bandwidth vs flops over the bf16 tensor peak
+        tf_peak, tf_src = load_tensor_peak()
+        flops_per_launch = args.batch * cfg.flops_per_frame(l_mean) * args.frames
+        t_bytes_us = bytes_per_frame / (hbm_gbs * 1e9) * 1e6
+        t_flops_us = args.batch * cfg.flops_per_frame(l_mean) / (tf_peak * 1e12) * 1e6
+        tensor_bound = tensor and t_flops_us >= t_bytes_us
         line = {
             "metric": "Mimi frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -346,15 +365,21 @@ def run_ours(args):
                 "l2": "no flush: each frame streams 271 MB of weights (> 126 MB L2) plus the KV cache",
                 "us_per_frame": 1e3 * kernel_ms_mean / args.frames,
                 "frame_latency_bs1": frame_lat,
-                "e2e_includes": "H2D prompt grid + sequential prefill + decode + D2H codes, via generate_batch()",
+                "e2e_includes": "H2D prompt grid + prefill (tensor-core tiles of up to 128 prompt positions) + decode + D2H codes, via generate_batch()",
             },
-            "roofline": {
+            "roofline": ({
+                "bound": "tensor", "achieved": flops_per_launch / (kernel_ms_mean * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": flops_per_launch / (kernel_ms_mean * 1e-3) / 1e12 / tf_peak, "peak_source": tf_src, "kernel": kernel_name,
+                "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": kernel_ms_mean,
+                "roof_us_per_step": {"flops": t_flops_us, "bytes": t_bytes_us}, "traffic": None,
+            } if tensor_bound else {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                 "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": kernel_ms_mean,
+                "roof_us_per_step": {"flops": t_flops_us, "bytes": t_bytes_us},
                 "traffic": ((traffic or {}).get("dram_bytes_per_frame") * args.frames
                             if traffic and dataflow and args.model == "smoltts_byte_150m" and args.batch == 1 else None),
-            },
+            }),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "clocks": clocks,

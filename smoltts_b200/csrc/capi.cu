@@ -91,7 +91,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int imax(int a, int b) { return a > b ? a : b; }
 
 struct WsLayout {
-    size_t x, h, xf, q, attn, act, xn, tmaps, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
+    size_t x, h, xf, q, attn, act, xn, tmaps, kpart, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
     size_t ll, ll_partial, ll_tok, ll_cand, ll_epoch, total;
 };
 
@@ -137,6 +137,7 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.act = take(B * imax(c.intermediate_size, c.fast_intermediate_size) * 2);
     L.xn = take(B * dmax * 2);
     L.tmaps = take((size_t)(smol::TM_LAYERS + (SMOL_MAX_LAYERS + SMOL_MAX_FAST_LAYERS) * 5) * smol::kTensorMapBytes);
+    L.kpart = take((size_t)smol::kTcKSplit * B * dmax * 4);
     L.fkv = take(B * c.n_fast_layer * 2 * depth * c.fast_n_local_heads * 64 * 2);
     L.token_logits = take(B * c.vocab_size * 4);
     L.depth_logits = take(B * depth * c.codebook_size * 4);
@@ -267,6 +268,7 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     d.q = (uint16_t*)(base + L.q); d.attn = (uint16_t*)(base + L.attn); d.act = (uint16_t*)(base + L.act);
     d.fkv = (uint16_t*)(base + L.fkv);
     d.xn = (uint16_t*)(base + L.xn); d.tmaps = (const unsigned char*)(base + L.tmaps);
+    d.kpart = (float*)(base + L.kpart); d.ws_rows = ws_rows(m->cfg);
     m->tmaps_ready = false;
     d.token_logits = (float*)(base + L.token_logits); d.depth_logits = (float*)(base + L.depth_logits);
     d.frame_tokens = (int32_t*)(base + L.frame_tokens);
@@ -448,11 +450,22 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
             A.finalize = 0;
             A.advance = 0;
             A.tc_part = 0;
-            if (bt == 0 && smol::tc_has_prestep(smol::unpack_phase(m->dm.prog[p]))) {
-                A.tc_part = 1;  // the grid barrier between pre-step and tiles becomes a launch boundary
-                CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
-                m->launches += 1;
+            const smol::Phase ph = smol::unpack_phase(m->dm.prog[p]);
+            const bool weights = ph.kind != smol::PH_ATTN && ph.kind != smol::PH_SAMPLE;
+            if (bt == 0 && weights) {
+                // the grid barriers between a phase's pre-step, tiles and post-step become launch boundaries
+                const bool post = smol::tc_has_poststep(ph);
+                if (smol::tc_has_prestep(ph)) {
+                    A.tc_part = 1;
+                    CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
+                    m->launches += 1;
+                }
                 A.tc_part = 2;
+                if (post) {
+                    CU(smol::decode_launch(m->dm, A, bt, m->n_ctas, m->smem[bt], (int)m->xs_bytes[bt], stream));
+                    m->launches += 1;
+                    A.tc_part = 3;
+                }
             }
             A.finalize = last ? finalize : 0;
             A.advance = (p == end - 1) ? advance : 0;

@@ -80,6 +80,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // other CTAs (issuing the next phase's weight copies) sits between the two.  All CTAs are co-resident
 // (cooperative launch).  `target` is the cumulative arrival count this barrier completes at; the
 // counter only ever grows (wrap-safe compare).
+// (Measured on B200: a two-level form -- 12 group counters whose last arrivers arrive on the root -- is SLOWER,
+//  3.3 us vs 2.2 us per barrier at 148 CTAs: the second dependent L2 hop costs more than 148 same-address atomics.)
 __device__ __forceinline__ void grid_arrive(uint32_t* ctr, uint32_t& target, uint32_t n_ctas) {
     target += n_ctas;
     __syncthreads();
@@ -835,11 +837,12 @@ __device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c,
 // BT == 0: the tensor-core variant (tc_phases.cuh) -- 128-row tiles, batch attention, cooperative launches only.
 template <int BT>
 __device__ __forceinline__ void run_phase(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph,
-                                          uint32_t& parity, umma::Pipe& pipe, uint32_t& target) {
+                                          uint32_t& parity, umma::Pipe& pipe, uint32_t& target, bool first_in_launch,
+                                          bool next_in_launch) {
     if (BT == 0) {
         if (ph.kind == PH_ATTN) phase_attn_batch(M, A, c, ph);
         else if (ph.kind == PH_SAMPLE) phase_sample(M, A, c, ph);
-        else phase_gemm_tc(M, A, c, ph, &g_tc_bars, pipe, target);
+        else phase_gemm_tc(M, A, c, ph, &g_tc_bars, pipe, target, first_in_launch, next_in_launch);
         return;
     }
     if (ph.kind == PH_ATTN) phase_attn(M, A, c, ph);
@@ -897,12 +900,14 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
                 stage_issue(c, phase_plan(M, ph));
                 st_it = it; st_p = p;
             }
-            run_phase<BT>(M, A, c, ph, parity, pipe, target);
+            run_phase<BT>(M, A, c, ph, parity, pipe, target, p == A.phase_begin, p + 1 < A.phase_end);
             if (prof_cta) {
                 __syncthreads();
                 if (prof) t1 = globaltimer_ns();
             }
-            if (c.cta == 0 && p == per_iter - 1 && A.mode == 1) {
+            // (tensor-core variant, one phase per launch: a phase may take up to three launches; bookkeeping runs in the last)
+            const bool final_part = A.tc_part == 0 || A.tc_part == (tc_has_poststep(ph) ? 3 : 2);
+            if (c.cta == 0 && p == per_iter - 1 && A.mode == 1 && final_part) {
                 // prefill bookkeeping: every sequence advances by the positions of this tile that lie inside its prompt
                 const int T = A.tile_t > 1 ? A.tile_t : 1;
                 for (int b = c.tid; b < A.real_batch; b += kThreads) {

@@ -75,6 +75,8 @@ struct DevModel {
     uint16_t* act;      // silu(w1 x) * w3 x               [B][max(inter,finter)]
     uint16_t* xn;       // tensor-core variant: RMSNorm output feeding the next weight phase  [B][max(dim,fdim)]
     const unsigned char* tmaps;  // tensor-core variant: TMA tensor maps (128 B each, TensorMapSlot), in the workspace
+    float* kpart;       // tensor-core variant: split-K partial sums of the wo / w2 tiles  [kTcKSplit][ws_rows][max(dim,fdim)] fp32
+    int ws_rows;        // rows of every workspace buffer
     uint16_t* fkv;      // fast KV  [B][n_flayer][2][depth][fn_kv*64]
     float* token_logits;  // [B][vocab]           (bf16-rounded values)
     float* depth_logits;  // [B][depth][codebook] (bf16-rounded values)
@@ -134,7 +136,8 @@ struct CallArgs {
     int repeat;       // profiling only: run the body of every weight phase 1 + repeat times
     int tile_t;       // prefill: prompt positions handled per iteration (rows = real_batch * tile_t share the weight pass)
     int real_batch;   // prefill: sequences (rows / tile_t)
-    int tc_part;      // tensor-core variant, one phase per launch: 1 = only the phase's distributed pre-step, 2 = only its tiles
+    int tc_part;      // tensor-core variant, one phase per launch: 1 = only the phase's distributed pre-step, 2 = only its tiles,
+                      // 3 = only its post-step (0 = the whole phase: cooperative launches)
     const int32_t* prompt;      // prefill: [B][n_rows][s_max]
     const int32_t* prompt_len;  // prefill: [B]
     int s_max;
@@ -207,6 +210,8 @@ __host__ __device__ inline int tm_layer_slot(int n_layer, int fast, int layer, i
     return TM_LAYERS + ((fast ? n_layer : 0) + layer) * 5 + which;
 }
 constexpr int kTensorMapBytes = 128;
+constexpr int kTcKSplit = 4;  // K slices of the wo / w2 tiles (their sum + residual + next RMSNorm is the phase's post-step)
+__host__ __device__ inline bool tc_has_poststep(const Phase& ph) { return ph.kind == PH_WO || ph.kind == PH_W2; }
 
 __host__ __device__ inline uint32_t pack_phase(const Phase& ph) {
     return (uint32_t)ph.kind | ((uint32_t)ph.fast << 4) | ((uint32_t)ph.layer << 8) | ((uint32_t)ph.depth_pos << 16);

@@ -22,6 +22,37 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return v;
 }
 
+// Tail shared by the row pre-/post-steps: the lane's chunks x[j] of row bg (lane-partial sum of squares ss) go to `raw`
+// (if any) as they are and, if norm_w is given, through RMSNorm (P:601-613: fp32 normalise, round to bf16, multiply by
+// the bf16 weight, round again) to M.xn.
+__device__ __forceinline__ void tc_norm_store(const DevModel& M, const Ctx& c, int bg, const float (&x)[3][8], float ss,
+                                              uint16_t* raw, const uint16_t* norm_w, int D) {
+    const int nch = D >> 3;
+    uint4 wv[3];  // issued before the reduction: the weight fetch overlaps it
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int ch = c.lane + 32 * j;
+        wv[j] = (norm_w != nullptr && ch < nch) ? __ldg(reinterpret_cast<const uint4*>(norm_w + ch * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    ss = warp_sum(ss);
+    const float mean = __fdiv_rn(ss, (float)D);
+    const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int ch = c.lane + 32 * j;
+        if (ch < nch) {
+            if (raw != nullptr) *reinterpret_cast<uint4*>(raw + (size_t)bg * D + ch * 8) = pack8(x[j]);
+            if (norm_w != nullptr) {
+                float wf[8], o[8];
+                unpack8(wv[j], wf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(x[j][e], r)), wf[e]);
+                *reinterpret_cast<uint4*>(M.xn + (size_t)bg * D + ch * 8) = pack8(o);
+            }
+        }
+    }
+}
+
 // Input pre-step of a normed weight phase, one warp per row over the whole grid: gather the row (token embedding
 // P:205-221, the slow hidden state or the previous depth code's embedding G:136-140, or a residual stream), keep the raw
 // row as the residual stream where the phase starts one (`spill`), and write RMSNorm(row) (P:601-613: fp32 normalise,
@@ -51,21 +82,43 @@ __device__ void tc_norm_rows(const DevModel& M, const CallArgs& A, const Ctx& c,
                 for (int e = 0; e < 8; ++e) ss = fmaf(x[j][e], x[j][e], ss);
             }
         }
-        ss = warp_sum(ss);
-        const float mean = __fdiv_rn(ss, (float)D);
-        const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
+        tc_norm_store(M, c, bg, x, ss, spill, norm_w, D);
+    }
+}
+
+// Post-step of the split-K phases (wo, w2), one warp per row: dst = res + bf16(sum of the K-slice partials, in slice
+// order) -- the Linear's bf16 output plus the residual (P:499-500) -- and, when the next phase of the launch is the
+// normed phase that reads dst (w13 after wo; the next layer's QKV or the head after w2), its RMSNorm into M.xn, so that
+// phase starts without a pre-step of its own.
+__device__ void tc_residual_finish(const DevModel& M, const CallArgs& A, const Ctx& c, const uint16_t* res, uint16_t* dst,
+                                   int D, int n_split, const uint16_t* norm_w) {
+    const int nch = D >> 3;
+    for (int bg = c.cta * kWarps + c.warp; bg < A.batch; bg += c.n_ctas * kWarps) {
+        float x[3][8];
+        float ss = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const int ch = c.lane + 32 * j;
             if (ch < nch) {
-                if (spill != nullptr) *reinterpret_cast<uint4*>(spill + (size_t)bg * D + ch * 8) = pack8(x[j]);
-                float wf[8], o[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(norm_w + ch * 8)), wf);
+                float acc[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(x[j][e], r)), wf[e]);
-                *reinterpret_cast<uint4*>(M.xn + (size_t)bg * D + ch * 8) = pack8(o);
+                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                for (int sp = 0; sp < n_split; ++sp) {
+                    const float* pp = M.kpart + ((size_t)sp * M.ws_rows + bg) * D + ch * 8;
+                    const float4 a = __ldcg(reinterpret_cast<const float4*>(pp)), b = __ldcg(reinterpret_cast<const float4*>(pp + 4));
+                    acc[0] = __fadd_rn(acc[0], a.x); acc[1] = __fadd_rn(acc[1], a.y); acc[2] = __fadd_rn(acc[2], a.z); acc[3] = __fadd_rn(acc[3], a.w);
+                    acc[4] = __fadd_rn(acc[4], b.x); acc[5] = __fadd_rn(acc[5], b.y); acc[6] = __fadd_rn(acc[6], b.z); acc[7] = __fadd_rn(acc[7], b.w);
+                }
+                float rf[8];
+                unpack8(ldcg_v4(res + (size_t)bg * D + ch * 8), rf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    x[j][e] = bf16_round(__fadd_rn(rf[e], bf16_round(acc[e])));
+                    ss = fmaf(x[j][e], x[j][e], ss);
+                }
             }
         }
+        tc_norm_store(M, c, bg, x, ss, dst, norm_w, D);
     }
 }
 
@@ -316,7 +369,7 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
 // distributed pre-step (tc_norm_rows, or the depth attention before a fast wo) followed by an extra grid barrier;
 // one-phase-per-launch mode runs the pre-step and the tiles as two launches instead (A.tc_part).
 __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, umma::Bars* bars,
-                              umma::Pipe& pipe, uint32_t& target) {
+                              umma::Pipe& pipe, uint32_t& target, bool first_in_launch, bool next_in_launch) {
     const bool fast = ph.fast != 0;
     const int kind = ph.kind;
     const int D = fast ? M.fdim : M.dim, F = fast ? M.finter : M.inter;
@@ -337,8 +390,11 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
     if (prof) ts = globaltimer_ns();
 
     // ---- distributed pre-step ----
-    if (tc_has_prestep(ph)) {
-        if (A.tc_part != 2) {
+    // (a normed phase that follows a wo / w2 inside one cooperative launch finds M.xn written by that phase's post-step)
+    const bool fed_by_post = A.cooperative && !first_in_launch &&
+                             (kind == PH_W13 || kind == PH_HEAD || (kind == PH_QKV && ph.layer > 0));
+    if (tc_has_prestep(ph) && !fed_by_post) {
+        if (A.tc_part == 0 || A.tc_part == 1) {
             if (kind == PH_WO) {
                 tc_fast_attention(M, A, c, ph.layer, ph.depth_pos);
             } else {
@@ -373,15 +429,20 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
     const void* tm_w1 = kind == PH_W13 ? tm + (size_t)kTensorMapBytes * tm_layer_slot(M.n_layer, fast ? 1 : 0, ph.layer, 3) : nullptr;
     const int w_row_base = (kind == PH_HEAD && fast && M.depthwise_output) ? ph.depth_pos * n_head_rows : 0;
 
+    // the residual phases (wo, w2) also cut K: their fp32 partials meet in the post-step
+    const bool has_post = kind == PH_WO || kind == PH_W2;
+    const int n_split = !has_post ? 1 : (K % (4 * umma::kBK) == 0) ? 4 : (K % (2 * umma::kBK) == 0) ? 2 : 1;
+    const int k_len = K / n_split;
     const int m_tiles = (A.batch + kTcRows - 1) / kTcRows;
     const int blk_cap = kind == PH_W13 ? umma::kMaxN / 2 : umma::kMaxN;
     int blk = 16;
-    while (blk < blk_cap && m_tiles * ((n_out + blk - 1) / blk) > c.n_ctas) blk += 16;
+    while (blk < blk_cap && m_tiles * ((n_out + blk - 1) / blk) * n_split > c.n_ctas) blk += 16;
     const int n_blocks = (n_out + blk - 1) / blk;
-    const int n_units = m_tiles * n_blocks;
+    const int n_units = (A.tc_part == 0 || A.tc_part == 2) ? m_tiles * n_blocks * n_split : 0;
 
     for (int u = c.cta; u < n_units; u += c.n_ctas) {
-        const int mt = u / n_blocks, nb = u - mt * n_blocks;
+        const int ks = u % n_split, un = u / n_split;
+        const int mt = un / n_blocks, nb = un - mt * n_blocks;
         const int m0 = mt * kTcRows, n0 = nb * blk;
         if (kind == PH_QKV && c.tid < kTcRows) {
             const int bg = min(m0 + c.tid, A.batch - 1);
@@ -392,7 +453,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
         umma::BSrc b0, b1;
         b0.tm = tm_w0; b0.row0 = w_row_base + n0; b0.n = blk;
         b1.tm = tm_w1; b1.row0 = n0; b1.n = tm_w1 != nullptr ? blk : 0;
-        umma::tile_mma_tma<kThreads, false>(ring, bars, pipe, K, tm_a, m0, b0, b1, [](int, int, uint4&) {});
+        umma::tile_mma_tma<kThreads, false>(ring, bars, pipe, k_len, tm_a, m0, b0, b1, [](int, int, uint4&) {}, ks * k_len);
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[2] += t - ts; ts = t; }
 
         if (kind == PH_W13) {
@@ -419,16 +480,10 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
                     *reinterpret_cast<float4*>(out + u0 + 4) = make_float4(bf16_round(acc[4]), bf16_round(acc[5]), bf16_round(acc[6]), bf16_round(acc[7]));
                     return;
                 }
-                if (kind != PH_QKV) {
-                    // wo: h = stream + wo(attn)   (P:499)      w2: stream = h + w2(act)   (P:500)
-                    const uint16_t* res = kind == PH_WO ? stream : M.h;
-                    uint16_t* dst = kind == PH_WO ? M.h : stream;
-                    const size_t o = (size_t)bg * D + u0;
-                    float rf[8], of[8];
-                    unpack8(ldcg_v4(res + o), rf);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) of[e] = __fadd_rn(rf[e], bf16_round(acc[e]));
-                    *reinterpret_cast<uint4*>(dst + o) = pack8(of);
+                if (kind != PH_QKV) {  // wo, w2: this K slice's partial sums (the post-step adds slices and residual)
+                    float* pp = M.kpart + ((size_t)ks * M.ws_rows + bg) * D + u0;
+                    *reinterpret_cast<float4*>(pp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
                     return;
                 }
                 float v[8];
@@ -470,6 +525,23 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
             });
         }
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[3] += t - ts; ts = t; }
+    }
+
+    // ---- post-step of the residual phases: wo: h = stream + wo(attn) (P:499); w2: stream = h + w2(act) (P:500) ----
+    if (has_post && A.tc_part != 2) {
+        if (A.cooperative) {
+            grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
+            grid_wait(M.barrier, target);
+        }
+        const uint16_t* next_norm = nullptr;
+        if (A.cooperative && next_in_launch) {
+            const int n_net = fast ? M.n_flayer : M.n_layer;
+            if (kind == PH_WO) next_norm = L.ffn_norm;
+            else if (ph.layer + 1 < n_net) next_norm = (fast ? M.fast_layers[ph.layer + 1] : M.layers[ph.layer + 1]).attention_norm;
+            else next_norm = fast ? M.fast_norm : M.norm;
+        }
+        tc_residual_finish(M, A, c, kind == PH_WO ? stream : M.h, kind == PH_WO ? M.h : stream, D, n_split, next_norm);
+        if (prof) { const unsigned long long t = globaltimer_ns(); seg[0] += t - ts; ts = t; }
     }
 }
 

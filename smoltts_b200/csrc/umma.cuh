@@ -370,8 +370,8 @@ struct BSrc {
 // SKIP (micro-benchmark only): 1 = no copies (the producer only arrives on `full`), 2 = no MMAs (plain arrives on `free`).
 template <int NT, bool XFORM, class Xform, int SKIP = 0>
 __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pipe& pipe, int K, const void* tm_a, int a_row0,
-                                             BSrc b0, BSrc b1, Xform xform) {
-    const int nk = K / kBK;
+                                             BSrc b0, BSrc b1, Xform xform, int k0 = 0) {
+    const int nk = K / kBK;  // K elements starting at column k0 of both operands (split-K units)
     const int tid = threadIdx.x;
     const int n_blk = b0.n + b1.n;
     const uint32_t idesc = instr_desc(n_blk);
@@ -388,10 +388,10 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
             return;
         }
         bar_expect_tx(&bars->full_[s], stage_tx);
-        tma_load_2d(a, tm_a, kc * kBK, a_row0, &bars->full_[s]);
-        for (int j = 0; j < b0.n; j += kBoxRowsB) tma_load_2d(b + j * (kBK * 2), b0.tm, kc * kBK, b0.row0 + j, &bars->full_[s]);
+        tma_load_2d(a, tm_a, k0 + kc * kBK, a_row0, &bars->full_[s]);
+        for (int j = 0; j < b0.n; j += kBoxRowsB) tma_load_2d(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s]);
         for (int j = 0; j < b1.n; j += kBoxRowsB)
-            tma_load_2d(b + (b0.n + j) * (kBK * 2), b1.tm, kc * kBK, b1.row0 + j, &bars->full_[s]);
+            tma_load_2d(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s]);
     };
     auto issue_mma = [&](int kc) {  // one thread
         const uint32_t g = g0 + (uint32_t)kc;
