@@ -22,46 +22,60 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return v;
 }
 
-// Tail shared by the row pre-/post-steps: the lane's chunks x[j] of row bg (lane-partial sum of squares ss) go to `raw`
-// (if any) as they are and, if norm_w is given, through RMSNorm (P:601-613: fp32 normalise, round to bf16, multiply by
-// the bf16 weight, round again) to M.xn.
-__device__ __forceinline__ void tc_norm_store(const DevModel& M, const Ctx& c, int bg, const float (&x)[3][8], float ss,
-                                              uint16_t* raw, const uint16_t* norm_w, int D) {
+// Row steps of the tensor-core variant (pre-step of a normed phase, post-step of a split-K phase).  Three warps per row
+// (one 16-byte chunk per lane: every load of a row is in flight at once), five rows per CTA and pass, rows spread over
+// the grid.  load(bg, ch, x) produces chunk ch of row bg; the row goes to `raw` (if any) as it is and, if norm_w is given,
+// through RMSNorm (P:601-613: fp32 normalise, round to bf16, multiply by the bf16 weight, round again) to M.xn.
+constexpr int kRowWarps = 3;
+constexpr int kRowsPerPass = kWarps / kRowWarps;
+
+template <class Load>
+__device__ __forceinline__ void tc_row_step(const DevModel& M, const CallArgs& A, const Ctx& c, int D, uint16_t* raw,
+                                            const uint16_t* norm_w, Load load) {
     const int nch = D >> 3;
-    uint4 wv[3];  // issued before the reduction: the weight fetch overlaps it
+    const int slot = c.warp / kRowWarps, wi = c.warp - slot * kRowWarps;
+    const int ch = wi * 32 + c.lane;
+    for (int row0 = c.cta * kRowsPerPass; row0 < A.batch; row0 += c.n_ctas * kRowsPerPass) {
+        const int bg = row0 + slot;
+        const bool act = slot < kRowsPerPass && bg < A.batch && ch < nch;
+        float x[8];
+        float ss = 0.f;
+        uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+        if (act) {
+            if (norm_w != nullptr) wv = __ldg(reinterpret_cast<const uint4*>(norm_w + ch * 8));
+            load(bg, ch, x);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int ch = c.lane + 32 * j;
-        wv[j] = (norm_w != nullptr && ch < nch) ? __ldg(reinterpret_cast<const uint4*>(norm_w + ch * 8)) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    ss = warp_sum(ss);
-    const float mean = __fdiv_rn(ss, (float)D);
-    const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int ch = c.lane + 32 * j;
-        if (ch < nch) {
-            if (raw != nullptr) *reinterpret_cast<uint4*>(raw + (size_t)bg * D + ch * 8) = pack8(x[j]);
+            for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+        }
+        ss = warp_sum(ss);
+        if (c.lane == 0) g_part[c.warp] = ss;
+        __syncthreads();
+        if (act) {
+            if (raw != nullptr) *reinterpret_cast<uint4*>(raw + (size_t)bg * D + ch * 8) = pack8(x);
             if (norm_w != nullptr) {
+                float t = 0.f;
+                for (int i = 0; i < kRowWarps; ++i) t += g_part[slot * kRowWarps + i];
+                const float mean = __fdiv_rn(t, (float)D);
+                const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
                 float wf[8], o[8];
-                unpack8(wv[j], wf);
+                unpack8(wv, wf);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(x[j][e], r)), wf[e]);
+                for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(x[e], r)), wf[e]);
                 *reinterpret_cast<uint4*>(M.xn + (size_t)bg * D + ch * 8) = pack8(o);
             }
         }
+        __syncthreads();
     }
 }
 
-// Input pre-step of a normed weight phase, one warp per row over the whole grid: gather the row (token embedding
-// P:205-221, the slow hidden state or the previous depth code's embedding G:136-140, or a residual stream), keep the raw
-// row as the residual stream where the phase starts one (`spill`), and write RMSNorm(row) (P:601-613: fp32 normalise,
-// round to bf16, multiply by the bf16 weight, round again) to M.xn, which the phase's tiles read through TMA.
+// Input pre-step of a normed weight phase: gather the row (token embedding P:205-221, the slow hidden state or the
+// previous depth code's embedding G:136-140, or a residual stream), keep the raw row as the residual stream where the
+// phase starts one (`spill`), and write RMSNorm(row) to M.xn, which the phase's tiles read through TMA.
 // src_kind: 0 token embedding, 1 slow hidden state, 2 embedding of the previous depth code, 3 `base` rows.
 __device__ void tc_norm_rows(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, int src_kind,
                              const uint16_t* base, uint16_t* spill, const uint16_t* norm_w, int D) {
-    const int nch = D >> 3;
-    for (int bg = c.cta * kWarps + c.warp; bg < A.batch; bg += c.n_ctas * kWarps) {
+    tc_row_step(M, A, c, D, spill, norm_w, [&](int bg, int ch, float (&x)[8]) {
+        if (src_kind == 0) { embed_chunk(M, A, c, bg, ch, x); return; }
         const uint16_t* src = base + (size_t)bg * D;
         if (src_kind == 1) {
             src = M.x + (size_t)bg * D;
@@ -70,56 +84,47 @@ __device__ void tc_norm_rows(const DevModel& M, const CallArgs& A, const Ctx& c,
             const int off = M.depthwise_wte ? (M.dup0 ? ph.depth_pos - 1 : ph.depth_pos) * M.codebook_size : 0;
             src = M.fast_embeddings + (size_t)(code + off) * D;
         }
-        float x[3][8];
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int ch = c.lane + 32 * j;
-            if (ch < nch) {
-                if (src_kind == 0) embed_chunk(M, A, c, bg, ch, x[j]);
-                else unpack8(ldcg_v4(src + ch * 8), x[j]);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) ss = fmaf(x[j][e], x[j][e], ss);
-            }
-        }
-        tc_norm_store(M, c, bg, x, ss, spill, norm_w, D);
-    }
+        unpack8(ldcg_v4(src + ch * 8), x);
+    });
 }
 
-// Post-step of the split-K phases (wo, w2), one warp per row: dst = res + bf16(sum of the K-slice partials, in slice
-// order) -- the Linear's bf16 output plus the residual (P:499-500) -- and, when the next phase of the launch is the
-// normed phase that reads dst (w13 after wo; the next layer's QKV or the head after w2), its RMSNorm into M.xn, so that
-// phase starts without a pre-step of its own.
+// Post-step of the split-K phases (wo, w2): dst = res + bf16(sum of the K-slice partials, in slice order) -- the Linear's
+// bf16 output plus the residual (P:499-500) -- and, when the next phase of the launch is the normed phase that reads dst
+// (w13 after wo; the next layer's QKV or the head after w2), its RMSNorm into M.xn, so that phase starts without a
+// pre-step of its own.
 __device__ void tc_residual_finish(const DevModel& M, const CallArgs& A, const Ctx& c, const uint16_t* res, uint16_t* dst,
                                    int D, int n_split, const uint16_t* norm_w) {
-    const int nch = D >> 3;
-    for (int bg = c.cta * kWarps + c.warp; bg < A.batch; bg += c.n_ctas * kWarps) {
-        float x[3][8];
-        float ss = 0.f;
+    tc_row_step(M, A, c, D, dst, norm_w, [&](int bg, int ch, float (&x)[8]) {
+        const uint4 rv = ldcg_v4(res + (size_t)bg * D + ch * 8);
+        float4 pa[kTcKSplit], pb[kTcKSplit];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int ch = c.lane + 32 * j;
-            if (ch < nch) {
-                float acc[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-                for (int sp = 0; sp < n_split; ++sp) {
-                    const float* pp = M.kpart + ((size_t)sp * M.ws_rows + bg) * D + ch * 8;
-                    const float4 a = __ldcg(reinterpret_cast<const float4*>(pp)), b = __ldcg(reinterpret_cast<const float4*>(pp + 4));
-                    acc[0] = __fadd_rn(acc[0], a.x); acc[1] = __fadd_rn(acc[1], a.y); acc[2] = __fadd_rn(acc[2], a.z); acc[3] = __fadd_rn(acc[3], a.w);
-                    acc[4] = __fadd_rn(acc[4], b.x); acc[5] = __fadd_rn(acc[5], b.y); acc[6] = __fadd_rn(acc[6], b.z); acc[7] = __fadd_rn(acc[7], b.w);
-                }
-                float rf[8];
-                unpack8(ldcg_v4(res + (size_t)bg * D + ch * 8), rf);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    x[j][e] = bf16_round(__fadd_rn(rf[e], bf16_round(acc[e])));
-                    ss = fmaf(x[j][e], x[j][e], ss);
-                }
+        for (int sp = 0; sp < kTcKSplit; ++sp) {
+            if (sp < n_split) {
+                const float* pp = M.kpart + ((size_t)sp * M.ws_rows + bg) * D + ch * 8;
+                pa[sp] = __ldcg(reinterpret_cast<const float4*>(pp));
+                pb[sp] = __ldcg(reinterpret_cast<const float4*>(pp + 4));
+            } else {
+                pa[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pb[sp] = pa[sp];
             }
         }
-        tc_norm_store(M, c, bg, x, ss, dst, norm_w, D);
-    }
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < kTcKSplit; ++sp) {
+            if (sp < n_split) {
+                acc[0] = __fadd_rn(acc[0], pa[sp].x); acc[1] = __fadd_rn(acc[1], pa[sp].y);
+                acc[2] = __fadd_rn(acc[2], pa[sp].z); acc[3] = __fadd_rn(acc[3], pa[sp].w);
+                acc[4] = __fadd_rn(acc[4], pb[sp].x); acc[5] = __fadd_rn(acc[5], pb[sp].y);
+                acc[6] = __fadd_rn(acc[6], pb[sp].z); acc[7] = __fadd_rn(acc[7], pb[sp].w);
+            }
+        }
+        float rf[8];
+        unpack8(rv, rf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = bf16_round(__fadd_rn(rf[e], bf16_round(acc[e])));
+    });
 }
 
 // Attention of the fast transformer for every (row, head) of the batch, one warp per pair, spread over the grid; the
