@@ -410,6 +410,8 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
         if (kc == nk - 1) commit(&bars->done);
     };
     if (!XFORM) {
+        // two working threads; everybody else sleeps in the block barrier below instead of polling `done` (512 polling
+        // threads take issue slots from the producer's and the MMA thread's dependent chains)
         if (tid == 32) {
             for (int kc = 0; kc < nk; ++kc) produce(kc);
         } else if (tid == 0) {
@@ -418,8 +420,15 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
                 bar_wait(&bars->full_[g % kStages], (g / kStages) & 1u);
                 issue_mma(kc);
             }
+            bar_wait(&bars->done, pipe.tile & 1u);
+            fence_before_sync();
         }
         __syncwarp();
+        __syncthreads();
+        pipe.chunk = g0 + (uint32_t)nk;
+        pipe.tile += 1;
+        fence_after_sync();
+        return;
     } else {
         if (tid == 32)
             for (int kc = 0; kc < kStages - 1 && kc < nk; ++kc) produce(kc);
