@@ -138,3 +138,103 @@ def test_tc_prefill_tile_sizes_and_batch_composition_bit_identical():
         b = _prefill_and_frames(model, prompts[20:21], 3, 16, prefill_tile=tile)
         assert torch.equal(a["kv"].view(torch.int16), b["kv"].view(torch.int16)), f"prefill tile {tile}"
         assert torch.equal(a["codes"], b["codes"])
+
+
+def test_tc_ragged_tiles_three_row_tiles():
+    """130 and 300 utterances (a second tile with 2 live rows; three tiles) against the same utterances in batches of 16:
+    bit-identical ids -- rows past the batch inside a tile are inert, tiles do not see each other."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=300, max_seq_len=96)
+    prompts = [prompt_grid(byte_prompt(8 + (b % 11), seed=500 + b), cfg) for b in range(300)]
+    gs = GenerationSettings(default_temp=0.0, default_fast_temp=0.0)
+    whole = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=4, seq_ids=list(range(300)))
+    part = generate_batch(model, prompts[:130], gs, audio_only=False, fixed_frames=4, seq_ids=list(range(130)))
+    for b in range(130):
+        assert torch.equal(part[b], whole[b]), f"sequence {b}: batch of 130 vs batch of 300"
+    for lo in (0, 120, 284):
+        sub = generate_batch(model, prompts[lo:lo + 16], gs, audio_only=False, fixed_frames=4, seq_ids=list(range(lo, lo + 16)))
+        for i in range(16):
+            assert torch.equal(sub[i], whole[lo + i]), f"sequence {lo + i}: batch of 16 vs batch of 300"
+
+
+def test_tc_stop_rule_and_sampling_inside_a_batch():
+    """<|im_end|> forced on some sequences of a 20-utterance batch in frame 2: they freeze (tokens, seq_len, step, codes)
+    while the others keep decoding inside the same multi-frame launch; sampled ids follow the CPU sampler spec on the
+    dumped logits with the counters (seed, step, seq_id, row) of each sequence."""
+    from oracle.sampler_oracle import sample_row
+
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=32)
+    B, R = 20, cfg.n_rows
+    seq_ids = list(range(700, 700 + B))
+    prompts = [prompt_grid(byte_prompt(12 + b, seed=800 + b), cfg) for b in range(B)]
+    padded, lens = pack_prompts(model, prompts)
+    batch = model.new_batch(B, max_positions=96, max_frames=8, seq_ids=seq_ids)
+    stopped = [3, 17]
+    try:
+        model.prefill(batch, padded, lens)
+        s = model.sampling(temp=0.8, fast_temp=0.7, top_k=40, top_p=0.9, seed=99, audio_only=True)
+        model.decode_frames(batch, s, 1)
+        torch.cuda.synchronize()
+        tl = model.debug_buffer("token_logits", B).cpu().numpy()
+        dl = model.debug_buffer("depth_logits", B).cpu().numpy()
+        got = batch.tokens.cpu().tolist()
+        for b in (0, 7, 19):
+            want = [sample_row(tl[b], 0.8, 40, 0.9, 0.0, 99, 0, seq_ids[b], 0)]
+            want += [sample_row(dl[b, i], 0.7, 0, 1.0, 0.0, 99, 0, seq_ids[b], 1 + i) for i in range(cfg.max_fast_seqlen)]
+            assert got[b] == want, f"seq {b}: {got[b]} != {want}"
+        force = torch.zeros(B, R, dtype=torch.int32, device=model.device)
+        force[:, 0] = 400
+        for b in stopped:
+            force[b, 0] = model.token_config.im_end_id
+        model.set_force(force)
+        model.decode_frames(batch, s, 1)
+        model.set_force(None)
+        frozen = (batch.tokens[stopped].clone(), batch.seq_len[stopped].clone())
+        model.decode_frames(batch, s, 4)
+        torch.cuda.synchronize()
+        assert batch.finished.tolist() == [1 if b in stopped else 0 for b in range(B)]
+        assert batch.step.tolist() == [2 if b in stopped else 6 for b in range(B)]
+        assert torch.equal(batch.tokens[stopped], frozen[0]) and torch.equal(batch.seq_len[stopped], frozen[1])
+        assert model.get_option("tc_ready") == 1
+    finally:
+        model.set_force(None)
+        batch.release()
+
+
+def test_tc_depth7_without_duplicate_code_0():
+    """duplicate_code_0 = False (7 depth steps, shifted embedding offsets) on the tensor-core variant:
+    16 utterances greedy-with-resync against the oracle."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=16, duplicate_code_0=False)
+    assert cfg.max_fast_seqlen == 7
+    B, n_frames = 16, 6
+    prompts = [prompt_grid(byte_prompt(20 + b, seed=900 + b), cfg) for b in range(B)]
+    want, margins = [], []
+    with torch.no_grad():
+        for p in prompts:
+            frames = orc.generate(p, OracleSettings(default_temp=0.0, default_fast_temp=0.0), fixed_frames=n_frames)
+            want.append([f.vq for f in frames])
+            margins.append([f.margins for f in frames])
+    want = torch.tensor(want, dtype=torch.int32)
+    padded, lens = pack_prompts(model, prompts)
+    batch = model.new_batch(B, max_positions=96, max_frames=n_frames)
+    flips, exact = [], 0
+    try:
+        model.prefill(batch, padded, lens)
+        s = model.sampling(ignore_stop=True)
+        for f in range(n_frames):
+            model.set_force(want[:, f].to(model.device).contiguous())
+            model.decode_frames(batch, s, 1)
+            torch.cuda.synchronize()
+            tl = model.debug_buffer("token_logits", B).cpu()
+            dl = model.debug_buffer("depth_logits", B).cpu()
+            for b in range(B):
+                mine = [int(tl[b].argmax())] + [int(dl[b, i].argmax()) for i in range(cfg.max_fast_seqlen)]
+                for r, (a, w) in enumerate(zip(mine, want[b, f].tolist())):
+                    if a == w:
+                        exact += 1
+                    else:
+                        flips.append((b, f, r, float(margins[b][f][r])))
+    finally:
+        model.set_force(None)
+        batch.release()
+    assert all(m <= TAU for *_, m in flips), f"argmax flipped at a confident decision: {flips}"
+    assert exact >= 0.9 * B * n_frames * cfg.n_rows
