@@ -58,6 +58,7 @@ struct SmolModel {
     int mode = 2;
     int repeat = 0;
     int prefill_tile = 0;  // option: cap of prompt positions per prefill iteration (0 = as many as fit)
+    int tc_attn_split = 0;  // option: cached positions per split of the batch attention (0 = the kernel's default)
     int tc_min_batch = 16; // rows (sequences, or prompt positions of a prefill tile) from which the tcgen05 variant runs
     int ll_flags = 0;  // data-flow kernel: A/B switches and hold-off override (tools/ll_ncu.py)
     int64_t launches = 0;
@@ -411,6 +412,7 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
     const int bt = use_tc(m, A.batch) ? 0 : smol::decode_batch_tile(A.batch);
     int rc;
     A.repeat = m->repeat;
+    A.tc_split = m->tc_attn_split;
     if (m->mode == 2 && whole_iters && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
         if ((rc = ensure_ll_tile(m, bt))) return rc;
         if (m->ll_state[bt] == 1) {
@@ -676,6 +678,11 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
     }
     if (!std::strcmp(name, "prefill_tile")) {
         m->prefill_tile = value > 0 ? (int)value : 0;
+        return SMOL_OK;
+    }
+    if (!std::strcmp(name, "tc_attn_split")) {
+        m->tc_attn_split = value > 0 ? (int)value : 0;
+        m->frame_key_valid = false;
         return SMOL_OK;
     }
     if (!std::strcmp(name, "tc_min_batch")) {  // 0 disables the tensor-core variant

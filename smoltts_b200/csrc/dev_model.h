@@ -138,6 +138,7 @@ struct CallArgs {
     int real_batch;   // prefill: sequences (rows / tile_t)
     int tc_part;      // tensor-core variant, one phase per launch: 1 = only the phase's distributed pre-step, 2 = only its tiles,
                       // 3 = only its post-step (0 = the whole phase: cooperative launches)
+    int tc_split;     // tensor-core variant: cached positions per attention split (0 = default)
     const int32_t* prompt;      // prefill: [B][n_rows][s_max]
     const int32_t* prompt_len;  // prefill: [B]
     int s_max;

@@ -14,7 +14,13 @@
 namespace smol {
 
 constexpr int kTcRows = umma::kM;
-constexpr int kTcSplit = kSplitMin;  // cached positions per attention split (ceil(L / 64) splits, at most kMaxSplits: the rule of every variant)
+constexpr int kTcSplit = 128;  // cached positions per attention split of the batch attention (CallArgs.tc_split overrides it;
+                               // measured 64 / 128 / 256 at L = 100 / 420 / 2200: gpurun_out/attn_split_ab.log)
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     uint4 v;
@@ -214,7 +220,12 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
         if (c.lane == 0) atomicMax(&g_flag, lmax);
     }
     __syncthreads();
-    int s_cap = (min(g_flag, cap) + kTcSplit - 1) / kTcSplit;
+    // split length: a function of the row's own length only (64 positions up to 256 cached positions, 128 beyond:
+    // measured at L = 100 / 420 / 2200, gpurun_out/attn_split_ab.log), or the caller's override
+    const int forced = A.tc_split >= 16 ? (A.tc_split & ~15) : 0;
+    auto split_of = [&](int L) { return forced ? forced : (L <= 4 * kSplitMin ? kSplitMin : kTcSplit); };
+    const int lmax = min(g_flag, cap);
+    int s_cap = max((lmax + split_of(lmax) - 1) / split_of(lmax), (min(lmax, 4 * kSplitMin) + split_of(1) - 1) / split_of(1));
     if (s_cap > kMaxSplits) s_cap = kMaxSplits;
     if (s_cap < 1) s_cap = 1;
     const int n_tasks = A.batch * Hkv * s_cap;
@@ -224,7 +235,7 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
         const int bs = row_seq(A, b);
         int Lb = ldcg_i32(A.b.seq_len + bs) + row_off(A, b) + 1;
         if (Lb > cap) Lb = cap;
-        int ns = (Lb + kTcSplit - 1) / kTcSplit;   // a function of the row's own length only
+        int ns = (Lb + split_of(Lb) - 1) / split_of(Lb);
         if (ns > kMaxSplits) ns = kMaxSplits;
         if (s >= ns) continue;
         int chunk = (Lb + ns - 1) / ns;
@@ -237,7 +248,7 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
             if (g >= G) continue;
             unpack8(ldcg_v4(M.q + (size_t)b * Hq * kHeadDim + (kvh * G + g) * kHeadDim + dch * 8), qf[g]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) qf[g][e] *= 0.125f;
+            for (int e = 0; e < 8; ++e) qf[g][e] *= 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e): softmax in base 2
         }
         float m[GM], l[GM], acc[GM][8];
 #pragma unroll
@@ -272,30 +283,49 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
                 pg_base = (pb + 16) / ps;
                 my_page = (pg_base + c.lane) * ps < p1 ? ldcg_i32(bt + pg_base + c.lane) : 0;
             }
+            // scores of the group's four positions for every head (log2 domain: q carries 1/8 * log2 e), then ONE
+            // running-max update per head and iteration -- a third fewer instructions than an update per position,
+            // and the phase is issue-bound (profiles/r1c: ~600 instructions per lane and 16 positions before)
+            float sc[GM][4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const bool valid = pb + j * 4 + psub < p1;
-                float kf[8], vf[8];
+                float kf[8];
                 unpack8(kk[j], kf);
+#pragma unroll
+                for (int g = 0; g < GM; ++g) {
+                    if (g >= G) continue;
+                    float t = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) t = fmaf(qf[g][e], kf[e], t);
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    t += __shfl_xor_sync(0xffffffffu, t, 4);
+                    sc[g][j] = valid ? t : -INFINITY;
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                if (g >= G) continue;
+                const float mn = fmaxf(fmaxf(m[g], fmaxf(sc[g][0], sc[g][1])), fmaxf(sc[g][2], sc[g][3]));
+                const float mref = (mn == -INFINITY) ? 0.f : mn;   // nothing seen yet: every factor below becomes 0
+                const float corr = ex2(m[g] - mref);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sc[g][j] = ex2(sc[g][j] - mref);
+                l[g] = fmaf(l[g], corr, (sc[g][0] + sc[g][1]) + (sc[g][2] + sc[g][3]));
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[g][e] *= corr;
+                m[g] = mn;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float vf[8];
                 unpack8(vv[j], vf);
 #pragma unroll
                 for (int g = 0; g < GM; ++g) {
                     if (g >= G) continue;
-                    float sc = 0.f;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) sc = fmaf(qf[g][e], kf[e], sc);
-                    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-                    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-                    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-                    if (valid) {
-                        const float mn = fmaxf(m[g], sc);
-                        const float corr = (m[g] == -INFINITY) ? 0.f : expf(m[g] - mn);
-                        const float pe = expf(sc - mn);
-                        l[g] = fmaf(l[g], corr, pe);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(acc[g][e], corr, pe * vf[e]);
-                        m[g] = mn;
-                    }
+                    for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(sc[g][j], vf[e], acc[g][e]);
                 }
             }
         }
@@ -308,8 +338,8 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
                 const float mo = __shfl_xor_sync(0xffffffffu, m[g], o);
                 const float lo = __shfl_xor_sync(0xffffffffu, l[g], o);
                 const float mn = fmaxf(m[g], mo);
-                const float c1 = (m[g] == -INFINITY) ? 0.f : expf(m[g] - mn);
-                const float c2 = (mo == -INFINITY) ? 0.f : expf(mo - mn);
+                const float c1 = (m[g] == -INFINITY) ? 0.f : ex2(m[g] - mn);
+                const float c2 = (mo == -INFINITY) ? 0.f : ex2(mo - mn);
                 l[g] = fmaf(l[g], c1, __fmul_rn(lo, c2));
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -349,20 +379,30 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
         old = __shfl_sync(0xffffffffu, old, 0);
         if (old != (uint32_t)(ns - 1)) continue;
         __threadfence();  // last split of this (row, kv head): combine all splits in split order
-        for (int g = 0; g < G; ++g) {
+        for (int g = 0; g < G; ++g) {  // lane i holds split i's (m, l); outputs: lane owns dims 2*lane, 2*lane+1
             const int hq = kvh * G + g;
             const float* base = M.partial + ((size_t)b * Hq + hq) * kMaxSplits * kPartialStride;
-            float Mg = -INFINITY;
-            for (int si = 0; si < ns; ++si) Mg = fmaxf(Mg, ldcg_f32(base + si * kPartialStride));
+            const float m_l = c.lane < ns ? ldcg_f32(base + c.lane * kPartialStride) : -INFINITY;
+            const float l_l = c.lane < ns ? ldcg_f32(base + c.lane * kPartialStride + 1) : 0.f;
+            const float Mg = warp_max(m_l);
+            const float sc_l = (m_l == -INFINITY) ? 0.f : ex2(m_l - Mg);
             float Lg = 0.f, O0 = 0.f, O1 = 0.f;
-            for (int si = 0; si < ns; ++si) {
-                const float* src = base + si * kPartialStride;
-                const float ms = ldcg_f32(src);
-                if (ms == -INFINITY) continue;
-                const float sc = expf(ms - Mg);
-                Lg = fmaf(ldcg_f32(src + 1), sc, Lg);
-                O0 = fmaf(ldcg_f32(src + 2 + 2 * c.lane), sc, O0);
-                O1 = fmaf(ldcg_f32(src + 3 + 2 * c.lane), sc, O1);
+            for (int si = 0; si < ns; si += 4) {
+                float2 o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    o[u] = si + u < ns ? __ldcg(reinterpret_cast<const float2*>(base + (si + u) * kPartialStride + 2 + 2 * c.lane))
+                                       : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float sc = __shfl_sync(0xffffffffu, sc_l, (si + u) & 31);
+                    const float ll = __shfl_sync(0xffffffffu, l_l, (si + u) & 31);
+                    if (si + u < ns) {
+                        Lg = fmaf(ll, sc, Lg);
+                        O0 = fmaf(o[u].x, sc, O0);
+                        O1 = fmaf(o[u].y, sc, O1);
+                    }
+                }
             }
             *reinterpret_cast<uint32_t*>(M.attn + (size_t)b * Hq * kHeadDim + hq * kHeadDim + 2 * c.lane) = pack_bf16(O0 / Lg, O1 / Lg);
         }

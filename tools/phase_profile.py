@@ -47,11 +47,15 @@ def main():
     ap.add_argument("--sampled", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--repeat", type=int, default=0, help="profiling: run every weight-phase body 1+repeat times")
+    ap.add_argument("--set", action="append", default=[], help="engine option name=value (smol_set_option), repeatable")
     a = ap.parse_args()
     cfg = named_config(a.model)
     need = a.prompt_bytes + 12 + a.frames + 8
     model = RQTransformer(cfg, max_batch=a.batch, max_seq_len=max(need, 256))
     model.load_state_dict(make_state_dict(cfg, seed=0))
+    for kv in a.set:
+        k, v = kv.split("=")
+        model.set_option(k, int(v))
     prompts = [prompt_grid(byte_prompt(a.prompt_bytes, seed=1 + b), cfg) for b in range(a.batch)]
     padded, lens = pack_prompts(model, prompts)
     batch = model.new_batch(a.batch, max_positions=need, max_frames=a.frames)
