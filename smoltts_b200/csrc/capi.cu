@@ -333,7 +333,10 @@ static int ensure_tmaps(SmolModel* m) {
     const uint64_t rows = (uint64_t)ws_rows(c);
     const int dmax = imax(c.dim, c.fast_dim), fmax = imax(c.intermediate_size, c.fast_intermediate_size);
     bool ok = true;
-    auto act = [&](int slot, const void* p, int K, int pitch) { ok = ok && smol::make_tensor_map_2d(&maps[slot], p, rows, K, pitch, 128); };
+    auto act = [&](int slot, const void* p, int K, int pitch) {
+        for (int i = 0; i < 3; ++i)  // 128-, 64- and 32-row boxes
+            ok = ok && smol::make_tensor_map_2d(&maps[slot + i * smol::TM_ACT_MAPS], p, rows, K, pitch, 128u >> i);
+    };
     auto wgt = [&](int slot, const void* p, uint64_t n, int K) { ok = ok && smol::make_tensor_map_2d(&maps[slot], p, n, K, K, 16); };
     act(smol::TM_XN_S, d.xn, c.dim, dmax);
     act(smol::TM_XN_F, d.xn, c.fast_dim, dmax);

@@ -202,10 +202,11 @@ __host__ __device__ inline bool tc_has_prestep(const Phase& ph) {
     return !(ph.kind == PH_W2 || (ph.kind == PH_WO && !ph.fast));
 }
 
-// Slots of the tensor-map table (DevModel.tmaps).  Activations: 128-row boxes; weights: 16-row boxes.
+// Slots of the tensor-map table (DevModel.tmaps).  Activations: boxes of 128 rows (slots 0-5), 64 rows (6-11: batches of
+// at most 64 rows load half a tile) and 32 rows (12-17); weights: 16-row boxes.
 enum TensorMapSlot {
-    TM_XN_S = 0, TM_XN_F, TM_ATTN_S, TM_ATTN_F, TM_ACT_S, TM_ACT_F, TM_HEAD, TM_FAST_OUT,
-    TM_LAYERS = 8  // then 5 per layer (wqkv, wo, w1, w3, w2): slow layers first, fast layers after them
+    TM_XN_S = 0, TM_XN_F, TM_ATTN_S, TM_ATTN_F, TM_ACT_S, TM_ACT_F, TM_ACT_MAPS = 6, TM_HEAD = 18, TM_FAST_OUT,
+    TM_LAYERS = 20  // then 5 per layer (wqkv, wo, w1, w3, w2): slow layers first, fast layers after them
 };
 __host__ __device__ inline int tm_layer_slot(int n_layer, int fast, int layer, int which) {
     return TM_LAYERS + ((fast ? n_layer : 0) + layer) * 5 + which;

@@ -466,8 +466,11 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
 
     // ---- operands: activation tile and weight rows through TMA ----
     const unsigned char* tm = M.tmaps;
-    const void* tm_a = tm + (size_t)kTensorMapBytes * (kind == PH_WO ? (fast ? TM_ATTN_F : TM_ATTN_S)
-                                                       : kind == PH_W2 ? (fast ? TM_ACT_F : TM_ACT_S) : (fast ? TM_XN_F : TM_XN_S));
+    const int box_idx = A.batch <= 32 ? 2 : A.batch <= 64 ? 1 : 0;   // activation box of 32 / 64 / 128 rows
+    const int a_rows = kTcRows >> box_idx;
+    const void* tm_a = tm + (size_t)kTensorMapBytes * (box_idx * TM_ACT_MAPS +
+                                                       (kind == PH_WO ? (fast ? TM_ATTN_F : TM_ATTN_S)
+                                                        : kind == PH_W2 ? (fast ? TM_ACT_F : TM_ACT_S) : (fast ? TM_XN_F : TM_XN_S)));
     const int which = kind == PH_QKV ? 0 : kind == PH_WO ? 1 : kind == PH_W13 ? 2 : 4;
     const void* tm_w0 = kind == PH_HEAD ? tm + (size_t)kTensorMapBytes * (fast ? TM_FAST_OUT : TM_HEAD)
                                         : tm + (size_t)kTensorMapBytes * tm_layer_slot(M.n_layer, fast ? 1 : 0, ph.layer, which);
@@ -498,7 +501,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
         umma::BSrc b0, b1;
         b0.tm = tm_w0; b0.row0 = w_row_base + n0; b0.n = blk;
         b1.tm = tm_w1; b1.row0 = n0; b1.n = tm_w1 != nullptr ? blk : 0;
-        umma::tile_mma_tma<kThreads, false>(ring, bars, pipe, k_len, tm_a, m0, b0, b1, [](int, int, uint4&) {}, ks * k_len);
+        umma::tile_mma_tma<kThreads, false>(ring, bars, pipe, k_len, tm_a, m0, b0, b1, [](int, int, uint4&) {}, ks * k_len, a_rows);
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[2] += t - ts; ts = t; }
 
         if (kind == PH_W13) {
@@ -513,7 +516,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
                     o[e] = __fmul_rn(sg, g);
                 }
                 *reinterpret_cast<uint4*>(M.act + (size_t)bg * F + u0) = pack8(o);
-            });
+            }, b0.n + b1.n);
         } else {
             umma::tile_epilogue(bars, blk, [&](int row, int c0, const float (&acc)[8]) {
                 const int bg = m0 + row, u0 = n0 + c0;
@@ -567,7 +570,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
                                     + (size_t)(p % ps) * kHeadDim + d;
                     *reinterpret_cast<uint4*>(dst) = packed;
                 }
-            });
+            }, b0.n + b1.n);
         }
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[3] += t - ts; ts = t; }
     }

@@ -32,7 +32,10 @@ constexpr int kStageA = kM * kBK * 2;        // 16 KB
 constexpr int kStageB = kMaxN * kBK * 2;     // 12 KB
 constexpr int kStageBytes = kStageA + kStageB;
 constexpr int kRingBytes = kStages * kStageBytes;  // 140 KB
-constexpr int kTmemCols = 128;               // allocation (power of two >= kMaxN)
+constexpr int kAcc = 1;                       // accumulators per tile (TMA form): K step q of a stage adds into accumulator q % kAcc.
+                                             // Measured with 4: no change (358 ns per 4 MMAs either way) -- an M = 128, K = 16
+                                             // tcgen05.mma costs ~165 cycles at N <= 32 whatever it depends on: issue-rate, not latency
+constexpr int kTmemCols = kAcc * kMaxN <= 128 ? 128 : 512;   // allocation (power of two >= kAcc * kMaxN)
 
 struct Bars {
     uint64_t free_[kStages];  // stage consumed by its MMAs (tcgen05.commit)
@@ -370,14 +373,16 @@ struct BSrc {
 // SKIP (micro-benchmark only): 1 = no copies (the producer only arrives on `full`), 2 = no MMAs (plain arrives on `free`).
 template <int NT, bool XFORM, class Xform, int SKIP = 0>
 __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pipe& pipe, int K, const void* tm_a, int a_row0,
-                                             BSrc b0, BSrc b1, Xform xform, int k0 = 0) {
+                                             BSrc b0, BSrc b1, Xform xform, int k0 = 0, int a_rows = kM) {
     const int nk = K / kBK;  // K elements starting at column k0 of both operands (split-K units)
     const int tid = threadIdx.x;
     const int n_blk = b0.n + b1.n;
     const uint32_t idesc = instr_desc(n_blk);
     const uint32_t tmem = bars->tmem_base;
     const uint32_t g0 = pipe.chunk;
-    const uint32_t stage_tx = (uint32_t)(kStageA + n_blk * kBK * 2);
+    // a_rows: rows of the activation box behind tm_a (fewer than 128 when the batch is small: the MMA still spans 128
+    // rows, the rest of the stage holds stale rows whose accumulator lanes nobody reads)
+    const uint32_t stage_tx = (uint32_t)((a_rows + n_blk) * kBK * 2);
     auto produce = [&](int kc) {  // one thread
         const uint32_t g = g0 + (uint32_t)kc;
         const int s = (int)(g % kStages);
@@ -405,7 +410,8 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
         fence_after_sync();
 #pragma unroll
         for (int q = 0; q < kBK / 16; ++q)
-            mma_bf16(tmem, smem_desc_sw128(a + q * 32), smem_desc_sw128(b + q * 32), idesc, (kc | q) ? 1u : 0u);
+            mma_bf16(tmem + (uint32_t)((q % kAcc) * n_blk), smem_desc_sw128(a + q * 32), smem_desc_sw128(b + q * 32), idesc,
+                     (kc > 0 || q >= kAcc) ? 1u : 0u);
         commit(&bars->free_[s]);
         if (kc == nk - 1) commit(&bars->done);
     };
@@ -465,15 +471,29 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
 // Hands 8 consecutive accumulator columns of one sequence to epi(row, col0, v[8]); with `paired` the thread also gets the
 // columns half a tile further (w1 | w3 halves): epi2(row, col0, gate[8], up[8]).  Ends with the fences + block barrier
 // that let the next tile overwrite the accumulator.
+// acc_stride > 0: the tile was accumulated in kAcc accumulators acc_stride columns apart (TMA form).
+__device__ __forceinline__ void tmem_ld8_sum(uint32_t taddr, int acc_stride, float (&v)[8]) {
+    tmem_ld8(taddr, v);
+    if (acc_stride > 0) {
+#pragma unroll
+        for (int a = 1; a < kAcc; ++a) {
+            float b[8];
+            tmem_ld8(taddr + (uint32_t)(a * acc_stride), b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], b[i]);
+        }
+    }
+}
+
 template <class Epi>
-__device__ __forceinline__ void tile_epilogue(Bars* bars, int n_cols, Epi epi) {
+__device__ __forceinline__ void tile_epilogue(Bars* bars, int n_cols, Epi epi, int acc_stride = 0) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = ((w & 3) << 5) | lane;
     const uint32_t base = bars->tmem_base + ((uint32_t)((w & 3) << 5) << 16);
     const int n_warps = blockDim.x >> 5;
     for (int cg = w >> 2; cg * 8 < n_cols; cg += n_warps >> 2) {
         float v[8];
-        tmem_ld8(base + (uint32_t)(cg * 8), v);
+        tmem_ld8_sum(base + (uint32_t)(cg * 8), acc_stride, v);
         epi(row, cg * 8, v);
     }
     fence_before_sync();
@@ -481,15 +501,15 @@ __device__ __forceinline__ void tile_epilogue(Bars* bars, int n_cols, Epi epi) {
     fence_after_sync();
 }
 template <class Epi2>
-__device__ __forceinline__ void tile_epilogue_paired(Bars* bars, int half_cols, Epi2 epi2) {
+__device__ __forceinline__ void tile_epilogue_paired(Bars* bars, int half_cols, Epi2 epi2, int acc_stride = 0) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = ((w & 3) << 5) | lane;
     const uint32_t base = bars->tmem_base + ((uint32_t)((w & 3) << 5) << 16);
     const int n_warps = blockDim.x >> 5;
     for (int cg = w >> 2; cg * 8 < half_cols; cg += n_warps >> 2) {
         float a[8], b[8];
-        tmem_ld8(base + (uint32_t)(cg * 8), a);
-        tmem_ld8(base + (uint32_t)(half_cols + cg * 8), b);
+        tmem_ld8_sum(base + (uint32_t)(cg * 8), acc_stride, a);
+        tmem_ld8_sum(base + (uint32_t)(half_cols + cg * 8), acc_stride, b);
         epi2(row, cg * 8, a, b);
     }
     fence_before_sync();

@@ -58,11 +58,11 @@ umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_bl
                     C[(size_t)row * 2 * n_blk + t * n_blk + c0 + i] = a[i];
                     C[(size_t)row * 2 * n_blk + t * n_blk + n_blk / 2 + c0 + i] = b[i];
                 }
-            });
+            }, variant >= 2 ? n_blk : 0);
         } else {
             umma::tile_epilogue(&bars, n_blk, [&](int row, int c0, const float (&v)[8]) {
                 for (int i = 0; i < 8; ++i) C[(size_t)row * 2 * n_blk + t * n_blk + c0 + i] = v[i];
-            });
+            }, variant >= 2 ? n_blk : 0);
         }
     }
     umma::teardown(&bars);
