@@ -1,5 +1,5 @@
 // Batched decode on the tensor cores: the weight phases of decode_kernel.cu as tcgen05 tiles (umma.cuh) for batches of
-// 16+ rows (sequences, or prompt positions of a prefill tile), plus the batch forms of the two attentions.
+// 9+ rows (sequences, or prompt positions of a prefill tile), plus the batch forms of the two attentions.
 // Included by decode_kernel.cu (uses its Ctx, grid barrier, embedding and row bookkeeping helpers).
 //
 // A weight phase Y[rows][n_out] = f(X)[rows][K] * W[n_out][K]^T is cut into units (128-row tile, block of `blk` weight

@@ -9,7 +9,7 @@ size-independent properties, since the CPU oracle cannot run them at full size i
   * config 5 (long-form, paged KV): thousands of frames across hundreds of KV pages at bs=32; a probe sequence equals its
     decode inside a batch of 16, and the cached positions / page table arithmetic hold (seq_len, step).
 
-Batches of 16+ run on the tcgen05 variant, whose dot products sum in the tensor core's order: results are bit-identical
+Batches of 9+ run on the tcgen05 variant, whose dot products sum in the tensor core's order: results are bit-identical
 across batch compositions, tile positions and launch modes of that variant (checked here), and agree with the bs=1
 data-flow kernel / the oracle up to near-tie decisions (tests/test_gpu_tc.py).
 """

@@ -216,7 +216,7 @@ def test_prefill_tiles_and_kernels_write_identical_kv(size, lens):
     cfg, sd, model, orc = model_and_oracle(size)
     B = len(lens)
     prompts = [prompt_grid(byte_prompt(n, seed=110 + b), cfg) for b, n in enumerate(lens)]
-    variants = [(0, 8 // B), (0, 1)] + ([(2, 1)] if B == 1 else []) + [(0, 3)]   # all below 16 rows: the CUDA-core variants
+    variants = [(0, 8 // B), (0, 1)] + ([(2, 1), (0, 3)] if B == 1 else [])   # all below 9 rows: the CUDA-core variants
     got = []
     for mode, tile in variants:
         model.set_option("mode", mode)

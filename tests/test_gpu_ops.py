@@ -2,7 +2,7 @@
 (smol_run_phases) on inputs copied bit-for-bit from the CPU oracle's trace, and its output is
 compared with the oracle's next tensor.  With identical inputs only the fp32 summation order
 differs, so the bar is: every element within 2 bf16 ulps and >= 98% of elements bit-identical.
-Batches of 16+ rows go through the tcgen05 tiles (tc_phases.cuh) and are held to the same bar."""
+Batches of 9+ rows go through the tcgen05 tiles (tc_phases.cuh) and are held to the same bar."""
 import numpy as np
 import pytest
 import torch
@@ -16,7 +16,7 @@ _OUTLIERS = {"frac": 0.0}
 
 
 def close_report(name, got, want, **kw):
-    """Tensor-core batches (16+ rows): up to 0.02 % of a tensor's elements may be one-ulp flips of an intermediate seen
+    """Tensor-core batches (9+ rows): up to 0.02 % of a tensor's elements may be one-ulp flips of an intermediate seen
     through a cancellation (gpu_util.close_report: outlier_frac)."""
     return _close_report(name, got, want, outlier_frac=_OUTLIERS["frac"], **kw)
 
@@ -110,7 +110,7 @@ def test_slow_layer_phases_match_oracle_trace(size, B, T):
         torch.cuda.synchronize()
         close_report("token_logits", model.debug_buffer("token_logits", B), logits)
         if B >= 16:
-            assert model.get_option("tc_ready") == 1, "batches of 16+ must run on the tensor-core variant"
+            assert model.get_option("tc_ready") == 1, "batches of 9+ rows must run on the tensor-core variant"
     finally:
         batch.release()
 

@@ -1,4 +1,4 @@
-"""The tcgen05 variant of the decode kernel (batches / prefill tiles of 16+ rows, csrc/tc_phases.cuh + umma.cuh).
+"""The tcgen05 variant of the decode kernel (batches / prefill tiles of 9+ rows, csrc/tc_phases.cuh + umma.cuh).
 
 Its dot products are summed by the tensor core, so it is not bit-identical to the CUDA-core variants; it is held to
   * the oracle's greedy ids up to near-tie decisions (greedy-with-resync, same rule and TAU as tests/test_gpu_decode.py);
@@ -91,7 +91,7 @@ def _prefill_and_frames(model, prompts, n_frames, tc_min_batch, mode=2, prefill_
                     tl=model.debug_buffer("token_logits", B).clone(), dl=model.debug_buffer("depth_logits", B).clone(),
                     seq_len=batch.seq_len.clone())
     finally:
-        model.set_option("tc_min_batch", 16)
+        model.set_option("tc_min_batch", 9)
         model.set_option("mode", 2)
         model.set_option("prefill_tile", 0)
         batch.release()
@@ -102,7 +102,7 @@ def test_tc_close_to_cuda_core_variant_and_mode_invariant(size):
     cfg, sd, model, orc = model_and_oracle(size, max_batch=32)
     B = 20
     prompts = [prompt_grid(byte_prompt(30 + b, seed=70 + b), cfg) for b in range(B)]
-    tc = _prefill_and_frames(model, prompts, 1, 16)
+    tc = _prefill_and_frames(model, prompts, 1, 9)
     cc = _prefill_and_frames(model, prompts, 1, 0)          # CUDA-core tiles of 8 rows, 8 prompt positions per iteration
     assert torch.equal(tc["seq_len"], cc["seq_len"])
     # prefill K/V (every layer: the error compounds with depth) and the first frame's logits
@@ -118,7 +118,7 @@ def test_tc_close_to_cuda_core_variant_and_mode_invariant(size):
         print(f"{size}: {name} rms diff {rms:.4f} max {mx:.4f}")
         assert rms < (0.04 if name == "tl" else 0.06) and mx < 0.3   # the reference's own bf16-vs-fp32 rms: 0.035 / 0.056
     # the per-phase CUDA-graph mode runs the same tiles (pre-step and tiles as two launches): bit-identical
-    g1 = _prefill_and_frames(model, prompts, 1, 16, mode=1)
+    g1 = _prefill_and_frames(model, prompts, 1, 9, mode=1)
     for k in ("kv", "codes", "tl", "dl"):
         assert torch.equal(_bits(tc[k]), _bits(g1[k])), f"{k}: persistent kernel vs per-phase graph"
     assert (tc["codes"] == cc["codes"]).float().mean().item() > 0.5   # a near-tie flip changes the rest of its frame
@@ -133,9 +133,9 @@ def test_tc_prefill_tile_sizes_and_batch_composition_bit_identical():
     for i in range(16):
         assert torch.equal(sub[i], whole[4 + i]), f"sequence {4 + i}: batch of 24 vs batch of 16"
     # one utterance, prefilled in tiles of 128 / 40 / 16 prompt positions (all tensor-core), then decoded at bs=1
-    a = _prefill_and_frames(model, prompts[20:21], 3, 16)
+    a = _prefill_and_frames(model, prompts[20:21], 3, 9)
     for tile in (40, 16):
-        b = _prefill_and_frames(model, prompts[20:21], 3, 16, prefill_tile=tile)
+        b = _prefill_and_frames(model, prompts[20:21], 3, 9, prefill_tile=tile)
         assert torch.equal(a["kv"].view(torch.int16), b["kv"].view(torch.int16)), f"prefill tile {tile}"
         assert torch.equal(a["codes"], b["codes"])
 
