@@ -357,6 +357,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(tmap), "r"(s2u(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// The same with an L2 eviction policy (createpolicy): weights that are read once per frame leave L2 first, weights that
+// every depth step re-reads stay.
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void* tmap, int c0, int c1, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(tmap), "r"(s2u(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // K-major, 128-byte swizzle (layout type 2), 8-row groups 1024 B apart, descriptor version 1.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -367,13 +383,15 @@ struct BSrc {
     const void* tm;
     int row0, n;
 };
+enum WeightPolicy { kWeightsDefault = 0, kWeightsStream = 1, kWeightsKeep = 2 };
 
 // acc[128][b0.n + b1.n] (TMEM) = A[rows a_row0.. +128][K] * [B0 rows | B1 rows]^T.  All NT threads call this with uniform
 // arguments; `ring` is 1024-byte aligned.  xform(r, k0, uint4&) rewrites elements [k0, k0 + 8) of tile row r (XFORM only).
 // SKIP (micro-benchmark only): 1 = no copies (the producer only arrives on `full`), 2 = no MMAs (plain arrives on `free`).
 template <int NT, bool XFORM, class Xform, int SKIP = 0>
 __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pipe& pipe, int K, const void* tm_a, int a_row0,
-                                             BSrc b0, BSrc b1, Xform xform, int k0 = 0, int a_rows = kM) {
+                                             BSrc b0, BSrc b1, Xform xform, int k0 = 0, int a_rows = kM,
+                                             int weight_policy = kWeightsDefault) {
     const int nk = K / kBK;  // K elements starting at column k0 of both operands (split-K units)
     const int tid = threadIdx.x;
     const int n_blk = b0.n + b1.n;
@@ -383,6 +401,7 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
     // a_rows: rows of the activation box behind tm_a (fewer than 128 when the batch is small: the MMA still spans 128
     // rows, the rest of the stage holds stale rows whose accumulator lanes nobody reads)
     const uint32_t stage_tx = (uint32_t)((a_rows + n_blk) * kBK * 2);
+    const uint64_t w_policy = weight_policy == kWeightsKeep ? l2_policy_evict_last() : l2_policy_evict_first();
     auto produce = [&](int kc) {  // one thread
         const uint32_t g = g0 + (uint32_t)kc;
         const int s = (int)(g % kStages);
@@ -394,9 +413,16 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
         }
         bar_expect_tx(&bars->full_[s], stage_tx);
         tma_load_2d(a, tm_a, k0 + kc * kBK, a_row0, &bars->full_[s]);
-        for (int j = 0; j < b0.n; j += kBoxRowsB) tma_load_2d(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s]);
-        for (int j = 0; j < b1.n; j += kBoxRowsB)
-            tma_load_2d(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s]);
+        if (weight_policy == kWeightsDefault) {
+            for (int j = 0; j < b0.n; j += kBoxRowsB) tma_load_2d(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s]);
+            for (int j = 0; j < b1.n; j += kBoxRowsB)
+                tma_load_2d(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s]);
+        } else {
+            for (int j = 0; j < b0.n; j += kBoxRowsB)
+                tma_load_2d_hint(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s], w_policy);
+            for (int j = 0; j < b1.n; j += kBoxRowsB)
+                tma_load_2d_hint(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s], w_policy);
+        }
     };
     auto issue_mma = [&](int kc) {  // one thread
         const uint32_t g = g0 + (uint32_t)kc;
