@@ -138,7 +138,7 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.attn = take(B * dmax * 2);
     L.act = take(B * imax(c.intermediate_size, c.fast_intermediate_size) * 2);
     L.xn = take(B * dmax * 2);
-    L.tmaps = take((size_t)(smol::TM_LAYERS + (SMOL_MAX_LAYERS + SMOL_MAX_FAST_LAYERS) * 5) * smol::kTensorMapBytes);
+    L.tmaps = take((size_t)smol::kTmTotal * smol::kTensorMapBytes);
     L.kpart = take((size_t)smol::kTcKSplit * B * dmax * 4);
     L.fkv = take(B * c.n_fast_layer * 2 * depth * c.fast_n_local_heads * 64 * 2);
     L.token_logits = take(B * c.vocab_size * 4);
@@ -328,8 +328,9 @@ static int ensure_tmaps(SmolModel* m) {
     if (m->tmaps_ready) return SMOL_OK;
     const SmolConfig& c = m->cfg;
     const DevModel& d = m->dm;
-    const int n_slots = smol::TM_LAYERS + (c.n_layer + c.n_fast_layer) * 5;
+    const int n_slots = smol::kTmTotal;
     std::vector<CUtensorMap> maps((size_t)n_slots);
+    std::memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
     static_assert(sizeof(CUtensorMap) == smol::kTensorMapBytes, "tensor map size");
     const uint64_t rows = (uint64_t)ws_rows(c);
     const int dmax = imax(c.dim, c.fast_dim), fmax = imax(c.intermediate_size, c.fast_intermediate_size);
@@ -338,25 +339,28 @@ static int ensure_tmaps(SmolModel* m) {
         for (int i = 0; i < 3; ++i)  // 128-, 64- and 32-row boxes
             ok = ok && smol::make_tensor_map_2d(&maps[slot + i * smol::TM_ACT_MAPS], p, rows, K, pitch, 128u >> i);
     };
-    auto wgt = [&](int slot, const void* p, uint64_t n, int K) { ok = ok && smol::make_tensor_map_2d(&maps[slot], p, n, K, K, 16); };
+    auto wgt = [&](int index, const void* p, uint64_t n, int K) {
+        for (int box = 16; box <= 16 * smol::kTmWeightBoxes; box += 16)
+            ok = ok && smol::make_tensor_map_2d(&maps[smol::tm_weight_slot(index, box)], p, n, K, K, (uint32_t)box);
+    };
     act(smol::TM_XN_S, d.xn, c.dim, dmax);
     act(smol::TM_XN_F, d.xn, c.fast_dim, dmax);
     act(smol::TM_ATTN_S, d.attn, c.dim, dmax);
     act(smol::TM_ATTN_F, d.attn, c.fast_dim, dmax);
     act(smol::TM_ACT_S, d.act, c.intermediate_size, fmax);
     act(smol::TM_ACT_F, d.act, c.fast_intermediate_size, fmax);
-    wgt(smol::TM_HEAD, d.head, c.vocab_size, c.dim);
-    wgt(smol::TM_FAST_OUT, d.fast_output, (uint64_t)c.codebook_size * (c.depthwise_output ? d.depth : 1), c.fast_dim);
+    wgt(0, d.head, c.vocab_size, c.dim);
+    wgt(1, d.fast_output, (uint64_t)c.codebook_size * (c.depthwise_output ? d.depth : 1), c.fast_dim);
     for (int f = 0; f < 2; ++f) {
         const int nl = f ? c.n_fast_layer : c.n_layer, D = f ? c.fast_dim : c.dim, F = f ? c.fast_intermediate_size : c.intermediate_size;
         const int qkv = ((f ? c.fast_n_head : c.n_head) + 2 * (f ? c.fast_n_local_heads : c.n_local_heads)) * 64;
         for (int l = 0; l < nl; ++l) {
             const smol::DevLayer& L = f ? d.fast_layers[l] : d.layers[l];
-            wgt(smol::tm_layer_slot(c.n_layer, f, l, 0), L.wqkv, qkv, D);
-            wgt(smol::tm_layer_slot(c.n_layer, f, l, 1), L.wo, D, D);
-            wgt(smol::tm_layer_slot(c.n_layer, f, l, 2), L.w1, F, D);
-            wgt(smol::tm_layer_slot(c.n_layer, f, l, 3), L.w3, F, D);
-            wgt(smol::tm_layer_slot(c.n_layer, f, l, 4), L.w2, D, F);
+            wgt(smol::tm_weight_index(c.n_layer, f, l, 0), L.wqkv, qkv, D);
+            wgt(smol::tm_weight_index(c.n_layer, f, l, 1), L.wo, D, D);
+            wgt(smol::tm_weight_index(c.n_layer, f, l, 2), L.w1, F, D);
+            wgt(smol::tm_weight_index(c.n_layer, f, l, 3), L.w3, F, D);
+            wgt(smol::tm_weight_index(c.n_layer, f, l, 4), L.w2, D, F);
         }
     }
     if (!ok) return fail(SMOL_ERR_CUDA, "cuTensorMapEncodeTiled failed for the tensor-core variant's operands");

@@ -883,7 +883,7 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
     uint32_t parity = 0;
     umma::Pipe pipe;
     pipe.chunk = 0; pipe.tile = 0;
-    if (BT == 0) umma::setup(&g_tc_bars, pipe);
+    if (BT == 0) umma::setup(&g_tc_bars, pipe, (uint32_t)umma::kAcc, 2u);
     const int per_iter = (A.mode == 1) ? phases_per_prefill_step(M.n_layer)
                                        : phases_per_frame(M.n_layer, M.n_flayer, M.depth);
     const bool prof_cta = (M.prof != nullptr) && c.cta == 0;  // CTA-uniform

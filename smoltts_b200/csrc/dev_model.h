@@ -203,13 +203,20 @@ __host__ __device__ inline bool tc_has_prestep(const Phase& ph) {
 }
 
 // Slots of the tensor-map table (DevModel.tmaps).  Activations: boxes of 128 rows (slots 0-5), 64 rows (6-11: batches of
-// at most 64 rows load half a tile) and 32 rows (12-17); weights: 16-row boxes.
+// at most 64 rows load half a tile) and 32 rows (12-17).  Weights: one map per matrix and box height 16 * (v + 1) rows,
+// v = 0..5, so that a tile's weight rows are ONE copy per stage (a TMA instruction costs its issuing thread ~60 ns).
 enum TensorMapSlot {
-    TM_XN_S = 0, TM_XN_F, TM_ATTN_S, TM_ATTN_F, TM_ACT_S, TM_ACT_F, TM_ACT_MAPS = 6, TM_HEAD = 18, TM_FAST_OUT,
-    TM_LAYERS = 20  // then 5 per layer (wqkv, wo, w1, w3, w2): slow layers first, fast layers after them
+    TM_XN_S = 0, TM_XN_F, TM_ATTN_S, TM_ATTN_F, TM_ACT_S, TM_ACT_F, TM_ACT_MAPS = 6, TM_WEIGHTS = 18
 };
-__host__ __device__ inline int tm_layer_slot(int n_layer, int fast, int layer, int which) {
-    return TM_LAYERS + ((fast ? n_layer : 0) + layer) * 5 + which;
+constexpr int kTmWeightBoxes = 6;
+constexpr int kTmWeightStride = 2 + 5 * (SMOL_MAX_LAYERS + SMOL_MAX_FAST_LAYERS);  // weight matrices a model can have
+constexpr int kTmTotal = TM_WEIGHTS + kTmWeightBoxes * kTmWeightStride;
+// weight index: 0 LM head, 1 depth heads, then 5 per layer (wqkv, wo, w1, w3, w2): slow layers first, fast layers after them
+__host__ __device__ inline int tm_weight_index(int n_layer, int fast, int layer, int which) {
+    return 2 + ((fast ? n_layer : 0) + layer) * 5 + which;
+}
+__host__ __device__ inline int tm_weight_slot(int weight_index, int box_rows) {
+    return TM_WEIGHTS + (box_rows / 16 - 1) * kTmWeightStride + weight_index;
 }
 constexpr int kTensorMapBytes = 128;
 constexpr int kTcKSplit = 4;  // K slices of the wo / w2 tiles (their sum + residual + next RMSNorm is the phase's post-step)

@@ -472,9 +472,8 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
                                                        (kind == PH_WO ? (fast ? TM_ATTN_F : TM_ATTN_S)
                                                         : kind == PH_W2 ? (fast ? TM_ACT_F : TM_ACT_S) : (fast ? TM_XN_F : TM_XN_S)));
     const int which = kind == PH_QKV ? 0 : kind == PH_WO ? 1 : kind == PH_W13 ? 2 : 4;
-    const void* tm_w0 = kind == PH_HEAD ? tm + (size_t)kTensorMapBytes * (fast ? TM_FAST_OUT : TM_HEAD)
-                                        : tm + (size_t)kTensorMapBytes * tm_layer_slot(M.n_layer, fast ? 1 : 0, ph.layer, which);
-    const void* tm_w1 = kind == PH_W13 ? tm + (size_t)kTensorMapBytes * tm_layer_slot(M.n_layer, fast ? 1 : 0, ph.layer, 3) : nullptr;
+    const int w_index0 = kind == PH_HEAD ? (fast ? 1 : 0) : tm_weight_index(M.n_layer, fast ? 1 : 0, ph.layer, which);
+    const int w_index1 = kind == PH_W13 ? tm_weight_index(M.n_layer, fast ? 1 : 0, ph.layer, 3) : -1;
     const int w_row_base = (kind == PH_HEAD && fast && M.depthwise_output) ? ph.depth_pos * n_head_rows : 0;
 
     // the residual phases (wo, w2) also cut K: their fp32 partials meet in the post-step
@@ -499,8 +498,9 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
         __syncthreads();
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[1] += t - ts; ts = t; }
         umma::BSrc b0, b1;
-        b0.tm = tm_w0; b0.row0 = w_row_base + n0; b0.n = blk;
-        b1.tm = tm_w1; b1.row0 = n0; b1.n = tm_w1 != nullptr ? blk : 0;
+        b0.tm = tm + (size_t)kTensorMapBytes * tm_weight_slot(w_index0, blk); b0.row0 = w_row_base + n0; b0.n = blk; b0.box = blk;
+        b1.tm = w_index1 >= 0 ? tm + (size_t)kTensorMapBytes * tm_weight_slot(w_index1, blk) : nullptr;
+        b1.row0 = n0; b1.n = w_index1 >= 0 ? blk : 0; b1.box = blk;
         // slow weights are read once per frame (evict first), the depth transformer's by every depth step (keep in L2):
         // measured DRAM reads 937 -> 891 MB per frame at bs=256, time unchanged (gpurun_out/l2hint_dram.csv)
         umma::tile_mma_tma<kThreads, false>(ring, bars, pipe, k_len, tm_a, m0, b0, b1, [](int, int, uint4&) {}, ks * k_len, a_rows,

@@ -32,10 +32,13 @@ constexpr int kStageA = kM * kBK * 2;        // 16 KB
 constexpr int kStageB = kMaxN * kBK * 2;     // 12 KB
 constexpr int kStageBytes = kStageA + kStageB;
 constexpr int kRingBytes = kStages * kStageBytes;  // 140 KB
-constexpr int kAcc = 1;                       // accumulators per tile (TMA form): K step q of a stage adds into accumulator q % kAcc.
-                                             // Measured with 4: no change (358 ns per 4 MMAs either way) -- an M = 128, K = 16
-                                             // tcgen05.mma costs ~165 cycles at N <= 32 whatever it depends on: issue-rate, not latency
-constexpr int kTmemCols = kAcc * kMaxN <= 128 ? 128 : 512;   // allocation (power of two >= kAcc * kMaxN)
+constexpr int kAcc = 4;                       // accumulators per tile (TMA form) = issuing threads: K step q of every stage is issued by
+                                             // thread 64 * q into accumulator q (disjoint TMEM column ranges, summed by the epilogue).
+                                             // Measured (tools/micro/umma_test a): ONE thread issuing the four tcgen05.mma of a stage
+                                             // needs ~360 ns per stage whatever M (64 / 128), N (16..32) or the accumulator dependencies
+                                             // are -- the issue path of the thread, not the tensor pipe; four issuing threads: 305 ns
+                                             // (then bounded by the TMA stream, 285 ns alone).
+constexpr int kTmemCols = 512;               // allocation (power of two >= kAcc * kMaxN)
 
 struct Bars {
     uint64_t free_[kStages];  // stage consumed by its MMAs (tcgen05.commit)
@@ -121,10 +124,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Called once per kernel by all threads (before any tile): barriers + TMEM allocation by warp 0.
-__device__ __forceinline__ void setup(Bars* bars, Pipe& pipe) {
+__device__ __forceinline__ void setup(Bars* bars, Pipe& pipe, uint32_t issuers = 1u, uint32_t producers = 1u) {
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { bar_init(&bars->free_[s], 1u); bar_init(&bars->full_[s], 1u); }
-        bar_init(&bars->done, 1u);
+        for (int s = 0; s < kStages; ++s) { bar_init(&bars->free_[s], issuers); bar_init(&bars->full_[s], producers); }
+        bar_init(&bars->done, issuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if ((threadIdx.x >> 5) == 0) tmem_alloc(&bars->tmem_base);
@@ -348,7 +351,6 @@ __device__ __forceinline__ void tile_mma(unsigned char* ring, Bars* bars, Pipe& 
 // Measured on B200 (tools/micro/umma_test): per-thread 16-byte loads (cp.async or registers) cost 0.7-1.0 us per stage --
 // 8 cache lines per warp instruction through the L1 pipe -- which is what this form removes.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kBoxRowsB = 16;   // weight rows per TMA box
 
 __device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(bar)), "r"(bytes) : "memory");
@@ -378,10 +380,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// One weight operand: rows [row0, row0 + n) of tensor map `tm` (n a multiple of 16).
+// One weight operand: rows [row0, row0 + n) of tensor map `tm`, copied in boxes of `box` rows (n a multiple of box).
 struct BSrc {
-    const void* tm;
-    int row0, n;
+    const void* tm;   // map whose box is `box` rows high
+    int row0, n, box;
 };
 enum WeightPolicy { kWeightsDefault = 0, kWeightsStream = 1, kWeightsKeep = 2 };
 
@@ -402,7 +404,10 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
     // rows, the rest of the stage holds stale rows whose accumulator lanes nobody reads)
     const uint32_t stage_tx = (uint32_t)((a_rows + n_blk) * kBK * 2);
     const uint64_t w_policy = weight_policy == kWeightsKeep ? l2_policy_evict_last() : l2_policy_evict_first();
-    auto produce = [&](int kc) {  // one thread
+    // Two producing threads (a TMA instruction costs its issuing thread ~60 ns: measured 285 / 341 / 655 ns per stage with
+    // 2 / 3 / 7 copies): `part` 0 = the activation box, 1 = the weight boxes, 2 = both (micro-benchmark variants).  Each
+    // part arrives on `full` with its own byte count.
+    auto produce = [&](int kc, int part) {
         const uint32_t g = g0 + (uint32_t)kc;
         const int s = (int)(g % kStages);
         if (g >= (uint32_t)kStages) bar_wait(&bars->free_[s], (g / kStages - 1u) & 1u);
@@ -411,17 +416,22 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&bars->full_[s])) : "memory");
             return;
         }
-        bar_expect_tx(&bars->full_[s], stage_tx);
-        tma_load_2d(a, tm_a, k0 + kc * kBK, a_row0, &bars->full_[s]);
-        if (weight_policy == kWeightsDefault) {
-            for (int j = 0; j < b0.n; j += kBoxRowsB) tma_load_2d(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s]);
-            for (int j = 0; j < b1.n; j += kBoxRowsB)
-                tma_load_2d(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s]);
-        } else {
-            for (int j = 0; j < b0.n; j += kBoxRowsB)
-                tma_load_2d_hint(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s], w_policy);
-            for (int j = 0; j < b1.n; j += kBoxRowsB)
-                tma_load_2d_hint(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s], w_policy);
+        if (part != 1) {
+            bar_expect_tx(&bars->full_[s], part == 2 ? stage_tx : (uint32_t)(a_rows * kBK * 2));
+            tma_load_2d(a, tm_a, k0 + kc * kBK, a_row0, &bars->full_[s]);
+        }
+        if (part != 0) {
+            if (part == 1) bar_expect_tx(&bars->full_[s], (uint32_t)(n_blk * kBK * 2));
+            if (weight_policy == kWeightsDefault) {
+                for (int j = 0; j < b0.n; j += b0.box) tma_load_2d(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s]);
+                for (int j = 0; j < b1.n; j += b1.box)
+                    tma_load_2d(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s]);
+            } else {
+                for (int j = 0; j < b0.n; j += b0.box)
+                    tma_load_2d_hint(b + j * (kBK * 2), b0.tm, k0 + kc * kBK, b0.row0 + j, &bars->full_[s], w_policy);
+                for (int j = 0; j < b1.n; j += b1.box)
+                    tma_load_2d_hint(b + (b0.n + j) * (kBK * 2), b1.tm, k0 + kc * kBK, b1.row0 + j, &bars->full_[s], w_policy);
+            }
         }
     };
     auto issue_mma = [&](int kc) {  // one thread
@@ -434,19 +444,56 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
             return;
         }
         fence_after_sync();
+        if (SKIP == 4) {  // experiment: A operand copied shared -> tensor memory (tcgen05.cp), MMA reads it from there
+#pragma unroll
+            for (int q = 0; q < kBK / 16; ++q) {
+                const uint32_t ta = tmem + 128u + 8u * (uint32_t)q;
+                asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(ta), "l"(smem_desc_sw128(a + q * 32)) : "memory");
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                    ::"r"(tmem), "r"(ta), "l"(smem_desc_sw128(b + q * 32)), "r"(idesc), "r"((kc | q) ? 1u : 0u) : "memory");
+            }
+        } else {
 #pragma unroll
         for (int q = 0; q < kBK / 16; ++q)
             mma_bf16(tmem + (uint32_t)((q % kAcc) * n_blk), smem_desc_sw128(a + q * 32), smem_desc_sw128(b + q * 32), idesc,
                      (kc > 0 || q >= kAcc) ? 1u : 0u);
-        commit(&bars->free_[s]);
-        if (kc == nk - 1) commit(&bars->done);
+        }
+        // (the barriers of the shipped form expect kAcc arrivals: one issuing thread commits kAcc times)
+#pragma unroll
+        for (int i = 0; i < (SKIP == 0 ? kAcc : 1); ++i) {
+            commit(&bars->free_[s]);
+            if (kc == nk - 1) commit(&bars->done);
+        }
     };
     if (!XFORM) {
         // two working threads; everybody else sleeps in the block barrier below instead of polling `done` (512 polling
         // threads take issue slots from the producer's and the MMA thread's dependent chains)
         if (tid == 32) {
-            for (int kc = 0; kc < nk; ++kc) produce(kc);
-        } else if (tid == 0) {
+            for (int kc = 0; kc < nk; ++kc) produce(kc, SKIP == 0 ? 0 : 2);
+        } else if (SKIP == 0 && tid == 96) {
+            for (int kc = 0; kc < nk; ++kc) produce(kc, 1);
+        } else if (SKIP == 0 && (tid & 63) == 0 && tid < 64 * kAcc) {
+            // kAcc issuing threads (warps 0, 2, 4, 6), one K step of every stage and one accumulator each; every one of them
+            // commits its own MMAs, so `free` and `done` are initialised with kAcc arrivals (setup(..., kAcc))
+            const int q = tid >> 6;
+            for (int kc = 0; kc < nk; ++kc) {
+                const uint32_t g = g0 + (uint32_t)kc;
+                const int s = (int)(g % kStages);
+                bar_wait(&bars->full_[s], (g / kStages) & 1u);
+                const uint32_t a = s2u(ring + (size_t)s * kStageBytes), b = a + kStageA;
+                fence_after_sync();
+#pragma unroll
+                for (int qq = 0; qq < kBK / 16; qq += kAcc)
+                    mma_bf16(tmem + (uint32_t)(q * n_blk), smem_desc_sw128(a + (qq + q) * 32), smem_desc_sw128(b + (qq + q) * 32), idesc,
+                             (kc > 0 || qq > 0) ? 1u : 0u);
+                commit(&bars->free_[s]);
+                if (kc == nk - 1) commit(&bars->done);
+            }
+            if (tid == 0) { bar_wait(&bars->done, pipe.tile & 1u); fence_before_sync(); }
+        } else if (SKIP != 0 && tid == 0) {  // micro-benchmark variants: one issuing thread
             for (int kc = 0; kc < nk; ++kc) {
                 const uint32_t g = g0 + (uint32_t)kc;
                 bar_wait(&bars->full_[g % kStages], (g / kStages) & 1u);
@@ -463,7 +510,7 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
         return;
     } else {
         if (tid == 32)
-            for (int kc = 0; kc < kStages - 1 && kc < nk; ++kc) produce(kc);
+            for (int kc = 0; kc < kStages - 1 && kc < nk; ++kc) { produce(kc, 0); produce(kc, 1); }
         __syncwarp();
         for (int kc = 0; kc < nk; ++kc) {
             const uint32_t g = g0 + (uint32_t)kc;
@@ -484,7 +531,7 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
             fence_async_smem();
             __syncthreads();
             if (tid == 0) issue_mma(kc);
-            if (tid == 32 && kc + kStages - 1 < nk) produce(kc + kStages - 1);
+            if (tid == 32 && kc + kStages - 1 < nk) { produce(kc + kStages - 1, 0); produce(kc + kStages - 1, 1); }
             __syncwarp();
         }
     }

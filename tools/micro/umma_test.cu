@@ -24,7 +24,7 @@ umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_bl
     unsigned char* ring = reinterpret_cast<unsigned char*>(((uintptr_t)ring_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) umma::Bars bars;
     umma::Pipe pipe;
-    umma::setup(&bars, pipe);
+    umma::setup(&bars, pipe, variant == 2 ? (uint32_t)umma::kAcc : 1u, variant == 2 ? 2u : 1u);
     for (int tt = 0; tt < tiles; ++tt) {
         const int t = tt & 1;
         auto row_a = [&](int r) { return r < m_valid ? A + (size_t)r * K : (const uint16_t*)nullptr; };
@@ -39,10 +39,13 @@ umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_bl
         };
         if (variant >= 2) {  // TMA staging (what the decode kernel uses): maps[0] = A (rows past m_valid are outside the map: zero)
             umma::BSrc b0, b1;
-            b0.tm = maps + 1; b0.row0 = t * n_blk; b0.n = paired ? n_blk / 2 : n_blk;
-            b1.tm = maps + 1; b1.row0 = t * n_blk + n_blk / 2; b1.n = paired ? n_blk / 2 : 0;
+            // maps[1]: weight boxes of n_blk rows, maps[2]: of n_blk / 2 rows (the paired halves)
+            b0.tm = maps + (paired ? 2 : 1); b0.row0 = t * n_blk; b0.n = paired ? n_blk / 2 : n_blk; b0.box = b0.n;
+            b1.tm = maps + 2; b1.row0 = t * n_blk + n_blk / 2; b1.n = paired ? n_blk / 2 : 0; b1.box = n_blk / 2;
             if (variant == 3) umma::tile_mma_tma<NT, false, decltype(xform), 1>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
             else if (variant == 4) umma::tile_mma_tma<NT, false, decltype(xform), 2>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (variant == 5) umma::tile_mma_tma<NT, false, decltype(xform), 4>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (variant == 6) umma::tile_mma_tma<NT, false, decltype(xform), 8>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
             else if (xf) umma::tile_mma_tma<NT, true>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
             else umma::tile_mma_tma<NT, false>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
         } else if (variant == 1) {  // cp.async staging (kept for the A/B timing)
@@ -58,11 +61,11 @@ umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_bl
                     C[(size_t)row * 2 * n_blk + t * n_blk + c0 + i] = a[i];
                     C[(size_t)row * 2 * n_blk + t * n_blk + n_blk / 2 + c0 + i] = b[i];
                 }
-            }, variant >= 2 ? n_blk : 0);
+            }, variant == 2 ? n_blk : 0);
         } else {
             umma::tile_epilogue(&bars, n_blk, [&](int row, int c0, const float (&v)[8]) {
                 for (int i = 0; i < 8; ++i) C[(size_t)row * 2 * n_blk + t * n_blk + c0 + i] = v[i];
-            }, variant >= 2 ? n_blk : 0);
+            }, variant == 2 ? n_blk : 0);
         }
     }
     umma::teardown(&bars);
@@ -94,9 +97,10 @@ static double run(int K, int n, int m_valid, int variant, int xf, int paired, in
     cudaMemset(dC, 0xFF, (size_t)128 * 2 * n * 4);
     const int smem = umma::kRingBytes + 1024;
     cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    CUtensorMap hmaps[2];
+    CUtensorMap hmaps[3];
     CUtensorMap* dmaps;
-    if (!smol::make_tensor_map_2d(&hmaps[0], dA, m_valid, K, K, 128) || !smol::make_tensor_map_2d(&hmaps[1], dB, 2 * n, K, K, 16)) {
+    if (!smol::make_tensor_map_2d(&hmaps[0], dA, m_valid, K, K, 128) || !smol::make_tensor_map_2d(&hmaps[1], dB, 2 * n, K, K, n) ||
+        !smol::make_tensor_map_2d(&hmaps[2], dB, 2 * n, K, K, n >= 32 ? n / 2 : n)) {
         printf("tensor map encode failed\n");
         exit(4);
     }
@@ -136,6 +140,19 @@ static double run(int K, int n, int m_valid, int variant, int xf, int paired, in
 
 int main(int argc, char** argv) {
     int bad = 0;
+    if (argc > 1 && argv[1][0] == 'a') {  // experiment: A operand staged in tensor memory (tcgen05.cp + TS MMA)
+        for (int n : {16, 32, 96}) {
+            double w = run(768, n, 128, 5, 0, 0, 1);
+            float us = 0;
+            run(3072, n, 128, 5, 0, 0, 1, 40, &us);
+            printf("A in TMEM: n=%2d max |err| = %.3g (K=768); K=3072: %.2f us per tile (%.0f ns per stage)\n", n, w, us, us * 1e3 / 48);
+            run(3072, n, 128, 6, 0, 0, 1, 40, &us);
+            printf("M = 64 instruction shape (timing only): n=%2d K=3072: %.2f us per tile (%.0f ns per stage)\n", n, us, us * 1e3 / 48);
+            run(3072, n, 128, 2, 0, 0, 1, 40, &us);
+            printf("shipped form (four issuing threads, four accumulators): n=%2d K=3072: %.2f us per tile (%.0f ns per stage)\n", n, us, us * 1e3 / 48);
+        }
+        return 0;
+    }
     if (argc > 1) {  // timing of the TMA form only (ring depth experiments: -DUMMA_STAGES=n)
         for (int variant : {2, 3, 4})
             for (int n : {16, 32, 96})
