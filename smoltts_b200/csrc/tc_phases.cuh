@@ -515,7 +515,9 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float a = bf16_round(ga[e]), g = bf16_round(up[e]);
-                    const float sg = bf16_round(__fdiv_rn(a, __fadd_rn(1.0f, expf(-a))));
+                    // F.silu in fp32, bf16 out: the fast exponential / division (relative error ~2^-21) move the bf16
+                    // result in ~0.02 % of the elements; the exact forms made this epilogue issue-bound (2.4 us per tile)
+                    const float sg = bf16_round(__fdividef(a, 1.0f + __expf(-a)));
                     o[e] = __fmul_rn(sg, g);
                 }
                 *reinterpret_cast<uint4*>(M.act + (size_t)bg * F + u0) = pack8(o);

@@ -544,18 +544,45 @@ __device__ __forceinline__ void tile_mma_tma(unsigned char* ring, Bars* bars, Pi
 // Hands 8 consecutive accumulator columns of one sequence to epi(row, col0, v[8]); with `paired` the thread also gets the
 // columns half a tile further (w1 | w3 halves): epi2(row, col0, gate[8], up[8]).  Ends with the fences + block barrier
 // that let the next tile overwrite the accumulator.
-// acc_stride > 0: the tile was accumulated in kAcc accumulators acc_stride columns apart (TMA form).
-__device__ __forceinline__ void tmem_ld8_sum(uint32_t taddr, int acc_stride, float (&v)[8]) {
-    tmem_ld8(taddr, v);
-    if (acc_stride > 0) {
+// acc_stride > 0: the tile was accumulated in kAcc accumulators acc_stride columns apart (TMA form).  All loads of a call
+// are issued before the one tcgen05.wait::ld.
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_sum(const uint32_t (&r)[kAcc][8], int n_acc, float (&v)[8]) {
 #pragma unroll
-        for (int a = 1; a < kAcc; ++a) {
-            float b[8];
-            tmem_ld8(taddr + (uint32_t)(a * acc_stride), b);
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[0][i]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], b[i]);
+    for (int a = 1; a < kAcc; ++a)
+        if (a < n_acc) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], __uint_as_float(r[a][i]));
         }
-    }
+}
+__device__ __forceinline__ void tmem_ld8_sum(uint32_t taddr, int acc_stride, float (&v)[8]) {
+    uint32_t r[kAcc][8];
+    const int n_acc = acc_stride > 0 ? kAcc : 1;
+#pragma unroll
+    for (int a = 0; a < kAcc; ++a)
+        if (a < n_acc) tmem_ld8_issue(taddr + (uint32_t)(a * acc_stride), r[a]);
+    tmem_ld_wait();
+    tmem_sum(r, n_acc, v);
+}
+__device__ __forceinline__ void tmem_ld8_sum2(uint32_t ta, uint32_t tb, int acc_stride, float (&va)[8], float (&vb)[8]) {
+    uint32_t ra[kAcc][8], rb[kAcc][8];
+    const int n_acc = acc_stride > 0 ? kAcc : 1;
+#pragma unroll
+    for (int a = 0; a < kAcc; ++a)
+        if (a < n_acc) {
+            tmem_ld8_issue(ta + (uint32_t)(a * acc_stride), ra[a]);
+            tmem_ld8_issue(tb + (uint32_t)(a * acc_stride), rb[a]);
+        }
+    tmem_ld_wait();
+    tmem_sum(ra, n_acc, va);
+    tmem_sum(rb, n_acc, vb);
 }
 
 template <class Epi>
@@ -581,8 +608,7 @@ __device__ __forceinline__ void tile_epilogue_paired(Bars* bars, int half_cols, 
     const int n_warps = blockDim.x >> 5;
     for (int cg = w >> 2; cg * 8 < half_cols; cg += n_warps >> 2) {
         float a[8], b[8];
-        tmem_ld8_sum(base + (uint32_t)(cg * 8), acc_stride, a);
-        tmem_ld8_sum(base + (uint32_t)(half_cols + cg * 8), acc_stride, b);
+        tmem_ld8_sum2(base + (uint32_t)(cg * 8), base + (uint32_t)(half_cols + cg * 8), acc_stride, a, b);
         epi2(row, cg * 8, a, b);
     }
     fence_before_sync();
