@@ -371,7 +371,9 @@ def run_ours(args):
                 "bound": "tensor", "achieved": flops_per_launch / (kernel_ms_mean * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": flops_per_launch / (kernel_ms_mean * 1e-3) / 1e12 / tf_peak, "peak_source": tf_src, "kernel": kernel_name,
                 "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": kernel_ms_mean,
-                "roof_us_per_step": {"flops": t_flops_us, "bytes": t_bytes_us}, "traffic": None,
+                "roof_us_per_step": {"flops": t_flops_us, "bytes": t_bytes_us},
+                "traffic": (((traffic or {}).get("tensor_core_bs256") or {}).get("dram_bytes_per_frame", 0) * args.frames or None)
+                           if args.model == "smoltts_byte_150m" and args.batch == 256 and args.prompt_bytes == 64 else None,
             } if tensor_bound else {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                 "peak_source": peak_src, "kernel": kernel_name,
