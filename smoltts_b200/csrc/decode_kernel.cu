@@ -793,7 +793,11 @@ __device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, c
 
 // Sampling of one id per sequence (G:88-99 slow, G:118-132 depth) and, after the last depth code,
 // frame assembly and the stop rule (G:143-166).
-__device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
+// tc_feed (tensor-core variant, cooperative launch, a depth step follows in the launch): the CTA that chose row b's id also
+// writes the next depth step's input -- the slow hidden state after the slow id, the embedding of the code after a depth
+// code (G:136-140) -- to the fast residual stream and its RMSNorm to M.xn, exactly as that step's own pre-step would
+// (tc_row_step: same chunks per warp, same order of additions), which then is skipped.
+__device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph, bool tc_feed = false) {
     const bool fast = ph.fast != 0;
     const int N = fast ? M.codebook_size : M.vocab;
     const int r = fast ? 1 + ph.depth_pos : 0;
@@ -830,6 +834,42 @@ __device__ void phase_sample(const DevModel& M, const CallArgs& A, const Ctx& c,
                 }
             }
         }
+        if (tc_feed) {
+            const int D = M.fdim, nch = D >> 3, ch = c.tid;
+            const int next_pos = fast ? ph.depth_pos + 1 : 0;
+            const uint16_t* row = !fast ? M.x + (size_t)b * D
+                                        : M.fast_embeddings + (size_t)(tok + (M.depthwise_wte ? (M.dup0 ? next_pos - 1 : next_pos) * M.codebook_size : 0)) * D;
+            const uint16_t* norm_w = M.fast_layers[0].attention_norm;
+            float x[8];
+            float ss = 0.f;
+            uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+            if (ch < nch) {
+                wv = __ldg(reinterpret_cast<const uint4*>(norm_w + ch * 8));
+                unpack8(ldcg_v4(row + ch * 8), x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+            }
+            ss = warp_sum(ss);
+            if (c.lane == 0) g_part[c.warp] = ss;
+            __syncthreads();
+            if (ch < nch) {
+                float t = 0.f;
+                for (int i = 0; i < 3; ++i) t += g_part[i];
+                const float mean = __fdiv_rn(t, (float)D);
+                const float rs = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
+                uint4 raw;
+                raw.x = pack_bf16(x[0], x[1]); raw.y = pack_bf16(x[2], x[3]); raw.z = pack_bf16(x[4], x[5]); raw.w = pack_bf16(x[6], x[7]);
+                *reinterpret_cast<uint4*>(M.xf + (size_t)b * D + ch * 8) = raw;
+                float wf[8];
+                unpack8(wv, wf);
+                uint4 o;
+                o.x = pack_bf16(__fmul_rn(bf16_round(__fmul_rn(x[0], rs)), wf[0]), __fmul_rn(bf16_round(__fmul_rn(x[1], rs)), wf[1]));
+                o.y = pack_bf16(__fmul_rn(bf16_round(__fmul_rn(x[2], rs)), wf[2]), __fmul_rn(bf16_round(__fmul_rn(x[3], rs)), wf[3]));
+                o.z = pack_bf16(__fmul_rn(bf16_round(__fmul_rn(x[4], rs)), wf[4]), __fmul_rn(bf16_round(__fmul_rn(x[5], rs)), wf[5]));
+                o.w = pack_bf16(__fmul_rn(bf16_round(__fmul_rn(x[6], rs)), wf[6]), __fmul_rn(bf16_round(__fmul_rn(x[7], rs)), wf[7]));
+                *reinterpret_cast<uint4*>(M.xn + (size_t)b * D + ch * 8) = o;
+            }
+        }
         __syncthreads();
     }
 }
@@ -841,7 +881,8 @@ __device__ __forceinline__ void run_phase(const DevModel& M, const CallArgs& A, 
                                           bool next_in_launch) {
     if (BT == 0) {
         if (ph.kind == PH_ATTN) phase_attn_batch(M, A, c, ph);
-        else if (ph.kind == PH_SAMPLE) phase_sample(M, A, c, ph);
+        else if (ph.kind == PH_SAMPLE)
+            phase_sample(M, A, c, ph, A.cooperative && next_in_launch && !A.fast_from_xf && !(ph.fast && ph.depth_pos == M.depth - 1));
         else phase_gemm_tc(M, A, c, ph, &g_tc_bars, pipe, target, first_in_launch, next_in_launch);
         return;
     }

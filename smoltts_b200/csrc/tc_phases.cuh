@@ -436,8 +436,10 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
 
     // ---- distributed pre-step ----
     // (a normed phase that follows a wo / w2 inside one cooperative launch finds M.xn written by that phase's post-step)
+    // (and the first QKV of a depth step finds its input written by the SAMPLE phase before it: phase_sample, tc_feed)
     const bool fed_by_post = A.cooperative && !first_in_launch &&
-                             (kind == PH_W13 || kind == PH_HEAD || (kind == PH_QKV && ph.layer > 0));
+                             (kind == PH_W13 || kind == PH_HEAD || (kind == PH_QKV && ph.layer > 0) ||
+                              (kind == PH_QKV && fast && ph.layer == 0 && !A.fast_from_xf));
     if (tc_has_prestep(ph) && !fed_by_post) {
         if (A.tc_part == 0 || A.tc_part == 1) {
             if (kind == PH_WO) {

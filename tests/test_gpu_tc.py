@@ -154,6 +154,10 @@ def test_tc_ragged_tiles_three_row_tiles():
         sub = generate_batch(model, prompts[lo:lo + 16], gs, audio_only=False, fixed_frames=4, seq_ids=list(range(lo, lo + 16)))
         for i in range(16):
             assert torch.equal(sub[i], whole[lo + i]), f"sequence {lo + i}: batch of 16 vs batch of 300"
+    for n in (9, 12):   # the smallest batches the tensor-core variant takes (tc_min_batch = 9)
+        sub = generate_batch(model, prompts[40:40 + n], gs, audio_only=False, fixed_frames=4, seq_ids=list(range(40, 40 + n)))
+        for i in range(n):
+            assert torch.equal(sub[i], whole[40 + i]), f"sequence {40 + i}: batch of {n} vs batch of 300"
 
 
 def test_tc_stop_rule_and_sampling_inside_a_batch():
