@@ -159,6 +159,8 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
 
 static int depth_of(const SmolConfig& c) { return c.num_codebooks - (c.duplicate_code_0 ? 0 : 1); }
 
+static int ensure_tmaps(SmolModel* m);
+
 extern "C" {
 
 int smol_abi_version(void) { return SMOL_ABI_VERSION; }
@@ -251,6 +253,8 @@ int smol_bind_weights(SmolModel* m, const SmolWeights* w) {
     m->weights_bound = true;
     m->tmaps_ready = false;
     m->frame_key_valid = false;
+    // tensor maps are built here, at setup time (a synchronous copy): compute calls stay asynchronous and capturable
+    if (m->ws_bound) return ensure_tmaps(m);
     return SMOL_OK;
 }
 
@@ -285,6 +289,7 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     CU(cudaMemset(base + L.frame_tokens, 0, L.partial - L.frame_tokens));
     m->ws_bound = true;
     m->frame_key_valid = false;
+    if (m->weights_bound) return ensure_tmaps(m);
     return SMOL_OK;
 }
 
@@ -324,9 +329,14 @@ static int ensure_configured(SmolModel* m) {
 
 // TMA tensor maps of the tcgen05 variant: encoded on the host and copied into the workspace once per bind (setup-time,
 // synchronous; compute calls never come here again).
+static bool tc_eligible(const SmolConfig& c) {  // the tiles stream K in 64-element stages
+    return (c.dim % 64) == 0 && (c.fast_dim % 64) == 0 && (c.intermediate_size % 64) == 0 && (c.fast_intermediate_size % 64) == 0;
+}
+
 static int ensure_tmaps(SmolModel* m) {
     if (m->tmaps_ready) return SMOL_OK;
     const SmolConfig& c = m->cfg;
+    if (!tc_eligible(c)) { m->tmaps_ready = true; return SMOL_OK; }  // such a model stays on the CUDA-core variants
     const DevModel& d = m->dm;
     const int n_slots = smol::kTmTotal;
     std::vector<CUtensorMap> maps((size_t)n_slots);
@@ -412,8 +422,7 @@ static int ensure_ll_tile(SmolModel* m, int bt) {
 
 // whole_iters: the call runs complete frames / complete prefill positions (what the data-flow kernel carries).
 static bool use_tc(const SmolModel* m, int rows) {
-    return m->tc_min_batch > 0 && rows >= m->tc_min_batch && (m->cfg.dim % 64) == 0 &&
-           (m->cfg.intermediate_size % 64) == 0 && (m->cfg.fast_intermediate_size % 64) == 0;
+    return m->tc_min_batch > 0 && rows >= m->tc_min_batch && tc_eligible(m->cfg);
 }
 
 static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_iters = false) {
