@@ -2,17 +2,19 @@
 //
 // One output tile = 128 sequences (TMEM lanes) x n_blk weight rows (TMEM columns, fp32), accumulated by
 // tcgen05.mma.cta_group::1.kind::f16 over K in ring stages of 64 elements.  Both operands are K-major
-// (activations [row][K], weights [out][K] -- the checkpoint's own layout), staged in shared memory in the
-// canonical no-swizzle layout of the UMMA shared-memory descriptor:
+// (activations [row][K], weights [out][K] -- the checkpoint's own layout).
+//
+// THE SHIPPED FORM is tile_mma_tma (further down): TMA tensor loads into 128-byte-swizzled stages, two producing
+// threads, four MMA-issuing threads with an accumulator each.  The two forms at the top of the file are its measured
+// predecessors, kept for the A/B in tools/micro/umma_test (profiles/r1c_umma_microbench.txt): they stage the operands
+// with per-thread 16-byte copies (cp.async, or registers) into the canonical NO-swizzle layout of the UMMA descriptor,
 //
 //     byte offset of element (row r, k) inside a stage = (k / 8) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 8) * 2
 //
-// i.e. 8-row x 16-byte core matrices, SBO = 128 B between 8-row groups, LBO = rows * 16 B between the
-// 16-byte K chunks.  Global -> shared goes through per-thread 16-byte cp.async copies (three stages in
-// flight), an optional in-place transform of the thread's own pieces (RMSNorm), fence.proxy.async and a
-// block barrier; ONE thread issues the four K=16 MMAs of the stage and commits them to the stage's
-// mbarrier, which is what frees the stage for re-use.  The accumulator is read back with
-// tcgen05.ld.32x32b (thread = one sequence, 8 consecutive columns per load).
+// (8-row x 16-byte core matrices, SBO = 128 B between 8-row groups, LBO = rows * 16 B between the 16-byte K chunks),
+// with an optional in-place transform of the thread's own pieces, fence.proxy.async and a block barrier per stage,
+// and cost 0.8-1.2 us per stage against 0.29-0.5 us.  All forms read the accumulator back with tcgen05.ld.32x32b
+// (thread = one sequence, 8 consecutive columns per load).
 #pragma once
 
 #include <stdint.h>
