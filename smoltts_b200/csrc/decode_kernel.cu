@@ -977,7 +977,7 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
             }
             if (sync) {
                 grid_wait(M.barrier, target);
-                if (BT == 0) fence_proxy_async_all();
+                if (BT == 0 && (c.tid == 32 || c.tid == 96)) fence_proxy_async_all();   // the threads that issue TMA loads
             }
             if (prof) {  // [2p] CTA 0's own time in the phase, [2p+1] its wait at the barrier that follows
                 const unsigned long long t2 = globaltimer_ns();

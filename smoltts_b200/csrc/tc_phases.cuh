@@ -460,7 +460,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
             fence_proxy_async_all();
             grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
             grid_wait(M.barrier, target);
-            fence_proxy_async_all();
+            if (c.tid == 32 || c.tid == 96) fence_proxy_async_all();   // the threads that issue TMA loads
         }
         if (A.tc_part == 1) return;
     }
