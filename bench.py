@@ -5,14 +5,22 @@
     python bench.py --impl reference [...]                          # the reference's CPU arithmetic (oracle port)
     torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, utterance-sharded
 
-A *step* is one pass of the hot path over one batch of synthetic input: ``--frames`` Mimi frames
-(default 1024 = BASELINE configs[1]) decoded for ``--batch`` utterances per GPU, starting from a
-prefilled 200-byte synthetic prompt.  ``value`` is whole-job frames/s with everything resident in HBM
-(CUDA events around the step launches, max over ranks); ``e2e`` is the same metric through the public
-``generate_batch`` API from host prompts (H2D of the prompt grid, prefill, decode, D2H of the codes).
-The line also carries the roofline of the decode kernel (algorithmic bytes of SURVEY §8(d) over its
-event-timed duration, against MEASURED_PEAKS.json), the CPU baseline (the oracle timed on the host
-cores on a bounded sample), the SM clocks sampled during the timed region and the launch count.
+A *step* is one pass of the hot path over one batch of synthetic input: ``frames`` Mimi frames decoded for
+``batch`` utterances per GPU, starting from a prefilled synthetic prompt.  The headline (top-level keys) is
+BASELINE.json configs[1]: smoltts_byte_150m greedy bs=1, 1024 frames -- ``value`` is whole-job frames/s with
+everything resident in HBM (CUDA events around the step launches, max over ranks), ``e2e`` the same metric through
+the public ``generate_batch`` API from pinned host prompts (H2D of the prompt grid, prefill, decode, D2H of the
+codes, and for N > 1 the host-side gather of every rank's codes on rank 0), for the same number of steps.
+
+The same line carries ``"configs"``: the other BASELINE.json configurations measured the same way in the same run
+(configs[2] bs=64 sampled, configs[3] bs=256 per GPU at two prompt lengths, configs[4] long-form bs=32 at the
+workload's mean context), each with its own ``roofline`` and ``e2e``.  Under ``--gpus N > 1`` every entry is the
+per-GPU batch sharded over the N ranks (weak scaling), so the bs=256/GPU 1 -> 8 curve is in the driver's records.
+
+Roofline: algorithmic bytes (unique weight bytes + KV bytes of the mean context) or flops per launch over
+the CUDA-event duration of the launch, against MEASURED_PEAKS.json; the binding roof (HBM / bf16 tensor) is named.
+``cpu_baseline``: the oracle port of the reference arithmetic timed on the host cores on a bounded sample taken AT THE
+WORKLOAD'S MEAN CONTEXT (so that ``--impl reference`` measures the same configuration as the GPU arm).
 """
 from __future__ import annotations
 
@@ -24,12 +32,60 @@ import subprocess
 import sys
 import tempfile
 import time
+from dataclasses import dataclass
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+CPU_SAMPLE_FRAMES = 128    # frames of one CPU-arm step (a bounded sample of the workload, centred on its mean context)
+
+
+@dataclass
+class Work:
+    """One workload: `frames` frames for `batch` utterances per GPU after a prompt of 12 + prompt_bytes tokens followed by
+    `history` synthetic audio columns (long-form configurations are sampled at their mean context: the history stands for
+    the frames already decoded)."""
+    key: str
+    model: str
+    batch: int
+    frames: int
+    prompt_bytes: int
+    sampled: bool = False
+    history: int = 0
+    note: str = ""
+
+    @property
+    def prompt_tokens(self) -> int:
+        return self.prompt_bytes + 12 + self.history
+
+    @property
+    def mean_context(self) -> float:
+        return self.prompt_tokens + (self.frames - 1) / 2.0
+
+    def name(self) -> str:
+        samp = "top-k50/top-p0.9/temp0.7 sampled" if self.sampled else "greedy"
+        hist = f" + {self.history} cached audio frames" if self.history else ""
+        return (f"{self.model} {samp} decode bs={self.batch}/GPU, {self.frames} frames/step, "
+                f"{self.prompt_bytes}-byte synthetic prompt ({self.prompt_bytes + 12} tokens){hist}")
+
+
+def headline_work(args) -> Work:
+    return Work("config2" if (args.batch, args.frames, args.sampled) == (1, 1024, False) else "custom", args.model, args.batch,
+                args.frames, args.prompt_bytes, args.sampled, args.history)
+
+
+def extra_works(model: str):
+    """BASELINE.json configs[2..4], each short enough for the default run."""
+    return [
+        Work("config3", model, 64, 256, 200, sampled=True, note="configs[2]: bs=64 sampled, 256 frames"),
+        Work("config4i", model, 256, 128, 64, note="configs[3] (i): bs=256 per GPU, 64-byte prompts, 128 frames (tensor-bound regime)"),
+        Work("config4ii", model, 256, 128, 200, note="configs[3] (ii): bs=256 per GPU, 200-byte prompts, 128 frames (KV-bound)"),
+        Work("config5", model, 32, 256, 200, history=1920,
+             note="configs[4]: long-form bs=32 per GPU, 4096-frame decode sampled at its mean context "
+                  "(256 frames after 1920 cached frames: contexts 2132..2387, mean 2259.5 = 212 + 4095/2)"),
+    ]
 
 
 def parse_args():
@@ -39,14 +95,19 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="smoltts_byte_150m")
-    ap.add_argument("--batch", type=int, default=1, help="utterances per GPU")
-    ap.add_argument("--frames", type=int, default=1024, help="Mimi frames per step")
+    ap.add_argument("--batch", type=int, default=1, help="utterances per GPU (headline)")
+    ap.add_argument("--frames", type=int, default=1024, help="Mimi frames per step (headline)")
     ap.add_argument("--prompt-bytes", type=int, default=200)
-    ap.add_argument("--sampled", action="store_true", help="configs[2]: temp 0.7 / top-k 50 / top-p 0.9, fast temp 0.7")
-    ap.add_argument("--mode", type=int, default=2, help="2 data-flow persistent kernel (default; batch <= 8, barrier kernel above), "
-                    "0 grid-barrier persistent kernel, 1 per-phase launches in a CUDA graph")
+    ap.add_argument("--history", type=int, default=0, help="synthetic audio columns cached behind the prompt")
+    ap.add_argument("--sampled", action="store_true", help="temp 0.7 / top-k 50 / top-p 0.9, fast temp 0.7")
+    ap.add_argument("--mode", type=int, default=2, help="2 data-flow persistent kernel (default), 0 grid-barrier persistent "
+                    "kernel, 1 per-phase launches in a CUDA graph")
+    ap.add_argument("--configs", default="auto", help="'auto': configs[2..4] next to the headline when the headline is configs[1]; "
+                    "'none'; or a comma list of config3,config4i,config4ii,config5")
+    ap.add_argument("--config-steps", type=int, default=5, help="timed steps of each entry of \"configs\" (3 warm-up steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (0 = %d)" % CPU_SAMPLE_FRAMES)
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (smol_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -71,7 +132,8 @@ def load_tensor_peak():
 
 
 def load_traffic():
-    """dram bytes per frame of the data-flow decode kernel from the committed ncu --set full capture (bs=1, 150m)."""
+    """Measured DRAM bytes per frame (ncu dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel, captured on
+    the bench's own workloads; profiles/traffic.json names the capture each figure comes from)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
@@ -133,79 +195,113 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synth_prompts(cfg, batch: int, n_bytes: int, first_seq: int):
-    from smoltts_b200.synth import byte_prompt, prompt_grid
+def synth_prompts(cfg, work: Work, first_seq: int):
+    """Utterance b: byte prompt of seed 1 + global id, then `history` synthetic audio columns (row 0 = 320 + first code)."""
+    import torch
 
-    return [prompt_grid(byte_prompt(n_bytes, seed=1 + first_seq + b), cfg) for b in range(batch)]
+    from smoltts_b200.synth import TOK_SEMANTIC0, byte_prompt, prompt_grid
+
+    out = []
+    for b in range(work.batch):
+        g = prompt_grid(byte_prompt(work.prompt_bytes, seed=1 + first_seq + b), cfg)
+        if work.history:
+            gen = torch.Generator().manual_seed(10_000 + first_seq + b)
+            codes = torch.randint(0, cfg.codebook_size, (cfg.n_rows - 1, work.history), generator=gen)
+            cols = torch.zeros(cfg.n_rows, work.history, dtype=torch.int64)
+            cols[1:] = codes
+            cols[0] = TOK_SEMANTIC0 + codes[0]
+            g = torch.cat([g, cols], dim=1)
+        out.append(g)
+    return out
 
 
-def settings_for(args):
+def settings_for(work: Work):
     from smoltts_b200 import GenerationSettings
 
-    if args.sampled:
+    if work.sampled:
         return GenerationSettings(default_temp=0.7, default_fast_temp=0.7, top_k=50, top_p=0.9, seed=1234)
     return GenerationSettings(default_temp=0.0, default_fast_temp=0.0)
 
 
-def workload_name(args) -> str:
-    samp = "top-k50/top-p0.9/temp0.7 sampled" if args.sampled else "greedy"
-    return (f"{args.model} {samp} decode bs={args.batch}/GPU, {args.frames} frames/step, "
-            f"{args.prompt_bytes}-byte synthetic prompt ({args.prompt_bytes + 12} tokens)")
+def public_config(work: Work, world: int) -> dict:
+    """What both arms (ours / --impl reference) report as the configuration they measure."""
+    return {"workload": work.name(), "model": work.model, "batch_per_gpu": work.batch, "frames_per_step": work.frames,
+            "prompt_tokens": work.prompt_tokens, "mean_context": work.mean_context,
+            "l2": "no flush: each frame streams 271 MB of weights (> 126 MB L2) plus the KV cache",
+            "sharding": f"utterance-parallel x{world}, no collective on the decode path"}
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (a port of the reference's arithmetic with a KV cache) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_decode_rate(args, n_frames: int, batch: int = 1):
-    import torch
+class CpuArm:
+    """`n_frames` frames decoded on the CPU for `work.batch` sequences with the KV cache pre-filled (untimed) so that the
+    sample's contexts are centred on the workload's mean context: the same configuration, a bounded sample of its frames."""
 
-    from oracle.dualar_oracle import DualAROracle, OracleSettings
-    from oracle.sampler_oracle import OracleSampler
-    from smoltts_b200.config import named_config
-    from smoltts_b200.synth import make_state_dict
+    def __init__(self, work: Work, n_frames: int):
+        import torch
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    cfg = named_config(args.model)
-    sd = make_state_dict(cfg, seed=0)
-    orc = DualAROracle(cfg, sd, dtype=torch.bfloat16, max_seq_len=max(cfg.max_seq_len, args.prompt_bytes + 12 + n_frames + 8))
-    prompts = synth_prompts(cfg, batch, args.prompt_bytes, 0)
-    cols = torch.stack(prompts, 0)
-    st = (OracleSettings(default_temp=0.7, default_fast_temp=0.7, top_k=50, top_p=0.9, seed=1234) if args.sampled
-          else OracleSettings(default_temp=0.0, default_fast_temp=0.0))
-    sampler = OracleSampler(seq_ids=list(range(batch))) if args.sampled else None
-    with torch.no_grad():
-        cache = orc.new_cache()
-        t0 = time.perf_counter()
-        nxt, *_ = orc.decode_frame(cols, cache, st, 0, sampler)  # prefill + first frame (excluded, as G:187-193)
-        t1 = time.perf_counter()
-        for f in range(1, n_frames + 1):
-            nxt, *_ = orc.decode_frame(nxt[:, :, None], cache, st, f, sampler)
-        t2 = time.perf_counter()
-    return {"frames_per_s": batch * n_frames / (t2 - t1), "prefill_s": t1 - t0, "decode_s": t2 - t1,
-            "threads": torch.get_num_threads(), "frames": n_frames, "batch": batch}
+        from oracle.dualar_oracle import DualAROracle, OracleSettings
+        from oracle.sampler_oracle import OracleSampler
+        from smoltts_b200.config import named_config
+        from smoltts_b200.synth import make_state_dict
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.torch = torch
+        self.work = work
+        self.n_frames = min(n_frames, work.frames)
+        cfg = named_config(work.model)
+        # columns cached before the sample starts: the prompt plus the frames the workload has decoded by then
+        self.skip = (work.frames - self.n_frames) // 2
+        w2 = Work(work.key, work.model, work.batch, work.frames, work.prompt_bytes, work.sampled, work.history + self.skip)
+        self.orc = DualAROracle(cfg, make_state_dict(cfg, seed=0), dtype=torch.bfloat16,
+                                max_seq_len=max(cfg.max_seq_len, w2.prompt_tokens + self.n_frames + 8))
+        self.cols = torch.stack(synth_prompts(cfg, w2, 0), 0)
+        self.st = (OracleSettings(default_temp=0.7, default_fast_temp=0.7, top_k=50, top_p=0.9, seed=1234) if work.sampled
+                   else OracleSettings(default_temp=0.0, default_fast_temp=0.0))
+        self.sampler = OracleSampler(seq_ids=list(range(work.batch))) if work.sampled else None
+        self.first_context = w2.prompt_tokens
+        self.threads = torch.get_num_threads()
+
+    def step(self):
+        torch = self.torch
+        with torch.no_grad():
+            cache = self.orc.new_cache()
+            t0 = time.perf_counter()
+            nxt, *_ = self.orc.decode_frame(self.cols, cache, self.st, 0, self.sampler)  # prefill + first frame: untimed (G:187-193)
+            t1 = time.perf_counter()
+            for f in range(1, self.n_frames + 1):
+                nxt, *_ = self.orc.decode_frame(nxt[:, :, None], cache, self.st, f, self.sampler)
+            t2 = time.perf_counter()
+        return {"decode_s": t2 - t1, "prefill_s": t1 - t0, "frames": self.n_frames * self.work.batch}
+
+    def sample_text(self) -> str:
+        w = self.work
+        return (f"{self.n_frames} of the step's {w.frames} frames, taken at the workload's mean context (contexts "
+                f"{self.first_context + 1}..{self.first_context + self.n_frames}, KV cache pre-filled untimed), bs={w.batch}, bf16 eager "
+                f"on CPU: oracle port of the reference's modeling/ arithmetic with a KV cache (prefill excluded as in lm/generate.py:187-214)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_frames = args.cpu_frames or 128  # ~3 s of CPU work per step
+    work = headline_work(args)
+    arm = CpuArm(work, args.cpu_frames or CPU_SAMPLE_FRAMES)
     per_step = []
     for i in range(args.warmup + args.steps):
-        r = cpu_decode_rate(args, n_frames, batch=args.batch)
+        r = arm.step()
         if i >= args.warmup:
             per_step.append(r)
-    total_frames = sum(r["frames"] * r["batch"] for r in per_step)
+    total_frames = sum(r["frames"] for r in per_step)
     total_s = sum(r["decode_s"] for r in per_step)
     value = total_frames / total_s
-    sample = (f"{n_frames} frames after a {args.prompt_bytes + 12}-token prefill, bs={args.batch}, bf16 eager on CPU "
-              f"(oracle port of modeling/ arithmetic with a KV cache; prefill excluded as in lm/generate.py:187-214)")
     line = {
         "impl": "reference", "metric": "Mimi frames/sec", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / len(per_step),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_cpu_step": n_frames},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": per_step[0]["threads"], "kind": "port", "sample": sample},
+        "config": public_config(work, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": arm.threads, "kind": "port", "sample": arm.sample_text()},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -215,41 +311,60 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def roofline_of(cfg, work: Work, kernel_ms: float, tensor_variant: bool, kernel_name: str, traffic_per_frame):
+    hbm_gbs, peak_src = load_peaks()
+    tf_peak, tf_src = load_tensor_peak()
+    l_mean = work.mean_context
+    bytes_per_frame = cfg.unique_weight_bytes() + work.batch * cfg.kv_bytes_per_position() * (l_mean + 1)
+    flops_per_frame = work.batch * cfg.flops_per_frame(l_mean)
+    t_bytes_us = bytes_per_frame / (hbm_gbs * 1e9) * 1e6
+    t_flops_us = flops_per_frame / (tf_peak * 1e12) * 1e6
+    common = {"kernel": kernel_name, "launch_ms": kernel_ms, "units_per_launch": work.frames,
+              "roof_us_per_frame_step": {"flops": t_flops_us, "bytes": t_bytes_us},
+              "traffic": (traffic_per_frame * work.frames) if traffic_per_frame else None}
+    if tensor_variant and t_flops_us >= t_bytes_us:
+        ach = flops_per_frame * work.frames / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "peak_source": tf_src,
+                "algorithmic_flops_per_launch": flops_per_frame * work.frames, **common}
+    ach = bytes_per_frame * work.frames / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_per_frame * work.frames, **common}
+
+
+def measure(work: Work, args, steps: int, warmup: int, ctx) -> dict:
+    """Device-resident value, e2e through generate_batch (+ gather on rank 0) and the roofline of one workload."""
     import torch
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from smoltts_b200 import RQTransformer, generate_batch, named_config
     from smoltts_b200.generate import _sampling, pack_prompts
+    from smoltts_b200.shard import gather_utterances
     from smoltts_b200.synth import make_state_dict
 
-    cfg = named_config(args.model)
-    n_prompt = args.prompt_bytes + 12
-    need = n_prompt + args.frames + 8
-    model = RQTransformer(cfg, max_batch=args.batch, max_seq_len=max(need, 256),
-                          kv_pages=2 * args.batch * ((max(need, 256) + 31) // 32))
-    model.load_state_dict(make_state_dict(cfg, seed=0))
+    dist, gloo, rank, world, local = ctx["dist"], ctx["gloo"], ctx["rank"], ctx["world"], ctx["local"]
+    cfg = named_config(work.model)
+    n_prompt = work.prompt_tokens
+    need = max(n_prompt + work.frames + 8, 256)
+    model = RQTransformer(cfg, max_batch=work.batch, max_seq_len=need, kv_pages=2 * work.batch * ((need + 31) // 32))
+    model.load_state_dict(ctx["weights"](work.model))
     model.set_option("mode", args.mode)
-    gs = settings_for(args)
-    prompts = synth_prompts(cfg, args.batch, args.prompt_bytes, rank * args.batch)
-    seq_ids = [rank * args.batch + b for b in range(args.batch)]
+    for kv in args.opt:
+        k, v = kv.split("=")
+        model.set_option(k, int(v))
+    gs = settings_for(work)
+    first = rank * work.batch
+    prompts = synth_prompts(cfg, work, first)
+    seq_ids = [first + b for b in range(work.batch)]
     dev = model.device
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     # ---- device-resident arm: prefill once, then every step decodes `frames` frames from the same state
     padded, lens = pack_prompts(model, prompts)
-    batch = model.new_batch(args.batch, max_positions=need, max_frames=args.frames, seq_ids=seq_ids)
+    batch = model.new_batch(work.batch, max_positions=n_prompt + work.frames + 1, max_frames=work.frames, seq_ids=seq_ids)
     sampling = _sampling(model, gs, audio_only=True, ignore_stop=True)
     model.prefill(batch, padded, lens)
     torch.cuda.synchronize()
@@ -263,37 +378,28 @@ def run_ours(args):
         batch.finished.zero_()
         batch.host_len = list(host_len0)
 
-    def step():
+    frame_clock = model.set_frame_clock(work.frames) if work.batch == 1 else None  # device-side per-frame stamps (sequence 0)
+    for _ in range(warmup):
         reset()
-        model.decode_frames(batch, sampling, args.frames)
-
-    frame_clock = model.set_frame_clock(args.frames) if args.batch == 1 else None  # device-side per-frame stamps (sequence 0)
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
+        model.decode_frames(batch, sampling, work.frames)
+    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = model.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    for i in range(args.steps):
+    for i in range(steps):
         reset()
         ev[i][0].record()
-        model.decode_frames(batch, sampling, args.frames)
+        model.decode_frames(batch, sampling, work.frames)
         ev[i][1].record()
     stop.record()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     launches = model.launch_count - launches0
     clocks = sampler.stop()
     total_ms = start.elapsed_time(stop)
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
     codes_check = int(batch.out_codes.sum().item())  # the result is really produced
     frame_lat = None
     if frame_clock is not None:  # stamps of the last timed step: p50 / p99 of the per-frame latency (BASELINE.json's second metric)
@@ -305,96 +411,119 @@ def run_ours(args):
             frame_lat = {"p50_us": float(d[int(0.50 * (d.size - 1))]), "p99_us": float(d[int(0.99 * (d.size - 1))]),
                          "max_us": float(d[-1]), "frames": int(d.size) + 1, "clock": "%globaltimer at frame assembly, on the device"}
         model.set_frame_clock(0)
+    batch.release()
 
-    # ---- end-to-end arm: public API from host prompts, H2D + prefill + decode + D2H every step
+    # ---- end-to-end arm: public API from pinned host prompts; H2D + prefill + decode + D2H (+ gather on rank 0) every step
     host_prompts = [p.pin_memory() for p in prompts]
-    for _ in range(max(1, min(args.warmup, 2))):
-        generate_batch(model, host_prompts, gs, audio_only=False, fixed_frames=args.frames, chunk=args.frames, seq_ids=seq_ids)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        outs = generate_batch(model, host_prompts, gs, audio_only=False, fixed_frames=work.frames, chunk=work.frames, seq_ids=seq_ids)
+        return gather_utterances(outs, gloo) if world > 1 else outs
+
+    for _ in range(max(1, min(warmup, 2))):
+        e2e_step()
+    barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        outs = generate_batch(model, host_prompts, gs, audio_only=False, fixed_frames=args.frames, chunk=args.frames,
-                              seq_ids=seq_ids)
+    for _ in range(steps):
+        got = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if rank == 0:
+        assert got is not None and len(got) == work.batch * world and tuple(got[-1].shape) == (cfg.n_rows, work.frames)
     h2d = int(padded.numel() * 4 + lens.numel() * 4)
-    d2h = int(args.batch * args.frames * cfg.n_rows * 4 + args.batch * 4)
+    d2h = int(work.batch * work.frames * cfg.n_rows * 4 + work.batch * 4)
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, e2e_s * 1e3, statistics.mean(kernel_ms)], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kernel_ms_mean = (float(v) for v in t.tolist())
+    total_ms, e2e_ms, kernel_ms = (float(v) for v in t.tolist())
+
+    dataflow = args.mode == 2 and work.batch <= model.get_option("ll_max_batch")
+    tensor = not dataflow and work.batch >= model.get_option("tc_min_batch") > 0
+    kernel_name = (model.kernel_name(work.batch) if hasattr(model, "kernel_name") else
+                   "smol_ll_kernel" if dataflow else "smol_decode_kernel<0> (tcgen05 tiles, TMA operand ring)" if tensor else "smol_decode_kernel")
+    traffic = load_traffic() or {}
+    tr = (traffic.get(work.key) or {}).get("dram_bytes_per_frame") if work.model == "smoltts_byte_150m" else None
+    res = {
+        "workload": work.name(), "note": work.note, "value": steps * work.frames * work.batch * world / (total_ms * 1e-3),
+        "unit": "frames/s", "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+        "us_per_frame_step": 1e3 * kernel_ms / work.frames,
+        "roofline": roofline_of(cfg, work, kernel_ms, tensor, kernel_name, tr),
+        "e2e": {"value": steps * work.frames * work.batch * world / (e2e_ms * 1e-3), "unit": "frames/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+                "includes": "H2D prompt grid + prefill + decode + D2H codes via generate_batch()"
+                            + (", + host-side gather of all ranks' codes on rank 0 (gloo)" if world > 1 else "")},
+        "clocks": clocks, "gpu_launches": launches, "check": codes_check, "frame_latency_bs1": frame_lat,
+        "launch_mode": ("data-flow persistent kernel (LL flag words, TMA producer warp), one launch per step" if dataflow
+                        else "persistent cooperative kernel with grid barriers, one launch per step" if args.mode != 1
+                        else "per-phase launches in a CUDA graph"),
+        "config": public_config(work, world),
+    }
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = gloo = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")  # host-side gather of the emitted codes; NCCL only times
+
+    from smoltts_b200.config import named_config
+    from smoltts_b200.synth import make_state_dict
+
+    wcache = {}
+
+    def weights(name):
+        if name not in wcache:
+            wcache[name] = make_state_dict(named_config(name), seed=0)
+        return wcache[name]
+
+    ctx = {"dist": dist, "gloo": gloo, "rank": rank, "world": world, "local": local, "weights": weights}
+    head = headline_work(args)
+    main = measure(head, args, args.steps, args.warmup, ctx)
+    entries = []
+    if args.configs != "none" and (args.configs != "auto" or head.key == "config2"):
+        wanted = None if args.configs == "auto" else set(args.configs.split(","))
+        for w in extra_works(args.model):
+            if wanted is None or w.key in wanted:
+                r = measure(w, args, max(1, min(args.steps, args.config_steps)), 3, ctx)
+                r["key"] = w.key
+                entries.append(r)
 
     if rank == 0:
-        frames_total = args.steps * args.frames * args.batch * world
-        value = frames_total / (total_ms * 1e-3)
-        e2e_value = e2e_steps * args.frames * args.batch * world / (e2e_ms * 1e-3)
-        hbm_gbs, peak_src = load_peaks()
-        l_mean = n_prompt + (args.frames - 1) / 2.0
-        w_unique = cfg.unique_weight_bytes()
-        bytes_per_frame = w_unique + args.batch * cfg.kv_bytes_per_position() * (l_mean + 1)
-        bytes_per_launch = bytes_per_frame * args.frames
-        achieved = bytes_per_launch / (kernel_ms_mean * 1e-3) / 1e9
-        traffic = load_traffic()
-        dataflow = args.mode == 2 and args.batch <= 1
-        tensor = not dataflow and args.batch >= model.get_option("tc_min_batch") > 0
-        kernel_name = ("smol_ll_kernel" if dataflow else "smol_decode_kernel<0> (tcgen05 tiles, TMA operand ring)" if tensor
-                       else "smol_decode_kernel")
-        launch_mode = ("data-flow persistent kernel (LL flag words, TMA producer warp), one launch per step" if dataflow
-                       else "persistent cooperative kernel with grid barriers" if args.mode != 1
-                       else "per-phase launches in a CUDA graph")
-        # which roof binds: bytes over HBM bandwidth vs flops over the bf16 tensor peak
-        tf_peak, tf_src = load_tensor_peak()
-        flops_per_launch = args.batch * cfg.flops_per_frame(l_mean) * args.frames
-        t_bytes_us = bytes_per_frame / (hbm_gbs * 1e9) * 1e6
-        t_flops_us = args.batch * cfg.flops_per_frame(l_mean) / (tf_peak * 1e12) * 1e6
-        tensor_bound = tensor and t_flops_us >= t_bytes_us
+        cfg_pub = dict(main["config"])  # identical in both arms (ours / --impl reference): the configuration measured
         line = {
-            "metric": "Mimi frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": workload_name(args), "model": args.model, "batch_per_gpu": args.batch,
-                "frames_per_step": args.frames, "prompt_tokens": n_prompt, "mean_context": l_mean,
-                "sharding": f"utterance-parallel x{world}, no collective on the decode path",
-                "launch_mode": launch_mode,
-                "l2": "no flush: each frame streams 271 MB of weights (> 126 MB L2) plus the KV cache",
-                "us_per_frame": 1e3 * kernel_ms_mean / args.frames,
-                "frame_latency_bs1": frame_lat,
-                "e2e_includes": "H2D prompt grid + prefill (tensor-core tiles of up to 128 prompt positions) + decode + D2H codes, via generate_batch()",
-            },
-            "roofline": ({
-                "bound": "tensor", "achieved": flops_per_launch / (kernel_ms_mean * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": flops_per_launch / (kernel_ms_mean * 1e-3) / 1e12 / tf_peak, "peak_source": tf_src, "kernel": kernel_name,
-                "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": kernel_ms_mean,
-                "roof_us_per_step": {"flops": t_flops_us, "bytes": t_bytes_us},
-                "traffic": (((traffic or {}).get("tensor_core_bs256") or {}).get("dram_bytes_per_frame", 0) * args.frames or None)
-                           if args.model == "smoltts_byte_150m" and args.batch == 256 and args.prompt_bytes == 64 else None,
-            } if tensor_bound else {
-                "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                "peak_source": peak_src, "kernel": kernel_name,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": kernel_ms_mean,
-                "roof_us_per_step": {"flops": t_flops_us, "bytes": t_bytes_us},
-                "traffic": ((traffic or {}).get("dram_bytes_per_frame") * args.frames
-                            if traffic and dataflow and args.model == "smoltts_byte_150m" and args.batch == 1 else None),
-            }),
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
-            "clocks": clocks,
-            "gpu_launches": launches,
-            "check": codes_check,
+            "metric": "Mimi frames/sec", "value": main["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg_pub, "roofline": main["roofline"],
+            "e2e": {k: v for k, v in main["e2e"].items() if k != "includes"}, "clocks": main["clocks"],
+            "gpu_launches": main["gpu_launches"] + sum(e["gpu_launches"] for e in entries), "check": main["check"],
+            "latency": {"us_per_frame": main["us_per_frame_step"], "frame_latency_bs1": main["frame_latency_bs1"]},
+            "detail": {"launch_mode": main["launch_mode"], "e2e_includes": main["e2e"]["includes"]},
+            "configs": [{k: e[k] for k in ("key", "workload", "note", "value", "unit", "ms_per_step", "steps", "warmup",
+                                           "us_per_frame_step", "roofline", "e2e", "clocks", "gpu_launches", "launch_mode")}
+                        for e in entries],
         }
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = args.cpu_frames or 480  # ~10 s of CPU work at ~46 frames/s
-            r = cpu_decode_rate(args, n_cpu, batch=args.batch)
-            line["cpu_baseline"] = {
-                "value": r["frames_per_s"], "unit": "frames/s", "cores": r["threads"], "kind": "port",
-                "sample": (f"{n_cpu} frames after a {n_prompt}-token prefill ({r['prefill_s']:.1f} s), bs={args.batch}, "
-                           f"bf16 eager CPU oracle, {r['decode_s']:.1f} s of decode")}
+            arm = CpuArm(head, args.cpu_frames or CPU_SAMPLE_FRAMES)
+            rs = [arm.step() for _ in range(4)]  # ~10-15 s of CPU work; the first pass warms the allocator up
+            rs = rs[1:]
+            line["cpu_baseline"] = {"value": sum(r["frames"] for r in rs) / sum(r["decode_s"] for r in rs), "unit": "frames/s",
+                                    "cores": arm.threads, "kind": "port", "sample": "3 x " + arm.sample_text()}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -21,4 +21,6 @@ from .model import (  # noqa: F401
     make_prompt_cache,
 )
 
+from .shard import ShardedGenerator, generate_sharded  # noqa: F401,E402
+
 __version__ = "0.1.0"

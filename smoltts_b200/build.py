@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsmoltts_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 SOURCES = ["decode_kernel.cu", "ll_kernel.cu", "capi.cu"]
-HEADERS = ["common.cuh", "dev_model.h", "sampler.cuh", "umma.cuh", "tc_phases.cuh", os.path.join("..", "..", "include", "smoltts_b200.h")]
+HEADERS = ["common.cuh", "dev_model.h", "sampler.cuh", "umma.cuh", "tc_phases.cuh", "tmap_host.h", os.path.join("..", "..", "include", "smoltts_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -26,6 +26,7 @@ cudaError_t sample_launch(const float* logits, int n, int batch, const SmolSampl
                           const int32_t* seq_id, const int32_t* step, int32_t* out, cudaStream_t stream);
 cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int batch, int n_rows, int row,
                                cudaStream_t stream);
+cudaError_t silu_lut_launch(uint16_t* lut, cudaStream_t stream);
 // data-flow kernel (ll_kernel.cu)
 size_t ll_smem_plan(const DevModel& M, int bt, int n_ctas, int* xs_bytes, int* res_bytes, int* scratch_bytes, int* ring_bytes);
 cudaError_t ll_configure(int bt, size_t smem);
@@ -93,7 +94,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int imax(int a, int b) { return a > b ? a : b; }
 
 struct WsLayout {
-    size_t x, h, xf, q, attn, act, xn, tmaps, kpart, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
+    size_t x, h, xf, q, attn, act, xn, silu_lut, tmaps, kpart, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
     size_t ll, ll_partial, ll_tok, ll_cand, ll_epoch, total;
 };
 
@@ -138,6 +139,7 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.attn = take(B * dmax * 2);
     L.act = take(B * imax(c.intermediate_size, c.fast_intermediate_size) * 2);
     L.xn = take(B * dmax * 2);
+    L.silu_lut = take(65536 * 2);
     L.tmaps = take((size_t)smol::kTmTotal * smol::kTensorMapBytes);
     L.kpart = take((size_t)smol::kTcKSplit * B * dmax * 4);
     L.fkv = take(B * c.n_fast_layer * 2 * depth * c.fast_n_local_heads * 64 * 2);
@@ -183,7 +185,9 @@ int smol_create(const SmolConfig* cfg, SmolModel** out) {
     if (c.vocab_size > smol::kThreads * 8 || c.codebook_size > smol::kThreads * 8) return bad("vocab / codebook above 4096 rows");
     const int depth = depth_of(c);
     if (depth < 1 || depth > smol::kMaxDepth) return bad("depth out of range");
-    if (c.page_size <= 0 || c.max_batch <= 0 || c.max_seq_len <= 0) return fail(SMOL_ERR_INVALID, "smol_create: bad capacity");
+    if (c.max_batch <= 0 || c.max_seq_len <= 0) return fail(SMOL_ERR_INVALID, "smol_create: bad capacity");
+    // the batch attention walks 16-position groups through a 32-entry page-id window: pages of 16 or 32 positions only
+    if (c.page_size != 16 && c.page_size != 32) return fail(SMOL_ERR_INVALID, "smol_create: page_size must be 16 or 32");
     if (!c.tie_word_embeddings) { /* output.weight must be bound */ }
 
     SmolModel* m = new SmolModel();
@@ -274,6 +278,8 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     d.q = (uint16_t*)(base + L.q); d.attn = (uint16_t*)(base + L.attn); d.act = (uint16_t*)(base + L.act);
     d.fkv = (uint16_t*)(base + L.fkv);
     d.xn = (uint16_t*)(base + L.xn); d.tmaps = (const unsigned char*)(base + L.tmaps);
+    d.silu_lut = (const uint16_t*)(base + L.silu_lut);
+    CU(smol::silu_lut_launch((uint16_t*)(base + L.silu_lut), nullptr));  // setup-time (synchronous with the memsets below)
     d.kpart = (float*)(base + L.kpart); d.ws_rows = ws_rows(m->cfg);
     m->tmaps_ready = false;
     d.token_logits = (float*)(base + L.token_logits); d.depth_logits = (float*)(base + L.depth_logits);
@@ -704,6 +710,7 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
     }
     if (!std::strcmp(name, "tc_min_batch")) {  // 0 disables the tensor-core variant
         m->tc_min_batch = value > 0 ? (int)value : 0;
+        m->frame_key_valid = false;  // a cached frame graph was captured for the other kernel variant
         return SMOL_OK;
     }
     if (!std::strcmp(name, "ll_flags")) {
@@ -731,6 +738,7 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!std::strcmp(name, "ll_smem_bytes")) return (int64_t)m->ll_smem[1];
     if (!std::strcmp(name, "ll_ring_bytes")) return (int64_t)m->ll_ring[1];
     if (!std::strcmp(name, "ll_ready")) return (int64_t)m->ll_state[1];
+    if (!std::strcmp(name, "ll_max_batch")) return (int64_t)m->dm.ll_batch;
     return -1;
 }
 

@@ -738,7 +738,9 @@ __device__ void phase_gemv(const DevModel& M, const CallArgs& A, const Ctx& c, c
                 float v0 = bf16_round(acc[0]), v1 = bf16_round(acc[1]);
                 if (n0 < k_end) {  // q and k rows: interleaved-pair RoPE with the bf16 table (P:616-640)
                     const int j = (n0 & (kHeadDim - 1)) >> 1;
-                    const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + ((size_t)pos * (kHeadDim / 2) + j) * 2));
+                    // (positions are bounded by the host's capacity checks; the clamp keeps a bad caller inside the table)
+                    const int tp = fast ? pos : min(pos, M.max_seq_len - 1);
+                    const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + ((size_t)tp * (kHeadDim / 2) + j) * 2));
                     const float co = bf_lo(cs), si = bf_hi(cs);
                     const float r0 = bf16_round(__fsub_rn(__fmul_rn(v0, co), __fmul_rn(v1, si)));
                     const float r1 = bf16_round(__fadd_rn(__fmul_rn(v1, co), __fmul_rn(v0, si)));
@@ -977,7 +979,7 @@ smol_decode_kernel(const __grid_constant__ DevModel M, const __grid_constant__ C
             }
             if (sync) {
                 grid_wait(M.barrier, target);
-                if (BT == 0 && (c.tid == 32 || c.tid == 96)) fence_proxy_async_all();   // the threads that issue TMA loads
+                if (BT == 0 && (c.tid == umma::kTmaProducerA || c.tid == umma::kTmaProducerB)) fence_proxy_async_all();   // the threads that issue TMA loads
             }
             if (prof) {  // [2p] CTA 0's own time in the phase, [2p+1] its wait at the barrier that follows
                 const unsigned long long t2 = globaltimer_ns();
@@ -1028,6 +1030,20 @@ cudaError_t sample_launch(const float* logits, int n, int batch, const SmolSampl
     cudaError_t e = cudaFuncSetAttribute(smol_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
     smol_sample_kernel<<<batch < 1024 ? batch : 1024, kThreads, smem, stream>>>(logits, n, batch, s, stream_id, seq_id, step, out);
+    return cudaGetLastError();
+}
+
+// silu over EVERY bf16 input, by the exact expression the GEMV epilogues use (F.silu in fp32, bf16 out; P:581): the
+// tensor-core epilogue and the data-flow kernel look the result up instead of evaluating exp and a division per element,
+// so all kernels round at the same points and agree bit for bit.
+__global__ void smol_silu_lut_kernel(uint16_t* lut) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536u) return;
+    const float a = __uint_as_float(i << 16);
+    lut[i] = f_to_bf(__fdiv_rn(a, __fadd_rn(1.0f, expf(-a))));
+}
+cudaError_t silu_lut_launch(uint16_t* lut, cudaStream_t stream) {
+    smol_silu_lut_kernel<<<256, 256, 0, stream>>>(lut);
     return cudaGetLastError();
 }
 

@@ -74,6 +74,7 @@ struct DevModel {
     uint16_t* attn;     // attention output                [B][max(dim,fdim)]
     uint16_t* act;      // silu(w1 x) * w3 x               [B][max(inter,finter)]
     uint16_t* xn;       // tensor-core variant: RMSNorm output feeding the next weight phase  [B][max(dim,fdim)]
+    const uint16_t* silu_lut;  // bf16 silu of every bf16 input [65536] (exact expression, filled at bind time)
     const unsigned char* tmaps;  // tensor-core variant: TMA tensor maps (128 B each, TensorMapSlot), in the workspace
     float* kpart;       // tensor-core variant: split-K partial sums of the wo / w2 tiles  [kTcKSplit][ws_rows][max(dim,fdim)] fp32
     int ws_rows;        // rows of every workspace buffer

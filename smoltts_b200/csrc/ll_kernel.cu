@@ -1143,7 +1143,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                 const int n0 = 2 * (u0 + jw);
                 if (kind == PH_QKV) {
                     if (n0 < k_end) {
-                        const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)s_pos * kHeadDim);
+                        const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)min(s_pos, M.max_seq_len - 1) * kHeadDim);
                         pre_first = __ldg(reinterpret_cast<const uint32_t*>(table + (n0 & (kHeadDim - 1))));
                     }
                 } else if (kind == PH_WO || kind == PH_W2) {
@@ -1187,7 +1187,7 @@ smol_ll_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallA
                         // loaded before the barrier
                     } else if (kind == PH_QKV) {
                         if (n0 < k_end) {
-                            const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)s_pos * kHeadDim);
+                            const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)min(s_pos, M.max_seq_len - 1) * kHeadDim);
                             pre = __ldg(reinterpret_cast<const uint32_t*>(table + (n0 & (kHeadDim - 1))));
                         }
                     } else if (kind == PH_WO || kind == PH_W2) {

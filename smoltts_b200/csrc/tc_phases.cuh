@@ -460,7 +460,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
             fence_proxy_async_all();
             grid_arrive(M.barrier, target, (uint32_t)c.n_ctas);
             grid_wait(M.barrier, target);
-            if (c.tid == 32 || c.tid == 96) fence_proxy_async_all();   // the threads that issue TMA loads
+            if (c.tid == umma::kTmaProducerA || c.tid == umma::kTmaProducerB) fence_proxy_async_all();   // the threads that issue TMA loads
         }
         if (A.tc_part == 1) return;
     }
@@ -505,7 +505,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
         b1.row0 = n0; b1.n = w_index1 >= 0 ? blk : 0; b1.box = blk;
         // slow weights are read once per frame (evict first), the depth transformer's by every depth step (keep in L2):
         // measured DRAM reads 937 -> 891 MB per frame at bs=256, time unchanged (gpurun_out/l2hint_dram.csv)
-        umma::tile_mma_tma<kThreads, false>(ring, bars, pipe, k_len, tm_a, m0, b0, b1, [](int, int, uint4&) {}, ks * k_len, a_rows,
+        umma::tile_mma_tma<kThreads>(ring, bars, pipe, k_len, tm_a, m0, b0, b1, ks * k_len, a_rows,
                                             fast ? umma::kWeightsKeep : umma::kWeightsStream);
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[2] += t - ts; ts = t; }
 
@@ -517,9 +517,9 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float a = bf16_round(ga[e]), g = bf16_round(up[e]);
-                    // F.silu in fp32, bf16 out: the fast exponential / division (relative error ~2^-21) move the bf16
-                    // result in ~0.02 % of the elements; the exact forms made this epilogue issue-bound (2.4 us per tile)
-                    const float sg = bf16_round(__fdividef(a, 1.0f + __expf(-a)));
+                    // F.silu in fp32, bf16 out: a is a bf16 value, so the exactly rounded result is a table look-up (the
+                    // exact exp / division made this epilogue issue-bound; a fast-math form moved 0.02 % of the results)
+                    const float sg = __uint_as_float((uint32_t)__ldg(M.silu_lut + (__float_as_uint(a) >> 16)) << 16);
                     o[e] = __fmul_rn(sg, g);
                 }
                 *reinterpret_cast<uint4*>(M.act + (size_t)bg * F + u0) = pack8(o);
@@ -545,11 +545,12 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = bf16_round(acc[e]);
                 const int p = pos[row];
+                const int tp = fast ? p : min(p, M.max_seq_len - 1);  // never past the RoPE table (host checks bound p)
                 if (u0 < k_end) {  // q and k rows: interleaved-pair RoPE with the bf16 table (P:616-640)
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) {
                         const int j = ((u0 + e) & (kHeadDim - 1)) >> 1;
-                        const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + ((size_t)p * (kHeadDim / 2) + j) * 2));
+                        const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + ((size_t)tp * (kHeadDim / 2) + j) * 2));
                         const float co = bf_lo(cs), si = bf_hi(cs);
                         const float r0 = bf16_round(__fsub_rn(__fmul_rn(v[e], co), __fmul_rn(v[e + 1], si)));
                         const float r1 = bf16_round(__fadd_rn(__fmul_rn(v[e + 1], co), __fmul_rn(v[e], si)));

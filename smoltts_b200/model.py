@@ -116,7 +116,8 @@ class DecodeBatch:
         self.seq_id = torch.tensor(ids, dtype=torch.int32, device=dev)
         self.step = torch.zeros(batch, dtype=torch.int32, device=dev)
         self.out_codes = torch.zeros(batch, max(max_frames, 1), R, dtype=torch.int32, device=dev)
-        self.capacity = self.max_pages * ps
+        # positions this batch may cache: its pages, and never past the RoPE table (max_seq_len rows)
+        self.capacity = min(self.max_pages * ps, model.max_seq_len)
         self.host_len = [0] * batch  # upper bound of seq_len known on the host (capacity checks)
         self.c = _capi.SmolBatch(
             tokens=self.tokens.data_ptr(), seq_len=self.seq_len.data_ptr(), block_table=self.block_table.data_ptr(),
@@ -293,6 +294,9 @@ class RQTransformer:
                   seq_ids: Optional[Sequence[int]] = None) -> DecodeBatch:
         if batch > self.max_batch:
             raise _capi.SmolError(_capi.SMOL_ERR_CAPACITY, f"batch {batch} > max_batch {self.max_batch}")
+        if max_positions is not None and max_positions > self.max_seq_len:
+            raise _capi.SmolError(_capi.SMOL_ERR_CAPACITY,
+                                  f"max_positions {max_positions} > max_seq_len {self.max_seq_len} (rows of the RoPE table)")
         return DecodeBatch(self, batch, max_positions or self.max_seq_len, max_frames, seq_ids)
 
     # ------------------------------------------------------------------ engine calls
@@ -343,8 +347,9 @@ class RQTransformer:
         sequence with its first len-1 columns cached and the last column pending."""
         B, R, s_max = prompts.shape
         host_len = lengths.tolist()
-        if max(host_len) > batch.capacity:
-            raise _capi.SmolError(_capi.SMOL_ERR_CAPACITY, "prompt longer than the sequence's KV pages")
+        # a prompt of n columns caches n - 1 positions on top of what the sequence already holds
+        if any(batch.host_len[b] + host_len[b] - 1 > batch.capacity for b in range(B)):
+            raise _capi.SmolError(_capi.SMOL_ERR_CAPACITY, "prompt (plus the positions already cached) exceeds the sequence's KV capacity")
         _capi.check(self.lib.smol_prefill(self._h, C.byref(batch.c), B, C.c_void_p(prompts.data_ptr()),
                                           C.c_void_p(lengths.data_ptr()), s_max, self._stream()))
         for b in range(B):
@@ -360,6 +365,8 @@ class RQTransformer:
             batch.host_len[b] += n_frames
 
     def slow_step(self, batch: DecodeBatch, advance: bool = True) -> None:
+        if advance and max(batch.host_len) + 1 > batch.capacity:
+            raise _capi.SmolError(_capi.SMOL_ERR_CAPACITY, f"one more position exceeds the KV capacity {batch.capacity} of the batch")
         _capi.check(self.lib.smol_slow_step(self._h, C.byref(batch.c), batch.batch, int(advance), self._stream()))
         if advance:
             for b in range(batch.batch):

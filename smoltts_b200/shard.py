@@ -47,3 +47,116 @@ def max_over_ranks(values: Sequence[float], dist=None, device=None) -> List[floa
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(v) for v in t.tolist()]
+
+
+# ------------------------------------------------------------------------------------------------
+# Product entry point: one worker process per GPU, utterances sharded, codes gathered on the caller
+# ------------------------------------------------------------------------------------------------
+def _engine_from_spec(spec: dict, device_index: int):
+    """Default worker factory: the CUDA engine on `device_index`, weights from a checkpoint directory
+    (``{"path": ...}``, reference layout: config.json + model.safetensors) or seeded synthetic weights
+    (``{"model": "smoltts_byte_150m", "seed": 0}``, benchmarks / tests)."""
+    import torch
+
+    from .config import named_config
+    from .model import RQTransformer
+    from .synth import make_state_dict
+
+    torch.cuda.set_device(device_index)
+    kw = dict(spec.get("engine", {}))
+    if "path" in spec:
+        return RQTransformer.from_pretrained(spec["path"], **kw)
+    cfg = named_config(spec["model"])
+    model = RQTransformer(cfg, **kw)
+    model.load_state_dict(make_state_dict(cfg, seed=int(spec.get("seed", 0))))
+    return model
+
+
+def _default_run(engine, prompts, settings, seq_ids, kwargs):
+    from .generate import generate_batch
+
+    return generate_batch(engine, prompts, settings, seq_ids=seq_ids, **kwargs)
+
+
+def _worker_main(rank: int, spec: dict, factory, run, tasks, results):
+    try:
+        engine = factory(spec, rank)
+        results.put((rank, "ready", None))
+    except Exception as e:  # the caller re-raises: a GPU without the CUDA library must fail loudly, not idle
+        results.put((rank, "error", repr(e)))
+        return
+    while True:
+        job = tasks.get()
+        if job is None:
+            return
+        job_id, prompts, settings, seq_ids, kwargs = job
+        try:
+            outs = run(engine, prompts, settings, seq_ids, kwargs) if prompts else []
+            results.put((rank, job_id, [t.cpu().contiguous() for t in outs]))
+        except Exception as e:
+            results.put((rank, "error", repr(e)))
+
+
+class ShardedGenerator:
+    """``gpus`` worker processes, each with a full weight replica and a private KV pool on its own GPU (SURVEY 8(e):
+    the path shards by utterance, no collective on the decode path).  ``generate`` gives worker r the contiguous
+    slice ``partition(len(prompts), gpus)[r]`` (``seq_id`` = global utterance index, so sampling does not depend on
+    the sharding) and returns every utterance's codes in the caller's order."""
+
+    def __init__(self, spec: dict, gpus: int, factory=_engine_from_spec, run=_default_run, start_method: str = "spawn"):
+        import torch.multiprocessing as mp
+
+        if gpus < 1:
+            raise ValueError("gpus must be >= 1")
+        self.gpus = gpus
+        ctx = mp.get_context(start_method)
+        self._results = ctx.Queue()
+        self._tasks = [ctx.Queue() for _ in range(gpus)]
+        self._procs = [ctx.Process(target=_worker_main, args=(r, spec, factory, run, self._tasks[r], self._results), daemon=True)
+                       for r in range(gpus)]
+        for p in self._procs:
+            p.start()
+        self._job = 0
+        for _ in range(gpus):
+            rank, tag, err = self._results.get()
+            if tag == "error":
+                self.close()
+                raise RuntimeError(f"worker {rank} failed to start: {err}")
+
+    def generate(self, prompts: Sequence[torch.Tensor], settings, **kwargs) -> List[torch.Tensor]:
+        self._job += 1
+        parts = partition(len(prompts), self.gpus)
+        for r, (lo, hi) in enumerate(parts):
+            self._tasks[r].put((self._job, [p.cpu() for p in prompts[lo:hi]], settings, list(range(lo, hi)), kwargs))
+        got: List[Optional[list]] = [None] * self.gpus
+        for _ in range(self.gpus):
+            rank, tag, payload = self._results.get()
+            if tag == "error":
+                raise RuntimeError(f"worker {rank}: {payload}")
+            assert tag == self._job
+            got[rank] = payload
+        return [t for part in got for t in part]
+
+    def close(self) -> None:
+        for q in self._tasks:
+            try:
+                q.put(None)
+            except Exception:
+                pass
+        for p in self._procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+        self._procs = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def generate_sharded(spec: dict, prompts: Sequence[torch.Tensor], settings, gpus: int, **kwargs) -> List[torch.Tensor]:
+    """One-shot form: start the workers, decode, gather, stop.  ``spec`` as for ``ShardedGenerator``."""
+    with ShardedGenerator(spec, gpus) as g:
+        return g.generate(prompts, settings, **kwargs)

@@ -24,7 +24,10 @@ from smoltts_b200.synth import byte_prompt, prompt_grid
 pytestmark = pytest.mark.gpu
 
 SIZES = ["smoltts_byte_tiny", "smoltts_byte_70m", "smoltts_byte_150m"]
-TAU = 0.25  # logit margin below which bf16 noise may legitimately flip an argmax
+TAU = 0.15  # logit margin below which bf16 noise may legitimately flip an argmax (largest flip margin ever observed: 0.14)
+# share of greedy decisions that must be identical to the oracle's BEFORE any resync: the rate measured on the B200
+# (DESIGN.md "Parity") minus a margin of ~2 decisions
+MIN_EXACT = {"smoltts_byte_tiny": 0.97, "smoltts_byte_70m": 0.94, "smoltts_byte_150m": 0.91}
 
 
 def _teacher_forced(model, grid, t0):
@@ -119,9 +122,11 @@ def test_greedy_with_resync_vs_oracle(size):
         model.set_force(None)
         batch.release()
     total = n_frames * cfg.n_rows
-    print(f"{size}: {exact}/{total} greedy decisions identical; flips (frame,row,oracle margin): {flips}")
+    first = (f"first divergence at frame {flips[0][0]} row {flips[0][1]} (decision {flips[0][0] * cfg.n_rows + flips[0][1]} of {total}), "
+             f"oracle margin {flips[0][2]:.4f}") if flips else "no divergence"
+    print(f"{size}: {exact}/{total} greedy decisions identical; {first}; flips (frame,row,oracle margin): {flips}")
     assert all(m <= TAU for _, _, m in flips), f"argmax flipped at a confident decision: {flips}"
-    assert exact >= 0.9 * total
+    assert exact >= MIN_EXACT[size] * total, f"{exact}/{total} identical decisions, below the measured rate"
 
 
 @pytest.mark.parametrize("size", ["smoltts_byte_tiny", "smoltts_byte_70m"])

@@ -19,7 +19,7 @@ from smoltts_b200.synth import byte_prompt, prompt_grid
 
 pytestmark = pytest.mark.gpu
 
-TAU = 0.25
+TAU = 0.15
 
 
 @pytest.mark.parametrize("size", ["smoltts_byte_tiny", "smoltts_byte_70m", "smoltts_byte_150m"])
@@ -65,7 +65,7 @@ def test_tc_greedy_with_resync_vs_oracle(size):
     total = B * n_frames * cfg.n_rows
     print(f"{size}: {exact}/{total} greedy decisions identical; flips (seq,frame,row,oracle margin): {flips}")
     assert all(m <= TAU for *_, m in flips), f"argmax flipped at a confident decision: {flips}"
-    assert exact >= 0.9 * total
+    assert exact >= 0.915 * total, f"{exact}/{total} identical decisions: below the measured rate (150m: 804/864 = 0.93)"
 
 
 def _bits(t):
@@ -241,4 +241,4 @@ def test_tc_depth7_without_duplicate_code_0():
         model.set_force(None)
         batch.release()
     assert all(m <= TAU for *_, m in flips), f"argmax flipped at a confident decision: {flips}"
-    assert exact >= 0.9 * B * n_frames * cfg.n_rows
+    assert exact >= 0.915 * B * n_frames * cfg.n_rows

@@ -85,3 +85,34 @@ def test_two_rank_sharding_matches_single_process():
     assert sorted(i for r in results for i in r[2]) == [0, 1, 2, 3, 4]
     want = _decode_slice(_all_prompts(), list(range(5)), n_frames)
     assert codes == [w.tolist() for w in want]
+
+
+# ---- the product entry point (ShardedGenerator / generate_sharded) with a CPU stand-in engine ----------------------
+def _oracle_factory(spec, rank):
+    torch.set_num_threads(1)
+    return {"rank": rank, "frames": spec["frames"]}
+
+
+def _oracle_run(engine, prompts, settings, seq_ids, kwargs):
+    return _decode_slice(prompts, seq_ids, engine["frames"])
+
+
+@pytest.mark.timeout(300)
+def test_sharded_generator_orders_and_gathers_like_one_process():
+    """Two worker processes behind ShardedGenerator (the CPU oracle standing in for the CUDA engine): utterances come back
+    in the caller's order with the ids of a single-process run; a second call reuses the workers; an empty shard is fine."""
+    from smoltts_b200.shard import ShardedGenerator
+
+    prompts = _all_prompts()
+    want = [w.tolist() for w in _decode_slice(prompts, list(range(5)), 2)]
+    with ShardedGenerator({"frames": 2}, gpus=2, factory=_oracle_factory, run=_oracle_run) as g:
+        assert [t.tolist() for t in g.generate(prompts, None)] == want
+        assert [t.tolist() for t in g.generate(prompts[:1], None)] == want[:1]   # worker 1 gets an empty slice
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box WITHOUT a CUDA device")
+def test_sharded_generator_fails_loudly_when_a_worker_cannot_start():
+    from smoltts_b200.shard import ShardedGenerator
+
+    with pytest.raises(RuntimeError, match="failed to start"):
+        ShardedGenerator({"model": "smoltts_byte_tiny"}, gpus=1)   # default factory: needs a CUDA device, there is none here

@@ -36,9 +36,9 @@ from tools.make_init import write_init  # noqa: E402
 
 SPEC = {
     # size: (n_text, n_audio, batch, greedy_prompt_bytes, greedy_frames)
-    "smoltts_byte_tiny": (20, 10, 2, 12, 8),
-    "smoltts_byte_70m": (28, 8, 2, 12, 6),
-    "smoltts_byte_150m": (28, 8, 1, 12, 4),
+    "smoltts_byte_tiny": (20, 10, 2, 12, 16),
+    "smoltts_byte_70m": (28, 8, 2, 12, 16),
+    "smoltts_byte_150m": (28, 8, 2, 12, 16),
 }
 SUB = 8  # fp32 logits are stored at every SUB-th vocabulary entry
 

@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../smoltts_b200/csrc/tmap_host.h"
-#include "../../smoltts_b200/csrc/umma.cuh"
+#include "umma_legacy.cuh"  // product umma.cuh + the retired tile forms
 
 using namespace smol;
 
@@ -42,12 +42,12 @@ umma_test_kernel(const uint16_t* A, const uint16_t* B, float* C, int K, int n_bl
             // maps[1]: weight boxes of n_blk rows, maps[2]: of n_blk / 2 rows (the paired halves)
             b0.tm = maps + (paired ? 2 : 1); b0.row0 = t * n_blk; b0.n = paired ? n_blk / 2 : n_blk; b0.box = b0.n;
             b1.tm = maps + 2; b1.row0 = t * n_blk + n_blk / 2; b1.n = paired ? n_blk / 2 : 0; b1.box = n_blk / 2;
-            if (variant == 3) umma::tile_mma_tma<NT, false, decltype(xform), 1>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
-            else if (variant == 4) umma::tile_mma_tma<NT, false, decltype(xform), 2>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
-            else if (variant == 5) umma::tile_mma_tma<NT, false, decltype(xform), 4>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
-            else if (variant == 6) umma::tile_mma_tma<NT, false, decltype(xform), 8>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
-            else if (xf) umma::tile_mma_tma<NT, true>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
-            else umma::tile_mma_tma<NT, false>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            if (variant == 3) umma::tile_mma_tma_exp<NT, false, decltype(xform), 1>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (variant == 4) umma::tile_mma_tma_exp<NT, false, decltype(xform), 2>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (variant == 5) umma::tile_mma_tma_exp<NT, false, decltype(xform), 4>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (variant == 6) umma::tile_mma_tma_exp<NT, false, decltype(xform), 8>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else if (xf) umma::tile_mma_tma_exp<NT, true, decltype(xform), 0>(ring, &bars, pipe, K, maps, 0, b0, b1, xform);
+            else umma::tile_mma_tma<NT>(ring, &bars, pipe, K, maps, 0, b0, b1);
         } else if (variant == 1) {  // cp.async staging (kept for the A/B timing)
             if (xf) umma::tile_mma_cpasync<NT, true>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
             else umma::tile_mma_cpasync<NT, false>(ring, &bars, pipe, K, n_blk, row_a, row_b, xform);
