@@ -33,6 +33,13 @@ cudaError_t ll_configure(int bt, size_t smem);
 cudaError_t ll_max_ctas(int bt, size_t smem, int* per_sm);
 cudaError_t ll_launch(const DevModel& M, const CallArgs& A, int bt, int n_ctas, size_t smem, int xs_bytes, int res_bytes,
                       int scratch_bytes, int ring_bytes, cudaStream_t stream);
+// second-generation data-flow kernel (ll2_kernel.cu)
+namespace ll2 { using SmemPlan = LL2SmemPlan; }
+bool ll2_plan(const DevModel& M, int holdoff, int flags, ll2::SmemPlan* sp, size_t* smem);
+cudaError_t ll2_configure(size_t smem);
+cudaError_t ll2_max_ctas(size_t smem, int* per_sm);
+cudaError_t ll2_launch(const DevModel& M, const CallArgs& A, const ll2::SmemPlan& sp, size_t smem, int n_ctas, cudaStream_t stream);
+cudaError_t ll2_pack_launch(uint16_t* dst, const uint16_t* a, const uint16_t* b, int rows, int K, cudaStream_t stream);
 }  // namespace smol
 
 using smol::CallArgs;
@@ -63,6 +70,14 @@ struct SmolModel {
     int tc_min_batch = 9;  // rows (sequences, or prompt positions of a prefill tile) from which the tcgen05 variant runs:
                            // measured crossover (150m, us per frame): bs 8: 2276 CUDA-core vs 2566 tensor-core; bs 12: 3642 vs 2577
     int ll_flags = 0;  // data-flow kernel: A/B switches and hold-off override (tools/ll_ncu.py)
+    // second-generation data-flow kernel
+    int ll_version = 2;        // option: 1 = first-generation kernel (A/B), 2 = ll2_kernel.cu
+    int ll2_state = 0;         // 0 unknown, 1 ready, -1 does not fit this model
+    int ll2_holdoff = 400;     // option "ll_holdoff": cycles between the end of a phase and the first poll of the next
+    int ll2_max_batch = 1;     // option: sequences (teams of CTAs) the kernel carries per launch
+    smol::ll2::SmemPlan ll2_sp;
+    size_t ll2_smem = 0;
+    bool packed_ready = false; // tensor-core GEMV layout of the bound weights (rebuilt after a weight / workspace bind)
     int64_t launches = 0;
     // mode 1: cached CUDA graph of one frame
     cudaGraphExec_t frame_graph = nullptr;
@@ -95,10 +110,10 @@ static int imax(int a, int b) { return a > b ? a : b; }
 
 struct WsLayout {
     size_t x, h, xf, q, attn, act, xn, silu_lut, tmaps, kpart, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
-    size_t ll, ll_partial, ll_tok, ll_cand, ll_epoch, total;
+    size_t ll, ll_partial, ll_tok, ll_cand, ll_epoch, ll2_score, ll2_tok, ll2_cand, packed, total;
 };
 
-static int ll_batch_of(const SmolConfig& c) { (void)c; return smol::kLLMaxBatch; }
+static int ll_batch_of(const SmolConfig& c) { (void)c; return smol::kLL2MaxTeams; }  // word regions for up to 8 teams
 
 // Word offsets of every phase's LL region for `bl` sequences x kLLRep replicas; returns the total words.
 static size_t ll_regions(const SmolConfig& c, int depth, int bl, uint32_t* off, uint16_t* len) {
@@ -115,6 +130,16 @@ static size_t ll_regions(const SmolConfig& c, int depth, int bl, uint32_t* off, 
         words += (size_t)n * bl * smol::kLLRep;
     }
     return words;
+}
+
+static int ll2_score_len(const SmolConfig& c) { return (c.max_seq_len + 511) / 512 * 512; }
+// every GEMV matrix once more, in the tensor-core GEMV layout of the second-generation data-flow kernel
+static size_t packed_bytes(const SmolConfig& c, int depth) {
+    auto layer = [](size_t qkv_rows, size_t D, size_t F) { return (qkv_rows * D + D * D + 3 * D * F) * 2; };
+    const size_t slow = layer((size_t)(c.n_head + 2 * c.n_local_heads) * 64, c.dim, c.intermediate_size);
+    const size_t fast = layer((size_t)(c.fast_n_head + 2 * c.fast_n_local_heads) * 64, c.fast_dim, c.fast_intermediate_size);
+    const size_t heads = ((size_t)c.vocab_size * c.dim + (size_t)c.codebook_size * (c.depthwise_output ? depth : 1) * c.fast_dim) * 2;
+    return c.n_layer * align_up(slow, 256) + c.n_fast_layer * align_up(fast, 256) + align_up(heads, 256) + 4096;
 }
 
 // Rows of the activation workspace: a prefill iteration carries up to this many prompt positions (one tensor-core tile).
@@ -155,6 +180,10 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.ll_tok = take((size_t)bl * (1 + depth) * smol::kLLMaxCtas * 8);
     L.ll_cand = take((size_t)(1 + depth) * smol::kLLRep * smol::kLLMaxCtas * 8);
     L.ll_epoch = take(256);
+    L.ll2_score = take((size_t)bl * 2 * c.n_head * ll2_score_len(c) * 8);
+    L.ll2_tok = take((size_t)bl * (1 + depth) * smol::kLLMaxCtas * 8);
+    L.ll2_cand = take((size_t)bl * (1 + depth) * smol::kLLRep * smol::kLLMaxCtas * 8);
+    L.packed = take(packed_bytes(c, depth));
     L.total = off;
     return L;
 }
@@ -162,6 +191,7 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
 static int depth_of(const SmolConfig& c) { return c.num_codebooks - (c.duplicate_code_0 ? 0 : 1); }
 
 static int ensure_tmaps(SmolModel* m);
+static int ensure_packed(SmolModel* m);
 
 extern "C" {
 
@@ -257,8 +287,12 @@ int smol_bind_weights(SmolModel* m, const SmolWeights* w) {
     m->weights_bound = true;
     m->tmaps_ready = false;
     m->frame_key_valid = false;
-    // tensor maps are built here, at setup time (a synchronous copy): compute calls stay asynchronous and capturable
-    if (m->ws_bound) return ensure_tmaps(m);
+    m->packed_ready = false;
+    // tensor maps and the packed GEMV layout are built here, at setup time: compute calls stay asynchronous and capturable
+    if (m->ws_bound) {
+        const int rc = ensure_tmaps(m);
+        return rc ? rc : ensure_packed(m);
+    }
     return SMOL_OK;
 }
 
@@ -289,13 +323,19 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     d.ll = (unsigned long long*)(base + L.ll); d.ll_partial = (unsigned long long*)(base + L.ll_partial);
     d.ll_tok = (unsigned long long*)(base + L.ll_tok); d.ll_epoch = (uint32_t*)(base + L.ll_epoch);
     d.ll_cand = (unsigned long long*)(base + L.ll_cand);
+    d.ll2_score = (unsigned long long*)(base + L.ll2_score); d.ll2_tok = (unsigned long long*)(base + L.ll2_tok);
+    d.ll2_cand = (unsigned long long*)(base + L.ll2_cand); d.ll2_score_len = ll2_score_len(m->cfg);
+    m->packed_ready = false;
     // split counters, barrier words and every LL word (epoch 0 = never written) must start at zero
     // (setup-time, synchronous)
-    CU(cudaMemset(base + L.split_count, 0, L.total - L.split_count));
+    CU(cudaMemset(base + L.split_count, 0, L.packed - L.split_count));
     CU(cudaMemset(base + L.frame_tokens, 0, L.partial - L.frame_tokens));
     m->ws_bound = true;
     m->frame_key_valid = false;
-    if (m->weights_bound) return ensure_tmaps(m);
+    if (m->weights_bound) {
+        const int rc = ensure_tmaps(m);
+        return rc ? rc : ensure_packed(m);
+    }
     return SMOL_OK;
 }
 
@@ -329,6 +369,7 @@ static int ensure_configured(SmolModel* m) {
     m->n_ctas = m->n_sms;
     if (m->n_ctas_override > 0 && m->n_ctas_override < m->n_ctas) m->n_ctas = m->n_ctas_override;
     for (int i = 0; i < 9; ++i) { m->tile_ready[i] = false; m->ll_state[i] = 0; }
+    if (m->ll2_state > 0) m->ll2_state = 0;
     m->configured = true;
     return SMOL_OK;
 }
@@ -385,6 +426,59 @@ static int ensure_tmaps(SmolModel* m) {
     return SMOL_OK;
 }
 
+// The bound weights once more in the tensor-core GEMV layout ([8-row group][K / 32][8][32], w1 / w3 groups interleaved),
+// written into the workspace by a device kernel at bind time (setup-time; the borrowed checkpoint tensors stay as they are
+// for the other kernels).
+static int ensure_packed(SmolModel* m) {
+    if (m->packed_ready) return SMOL_OK;
+    const SmolConfig& c = m->cfg;
+    DevModel& d = m->dm;
+    if (c.dim % 32 || c.fast_dim % 32 || c.intermediate_size % 32 || c.fast_intermediate_size % 32 || c.vocab_size % 8 || c.codebook_size % 8) {
+        m->packed_ready = true;   // such a model stays on the other kernels (ll2_plan refuses it)
+        m->ll2_state = -1;
+        return SMOL_OK;
+    }
+    char* ws = reinterpret_cast<char*>(d.x) - ws_layout(c, d.depth).x;
+    char* p = ws + ws_layout(c, d.depth).packed;
+    auto put = [&](const uint16_t* a, const uint16_t* b, int rows, int K) -> const uint16_t* {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(p);
+        p += align_up((size_t)rows * (b ? 2 : 1) * K * 2, 256);
+        return smol::ll2_pack_launch(dst, a, b, rows, K, nullptr) == cudaSuccess ? dst : nullptr;
+    };
+    bool ok = true;
+    for (int f = 0; f < 2; ++f) {
+        const int nl = f ? c.n_fast_layer : c.n_layer, D = f ? c.fast_dim : c.dim, F = f ? c.fast_intermediate_size : c.intermediate_size;
+        const int qkv = ((f ? c.fast_n_head : c.n_head) + 2 * (f ? c.fast_n_local_heads : c.n_local_heads)) * 64;
+        for (int l = 0; l < nl; ++l) {
+            smol::DevLayer& L = f ? d.fast_layers[l] : d.layers[l];
+            L.pk_wqkv = put(L.wqkv, nullptr, qkv, D);
+            L.pk_wo = put(L.wo, nullptr, D, D);
+            L.pk_w13 = put(L.w1, L.w3, F, D);
+            L.pk_w2 = put(L.w2, nullptr, D, F);
+            ok = ok && L.pk_wqkv && L.pk_wo && L.pk_w13 && L.pk_w2;
+        }
+    }
+    d.pk_head = put(d.head, nullptr, c.vocab_size, c.dim);
+    d.pk_fast_output = put(d.fast_output, nullptr, c.codebook_size * (c.depthwise_output ? d.depth : 1), c.fast_dim);
+    ok = ok && d.pk_head && d.pk_fast_output;
+    if (!ok) return fail(SMOL_ERR_CUDA, "packing the weights for the data-flow kernel failed");
+    CU(cudaDeviceSynchronize());   // setup-time only
+    m->packed_ready = true;
+    m->frame_key_valid = false;
+    return SMOL_OK;
+}
+
+static int ensure_ll2(SmolModel* m) {
+    if (m->ll2_state != 0) return SMOL_OK;
+    m->ll2_sp = smol::ll2::SmemPlan();
+    if (!smol::ll2_plan(m->dm, m->ll2_holdoff, m->ll_flags, &m->ll2_sp, &m->ll2_smem) || m->n_ctas > 7 * 32) { m->ll2_state = -1; return SMOL_OK; }
+    CU(smol::ll2_configure(m->ll2_smem));
+    int per_sm = 0;
+    CU(smol::ll2_max_ctas(m->ll2_smem, &per_sm));
+    m->ll2_state = per_sm >= 1 ? 1 : -1;
+    return SMOL_OK;
+}
+
 // Shared-memory budget and function attributes of the kernel variant for this batch tile.
 static int ensure_tile(SmolModel* m, int bt) {
     if (bt == 0) {
@@ -436,7 +530,20 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
     int rc;
     A.repeat = m->repeat;
     A.tc_split = m->tc_attn_split;
-    if (m->mode == 2 && whole_iters && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
+    if (m->mode == 2 && whole_iters && A.mode == 0 && m->ll_version == 2 && A.batch <= m->ll2_max_batch && A.batch <= smol::kLL2MaxTeams &&
+        A.batch <= m->n_ctas) {
+        if ((rc = ensure_ll2(m))) return rc;
+        if (m->ll2_state == 1) {
+            if (A.n_iter == 0) return SMOL_OK;
+            A.team_ctas = m->n_ctas / A.batch;
+            m->ll2_sp.holdoff = m->ll2_holdoff;
+            m->ll2_sp.flags = m->ll_flags;
+            CU(smol::ll2_launch(m->dm, A, m->ll2_sp, m->ll2_smem, A.team_ctas * A.batch, stream));
+            m->launches += 1;
+            return SMOL_OK;
+        }
+    }
+    if (m->mode == 2 && whole_iters && m->ll_version == 1 && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
         if ((rc = ensure_ll_tile(m, bt))) return rc;
         if (m->ll_state[bt] == 1) {
             if (A.n_iter == 0 && !A.finalize) return SMOL_OK;
@@ -717,6 +824,20 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
         m->ll_flags = (int)value;
         return SMOL_OK;
     }
+    if (!std::strcmp(name, "ll_version")) {
+        if (value != 1 && value != 2) return fail(SMOL_ERR_INVALID, "ll_version must be 1 or 2");
+        m->ll_version = (int)value;
+        return SMOL_OK;
+    }
+    if (!std::strcmp(name, "ll_holdoff")) {
+        m->ll2_holdoff = value > 0 ? (int)value : 0;
+        return SMOL_OK;
+    }
+    if (!std::strcmp(name, "ll_max_batch")) {
+        if (value < 0 || value > smol::kLL2MaxTeams) return fail(SMOL_ERR_INVALID, "ll_max_batch must be in [0, 8]");
+        m->ll2_max_batch = (int)value;
+        return SMOL_OK;
+    }
     if (!std::strcmp(name, "n_ctas")) {
         if (value < 0) return fail(SMOL_ERR_INVALID, "n_ctas must be >= 0");
         m->n_ctas_override = (int)value;
@@ -737,8 +858,13 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!std::strcmp(name, "tc_ready")) return m->tile_ready[0] ? 1 : 0;
     if (!std::strcmp(name, "ll_smem_bytes")) return (int64_t)m->ll_smem[1];
     if (!std::strcmp(name, "ll_ring_bytes")) return (int64_t)m->ll_ring[1];
-    if (!std::strcmp(name, "ll_ready")) return (int64_t)m->ll_state[1];
-    if (!std::strcmp(name, "ll_max_batch")) return (int64_t)m->dm.ll_batch;
+    if (!std::strcmp(name, "ll_ready")) return (int64_t)(m->ll_version == 2 ? m->ll2_state : m->ll_state[1]);
+    if (!std::strcmp(name, "ll_max_batch")) return (int64_t)(m->ll_version == 2 ? m->ll2_max_batch : 1);
+    if (!std::strcmp(name, "ll1_ready")) return (int64_t)m->ll_state[1];
+    if (!std::strcmp(name, "ll_version")) return (int64_t)m->ll_version;
+    if (!std::strcmp(name, "ll_holdoff")) return (int64_t)m->ll2_holdoff;
+    if (!std::strcmp(name, "ll2_smem_bytes")) return (int64_t)m->ll2_smem;
+    if (!std::strcmp(name, "ll2_slots")) return (int64_t)m->ll2_sp.n_slots;
     return -1;
 }
 

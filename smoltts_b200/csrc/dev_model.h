@@ -28,6 +28,26 @@ constexpr int kLLMaxBatch = 1;         // sequences the data-flow kernel carries
 constexpr int kLLRep = 8;              // replicas of every broadcast vector (spreads the polls over L2 slices)
 constexpr int kLLMaxCtas = 256;        // token words are published once per CTA
 
+// ---- data-flow kernel, second generation (ll2_kernel.cu): tensor-core GEMV, team of CTAs per sequence ----
+constexpr int kLL2Warps = 7;             // consumer warps; the 8th warp streams the weights.  8 warps = 2 per scheduler: up to 255
+                                         // registers per thread (a 9th warp caps the kernel at 168 and the main loop spills -- and a
+                                         // spill is an L2 round trip here, the L1 being what 220 KB of shared memory leave)
+constexpr int kLL2Threads = (kLL2Warps + 1) * 32;
+constexpr int kLL2MaxTeams = 8;          // sequences one launch can carry (one team of CTAs each)
+constexpr int kLL2ChunkKb = 24;          // k-blocks (of 32 elements) per ring stage
+constexpr int kLL2SlotBytes = 2 * kLL2ChunkKb * 512;  // one ring slot: a tile of 2 x 8 rows x 24 k-blocks = 24 KB
+constexpr int kLL2ScoreBlock = 64;       // cached positions per attention score unit
+constexpr int kLL2AttnBlock = 512;       // positions per softmax block (the reference's CPU SDPA kernel: kvSplitSize)
+constexpr int kLL2PvDims = 8;            // head dims per PV unit
+constexpr int kLL2Depth = 8;             // depth positions whose K/V the kernel keeps in shared memory
+
+struct LL2SmemPlan {   // second-generation data-flow kernel: byte offsets into dynamic shared memory + launch-time knobs
+    int xbuf, res_x, res_h, part, desc, fq, fkv, scratch, ring;
+    int n_slots;
+    int holdoff;       // cycles between the end of a phase and the first poll of the next
+    int flags;         // experiment switches
+};
+
 struct DevLayer {
     const uint16_t* wqkv;
     const uint16_t* wo;
@@ -36,6 +56,12 @@ struct DevLayer {
     const uint16_t* w2;
     const uint16_t* attention_norm;
     const uint16_t* ffn_norm;
+    // tensor-core GEMV layout of the same matrices (ll2_kernel.cu; packed at bind time into the workspace):
+    // [group of 8 rows][K / 32][8 rows][32 elements]; pk_w13 interleaves the groups of w1 (even) and w3 (odd)
+    const uint16_t* pk_wqkv;
+    const uint16_t* pk_wo;
+    const uint16_t* pk_w13;
+    const uint16_t* pk_w2;
 };
 
 struct DevModel {
@@ -102,6 +128,14 @@ struct DevModel {
     uint32_t ll_step_words;          // words between the regions of the same phase of two consecutive depth steps
     uint32_t ll_off[kMaxProg];
     uint16_t ll_len[kMaxProg];
+
+    // second-generation data-flow kernel
+    const uint16_t* pk_head;         // packed LM head
+    const uint16_t* pk_fast_output;  // packed depth heads (row groups in checkpoint order)
+    unsigned long long* ll2_score;   // attention scores {fp32 bits, epoch} [teams][2][n_head][ll2_score_len] words
+    unsigned long long* ll2_tok;     // sampled ids [teams][n_rows][kLLMaxCtas] words
+    unsigned long long* ll2_cand;    // greedy candidates [teams][n_rows][kLLRep][kLLMaxCtas] words
+    int ll2_score_len;
 };
 
 // Words (8 bytes, two bf16 + epoch) one sequence publishes in a phase; multiples of 16 words (128 B).
@@ -140,6 +174,7 @@ struct CallArgs {
     int tc_part;      // tensor-core variant, one phase per launch: 1 = only the phase's distributed pre-step, 2 = only its tiles,
                       // 3 = only its post-step (0 = the whole phase: cooperative launches)
     int tc_split;     // tensor-core variant: cached positions per attention split (0 = default)
+    int team_ctas;    // second-generation data-flow kernel: CTAs per sequence (one team each); grid = batch * team_ctas
     const int32_t* prompt;      // prefill: [B][n_rows][s_max]
     const int32_t* prompt_len;  // prefill: [B]
     int s_max;

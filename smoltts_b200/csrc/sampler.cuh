@@ -92,8 +92,8 @@ __device__ __forceinline__ int block_argmax(const float* lg, int n, SampleScratc
     return ti;
 }
 
-// All NT threads call this.  lg: shared memory, n <= NT * kSampleMaxPerThread.
-template <int NT>
+// All NT threads call this.  lg: shared memory, n <= NT * kSampleMaxPerThread (template parameter: entries per thread).
+template <int NT, int kSampleMaxPerThread = smol::kSampleMaxPerThread>
 static __device__ __forceinline__ int sample_row(const float* lg, int n, float temp, int top_k, float top_p, float min_p,
                           unsigned long long seed, uint32_t step, uint32_t seq_id, uint32_t stream,
                           SampleScratch& sc) {

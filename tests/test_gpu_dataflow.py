@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def _run(model, mode, prompts, n_frames, chunk, seq_ids, **skw):
     model.set_option("mode", mode)
+    model.set_option("ll_version", 1)   # this file pins the FIRST-generation data-flow kernel (same summation order as the barrier kernel)
     try:
         B = len(prompts)
         padded, lens = pack_prompts(model, prompts)
@@ -41,6 +42,7 @@ def _run(model, mode, prompts, n_frames, chunk, seq_ids, **skw):
         return out
     finally:
         model.set_option("mode", 2)
+        model.set_option("ll_version", 2)
 
 
 def _same(a, b, what):
@@ -69,7 +71,7 @@ def test_dataflow_equals_barrier_kernel_greedy(size, B, n_prompt, n_frames, chun
     ids = list(range(3, 3 + B))
     ref = _run(model, 0, prompts, n_frames, chunk, ids)
     got = _run(model, 2, prompts, n_frames, chunk, ids)
-    assert model.get_option("ll_ready") == 1 or B > 1
+    assert model.get_option("ll1_ready") == 1 or B > 1
     _same(ref, got, f"{size} B={B}")
 
 
@@ -91,7 +93,7 @@ def test_dataflow_long_context_many_splits(size, n_prompt):
     prompts = [prompt_grid(byte_prompt(n_prompt, seed=70), cfg)]
     ref = _run(model, 0, prompts, 6, 6, None)
     got = _run(model, 2, prompts, 6, 6, None)
-    assert model.get_option("ll_ready") == 1
+    assert model.get_option("ll1_ready") == 1
     _same(ref, got, f"long context {size} {n_prompt}")
 
 
@@ -102,7 +104,7 @@ def test_dataflow_depth7_without_duplicate_code_0():
     prompts = [prompt_grid(byte_prompt(30, seed=75), cfg)]
     ref = _run(model, 0, prompts, 10, 4, None)
     got = _run(model, 2, prompts, 10, 4, None)
-    assert model.get_option("ll_ready") == 1
+    assert model.get_option("ll1_ready") == 1
     _same(ref, got, "depth 7")
 
 
@@ -134,6 +136,7 @@ def test_dataflow_stop_rule_single_sequence():
     res = {}
     for mode in (0, 2):
         model.set_option("mode", mode)
+        model.set_option("ll_version", 1)
         padded, lens = pack_prompts(model, prompts)
         batch = model.new_batch(1, max_positions=64, max_frames=8)
         try:
@@ -151,6 +154,7 @@ def test_dataflow_stop_rule_single_sequence():
         finally:
             model.set_force(None)
             model.set_option("mode", 2)
+            model.set_option("ll_version", 2)
             batch.release()
     assert res[0][3].tolist() == [1] and res[0][2].tolist() == [2]
     for a, b in zip(res[0], res[2]):
@@ -184,6 +188,7 @@ def test_dataflow_stop_rule_and_force():
         finally:
             model.set_force(None)
             model.set_option("mode", 2)
+            model.set_option("ll_version", 2)
             batch.release()
     assert res[0][3].tolist() == [0, 1] and res[0][2].tolist() == [6, 2]
     for a, b in zip(res[0], res[2]):
@@ -220,6 +225,7 @@ def test_prefill_tiles_and_kernels_write_identical_kv(size, lens):
     got = []
     for mode, tile in variants:
         model.set_option("mode", mode)
+        model.set_option("ll_version", 1)
         model.set_option("prefill_tile", tile)
         padded, lens_t = pack_prompts(model, prompts)
         batch = model.new_batch(B, max_positions=128, max_frames=4)
@@ -232,6 +238,7 @@ def test_prefill_tiles_and_kernels_write_identical_kv(size, lens):
             got.append((model.kv_view()[pages].clone(), batch.seq_len.clone(), batch.tokens.clone(), batch.out_codes.clone()))
         finally:
             model.set_option("mode", 2)
+            model.set_option("ll_version", 2)
             model.set_option("prefill_tile", 0)
             batch.release()
     assert got[0][1].tolist() == [n + 12 - 1 + 2 for n in lens]
