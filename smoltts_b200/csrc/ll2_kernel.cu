@@ -43,7 +43,6 @@ constexpr int kCons = kNW * 32;
 constexpr int kMaxSlots = 8;
 constexpr int kDescWords = 16;
 constexpr int kGather = 4;        // 16-byte polls per thread and vector: 2 words x 224 threads x 4 = 1792 words >= K 3072 / 2
-constexpr int kFrag = 4;          // k-blocks of a 24-block stage one warp carries at most (24 / 7 rounded up)
 constexpr int kMaxBlocks = 16;    // softmax blocks of 512 positions a PV unit carries (contexts up to 8192)
 constexpr int kMaxSeg = kMaxBlocks * 8;  // 64-position segments of a context
 constexpr int kBtabCache = 256;
@@ -112,6 +111,17 @@ __device__ __forceinline__ uint2 ld_relaxed_v2(const void* p) {
 }
 __device__ __forceinline__ void st_relaxed_v2(void* p, uint32_t a, uint32_t b) {
     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+// read-only loads the compiler may not move (issued early so that their latency hides behind a wait)
+__device__ __forceinline__ uint2 ldnc_v2(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ldnc_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ uint32_t ll_get(const unsigned long long* w, uint32_t epoch) {
     uint2 v = ld_relaxed_v2(w);
@@ -559,9 +569,10 @@ __device__ __forceinline__ unsigned long long* score_words(const DevModel& M, co
     return M.ll2_score + (((size_t)tm.team * 2 + (layer & 1)) * M.n_head + hq) * (size_t)M.ll2_score_len;
 }
 __device__ __forceinline__ const uint16_t* kv_row(const DevModel& M, const Seq& sq, int layer, int is_v, int kvh, int pos) {
-    const int ps = M.page_size, pg = pos / ps;
+    const int sh = M.page_size == 32 ? 5 : 4;   // pages of 16 or 32 positions (smol_create): no integer division here
+    const int pg = pos >> sh;
     const int page = pg < kBtabCache ? s_btab[pg] : ldcg_i32(sq.btab + pg);
-    return M.kv_pool + ((((size_t)page * M.n_layer + layer) * 2 + is_v) * M.n_kv + kvh) * ((size_t)ps * kHeadDim) + (size_t)(pos % ps) * kHeadDim;
+    return M.kv_pool + (((((size_t)page * M.n_layer + layer) * 2 + is_v) * M.n_kv + kvh) << (sh + 6)) + (size_t)(pos & ((1 << sh) - 1)) * kHeadDim;
 }
 
 __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, const Team tm, int layer, int p,
@@ -590,14 +601,11 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
         const int p1 = min(Lb, p0 + kLL2ScoreBlock);
         const int chunk = tid & 7;
         uint4 kk[kRounds];
-        bool valid[kRounds], newest[kRounds];
 #pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
+        for (int r = 0; r < kRounds; ++r) {   // cached keys: in flight before q arrives
             const int pos = p0 + (tid >> 3) + kPosPerRound * r;
-            valid[r] = pos < p1;
-            newest[r] = valid[r] && pos == pos_new;
             kk[r] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid[r] && !newest[r]) kk[r] = ldcg_v4(kv_row(M, sq, layer, 0, kvh, pos) + chunk * 8);   // in flight before q arrives
+            if (pos < p1 && pos != pos_new) kk[r] = ldcg_v4(kv_row(M, sq, layer, 0, kvh, pos) + chunk * 8);
         }
         // q of the group's heads (G * 32 words): one 16-byte poll per thread; pre-scaled by 1/sqrt(64) (exact)
         if (tid < G * 16) {
@@ -609,9 +617,9 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
                    make_uint4(__float_as_uint(bf_lo(v.x) * 0.125f), __float_as_uint(bf_hi(v.x) * 0.125f),
                               __float_as_uint(bf_lo(v.z) * 0.125f), __float_as_uint(bf_hi(v.z) * 0.125f)));
         }
-#pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            if (newest[r]) {  // the newest position's key comes from the QKV phase's words
+        {   // the newest position's key comes from the QKV phase's words (at most one round of 8 threads owns it)
+            const int rel = pos_new - p0 - (tid >> 3);
+            if (pos_new < p1 && rel >= 0 && rel % kPosPerRound == 0 && rel / kPosPerRound < kRounds) {
                 const unsigned long long* kp = qkv + q_words + kvh * 32 + chunk * 4;
                 uint4 a = ld_relaxed_v4(kp), b = ld_relaxed_v4(kp + 2);
                 uint32_t spins = 0;
@@ -619,7 +627,11 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
                     LL2_SPIN_GUARD(spins);
                     a = ld_relaxed_v4(kp); b = ld_relaxed_v4(kp + 2);
                 }
-                kk[r] = make_uint4(a.x, a.z, b.x, b.z);
+                const uint4 kn = make_uint4(a.x, a.z, b.x, b.z);
+                const int rn = rel / kPosPerRound;
+#pragma unroll
+                for (int r = 0; r < kRounds; ++r)
+                    if (r == rn) kk[r] = kn;
             }
         }
         csync();
@@ -628,6 +640,7 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
             float kf[8];
             unpack8(kk[r], kf);
             const int pos = p0 + (tid >> 3) + kPosPerRound * r;
+#pragma unroll 1
             for (int h = 0; h < G; ++h) {
                 const uint32_t qa = scratch + (uint32_t)(h * kHeadDim + chunk * 8) * 4u;
                 const uint4 q0 = lds_v4(qa), q1 = lds_v4(qa + 16u);
@@ -639,7 +652,7 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
                 sc += __shfl_xor_sync(0xffffffffu, sc, 1);
                 sc += __shfl_xor_sync(0xffffffffu, sc, 2);
                 sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-                if (chunk == 0 && valid[r]) st_relaxed_v2(score_words(M, tm, layer, kvh * G + h) + pos, __float_as_uint(sc), epoch);
+                if (chunk == 0 && pos < p1) st_relaxed_v2(score_words(M, tm, layer, kvh * G + h) + pos, __float_as_uint(sc), epoch);
             }
         }
         csync();
@@ -653,29 +666,30 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
     // memory and are added in segment order.
     const int nb = (Lb + kLL2AttnBlock - 1) / kLL2AttnBlock;
     const uint32_t red = scratch + (uint32_t)(nseg * kLL2ScoreBlock) * 4u;   // [segment][8 dims + denominator]
+    const int seg_new = pos_new >> 6;
+    const bool own_new = pos_new < Lb && (seg_new % kNW) == warp && ((pos_new & 63) >> 1) == lane;
     bool waited = false;
     for (int v = tm.cta - (n_su % tm.n); v < n_pv; v += tm.n) {
         if (v < 0) continue;
         const int hq = v / (kHeadDim / kLL2PvDims), ds = v - hq * (kHeadDim / kLL2PvDims), kvh = hq / G;
+        // cached value rows of a segment (the newest position is patched in from the QKV phase's words)
         auto load_v = [&](int sgm, int j) -> uint4 {
             const int pos = sgm * kLL2ScoreBlock + 2 * lane + j;
-            if (sgm >= nseg || pos >= Lb) return make_uint4(0u, 0u, 0u, 0u);
-            if (pos == pos_new) {  // the newest position's value comes from the QKV phase's words
-                const unsigned long long* vp = qkv + k_end_words + kvh * 32 + ds * 4;
-                uint4 a = ld_relaxed_v4(vp), b = ld_relaxed_v4(vp + 2);
-                uint32_t spins = 0;
-                while (a.y != e_qkv || a.w != e_qkv || b.y != e_qkv || b.w != e_qkv) {
-                    LL2_SPIN_GUARD(spins);
-                    a = ld_relaxed_v4(vp); b = ld_relaxed_v4(vp + 2);
-                }
-                return make_uint4(a.x, a.z, b.x, b.z);
-            }
+            if (sgm >= nseg || pos >= Lb || pos == pos_new) return make_uint4(0u, 0u, 0u, 0u);
             return ldcg_v4(kv_row(M, sq, layer, 1, kvh, pos) + ds * kLL2PvDims);
         };
-        // V rows of the first four rounds (1792 positions): in flight before the scores are polled
-        uint4 vv[4][2];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { vv[r][0] = load_v(r * kNW + warp, 0); vv[r][1] = load_v(r * kNW + warp, 1); }
+        uint4 va = load_v(warp, 0), vb = load_v(warp, 1);   // first round: in flight before the scores are polled
+        uint4 vnew = make_uint4(0u, 0u, 0u, 0u);
+        if (own_new) {
+            const unsigned long long* vp = qkv + k_end_words + kvh * 32 + ds * 4;
+            uint4 a = ld_relaxed_v4(vp), b = ld_relaxed_v4(vp + 2);
+            uint32_t spins = 0;
+            while (a.y != e_qkv || a.w != e_qkv || b.y != e_qkv || b.w != e_qkv) {
+                LL2_SPIN_GUARD(spins);
+                a = ld_relaxed_v4(vp); b = ld_relaxed_v4(vp + 2);
+            }
+            vnew = make_uint4(a.x, a.z, b.x, b.z);
+        }
         if (!waited && holdoff > 0) {  // the scores are at least one hand-off away
             const uint32_t t0 = clock32_now();
             while (clock32_now() - t0 < (uint32_t)holdoff) {}
@@ -683,6 +697,7 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
         }
         // scores of this head -> shared memory (fp32), four rounds of polls in flight at a time
         const unsigned long long* sw = score_words(M, tm, layer, hq);
+#pragma unroll 1
         for (int r0 = 0; r0 * kNW < nseg; r0 += 4) {
             uint4 s4[4];
 #pragma unroll
@@ -716,11 +731,16 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
             }
         }
         csync();
-        // the warp walks its segments in ascending order and keeps the running maximum of all blocks up to the current one
+        // the warp walks its segments in ascending order and keeps the running maximum of all blocks up to the current one;
+        // the next segment's value rows are in flight while the current one is reduced
         float m_run = -INFINITY;
         int seg_seen = 0;
-        auto seg_step = [&](int sgm, const uint4& va, const uint4& vb) {
+#pragma unroll 1
+        for (int sgm = warp; sgm < nseg; sgm += kNW) {
+            const uint4 na = load_v(sgm + kNW, 0), nb2 = load_v(sgm + kNW, 1);
+            if (own_new && sgm == seg_new) { if (pos_new & 1) vb = vnew; else va = vnew; }
             const int upto = min(nseg, ((sgm >> 3) + 1) * 8);   // segments of the blocks up to this segment's block
+#pragma unroll 1
             for (; seg_seen < upto; ++seg_seen) m_run = fmaxf(m_run, s_bmax[seg_seen]);
             const int pos = sgm * kLL2ScoreBlock + 2 * lane;
             const uint2 sp = make_uint2(lds_u32(scratch + (uint32_t)pos * 4u), lds_u32(scratch + (uint32_t)pos * 4u + 4u));
@@ -764,15 +784,7 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
             // lane with bits (16, 8, 4) = (b2, b1, b0) holds dim 4 * b2 + 2 * b1 + b0
             if ((lane & 3) == 0) sts_f32(red + (uint32_t)(sgm * 9 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)) * 4u, acc[0]);
             if (lane == 0) sts_f32(red + (uint32_t)(sgm * 9 + 8) * 4u, ls);
-        };
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (r * kNW + warp < nseg) seg_step(r * kNW + warp, vv[r][0], vv[r][1]);
-        }
-#pragma unroll 1
-        for (int sgm = 4 * kNW + warp; sgm < nseg; sgm += kNW) {
-            const uint4 va = load_v(sgm, 0), vb = load_v(sgm, 1);
-            seg_step(sgm, va, vb);
+            va = na; vb = nb2;
         }
         csync();
         if (warp == 0) {
@@ -780,6 +792,7 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
             // (dst = dst * c + PV_b; l = l_b + c * l)
             float dst = 0.f, l = 0.f, m_prev = -INFINITY;
             const int d = lane & 7;
+#pragma unroll 1
             for (int b = 0; b < nb; ++b) {
                 const int s0 = b * 8, s1 = min(nseg, s0 + 8);
                 float bm = -INFINITY, o = 0.f, li = 0.f;
@@ -1003,14 +1016,20 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             const int len_out = (int)(d3.w & 0xffffu), n_src = (int)(d3.w >> 16);
             const int i0 = (int)d3.y;
 
-            // this warp's k-blocks of a full-K stage (normed phases: K = model dim, one stage per tile)
-            const int kb_lo = (kb * warp) / kNW, kb_hi = (kb * (warp + 1)) / kNW;
-            // norm weights of the warp's K slice: independent of the input, in flight during the wait
-            uint4 nwv[kFrag];
-#pragma unroll
-            for (int j = 0; j < kFrag; ++j) {
-                nwv[j] = make_uint4(0u, 0u, 0u, 0u);
-                if (normed && kb_lo + j < kb_hi) nwv[j] = __ldg(reinterpret_cast<const uint4*>(normw + (kb_lo + j) * 32 + c * 8));
+            const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
+            const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
+            // Operands that do not depend on the input are loaded NOW (volatile: the compiler must not sink them below the
+            // wait): the norm weights of the 4 elements this thread will normalise, and -- in the warp that will reduce the
+            // phase's first tile -- the RoPE pair of its row.
+            uint2 nw2 = make_uint2(0u, 0u);
+            if (normed && tid < K / 4) nw2 = ldnc_v2(normw + 4 * tid);
+            uint32_t rope0 = 0u;
+            if (kind == PH_QKV && n_items > 0 && warp == (int)(tile_ctr % kNW) && lane < 16) {
+                const int n = (i0 + (lane >> 3)) * 8 + (lane & 7);
+                if (n < k_end) {
+                    const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)min(s_pos, M.max_seq_len - 1) * kHeadDim);
+                    rope0 = ldnc_u32(table + (n & (kHeadDim - 2)));
+                }
             }
             if (kind == PH_HEAD && tid == 0) s_best = 0u;
 
@@ -1038,26 +1057,23 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                 continue;
             }
 
-            // ---- RMSNorm (P:601-613) of the warp's own K slice, straight into B fragments ----------------------------
-            uint4 bfrag[kFrag];
+            // ---- RMSNorm (P:601-613), in place: every thread normalises four elements of the staged row ------------------
             if (normed) {
                 float t = 0.f;
 #pragma unroll
                 for (int w = 0; w < kNW; ++w) t = __fadd_rn(t, s_ssq[w]);
                 const float mean = __fdiv_rn(t, (float)K);
                 const float rr = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
-#pragma unroll
-                for (int j = 0; j < kFrag; ++j) {
-                    bfrag[j] = make_uint4(0u, 0u, 0u, 0u);
-                    if (kb_lo + j < kb_hi) {
-                        float x[8], wf[8], o[8];
-                        unpack8(lds_v4(XB + (uint32_t)((kb_lo + j) * 32 + c * 8) * 2u), x);
-                        unpack8(nwv[j], wf);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = bf16_round(__fmul_rn(bf16_round(__fmul_rn(x[e], rr)), wf[e]));
-                        bfrag[j] = pack8(o);
-                    }
+                if (tid < K / 4) {
+                    const uint32_t a = XB + (uint32_t)tid * 8u;
+                    const uint32_t x0 = lds_u32(a), x1 = lds_u32(a + 4u);
+                    const float o0 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_lo(x0), rr)), bf_lo(nw2.x)));
+                    const float o1 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_hi(x0), rr)), bf_hi(nw2.x)));
+                    const float o2 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_lo(x1), rr)), bf_lo(nw2.y)));
+                    const float o3 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_hi(x1), rr)), bf_hi(nw2.y)));
+                    sts_v2(a, pack_bf16(o0, o1), pack_bf16(o2, o3));
                 }
+                csync();
             }
             LL2_TRACE(3);
             if (fast && kind == PH_HEAD && depth_pos == M.depth - 1) __threadfence();  // release side of the once-per-frame fence
@@ -1066,12 +1082,11 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             const int groups = kind == PH_W13 ? 2 * n_items : n_items;
             const int tiles = phase_tiles(kind, n_items), chunks = phase_chunks(K);
             uint32_t stage = (uint32_t)(it * s_spf) + d3.z;
-            const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
-            const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
 #pragma unroll 1
             for (int t = 0; t < tiles; ++t) {
                 const bool two = groups - 2 * t >= 2;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                // two accumulators (even / odd k-blocks of the warp's slice): half the dependent MMA chain; added at the end
+                float acc[4] = {0.f, 0.f, 0.f, 0.f}, acd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
                 for (int kc = 0; kc < chunks; ++kc, ++stage) {
                     const int kb0 = kc * kLL2ChunkKb, nkb = min(kLL2ChunkKb, kb - kb0);
@@ -1079,27 +1094,22 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                     const uint32_t slot = stage % NSLOTS;
                     mbar_wait(full0 + 8u * slot, (stage / NSLOTS) & 1u);
                     const uint32_t base = RING + slot * (uint32_t)kLL2SlotBytes + (uint32_t)lane * 16u;
-                    if (normed) {   // one stage per tile (K = model dim): the warp's <= 4 k-blocks against its B fragments
-#pragma unroll
-                        for (int jj = 0; jj < kFrag; ++jj) {
-                            if (lo + jj < hi) {
-                                const int j = lo + jj;
-                                const uint4 a_lo = lds_v4(base + (uint32_t)j * 512u);
-                                uint4 a_hi = make_uint4(0u, 0u, 0u, 0u);
-                                if (two) a_hi = lds_v4(base + (uint32_t)(nkb + j) * 512u);
-                                mma_bf16_16816(acc, a_lo.x, a_hi.x, a_lo.y, a_hi.y, bfrag[jj].x, bfrag[jj].y);
-                                mma_bf16_16816(acc, a_lo.z, a_hi.z, a_lo.w, a_hi.w, bfrag[jj].z, bfrag[jj].w);
-                            }
-                        }
-                    } else {
-#pragma unroll 3
-                        for (int j = lo; j < hi; ++j) {
-                            const uint4 a_lo = lds_v4(base + (uint32_t)j * 512u);
-                            uint4 a_hi = make_uint4(0u, 0u, 0u, 0u);
-                            if (two) a_hi = lds_v4(base + (uint32_t)(nkb + j) * 512u);
-                            const uint4 b = lds_v4(XB + (uint32_t)((kb0 + j) * 32 + c * 8) * 2u);
-                            mma_bf16_16816(acc, a_lo.x, a_hi.x, a_lo.y, a_hi.y, b.x, b.y);
-                            mma_bf16_16816(acc, a_lo.z, a_hi.z, a_lo.w, a_hi.w, b.z, b.w);
+                    const uint32_t xb = XB + (uint32_t)(kb0 * 32 + c * 8) * 2u;
+#pragma unroll 2
+                    for (int j = lo; j < hi; j += 2) {
+                        const uint4 a_lo = lds_v4(base + (uint32_t)j * 512u);
+                        uint4 a_hi = make_uint4(0u, 0u, 0u, 0u);
+                        if (two) a_hi = lds_v4(base + (uint32_t)(nkb + j) * 512u);
+                        const uint4 bx = lds_v4(xb + (uint32_t)j * 64u);
+                        mma_bf16_16816(acc, a_lo.x, a_hi.x, a_lo.y, a_hi.y, bx.x, bx.y);
+                        mma_bf16_16816(acc, a_lo.z, a_hi.z, a_lo.w, a_hi.w, bx.z, bx.w);
+                        if (j + 1 < hi) {
+                            const uint4 c_lo = lds_v4(base + (uint32_t)(j + 1) * 512u);
+                            uint4 c_hi = make_uint4(0u, 0u, 0u, 0u);
+                            if (two) c_hi = lds_v4(base + (uint32_t)(nkb + j + 1) * 512u);
+                            const uint4 by = lds_v4(xb + (uint32_t)(j + 1) * 64u);
+                            mma_bf16_16816(acd, c_lo.x, c_hi.x, c_lo.y, c_hi.y, by.x, by.y);
+                            mma_bf16_16816(acd, c_lo.z, c_hi.z, c_lo.w, c_hi.w, by.z, by.w);
                         }
                     }
                     __syncwarp();
@@ -1108,8 +1118,8 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                 // partial sums of the warp: row slot g (acc[0]) and g + 8 (acc[2]); every column carries the same vector
                 const uint32_t pbuf = PART + (tile_ctr & 1u) * (uint32_t)(kNW * 16 * 4);
                 if (c == 0) {
-                    sts_f32(pbuf + (uint32_t)(warp * 16 + g) * 4u, acc[0]);
-                    sts_f32(pbuf + (uint32_t)(warp * 16 + 8 + g) * 4u, acc[2]);
+                    sts_f32(pbuf + (uint32_t)(warp * 16 + g) * 4u, __fadd_rn(acc[0], acd[0]));
+                    sts_f32(pbuf + (uint32_t)(warp * 16 + 8 + g) * 4u, __fadd_rn(acc[2], acd[2]));
                 }
                 if (t == tiles - 1) LL2_TRACE(4);
                 csync();
@@ -1129,8 +1139,7 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                         n = (i0 + t) * 8 + lane;
                         valid = lane < 8;
                         const float a = bf16_round(v), gt = bf16_round(up);
-                        // F.silu in fp32, bf16 out (P:581): exact table over all bf16 inputs
-                        const float sg = __uint_as_float((uint32_t)__ldg(M.silu_lut + (__float_as_uint(a) >> 16)) << 16);
+                        const float sg = bf16_round(__fdiv_rn(a, __fadd_rn(1.0f, expf(-a))));  // F.silu in fp32, bf16 out (P:581)
                         val = bf16_round(__fmul_rn(sg, gt));
                     } else {
                         const int item = 2 * t + (lane >> 3);
@@ -1140,8 +1149,11 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                         if (kind == PH_QKV) {
                             const float other = __shfl_xor_sync(0xffffffffu, val, 1);
                             if (valid && n < k_end) {  // q and k rows: interleaved-pair RoPE with the bf16 table (P:616-640)
-                                const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)min(s_pos, M.max_seq_len - 1) * kHeadDim);
-                                const uint32_t cs = __ldg(reinterpret_cast<const uint32_t*>(table + (n & (kHeadDim - 2))));
+                                uint32_t cs = rope0;
+                                if (t > 0) {
+                                    const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)min(s_pos, M.max_seq_len - 1) * kHeadDim);
+                                    cs = ldnc_u32(table + (n & (kHeadDim - 2)));
+                                }
                                 const float co = bf_lo(cs), si = bf_hi(cs);
                                 val = (n & 1) ? bf16_round(__fadd_rn(__fmul_rn(val, co), __fmul_rn(other, si)))
                                               : bf16_round(__fsub_rn(__fmul_rn(val, co), __fmul_rn(other, si)));
