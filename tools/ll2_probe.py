@@ -142,6 +142,29 @@ def timing(args):
             print(f"  {label:8s} {k:12s} x{n:3d} " + " ".join(f"{x / n:8.0f}" for x in v))
             tot += v[6]
         print(f"  {label}: {tot:.0f} cycles per frame in phases")
+    # skew trace: %globaltimer of every CTA when its input is staged (0) and at the end of the phase (1)
+    skew = prof.cpu().numpy()[2 * 512 + 64 + 2 * 512 * 8:].reshape(256, 512, 2).astype(float)
+    n_ctas = int((skew[:, 0, 1] > 0).sum())
+    if n_ctas > 1:
+        P = model.phase_count
+        acc = {}
+        for p in range(1, P):
+            end_prev, arr, end = skew[:n_ctas, p - 1, 1], skew[:n_ctas, p, 0], skew[:n_ctas, p, 1]
+            if (end_prev <= 0).any() or (end <= 0).any():
+                continue
+            k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
+            have = arr > 0
+            a0 = acc.setdefault(k, [[], [], [], []])
+            a0[0].append(end.max() - end_prev.max())                        # phase period: last end -> last end
+            a0[1].append(end.max() - np.median(end))                        # spread of the ends
+            if have.any():
+                a0[2].append(np.median(arr[have]) - end_prev.max())         # last producer done -> median consumer staged
+                a0[3].append(end.max() - np.median(arr[have]))              # median staged -> last end (the chain of the slowest CTA)
+        print(f"skew trace of the last frame over {n_ctas} CTAs (ns): period (last end -> last end) | end spread (max - median) | "
+              f"last end of the previous phase -> median input staged | median staged -> last end")
+        for k, (per, sp, gap, chain) in acc.items():
+            print(f"  {k:12s} x{len(per):3d} period {np.mean(per):7.0f} | spread {np.mean(sp):6.0f} | hand-off "
+                  f"{(np.mean(gap) if gap else float('nan')):6.0f} | chain {(np.mean(chain) if chain else float('nan')):6.0f}")
 
 
 def main():
