@@ -167,7 +167,6 @@ __shared__ uint32_t s_best;             // HEAD phases: the CTA's best (logit, i
 __shared__ int s_pos, s_step, s_fin;    // cached positions (seq_len) / frames emitted / stop flag, tracked by every CTA
 __shared__ int s_tok[kMaxRows];         // pending input column
 __shared__ int s_nw[kMaxRows];          // ids chosen in the current frame
-__shared__ int s_spf;                   // ring stages per iteration
 __shared__ uint32_t s_epoch0;           // phases executed by earlier launches
 __shared__ int s_btab[kBtabCache];      // the sequence's block table (constant during a launch)
 __shared__ float s_bmax[kMaxSeg];       // PV units: maxima of the 64-position segments
@@ -189,7 +188,7 @@ struct Team {
 //        11    K | n_items << 16
 //        12    kind | fast << 4 | layer << 8 | depth_pos << 16
 //        13    first item of this CTA
-//        14    ordinal of the phase's first ring stage inside an iteration
+//        14    (unused)
 //        15    len_out (words per replica of the output region) | n_src_words << 16
 __device__ __forceinline__ int phase_rows(const DevModel& M, const Phase& ph) {
     const bool fast = ph.fast != 0;
@@ -300,7 +299,7 @@ __device__ __noinline__ void producer(const CallArgs& A, const SmemPlan& SP, uin
     const uint32_t full0 = smem_u32(s_full), empty0 = smem_u32(s_empty);
     const uint32_t ring = sm0 + (uint32_t)SP.ring;
     const uint32_t ns = (uint32_t)SP.n_slots;
-    uint32_t stage = 0;
+    uint32_t stage = 0, slot = 0, par = 0;   // stages are produced strictly in order: slot / parity run along
     for (int it = 0; it < A.n_iter; ++it) {
         for (int p = 0; p < A.phase_end; ++p) {
             const uint32_t dsc = sm0 + (uint32_t)SP.desc + (uint32_t)p * (kDescWords * 4u);
@@ -320,8 +319,7 @@ __device__ __noinline__ void producer(const CallArgs& A, const SmemPlan& SP, uin
                 const int ng = min(2, groups - 2 * t);
                 for (int kc = 0; kc < chunks; ++kc) {
                     const int kb0 = kc * kLL2ChunkKb, nkb = min(kLL2ChunkKb, kb - kb0);
-                    const uint32_t slot = stage % ns;
-                    if (stage >= ns) mbar_wait(empty0 + 8u * slot, ((stage / ns) - 1u) & 1u);
+                    if (stage >= ns) mbar_wait(empty0 + 8u * slot, par ^ 1u);
                     const uint32_t bytes = (uint32_t)(ng * nkb * 512);
                     const uint32_t bar = full0 + 8u * slot;
                     mbar_expect_tx(bar, bytes);
@@ -329,6 +327,7 @@ __device__ __noinline__ void producer(const CallArgs& A, const SmemPlan& SP, uin
                         bulk_g2s(ring + slot * (uint32_t)kLL2SlotBytes + (uint32_t)(g * nkb * 512),
                                  wp + (size_t)(2 * t + g) * group_bytes + (size_t)kb0 * 512, (uint32_t)(nkb * 512), bar, pol);
                     ++stage;
+                    if (++slot == ns) { slot = 0u; par ^= 1u; }
                 }
             }
         }
@@ -946,19 +945,7 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
         for (int i = tid; i < kBtabCache && i < A.b.max_pages; i += kLL2Threads) s_btab[i] = ldcg_i32(sq.btab + i);
     }
     __syncthreads();
-    if (tid == 0) {  // sequential pass: ring stage ordinals of one iteration
-        uint32_t stage = 0;
-        for (int p = 0; p < per_iter; ++p) {
-            const uint32_t dsc = DSC0 + (uint32_t)p * (kDescWords * 4u);
-            const uint32_t kn = lds_u32(dsc + 44u), kind = lds_u32(dsc + 48u) & 15u;
-            const int n_items = (int)(kn >> 16), K = (int)(kn & 0xffffu);
-            sts_u32(dsc + 56u, stage);
-            if (kind == PH_ATTN || kind == PH_SAMPLE || n_items == 0) continue;
-            stage += (uint32_t)(phase_tiles((int)kind, n_items) * phase_chunks(K));
-        }
-        s_spf = (int)stage;
-        s_epoch0 = (uint32_t)ldcg_i32(M.ll_epoch);
-    }
+    if (tid == 0) s_epoch0 = (uint32_t)ldcg_i32(M.ll_epoch);
     __syncthreads();
 
     if (warp == kNW) {  // the TMA producer warp
@@ -980,6 +967,7 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
 
     uint32_t tile_ctr = 0;   // tiles reduced so far: the reducing warp rotates with it
     uint32_t pass_ctr = 0;   // passes so far: parity of the partial-sum buffer
+    uint32_t cslot = 0, cpar = 0;   // ring slot and parity of the next stage this CTA consumes
     const int g = lane >> 2, c = lane & 3;
     uint32_t t_end = clock32_now();
     for (int it = 0; it < A.n_iter; ++it) {
@@ -1088,50 +1076,63 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             // ---- tiles: 16 row slots x K on the tensor cores, K split over the warps ---------------------------------
             const int groups = kind == PH_W13 ? 2 * n_items : n_items;
             const int tiles = phase_tiles(kind, n_items), chunks = phase_chunks(K);
-            const uint32_t stage0 = (uint32_t)(it * s_spf) + d3.z;
             // Tiles go through the tensor cores in PASSES of up to 4 (one-stage tiles, K <= 768): every warp carries its K slice
             // through all tiles of the pass (the B fragment is loaded once per k-block), then ONE barrier, then the tiles of the
             // pass are reduced / published by different warps at the same time.  Multi-stage tiles (K = 3072) go one per pass.
+            // Ring stages are consumed strictly in order: (cslot, cpar) is the slot and parity of the next one.
 #pragma unroll 1
             for (int t0 = 0; t0 < tiles;) {
                 const int nt = chunks == 1 ? min(4, tiles - t0) : 1;
-                float acc[4][4];
+                // two accumulators per tile (the two MMA steps of a k-block): no MMA waits for the one issued just before it
+                float acc[4][4], acd[4][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { acc[i][e] = 0.f; acd[i][e] = 0.f; }
+                }
 #pragma unroll 1
                 for (int kc = 0; kc < chunks; ++kc) {
                     const int kb0 = kc * kLL2ChunkKb, nkb = min(kLL2ChunkKb, kb - kb0);
                     const int lo = (nkb * warp) / kNW, hi = (nkb * (warp + 1)) / kNW;
                     uint32_t abase[4];
+                    uint32_t sl = cslot, pr = cpar;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         abase[i] = 0u;
                         if (i < nt) {
-                            const uint32_t st = stage0 + (uint32_t)((t0 + i) * chunks + kc), slot = st % NSLOTS;
-                            mbar_wait(full0 + 8u * slot, (st / NSLOTS) & 1u);
-                            abase[i] = RING + slot * (uint32_t)kLL2SlotBytes + (uint32_t)lane * 16u;
+                            mbar_wait(full0 + 8u * sl, pr);
+                            abase[i] = RING + sl * (uint32_t)kLL2SlotBytes + (uint32_t)lane * 16u;
+                            if (++sl == NSLOTS) { sl = 0u; pr ^= 1u; }
                         }
                     }
                     const uint32_t xb = XB + (uint32_t)(kb0 * 32 + c * 8) * 2u;
+                    const uint32_t up = (uint32_t)nkb * 512u;     // the upper 8-row group of a tile follows the lower one
 #pragma unroll 1
                     for (int j = lo; j < hi; ++j) {
                         const uint4 bx = lds_v4(xb + (uint32_t)j * 64u);
+                        uint4 al[4], ah[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
+                            al[i] = make_uint4(0u, 0u, 0u, 0u); ah[i] = al[i];
                             if (i < nt) {
-                                const uint4 a_lo = lds_v4(abase[i] + (uint32_t)j * 512u);
-                                uint4 a_hi = make_uint4(0u, 0u, 0u, 0u);
-                                if (groups - 2 * (t0 + i) >= 2) a_hi = lds_v4(abase[i] + (uint32_t)(nkb + j) * 512u);
-                                mma_bf16_16816(acc[i], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bx.x, bx.y);
-                                mma_bf16_16816(acc[i], a_lo.z, a_hi.z, a_lo.w, a_hi.w, bx.z, bx.w);
+                                al[i] = lds_v4(abase[i] + (uint32_t)j * 512u);
+                                if (groups - 2 * (t0 + i) >= 2) ah[i] = lds_v4(abase[i] + up + (uint32_t)j * 512u);
                             }
                         }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i < nt) mma_bf16_16816(acc[i], al[i].x, ah[i].x, al[i].y, ah[i].y, bx.x, bx.y);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i < nt) mma_bf16_16816(acd[i], al[i].z, ah[i].z, al[i].w, ah[i].w, bx.z, bx.w);
                     }
                     __syncwarp();
                     if (lane < nt) {   // lane i hands back the stage of tile i
-                        const uint32_t st = stage0 + (uint32_t)((t0 + lane) * chunks + kc);
-                        mbar_arrive(empty0 + 8u * (st % NSLOTS));
+                        uint32_t r = cslot + (uint32_t)lane;
+                        if (r >= NSLOTS) r -= NSLOTS;
+                        mbar_arrive(empty0 + 8u * r);
                     }
+                    cslot = sl; cpar = pr;
                 }
                 // partial sums of the warp: row slot g (acc[.][0]) and g + 8 (acc[.][2]); every column carries the same vector
                 const uint32_t pbuf = PART + (pass_ctr & 1u) * (uint32_t)(4 * kNW * 16 * 4);
@@ -1139,8 +1140,8 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (i < nt) {
-                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + g) * 4u, acc[i][0]);
-                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + 8 + g) * 4u, acc[i][2]);
+                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + g) * 4u, __fadd_rn(acc[i][0], acd[i][0]));
+                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + 8 + g) * 4u, __fadd_rn(acc[i][2], acd[i][2]));
                         }
                     }
                 }

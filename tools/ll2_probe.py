@@ -167,6 +167,38 @@ def timing(args):
                   f"{(np.mean(gap) if gap else float('nan')):6.0f} | chain {(np.mean(chain) if chain else float('nan')):6.0f}")
 
 
+def teams(args):
+    """Batches of 2..8 on the data-flow kernel: one team of CTAs per sequence.  Every sequence must decode exactly as it does
+    alone (rows over CTAs, K over warps: the arithmetic does not depend on the team size)."""
+    cfg = named_config(args.model)
+    need = args.prompt_bytes + 12 + 64 + 8
+    model = RQTransformer(cfg, max_batch=8, max_seq_len=max(need, 256))
+    model.load_state_dict(make_state_dict(cfg, seed=0))
+    model.set_option("ll_max_batch", 8)
+    gs = GenerationSettings(default_temp=0.0, default_fast_temp=0.0)
+    prompts = [prompt_grid(byte_prompt(args.prompt_bytes - 7 * b, seed=1 + b), cfg) for b in range(8)]
+    solo = [generate_batch(model, [p], gs, audio_only=False, fixed_frames=12, seq_ids=[b])[0] for b, p in enumerate(prompts[:4])]
+    for B in (2, 3, 4):
+        outs = generate_batch(model, prompts[:B], gs, audio_only=False, fixed_frames=12, seq_ids=list(range(B)))
+        same = [bool(torch.equal(outs[b], solo[b])) for b in range(B)]
+        print(f"teams: batch of {B}: rows identical to their solo decode: {same}")
+    for B in (1, 2, 4, 8):
+        padded, lens = pack_prompts(model, prompts[:B])
+        batch = model.new_batch(B, max_positions=need, max_frames=64)
+        s = _sampling(model, gs, True, ignore_stop=True)
+        model.prefill(batch, padded, lens)
+        model.decode_frames(batch, s, 8)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model.decode_frames(batch, s, 48)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 48
+        print(f"teams: bs={B}: {us:8.1f} us per frame step -> {B / us * 1e6:9.0f} frames/s")
+        batch.release()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="smoltts_byte_150m")
@@ -176,6 +208,7 @@ def main():
     ap.add_argument("--trace-holdoff", type=int, default=400)
     ap.add_argument("--skip-check", action="store_true")
     ap.add_argument("--skip-timing", action="store_true")
+    ap.add_argument("--teams", action="store_true")
     a = ap.parse_args()
     if not a.skip_check:
         check("smoltts_byte_tiny", 8, 20)
@@ -184,6 +217,8 @@ def main():
         check("smoltts_byte_150m", 4, 700)
     if not a.skip_timing:
         timing(a)
+    if a.teams:
+        teams(a)
 
 
 if __name__ == "__main__":
