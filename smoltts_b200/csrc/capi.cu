@@ -426,14 +426,14 @@ static int ensure_tmaps(SmolModel* m) {
     return SMOL_OK;
 }
 
-// The bound weights once more in the tensor-core GEMV layout ([8-row group][K / 32][8][32], w1 / w3 groups interleaved),
+// The bound weights once more in the tensor-core GEMV layout ([16-row tile][K / 32][MMA step][lane][16 B]: ll2_kernel.cu),
 // written into the workspace by a device kernel at bind time (setup-time; the borrowed checkpoint tensors stay as they are
 // for the other kernels).
 static int ensure_packed(SmolModel* m) {
     if (m->packed_ready) return SMOL_OK;
     const SmolConfig& c = m->cfg;
     DevModel& d = m->dm;
-    if (c.dim % 32 || c.fast_dim % 32 || c.intermediate_size % 32 || c.fast_intermediate_size % 32 || c.vocab_size % 8 || c.codebook_size % 8) {
+    if (c.dim % 32 || c.fast_dim % 32 || c.intermediate_size % 32 || c.fast_intermediate_size % 32 || c.vocab_size % 16 || c.codebook_size % 16) {
         m->packed_ready = true;   // such a model stays on the other kernels (ll2_plan refuses it)
         m->ll2_state = -1;
         return SMOL_OK;

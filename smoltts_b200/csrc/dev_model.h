@@ -57,7 +57,8 @@ struct DevLayer {
     const uint16_t* attention_norm;
     const uint16_t* ffn_norm;
     // tensor-core GEMV layout of the same matrices (ll2_kernel.cu; packed at bind time into the workspace):
-    // [group of 8 rows][K / 32][8 rows][32 elements]; pk_w13 interleaves the groups of w1 (even) and w3 (odd)
+    // [tile of 16 rows][K / 32][MMA step][lane][16 bytes = the lane's A fragment]; a pk_w13 tile is 8 rows of w1 over
+    // the same 8 rows of w3
     const uint16_t* pk_wqkv;
     const uint16_t* pk_wo;
     const uint16_t* pk_w13;

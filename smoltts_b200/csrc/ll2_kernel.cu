@@ -239,7 +239,8 @@ __device__ __forceinline__ void build_desc(const DevModel& M, const Team& tm, in
     int src_kind = 3, nrep = kLLRep, n_items = 0, i0 = 0, K = 0, gather = 0, n_src = 0, e_back = 1;
     if (kind != PH_ATTN && kind != PH_SAMPLE) {
         K = phase_k(M, ph);
-        const int items = phase_rows(M, ph) / 8;
+        // work item = one MMA tile of 16 row slots: 16 rows of the matrix, or 8 rows of w1 over the same 8 rows of w3
+        const int items = phase_rows(M, ph) / (kind == PH_W13 ? 8 : 16);
         i0 = (items * tm.cta) / tm.n;
         n_items = (items * (tm.cta + 1)) / tm.n - i0;
         int p_src = p - 1;
@@ -268,8 +269,7 @@ __device__ __forceinline__ void build_desc(const DevModel& M, const Team& tm, in
                                             : M.token_logits + (size_t)tm.team * M.vocab);
             nrep = 1;  // logits words are read by the team's sampler CTA only (greedy rows use the candidate words)
         }
-        const int gpi = kind == PH_W13 ? 2 : 1;  // 8-row groups per item
-        const unsigned long long wp = (unsigned long long)(phase_weights(M, ph) + (size_t)i0 * gpi * 8 * K);
+        const unsigned long long wp = (unsigned long long)(phase_weights(M, ph) + (size_t)i0 * 16 * K);   // 16 K elements per tile
         // normed phases stage the residual stream for everybody (the wo / w2 epilogues need their rows of it)
         gather = (kind == PH_QKV || kind == PH_W13) ? 1 : (n_items > 0 ? 1 : 0);
         w[0] = (uint32_t)src; w[1] = (uint32_t)(src >> 32);
@@ -287,8 +287,7 @@ __device__ __forceinline__ void build_desc(const DevModel& M, const Team& tm, in
 #pragma unroll
     for (int i = 0; i < kDescWords / 4; ++i) sts_v4(dsc + 16u * i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
 }
-// tiles (16 row slots) and ring stages of a phase for this CTA
-__device__ __forceinline__ int phase_tiles(int kind, int n_items) { return kind == PH_W13 ? n_items : (n_items + 1) / 2; }
+// ring stages of a tile: K in chunks of kLL2ChunkKb k-blocks
 __device__ __forceinline__ int phase_chunks(int K) { return (K / 32 + kLL2ChunkKb - 1) / kLL2ChunkKb; }
 
 // ---- TMA producer (one lane of the last warp) -------------------------------------------------------------
@@ -312,20 +311,16 @@ __device__ __noinline__ void producer(const CallArgs& A, const SmemPlan& SP, uin
             // the slow transformer's weights are read once per frame: evict first; the depth transformer's are re-read
             // by every depth step: keep them in L2
             const uint64_t pol = (fast && kind != PH_HEAD) ? pol_keep : pol_stream;
-            const int groups = kind == PH_W13 ? 2 * n_items : n_items;
-            const int tiles = phase_tiles(kind, n_items), chunks = phase_chunks(K), kb = K / 32;
-            const size_t group_bytes = (size_t)K * 16;
+            const int tiles = n_items, chunks = phase_chunks(K), kb = K / 32;
+            const size_t tile_bytes = (size_t)K * 32;
             for (int t = 0; t < tiles; ++t) {
-                const int ng = min(2, groups - 2 * t);
                 for (int kc = 0; kc < chunks; ++kc) {
                     const int kb0 = kc * kLL2ChunkKb, nkb = min(kLL2ChunkKb, kb - kb0);
                     if (stage >= ns) mbar_wait(empty0 + 8u * slot, par ^ 1u);
-                    const uint32_t bytes = (uint32_t)(ng * nkb * 512);
+                    const uint32_t bytes = (uint32_t)(nkb * 1024);
                     const uint32_t bar = full0 + 8u * slot;
                     mbar_expect_tx(bar, bytes);
-                    for (int g = 0; g < ng; ++g)
-                        bulk_g2s(ring + slot * (uint32_t)kLL2SlotBytes + (uint32_t)(g * nkb * 512),
-                                 wp + (size_t)(2 * t + g) * group_bytes + (size_t)kb0 * 512, (uint32_t)(nkb * 512), bar, pol);
+                    bulk_g2s(ring + slot * (uint32_t)kLL2SlotBytes, wp + (size_t)t * tile_bytes + (size_t)kb0 * 1024, bytes, bar, pol);
                     ++stage;
                     if (++slot == ns) { slot = 0u; par ^= 1u; }
                 }
@@ -905,6 +900,27 @@ __device__ __noinline__ void kv_append(const DevModel& M, const CallArgs& A, int
     *reinterpret_cast<uint32_t*>(dst) = word;
 }
 
+// The warp's k-blocks [lo, hi) of a stage against NT tiles.  A tile's k-block is 1024 bytes: for each of the two MMA steps
+// 32 lanes x 16 bytes = the lane's A fragment (a0..a3) exactly as mma.m16n8k16 wants it (ll2 packing, smol_pack_kernel);
+// the B fragment (the activation vector, the same in all 8 columns) is 16 bytes per lane for both steps.
+template <int NT>
+__device__ __forceinline__ void mma_pass(float (&acc)[4][4], float (&acd)[4][4], const uint32_t (&abase)[4], uint32_t xb, int lo, int hi) {
+#pragma unroll 1
+    for (int j = lo; j < hi; ++j) {
+        const uint4 bx = lds_v4(xb + (uint32_t)j * 64u);
+        uint4 a0[NT], a1[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            a0[i] = lds_v4(abase[i] + (uint32_t)j * 1024u);
+            a1[i] = lds_v4(abase[i] + (uint32_t)j * 1024u + 512u);
+        }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) mma_bf16_16816(acc[i], a0[i].x, a0[i].y, a0[i].z, a0[i].w, bx.x, bx.y);
+#pragma unroll
+        for (int i = 0; i < NT; ++i) mma_bf16_16816(acd[i], a1[i].x, a1[i].y, a1[i].z, a1[i].w, bx.z, bx.w);
+    }
+}
+
 template <bool kTrace>
 __global__ void __launch_bounds__(kLL2Threads, 1)
 smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallArgs A, const __grid_constant__ SmemPlan SP) {
@@ -1020,7 +1036,7 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             if (normed && tid < K / 4) nw2 = ldnc_v2(normw + 4 * tid);
             uint32_t rope0 = 0u;
             if (kind == PH_QKV && n_items > 0 && warp == (int)(tile_ctr % kNW) && lane < 16) {
-                const int n = (i0 + (lane >> 3)) * 8 + (lane & 7);
+                const int n = i0 * 16 + lane;
                 if (n < k_end) {
                     const uint16_t* table = reinterpret_cast<const uint16_t*>(aux) + (fast ? 0 : (size_t)min(s_pos, M.max_seq_len - 1) * kHeadDim);
                     rope0 = ldnc_u32(table + (n & (kHeadDim - 2)));
@@ -1074,8 +1090,7 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             if (fast && kind == PH_HEAD && depth_pos == M.depth - 1) __threadfence();  // release side of the once-per-frame fence
 
             // ---- tiles: 16 row slots x K on the tensor cores, K split over the warps ---------------------------------
-            const int groups = kind == PH_W13 ? 2 * n_items : n_items;
-            const int tiles = phase_tiles(kind, n_items), chunks = phase_chunks(K);
+            const int tiles = n_items, chunks = phase_chunks(K);
             // Tiles go through the tensor cores in PASSES of up to 4 (one-stage tiles, K <= 768): every warp carries its K slice
             // through all tiles of the pass (the B fragment is loaded once per k-block), then ONE barrier, then the tiles of the
             // pass are reduced / published by different warps at the same time.  Multi-stage tiles (K = 3072) go one per pass.
@@ -1098,33 +1113,20 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                     uint32_t sl = cslot, pr = cpar;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        abase[i] = 0u;
+                        abase[i] = RING;
                         if (i < nt) {
                             mbar_wait(full0 + 8u * sl, pr);
                             abase[i] = RING + sl * (uint32_t)kLL2SlotBytes + (uint32_t)lane * 16u;
                             if (++sl == NSLOTS) { sl = 0u; pr ^= 1u; }
                         }
                     }
+                    if (t0 == 0 && kc == 0) LL2_TRACE(7);   // the pass's weights are in shared memory
                     const uint32_t xb = XB + (uint32_t)(kb0 * 32 + c * 8) * 2u;
-                    const uint32_t up = (uint32_t)nkb * 512u;     // the upper 8-row group of a tile follows the lower one
-#pragma unroll 1
-                    for (int j = lo; j < hi; ++j) {
-                        const uint4 bx = lds_v4(xb + (uint32_t)j * 64u);
-                        uint4 al[4], ah[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            al[i] = make_uint4(0u, 0u, 0u, 0u); ah[i] = al[i];
-                            if (i < nt) {
-                                al[i] = lds_v4(abase[i] + (uint32_t)j * 512u);
-                                if (groups - 2 * (t0 + i) >= 2) ah[i] = lds_v4(abase[i] + up + (uint32_t)j * 512u);
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (i < nt) mma_bf16_16816(acc[i], al[i].x, ah[i].x, al[i].y, ah[i].y, bx.x, bx.y);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (i < nt) mma_bf16_16816(acd[i], al[i].z, ah[i].z, al[i].w, ah[i].w, bx.z, bx.w);
+                    switch (nt) {
+                        case 1: mma_pass<1>(acc, acd, abase, xb, lo, hi); break;
+                        case 2: mma_pass<2>(acc, acd, abase, xb, lo, hi); break;
+                        case 3: mma_pass<3>(acc, acd, abase, xb, lo, hi); break;
+                        default: mma_pass<4>(acc, acd, abase, xb, lo, hi); break;
                     }
                     __syncwarp();
                     if (lane < nt) {   // lane i hands back the stage of tile i
@@ -1169,9 +1171,8 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                         const float sg = bf16_round(__fdiv_rn(a, __fadd_rn(1.0f, expf(-a))));  // F.silu in fp32, bf16 out (P:581)
                         val = bf16_round(__fmul_rn(sg, gt));
                     } else {
-                        const int item = 2 * t + (lane >> 3);
-                        n = (i0 + item) * 8 + (lane & 7);
-                        valid = lane < 16 && item < n_items;
+                        n = (i0 + t) * 16 + lane;
+                        valid = lane < 16;
                         val = bf16_round(v);
                         if (kind == PH_QKV) {
                             const float other = __shfl_xor_sync(0xffffffffu, val, 1);
@@ -1231,21 +1232,28 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
 }
 
 // ---- bind-time packing of a weight matrix into the tensor-core GEMV layout ------------------------------------------
-// dst [group][K / 32][8][32]; group g of a plain matrix = rows 8 g .. 8 g + 7 of `a`; interleaved (w1 | w3): even groups
-// from `a`, odd groups from `b`.
+// dst [tile][K / 32][step 2][lane 32][16 bytes]: the A fragment of lane (g = lane / 4, c = lane % 4) for MMA step s of the
+// k-block = { lo[e], hi[e], lo[e + 2], hi[e + 2] } with e = 8 c + 4 s (element pairs) -- lo = row g of the tile's lower
+// half, hi = row g of its upper half.  Plain matrix: tile t = rows 16 t .. 16 t + 15 (lower = first 8).  Gated MLP
+// (b != nullptr): tile t = rows 8 t .. 8 t + 7 of w1 (lower) over the same rows of w3 (upper).
 __global__ void smol_pack_kernel(uint16_t* dst, const uint16_t* a, const uint16_t* b, int rows, int K) {
-    const size_t chunks = (size_t)rows * (b ? 2 : 1) * (K / 8);   // 16-byte pieces
+    const int kbn = K / 32;
+    const size_t tiles = (size_t)(b ? rows / 8 : rows / 16);
+    const size_t chunks = tiles * kbn * 64;   // 16-byte pieces
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x) {
-        const int c8 = (int)(i & 3);
-        const int r = (int)((i >> 2) & 7);
-        const size_t rest = i >> 5;
-        const int kbn = K / 32;
+        const int lane = (int)(i & 31), step = (int)((i >> 5) & 1);
+        const size_t rest = i >> 6;
         const int kbi = (int)(rest % kbn);
-        const size_t grp = rest / kbn;
-        const uint16_t* m = a;
-        size_t sg = grp;
-        if (b) { m = (grp & 1) ? b : a; sg = grp >> 1; }
-        const uint4 v = *reinterpret_cast<const uint4*>(m + (sg * 8 + r) * (size_t)K + kbi * 32 + c8 * 8);
+        const size_t tile = rest / kbn;
+        const int g = lane >> 2, c = lane & 3;
+        const uint16_t* lo = b ? a + (tile * 8 + g) * (size_t)K : a + (tile * 16 + g) * (size_t)K;
+        const uint16_t* hi = b ? b + (tile * 8 + g) * (size_t)K : a + (tile * 16 + 8 + g) * (size_t)K;
+        const int e = kbi * 32 + 8 * c + 4 * step;
+        uint4 v;
+        v.x = *reinterpret_cast<const uint32_t*>(lo + e);
+        v.y = *reinterpret_cast<const uint32_t*>(hi + e);
+        v.z = *reinterpret_cast<const uint32_t*>(lo + e + 2);
+        v.w = *reinterpret_cast<const uint32_t*>(hi + e + 2);
         *reinterpret_cast<uint4*>(dst + i * 8) = v;
     }
 }
@@ -1270,7 +1278,7 @@ bool ll2_plan(const DevModel& M, int holdoff, int flags, ll2::SmemPlan* sp, size
     if (M.dim != M.fdim) return false;
     if (M.dim % 32 || M.inter % 32 || M.finter % 32) return false;
     if (M.dim > 768 || M.inter > 3072 || M.finter > 3072) return false;   // three B fragments per warp, kGather polls per thread
-    if (M.vocab % 8 || M.codebook_size % 8) return false;
+    if (M.vocab % 16 || M.codebook_size % 16 || M.dim % 16 || M.inter % 16 || M.finter % 16) return false;   // 16-row tiles
     if (M.vocab > ll2::kCons * 12 || M.codebook_size > ll2::kCons * 12) return false;
     if (phases_per_frame(M.n_layer, M.n_flayer, M.depth) > kMaxProg / 2) return false;
     if (M.max_seq_len > ll2::kMaxBlocks * kLL2AttnBlock) return false;

@@ -119,7 +119,7 @@ def timing(args):
     model.set_profile(False)
     trace = prof.cpu().numpy()[2 * 512 + 64: 2 * 512 + 64 + 2 * 512 * 8].reshape(2, 512, 8)
     print(f"profiling build, hold-off {args.trace_holdoff}: {us:.1f} us/frame")
-    names = ["staged", "bar1", "bfrag", "mma", "bar2", "epilogue", "total"]
+    names = ["staged", "bar1", "bfrag", "weights", "mma", "bar2", "epilogue", "total"]
     print("cycle trace of the last frame, mean cycles per phase kind: " + " | ".join(names))
     for slot, label in ((0, "CTA 0"), (1, "CTA n/2")):
         acc = {}
@@ -129,18 +129,19 @@ def timing(args):
                 continue
             k = phase_kind(p, cfg.n_layer, cfg.n_fast_layer)
             if t[2] == 0:
-                d = [0, 0, 0, 0, 0, 0, t[6] - t[0]]
+                d = [0, 0, 0, 0, 0, 0, 0, t[6] - t[0]]
             else:
                 t3 = t[3] if t[3] else t[2]
-                t4 = t[4] if t[4] else t3
+                t7 = t[7] if t[7] else t3
+                t4 = t[4] if t[4] else t7
                 t5 = t[5] if t[5] else t4
-                d = [t[1] - t[0], t[2] - t[1], t3 - t[2], t4 - t3, t5 - t4, t[6] - t5, t[6] - t[0]]
-            a0, n0 = acc.get(k, ([0.0] * 7, 0))
+                d = [t[1] - t[0], t[2] - t[1], t3 - t[2], t7 - t3, t4 - t7, t5 - t4, t[6] - t5, t[6] - t[0]]
+            a0, n0 = acc.get(k, ([0.0] * 8, 0))
             acc[k] = ([x + y for x, y in zip(a0, d)], n0 + 1)
         tot = 0.0
         for k, (v, n) in acc.items():
             print(f"  {label:8s} {k:12s} x{n:3d} " + " ".join(f"{x / n:8.0f}" for x in v))
-            tot += v[6]
+            tot += v[7]
         print(f"  {label}: {tot:.0f} cycles per frame in phases")
     # skew trace: %globaltimer of every CTA when its input is staged (0) and at the end of the phase (1)
     skew = prof.cpu().numpy()[2 * 512 + 64 + 2 * 512 * 8:].reshape(256, 512, 2).astype(float)
