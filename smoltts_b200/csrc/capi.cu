@@ -471,7 +471,7 @@ static int ensure_packed(SmolModel* m) {
 static int ensure_ll2(SmolModel* m) {
     if (m->ll2_state != 0) return SMOL_OK;
     m->ll2_sp = smol::ll2::SmemPlan();
-    if (!smol::ll2_plan(m->dm, m->ll2_holdoff, m->ll_flags, &m->ll2_sp, &m->ll2_smem) || m->n_ctas > 7 * 32) { m->ll2_state = -1; return SMOL_OK; }
+    if (!smol::ll2_plan(m->dm, m->ll2_holdoff, m->ll_flags, &m->ll2_sp, &m->ll2_smem) || m->n_ctas > smol::kLLMaxCtas) { m->ll2_state = -1; return SMOL_OK; }
     CU(smol::ll2_configure(m->ll2_smem));
     int per_sm = 0;
     CU(smol::ll2_max_ctas(m->ll2_smem, &per_sm));

@@ -29,10 +29,13 @@
 // slow step P:223-260 / M:173-192; depth loop P:409-448, M:194-220, G:110-141; sampling G:88-99,118-132; frame
 // assembly + stop rule G:143-171.
 
-#define SMOL_BLOCK_SYNC() asm volatile("bar.sync 1, 224;" ::: "memory")  // the 7 consumer warps
-
 #include "common.cuh"
 #include "dev_model.h"
+
+#define LL2_STR2(x) #x
+#define LL2_STR(x) LL2_STR2(x)
+#define SMOL_BLOCK_SYNC() asm volatile("bar.sync 1, " LL2_STR(LL2_WARPS) " * 32;" ::: "memory")  // the consumer warps
+
 #include "sampler.cuh"
 
 namespace smol {
@@ -42,7 +45,9 @@ constexpr int kNW = kLL2Warps;
 constexpr int kCons = kNW * 32;
 constexpr int kMaxSlots = 8;
 constexpr int kDescWords = 16;
-constexpr int kGather = 4;        // 16-byte polls per thread and vector: 2 words x 224 threads x 4 = 1792 words >= K 3072 / 2
+constexpr int kGather = (768 + kCons - 1) / kCons;   // 16-byte polls (2 words) per thread and vector: covers K = 3072 (1536 words)
+constexpr int kNormPer = (192 + kCons - 1) / kCons;  // 4-element chunks a thread normalises (K <= 768)
+constexpr int kSampPer = (2560 + kCons - 1) / kCons; // logits per thread in the sampler
 constexpr int kMaxBlocks = 16;    // softmax blocks of 512 positions a PV unit carries (contexts up to 8192)
 constexpr int kMaxSeg = kMaxBlocks * 8;  // 64-position segments of a context
 constexpr int kBtabCache = 256;
@@ -831,7 +836,7 @@ __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, 
         // greedy: every CTA published its best (logit, index) with the HEAD phase's epoch; everybody reduces them
         const unsigned long long* src = cand_words(M, tm, r, tm.cta % kLLRep);
         uint32_t best = 0u;
-        if (tid < tm.n) best = ll_get(src + tid, epoch - 1);
+        for (int i = tid; i < tm.n; i += kCons) { const uint32_t cnd = ll_get(src + i, epoch - 1); best = cnd > best ? cnd : best; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -854,7 +859,7 @@ __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, 
         csync();
         const float temp = fast ? A.s.fast_temp : A.s.temp;
         const uint32_t seq_id = sq.seq_id ? (uint32_t)ldcg_i32(sq.seq_id) : 0u;
-        tok = sample_row<kCons, 12>(lg, N, temp, fast ? 0 : A.s.top_k, fast ? 1.0f : A.s.top_p, A.s.min_p, A.s.seed,
+        tok = sample_row<kCons, kSampPer>(lg, N, temp, fast ? 0 : A.s.top_k, fast ? 1.0f : A.s.top_p, A.s.min_p, A.s.seed,
                                     (uint32_t)s_step, seq_id, (uint32_t)r, s_sc);
     }
     const bool last = fast && depth_pos == M.depth - 1;
@@ -862,7 +867,7 @@ __device__ __noinline__ void phase_sample(const DevModel& M, const CallArgs& A, 
         if (tid == 0) s_nw[r] = tok;
     } else {
         if (last) __threadfence();  // frame boundary: keep the release chain cumulative
-        if (tid < tm.n) st_relaxed_v2(tok_words(M, tm, r) + tid, (uint32_t)tok, epoch);
+        for (int i = tid; i < tm.n; i += kCons) st_relaxed_v2(tok_words(M, tm, r) + i, (uint32_t)tok, epoch);
         if (tid == 0) s_nw[r] = tok;
     }
     if (tm.cta == 0 && tid == 0) {
@@ -1032,8 +1037,12 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             // Operands that do not depend on the input are loaded NOW (volatile: the compiler must not sink them below the
             // wait): the norm weights of the 4 elements this thread will normalise, and -- in the warp that will reduce the
             // phase's first tile -- the RoPE pair of its row.
-            uint2 nw2 = make_uint2(0u, 0u);
-            if (normed && tid < K / 4) nw2 = ldnc_v2(normw + 4 * tid);
+            uint2 nw2[kNormPer];
+#pragma unroll
+            for (int q = 0; q < kNormPer; ++q) {
+                nw2[q] = make_uint2(0u, 0u);
+                if (normed && tid + q * kCons < K / 4) nw2[q] = ldnc_v2(normw + 4 * (tid + q * kCons));
+            }
             uint32_t rope0 = 0u;
             if (kind == PH_QKV && n_items > 0 && warp == (int)(tile_ctr % kNW) && lane < 16) {
                 const int n = i0 * 16 + lane;
@@ -1075,14 +1084,17 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                 for (int w = 0; w < kNW; ++w) t = __fadd_rn(t, s_ssq[w]);
                 const float mean = __fdiv_rn(t, (float)K);
                 const float rr = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, M.eps)));
-                if (tid < K / 4) {
-                    const uint32_t a = XB + (uint32_t)tid * 8u;
-                    const uint32_t x0 = lds_u32(a), x1 = lds_u32(a + 4u);
-                    const float o0 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_lo(x0), rr)), bf_lo(nw2.x)));
-                    const float o1 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_hi(x0), rr)), bf_hi(nw2.x)));
-                    const float o2 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_lo(x1), rr)), bf_lo(nw2.y)));
-                    const float o3 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_hi(x1), rr)), bf_hi(nw2.y)));
-                    sts_v2(a, pack_bf16(o0, o1), pack_bf16(o2, o3));
+#pragma unroll
+                for (int q = 0; q < kNormPer; ++q) {
+                    if (tid + q * kCons < K / 4) {
+                        const uint32_t a = XB + (uint32_t)(tid + q * kCons) * 8u;
+                        const uint32_t x0 = lds_u32(a), x1 = lds_u32(a + 4u);
+                        const float o0 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_lo(x0), rr)), bf_lo(nw2[q].x)));
+                        const float o1 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_hi(x0), rr)), bf_hi(nw2[q].x)));
+                        const float o2 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_lo(x1), rr)), bf_lo(nw2[q].y)));
+                        const float o3 = bf16_round(__fmul_rn(bf16_round(__fmul_rn(bf_hi(x1), rr)), bf_hi(nw2[q].y)));
+                        sts_v2(a, pack_bf16(o0, o1), pack_bf16(o2, o3));
+                    }
                 }
                 csync();
             }
@@ -1279,7 +1291,7 @@ bool ll2_plan(const DevModel& M, int holdoff, int flags, ll2::SmemPlan* sp, size
     if (M.dim % 32 || M.inter % 32 || M.finter % 32) return false;
     if (M.dim > 768 || M.inter > 3072 || M.finter > 3072) return false;   // three B fragments per warp, kGather polls per thread
     if (M.vocab % 16 || M.codebook_size % 16 || M.dim % 16 || M.inter % 16 || M.finter % 16) return false;   // 16-row tiles
-    if (M.vocab > ll2::kCons * 12 || M.codebook_size > ll2::kCons * 12) return false;
+    if (M.vocab > ll2::kCons * ll2::kSampPer || M.codebook_size > ll2::kCons * ll2::kSampPer) return false;
     if (phases_per_frame(M.n_layer, M.n_flayer, M.depth) > kMaxProg / 2) return false;
     if (M.max_seq_len > ll2::kMaxBlocks * kLL2AttnBlock) return false;
     const int kmax = M.inter > M.finter ? M.inter : M.finter;
