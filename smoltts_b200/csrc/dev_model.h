@@ -30,13 +30,12 @@ constexpr int kLLMaxCtas = 256;        // token words are published once per CTA
 
 // ---- data-flow kernel, second generation (ll2_kernel.cu): tensor-core GEMV, team of CTAs per sequence ----
 #ifndef LL2_WARPS
-#define LL2_WARPS 4
+#define LL2_WARPS 7
 #endif
-constexpr int kLL2Warps = LL2_WARPS;     // consumer warps; one more warp streams the weights.  ONE consumer warp per scheduler: most
-                                         // of a phase's instructions are control / addressing that every warp repeats, and two warps
-                                         // on one scheduler take turns at them (measured: 7 consumer warps -> 656 us per frame).  At
-                                         // most 8 warps in all keeps the register budget at 255 (a 9th caps it at 168 and the main loop
-                                         // spills -- a spill is an L2 round trip here, the L1 being what 220 KB of shared memory leave)
+constexpr int kLL2Warps = LL2_WARPS;     // consumer warps; one more warp streams the weights.  8 warps in all = 2 per scheduler: up to
+                                         // 255 registers per thread (a 9th warp caps the kernel at 168 and the main loop spills -- a
+                                         // spill is an L2 round trip here, the L1 being what 220 KB of shared memory leave).  Measured
+                                         // A/B (build parameter): 4 consumer warps 722 us per frame, 7 consumer warps 660 us
 constexpr int kLL2Threads = (kLL2Warps + 1) * 32;
 constexpr int kLL2MaxTeams = 8;          // sequences one launch can carry (one team of CTAs each)
 constexpr int kLL2ChunkKb = 24;          // k-blocks (of 32 elements) per ring stage

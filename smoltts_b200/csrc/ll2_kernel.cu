@@ -429,23 +429,34 @@ __device__ __noinline__ uint4 embed_chunk(const DevModel& M, int ch) {
 // ---- staging of a phase's input vector ---------------------------------------------------------------------
 // All consumer threads poll two words (one 16-byte load) per round of 512 words; a retry re-reads only what is missing.
 // The payloads land in shared memory as bf16 (dst, and dst2 if nonzero); returns the thread's sum of squares.
-__device__ __noinline__ float gather_words(const unsigned long long* src, int n_words, uint32_t e_src, uint32_t dst, uint32_t dst2) {
+__device__ __noinline__ float gather_words(const unsigned long long* src, int n_words, uint32_t e_src, uint32_t dst, uint32_t dst2, int stagger) {
     const int tid = threadIdx.x;
-    uint4 v[kGather];
+    uint4 v[kGather], w[kGather];
     bool need[kGather];
 #pragma unroll
     for (int i = 0; i < kGather; ++i) {
-        const int w = 2 * (tid + kCons * i);
-        need[i] = w < n_words;
+        const int wd = 2 * (tid + kCons * i);
+        need[i] = wd < n_words;
         v[i] = make_uint4(0u, e_src, 0u, e_src);
-        if (need[i]) v[i] = ld_relaxed_v4(src + w);
+        if (need[i]) v[i] = ld_relaxed_v4(src + wd);
+    }
+    // a second poll of every word half a round trip behind the first: a word that lands is seen after half the poll period
+    if (stagger > 0) { const uint32_t t0 = clock32_now(); while (clock32_now() - t0 < (uint32_t)stagger) {} }
+#pragma unroll
+    for (int i = 0; i < kGather; ++i) {
+        w[i] = v[i];
+        if (need[i] && stagger > 0) w[i] = ld_relaxed_v4(src + 2 * (tid + kCons * i));
     }
     uint32_t spins = 0;
     for (;;) {
         bool ready = true;
 #pragma unroll
         for (int i = 0; i < kGather; ++i) {
-            if (v[i].y != e_src || v[i].w != e_src) { ready = false; v[i] = ld_relaxed_v4(src + 2 * (tid + kCons * i)); }
+            if (v[i].y != e_src || v[i].w != e_src) {
+                v[i] = w[i];                                           // the poll issued half a period later
+                w[i] = ld_relaxed_v4(src + 2 * (tid + kCons * i));     // and the next one behind it
+                if (v[i].y != e_src || v[i].w != e_src) ready = false;
+            }
         }
         if (ready) break;
         LL2_SPIN_GUARD(spins);
@@ -905,24 +916,62 @@ __device__ __noinline__ void kv_append(const DevModel& M, const CallArgs& A, int
     *reinterpret_cast<uint32_t*>(dst) = word;
 }
 
-// The warp's k-blocks [lo, hi) of a stage against NT tiles.  A tile's k-block is 1024 bytes: for each of the two MMA steps
-// 32 lanes x 16 bytes = the lane's A fragment (a0..a3) exactly as mma.m16n8k16 wants it (ll2 packing, smol_pack_kernel);
-// the B fragment (the activation vector, the same in all 8 columns) is 16 bytes per lane for both steps.
+// One pass of NT tiles through the tensor cores: for every K chunk (ring stage per tile) the warp carries its k-blocks
+// through all NT tiles, then leaves its partial sums (row slots g and g + 8 of every tile) in shared memory.
+// A tile's k-block is 1024 bytes: for each of the two MMA steps 32 lanes x 16 bytes = the lane's A fragment (a0..a3)
+// exactly as mma.m16n8k16 wants it (smol_pack_kernel); the B fragment (the activation vector, the same in all 8 columns)
+// is 16 bytes per lane for both steps.  Two accumulators per tile (one per MMA step): no MMA waits for the one issued
+// just before it.  Ring stages are consumed strictly in order: (cslot, cpar) = slot and parity of the next one.
 template <int NT>
-__device__ __forceinline__ void mma_pass(float (&acc)[4][4], float (&acd)[4][4], const uint32_t (&abase)[4], uint32_t xb, int lo, int hi) {
+__device__ __forceinline__ void tile_pass(int kb, int chunks, int warp, int lane, uint32_t full0, uint32_t empty0, uint32_t ringl,
+                                          uint32_t ns, uint32_t xbl, uint32_t pw, bool writer, uint32_t& cslot, uint32_t& cpar) {
+    float acc[NT][4], acd[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc[i][e] = 0.f; acd[i][e] = 0.f; }
+    }
 #pragma unroll 1
-    for (int j = lo; j < hi; ++j) {
-        const uint4 bx = lds_v4(xb + (uint32_t)j * 64u);
-        uint4 a0[NT], a1[NT];
+    for (int kc = 0; kc < chunks; ++kc) {
+        const int kb0 = kc * kLL2ChunkKb, nkb = min(kLL2ChunkKb, kb - kb0);
+        const int lo = (nkb * warp) / kNW, hi = (nkb * (warp + 1)) / kNW;
+        uint32_t abase[NT];
+        uint32_t sl = cslot, pr = cpar;
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            a0[i] = lds_v4(abase[i] + (uint32_t)j * 1024u);
-            a1[i] = lds_v4(abase[i] + (uint32_t)j * 1024u + 512u);
+            mbar_wait(full0 + 8u * sl, pr);
+            abase[i] = ringl + sl * (uint32_t)kLL2SlotBytes;
+            if (++sl == ns) { sl = 0u; pr ^= 1u; }
         }
+        const uint32_t xb = xbl + (uint32_t)kb0 * 64u;
+#pragma unroll 1
+        for (int j = lo; j < hi; ++j) {
+            const uint4 bx = lds_v4(xb + (uint32_t)j * 64u);
+            uint4 a0[NT], a1[NT];
 #pragma unroll
-        for (int i = 0; i < NT; ++i) mma_bf16_16816(acc[i], a0[i].x, a0[i].y, a0[i].z, a0[i].w, bx.x, bx.y);
+            for (int i = 0; i < NT; ++i) {
+                a0[i] = lds_v4(abase[i] + (uint32_t)j * 1024u);
+                a1[i] = lds_v4(abase[i] + (uint32_t)j * 1024u + 512u);
+            }
 #pragma unroll
-        for (int i = 0; i < NT; ++i) mma_bf16_16816(acd[i], a1[i].x, a1[i].y, a1[i].z, a1[i].w, bx.z, bx.w);
+            for (int i = 0; i < NT; ++i) mma_bf16_16816(acc[i], a0[i].x, a0[i].y, a0[i].z, a0[i].w, bx.x, bx.y);
+#pragma unroll
+            for (int i = 0; i < NT; ++i) mma_bf16_16816(acd[i], a1[i].x, a1[i].y, a1[i].z, a1[i].w, bx.z, bx.w);
+        }
+        __syncwarp();
+        if (lane < NT) {   // lane i hands back the stage of tile i
+            uint32_t r = cslot + (uint32_t)lane;
+            if (r >= ns) r -= ns;
+            mbar_arrive(empty0 + 8u * r);
+        }
+        cslot = sl; cpar = pr;
+    }
+    if (writer) {   // lanes with c == 0: row slot g (acc[.][0]) and g + 8 (acc[.][2]); every column carries the same vector
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            sts_f32(pw + (uint32_t)(i * kNW * 16) * 4u, __fadd_rn(acc[i][0], acd[i][0]));
+            sts_f32(pw + (uint32_t)(i * kNW * 16 + 8) * 4u, __fadd_rn(acc[i][2], acd[i][2]));
+        }
     }
 }
 
@@ -1060,7 +1109,7 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             } else if (do_gather) {
                 if (SP.holdoff > 0) { while (clock32_now() - t_end < (uint32_t)SP.holdoff) {} }
                 if (kind == PH_WO && fast) fast_attention(M, layer, depth_pos, src, e_src, FQ, FKV, XB);
-                else ss = gather_words(src, n_src, e_src, XB, (normed && kind != PH_HEAD) ? res : 0u);
+                else ss = gather_words(src, n_src, e_src, XB, (normed && kind != PH_HEAD) ? res : 0u, SP.flags & 0xffff);
             }
             LL2_TRACE(1);
             if (normed) {
@@ -1110,54 +1159,14 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
 #pragma unroll 1
             for (int t0 = 0; t0 < tiles;) {
                 const int nt = chunks == 1 ? min(4, tiles - t0) : 1;
-                // two accumulators per tile (the two MMA steps of a k-block): no MMA waits for the one issued just before it
-                float acc[4][4], acd[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { acc[i][e] = 0.f; acd[i][e] = 0.f; }
-                }
-#pragma unroll 1
-                for (int kc = 0; kc < chunks; ++kc) {
-                    const int kb0 = kc * kLL2ChunkKb, nkb = min(kLL2ChunkKb, kb - kb0);
-                    const int lo = (nkb * warp) / kNW, hi = (nkb * (warp + 1)) / kNW;
-                    uint32_t abase[4];
-                    uint32_t sl = cslot, pr = cpar;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        abase[i] = RING;
-                        if (i < nt) {
-                            mbar_wait(full0 + 8u * sl, pr);
-                            abase[i] = RING + sl * (uint32_t)kLL2SlotBytes + (uint32_t)lane * 16u;
-                            if (++sl == NSLOTS) { sl = 0u; pr ^= 1u; }
-                        }
-                    }
-                    if (t0 == 0 && kc == 0) LL2_TRACE(7);   // the pass's weights are in shared memory
-                    const uint32_t xb = XB + (uint32_t)(kb0 * 32 + c * 8) * 2u;
-                    switch (nt) {
-                        case 1: mma_pass<1>(acc, acd, abase, xb, lo, hi); break;
-                        case 2: mma_pass<2>(acc, acd, abase, xb, lo, hi); break;
-                        case 3: mma_pass<3>(acc, acd, abase, xb, lo, hi); break;
-                        default: mma_pass<4>(acc, acd, abase, xb, lo, hi); break;
-                    }
-                    __syncwarp();
-                    if (lane < nt) {   // lane i hands back the stage of tile i
-                        uint32_t r = cslot + (uint32_t)lane;
-                        if (r >= NSLOTS) r -= NSLOTS;
-                        mbar_arrive(empty0 + 8u * r);
-                    }
-                    cslot = sl; cpar = pr;
-                }
-                // partial sums of the warp: row slot g (acc[.][0]) and g + 8 (acc[.][2]); every column carries the same vector
                 const uint32_t pbuf = PART + (pass_ctr & 1u) * (uint32_t)(4 * kNW * 16 * 4);
-                if (c == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (i < nt) {
-                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + g) * 4u, __fadd_rn(acc[i][0], acd[i][0]));
-                            sts_f32(pbuf + (uint32_t)((i * kNW + warp) * 16 + 8 + g) * 4u, __fadd_rn(acc[i][2], acd[i][2]));
-                        }
-                    }
+                const uint32_t ringl = RING + (uint32_t)lane * 16u, xbl = XB + (uint32_t)c * 16u;
+                const uint32_t pw = pbuf + (uint32_t)(warp * 16 + g) * 4u;
+                switch (nt) {
+                    case 1: tile_pass<1>(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar); break;
+                    case 2: tile_pass<2>(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar); break;
+                    case 3: tile_pass<3>(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar); break;
+                    default: tile_pass<4>(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar); break;
                 }
                 if (t0 + nt == tiles) LL2_TRACE(4);
                 csync();

@@ -105,11 +105,14 @@ def timing(args):
     for version, holdoffs in ((1, [0]), (2, [int(h) for h in args.holdoffs.split(",")])):
         model.set_option("ll_version", version)
         for h in holdoffs:
-            model.set_option("ll_holdoff", h)
-            run(8)
-            us = [run(args.frames) for _ in range(3)]
-            codes = int(batch.out_codes.sum().item())
-            print(f"ll_version={version} holdoff={h:5d} cycles: {min(us):8.1f} us/frame (runs {', '.join(f'{u:.1f}' for u in us)}) check={codes}")
+            for st in ([0] if version == 1 else [int(x) for x in args.staggers.split(",")]):
+                model.set_option("ll_holdoff", h)
+                model.set_option("ll_flags", st)
+                run(8)
+                us = [run(args.frames) for _ in range(3)]
+                codes = int(batch.out_codes.sum().item())
+                print(f"ll_version={version} holdoff={h:5d} stagger={st:4d} cycles: {min(us):8.1f} us/frame (runs {', '.join(f'{u:.1f}' for u in us)}) check={codes}")
+    model.set_option("ll_flags", args.trace_stagger)
     # cycle trace at the default hold-off
     model.set_option("ll_version", 2)
     model.set_option("ll_holdoff", args.trace_holdoff)
@@ -207,6 +210,8 @@ def main():
     ap.add_argument("--prompt-bytes", type=int, default=200)
     ap.add_argument("--holdoffs", default="0,200,400,600,800")
     ap.add_argument("--trace-holdoff", type=int, default=400)
+    ap.add_argument("--staggers", default="0,250,350")
+    ap.add_argument("--trace-stagger", type=int, default=0)
     ap.add_argument("--skip-check", action="store_true")
     ap.add_argument("--skip-timing", action="store_true")
     ap.add_argument("--teams", action="store_true")
