@@ -429,34 +429,25 @@ __device__ __noinline__ uint4 embed_chunk(const DevModel& M, int ch) {
 // ---- staging of a phase's input vector ---------------------------------------------------------------------
 // All consumer threads poll two words (one 16-byte load) per round of 512 words; a retry re-reads only what is missing.
 // The payloads land in shared memory as bf16 (dst, and dst2 if nonzero); returns the thread's sum of squares.
-__device__ __noinline__ float gather_words(const unsigned long long* src, int n_words, uint32_t e_src, uint32_t dst, uint32_t dst2, int stagger) {
+__device__ __noinline__ float gather_words(const unsigned long long* src, int n_words, uint32_t e_src, uint32_t dst, uint32_t dst2) {
+    // (A second, staggered poll of every word -- half a round trip behind the first -- was measured: the extra L2 poll
+    //  traffic costs more than the earlier discovery gains, 721 vs 656 us per frame.)
     const int tid = threadIdx.x;
-    uint4 v[kGather], w[kGather];
+    uint4 v[kGather];
     bool need[kGather];
 #pragma unroll
     for (int i = 0; i < kGather; ++i) {
-        const int wd = 2 * (tid + kCons * i);
-        need[i] = wd < n_words;
+        const int w = 2 * (tid + kCons * i);
+        need[i] = w < n_words;
         v[i] = make_uint4(0u, e_src, 0u, e_src);
-        if (need[i]) v[i] = ld_relaxed_v4(src + wd);
-    }
-    // a second poll of every word half a round trip behind the first: a word that lands is seen after half the poll period
-    if (stagger > 0) { const uint32_t t0 = clock32_now(); while (clock32_now() - t0 < (uint32_t)stagger) {} }
-#pragma unroll
-    for (int i = 0; i < kGather; ++i) {
-        w[i] = v[i];
-        if (need[i] && stagger > 0) w[i] = ld_relaxed_v4(src + 2 * (tid + kCons * i));
+        if (need[i]) v[i] = ld_relaxed_v4(src + w);
     }
     uint32_t spins = 0;
     for (;;) {
         bool ready = true;
 #pragma unroll
         for (int i = 0; i < kGather; ++i) {
-            if (v[i].y != e_src || v[i].w != e_src) {
-                v[i] = w[i];                                           // the poll issued half a period later
-                w[i] = ld_relaxed_v4(src + 2 * (tid + kCons * i));     // and the next one behind it
-                if (v[i].y != e_src || v[i].w != e_src) ready = false;
-            }
+            if (v[i].y != e_src || v[i].w != e_src) { ready = false; v[i] = ld_relaxed_v4(src + 2 * (tid + kCons * i)); }
         }
         if (ready) break;
         LL2_SPIN_GUARD(spins);
@@ -975,6 +966,44 @@ __device__ __forceinline__ void tile_pass(int kb, int chunks, int warp, int lane
     }
 }
 
+// A multi-stage tile (K = 3072: 4 ring stages): the warp takes ONE contiguous range of the tile's k-blocks -- it waits for
+// the stage(s) the range touches, runs one loop, and only then hands all stages back (every warp arrives once per stage).
+__device__ __forceinline__ void tile_pass_long(int kb, int chunks, int warp, int lane, uint32_t full0, uint32_t empty0, uint32_t ringl,
+                                               uint32_t ns, uint32_t xbl, uint32_t pw, bool writer, uint32_t& cslot, uint32_t& cpar) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acd[4] = {0.f, 0.f, 0.f, 0.f};
+    const int lo = (kb * warp) / kNW, hi = (kb * (warp + 1)) / kNW;
+    int cur = -1;
+    uint32_t abase = 0u;
+#pragma unroll 1
+    for (int j = lo; j < hi; ++j) {
+        const int kc = j / kLL2ChunkKb;
+        if (kc != cur) {   // first k-block of a stage: slot and parity follow from the running (cslot, cpar)
+            uint32_t sl = cslot + (uint32_t)kc, pr = cpar;
+            if (sl >= ns) { sl -= ns; pr ^= 1u; }
+            mbar_wait(full0 + 8u * sl, pr);
+            abase = ringl + sl * (uint32_t)kLL2SlotBytes - (uint32_t)(kc * kLL2ChunkKb) * 1024u;
+            cur = kc;
+        }
+        const uint4 bx = lds_v4(xbl + (uint32_t)j * 64u);
+        const uint4 a0 = lds_v4(abase + (uint32_t)j * 1024u), a1 = lds_v4(abase + (uint32_t)j * 1024u + 512u);
+        mma_bf16_16816(acc, a0.x, a0.y, a0.z, a0.w, bx.x, bx.y);
+        mma_bf16_16816(acd, a1.x, a1.y, a1.z, a1.w, bx.z, bx.w);
+    }
+    __syncwarp();
+    if (lane < chunks) {   // lane i hands back stage i of the tile
+        uint32_t r = cslot + (uint32_t)lane;
+        if (r >= ns) r -= ns;
+        mbar_arrive(empty0 + 8u * r);
+    }
+    uint32_t sl = cslot + (uint32_t)chunks;
+    if (sl >= ns) { sl -= ns; cpar ^= 1u; }
+    cslot = sl;
+    if (writer) {
+        sts_f32(pw, __fadd_rn(acc[0], acd[0]));
+        sts_f32(pw + 32u, __fadd_rn(acc[2], acd[2]));
+    }
+}
+
 template <bool kTrace>
 __global__ void __launch_bounds__(kLL2Threads, 1)
 smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ CallArgs A, const __grid_constant__ SmemPlan SP) {
@@ -1109,7 +1138,7 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
             } else if (do_gather) {
                 if (SP.holdoff > 0) { while (clock32_now() - t_end < (uint32_t)SP.holdoff) {} }
                 if (kind == PH_WO && fast) fast_attention(M, layer, depth_pos, src, e_src, FQ, FKV, XB);
-                else ss = gather_words(src, n_src, e_src, XB, (normed && kind != PH_HEAD) ? res : 0u, SP.flags & 0xffff);
+                else ss = gather_words(src, n_src, e_src, XB, (normed && kind != PH_HEAD) ? res : 0u);
             }
             LL2_TRACE(1);
             if (normed) {
@@ -1162,7 +1191,8 @@ smol_ll2_kernel(const __grid_constant__ DevModel M, const __grid_constant__ Call
                 const uint32_t pbuf = PART + (pass_ctr & 1u) * (uint32_t)(4 * kNW * 16 * 4);
                 const uint32_t ringl = RING + (uint32_t)lane * 16u, xbl = XB + (uint32_t)c * 16u;
                 const uint32_t pw = pbuf + (uint32_t)(warp * 16 + g) * 4u;
-                switch (nt) {
+                if (chunks > 1) tile_pass_long(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar);
+                else switch (nt) {
                     case 1: tile_pass<1>(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar); break;
                     case 2: tile_pass<2>(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar); break;
                     case 3: tile_pass<3>(kb, chunks, warp, lane, full0, empty0, ringl, NSLOTS, xbl, pw, c == 0, cslot, cpar); break;
@@ -1322,7 +1352,7 @@ bool ll2_plan(const DevModel& M, int holdoff, int flags, ll2::SmemPlan* sp, size
     off = (off + 1023) / 1024 * 1024;
     sp->ring = (int)off;
     const size_t budget = 227 * 1024 - 4096;   // static shared memory (barriers, sampler scratch, state) stays below 4 KB
-    if (off + 2 * (size_t)kLL2SlotBytes > budget) return false;
+    if (off + 4 * (size_t)kLL2SlotBytes > budget) return false;   // a K = 3072 tile holds four stages at once
     int n_slots = (int)((budget - off) / kLL2SlotBytes);
     if (n_slots > ll2::kMaxSlots) n_slots = ll2::kMaxSlots;
     sp->n_slots = n_slots;
