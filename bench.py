@@ -441,8 +441,8 @@ def measure(work: Work, args, steps: int, warmup: int, ctx) -> dict:
 
     dataflow = args.mode == 2 and work.batch <= model.get_option("ll_max_batch")
     tensor = not dataflow and work.batch >= model.get_option("tc_min_batch") > 0
-    kernel_name = (model.kernel_name(work.batch) if hasattr(model, "kernel_name") else
-                   "smol_ll_kernel" if dataflow else "smol_decode_kernel<0> (tcgen05 tiles, TMA operand ring)" if tensor else "smol_decode_kernel")
+    kernel_name = (("smol_ll2_kernel (tensor-core GEMV, LL flag words)" if model.get_option("ll_version") == 2 else "smol_ll_kernel") if dataflow
+                   else "smol_decode_kernel<0> (tcgen05 tiles, TMA operand ring)" if tensor else "smol_decode_kernel")
     traffic = load_traffic() or {}
     tr = (traffic.get(work.key) or {}).get("dram_bytes_per_frame") if work.model == "smoltts_byte_150m" else None
     res = {
@@ -455,7 +455,7 @@ def measure(work: Work, args, steps: int, warmup: int, ctx) -> dict:
                 "includes": "H2D prompt grid + prefill + decode + D2H codes via generate_batch()"
                             + (", + host-side gather of all ranks' codes on rank 0 (gloo)" if world > 1 else "")},
         "clocks": clocks, "gpu_launches": launches, "check": codes_check, "frame_latency_bs1": frame_lat,
-        "launch_mode": ("data-flow persistent kernel (LL flag words, TMA producer warp), one launch per step" if dataflow
+        "launch_mode": ("data-flow persistent kernel (LL flag words, TMA producer warp, one team of CTAs per sequence), one launch per step" if dataflow
                         else "persistent cooperative kernel with grid barriers, one launch per step" if args.mode != 1
                         else "per-phase launches in a CUDA graph"),
         "config": public_config(work, world),

@@ -74,7 +74,8 @@ struct SmolModel {
     int ll_version = 2;        // option: 1 = first-generation kernel (A/B), 2 = ll2_kernel.cu
     int ll2_state = 0;         // 0 unknown, 1 ready, -1 does not fit this model
     int ll2_holdoff = 400;     // option "ll_holdoff": cycles between the end of a phase and the first poll of the next
-    int ll2_max_batch = 1;     // option: sequences (teams of CTAs) the kernel carries per launch
+    int ll2_max_batch = 8;     // option: sequences (teams of CTAs) the kernel carries per launch; larger batches go to the
+                               // barrier kernel / its tcgen05 variant (measured at bs=8: 1.5 ms per frame step against 2.3 ms)
     smol::ll2::SmemPlan ll2_sp;
     size_t ll2_smem = 0;
     bool packed_ready = false; // tensor-core GEMV layout of the bound weights (rebuilt after a weight / workspace bind)

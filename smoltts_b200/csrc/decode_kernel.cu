@@ -90,13 +90,11 @@ __device__ __forceinline__ void grid_arrive(uint32_t* ctr, uint32_t& target, uin
 }
 __device__ __forceinline__ void grid_wait(uint32_t* ctr, uint32_t target) {
     if (threadIdx.x == 0) {
-        // relaxed polls (one L2 round trip each, nothing else), ONE acquire fence once the count is there: an acquiring load
-        // in the loop pays the fence on every iteration
+        // (relaxed polls + one acquire fence after the loop were measured: 2.95 vs 2.84 ms per step at bs=256 -- not faster)
         uint32_t v;
         do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         } while ((int32_t)(v - target) < 0);
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }

@@ -167,9 +167,11 @@ def test_modes_and_batch_composition_are_bit_identical():
     gs = GenerationSettings(default_temp=0.8, default_fast_temp=0.6, top_k=40, top_p=0.9, seed=77)
     try:
         model.set_option("tc_min_batch", 0)
+        model.set_option("ll_max_batch", 0)   # the data-flow kernel (batches of 1..8 by default) has its own test: test_gpu_ll2.py
         _modes_and_composition(model, prompts, gs)
     finally:
         model.set_option("tc_min_batch", 9)
+        model.set_option("ll_max_batch", 8)
         model.set_option("mode", 2)
 
 
@@ -188,13 +190,9 @@ def _modes_and_composition(model, prompts, gs):
     dflt = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=20, chunk=9)
     for a, b in zip(ref, dflt):
         assert torch.equal(a, b)
-    # alone: on the same (barrier) kernel -- the bs=1 data-flow kernel sums its dot products on the tensor cores, in another
-    # order; its own invariances are tests/test_gpu_ll2.py, its parity the oracle tests of this file
-    model.set_option("ll_max_batch", 0)
-    try:
-        solo = generate_batch(model, prompts[4:5], gs, audio_only=False, fixed_frames=20, seq_ids=[4])
-    finally:
-        model.set_option("ll_max_batch", 1)
+    # alone / in a batch of 3: still on the barrier kernel (the data-flow kernel sums its dot products on the tensor cores, in
+    # another order; its own invariances are tests/test_gpu_ll2.py, its parity the oracle tests of this file)
+    solo = generate_batch(model, prompts[4:5], gs, audio_only=False, fixed_frames=20, seq_ids=[4])
     assert torch.equal(solo[0], ref[4])
     trio = generate_batch(model, prompts[3:6], gs, audio_only=False, fixed_frames=20, seq_ids=[3, 4, 5])
     assert torch.equal(trio[1], ref[4])

@@ -187,3 +187,51 @@ def test_ll2_frame_clock_is_monotonic():
     assert all(b > a > 0 for a, b in zip(ns, ns[1:])), ns
     assert (ns[-1] - ns[0]) / 15 < 5e6, "more than 5 ms per frame on the tiny model"
     assert torch.equal(ref["codes"], got["codes"])
+
+
+@pytest.mark.parametrize("size,B", [("smoltts_byte_tiny", 8), ("smoltts_byte_70m", 3), ("smoltts_byte_150m", 5)])
+def test_ll2_teams_decode_every_sequence_as_if_alone(size, B):
+    """Batches of 2..8: one team of CTAs per sequence, each with its own word regions.  Rows over CTAs, K over warps: the
+    arithmetic does not depend on the team size, so every sequence must decode bit for bit as it does alone on 148 CTAs --
+    greedy and sampled (counters keyed by the global utterance id)."""
+    from smoltts_b200 import GenerationSettings, generate_batch
+
+    cfg, sd, model, orc = model_and_oracle(size, max_batch=8)
+    assert model.get_option("ll_max_batch") == 8
+    prompts = [prompt_grid(byte_prompt(14 + 9 * b, seed=120 + b), cfg) for b in range(B)]
+    ids = list(range(50, 50 + B))
+    for gs in (GenerationSettings(default_temp=0.0, default_fast_temp=0.0),
+               GenerationSettings(default_temp=0.8, default_fast_temp=0.6, top_k=40, top_p=0.9, seed=77)):
+        together = generate_batch(model, prompts, gs, audio_only=False, fixed_frames=10, chunk=4, seq_ids=ids)
+        assert model.get_option("ll_ready") == 1
+        for b in range(B):
+            alone = generate_batch(model, prompts[b:b + 1], gs, audio_only=False, fixed_frames=10, seq_ids=ids[b:b + 1])[0]
+            assert torch.equal(together[b], alone), f"{size}: sequence {b} of a batch of {B} differs from its solo decode"
+
+
+def test_ll2_team_stop_rule_freezes_one_sequence():
+    """<|im_end|> forced on sequence 1 in frame 2: its team freezes (tokens, seq_len, step) while sequence 0 keeps decoding
+    inside the same launches."""
+    cfg, sd, model, orc = model_and_oracle("smoltts_byte_tiny", max_batch=8)
+    B, R = 2, cfg.n_rows
+    prompts = [prompt_grid(byte_prompt(12 + b, seed=80 + b), cfg) for b in range(B)]
+    padded, lens = pack_prompts(model, prompts)
+    batch = model.new_batch(B, max_positions=64, max_frames=8)
+    try:
+        model.prefill(batch, padded, lens)
+        s = model.sampling(audio_only=True)
+        model.decode_frames(batch, s, 1)
+        force = torch.zeros(B, R, dtype=torch.int32, device=model.device)
+        force[:, 0] = 400
+        force[1, 0] = model.token_config.im_end_id
+        model.set_force(force)
+        model.decode_frames(batch, s, 1)
+        model.set_force(None)
+        model.decode_frames(batch, s, 4)
+        torch.cuda.synchronize()
+        assert batch.finished.tolist() == [0, 1] and batch.step.tolist() == [6, 2]
+        assert batch.seq_len.tolist() == [int(lens[0]) - 1 + 6, int(lens[1]) - 1 + 2]
+        assert batch.tokens[1, 0].item() == model.token_config.im_end_id
+    finally:
+        model.set_force(None)
+        batch.release()

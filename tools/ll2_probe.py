@@ -113,6 +113,14 @@ def timing(args):
                 codes = int(batch.out_codes.sum().item())
                 print(f"ll_version={version} holdoff={h:5d} stagger={st:4d} cycles: {min(us):8.1f} us/frame (runs {', '.join(f'{u:.1f}' for u in us)}) check={codes}")
     model.set_option("ll_flags", args.trace_stagger)
+    model.set_option("ll_version", 2)
+    model.set_option("ll_holdoff", args.trace_holdoff)
+    for n in [int(x) for x in args.n_ctas.split(",") if x]:
+        model.set_option("n_ctas", n)
+        run(8)
+        us = [run(args.frames) for _ in range(2)]
+        print(f"ll_version=2 n_ctas={n:4d}: {min(us):8.1f} us/frame")
+    model.set_option("n_ctas", 0)
     # cycle trace at the default hold-off
     model.set_option("ll_version", 2)
     model.set_option("ll_holdoff", args.trace_holdoff)
@@ -212,6 +220,7 @@ def main():
     ap.add_argument("--trace-holdoff", type=int, default=400)
     ap.add_argument("--staggers", default="0,250,350")
     ap.add_argument("--trace-stagger", type=int, default=0)
+    ap.add_argument("--n-ctas", default="", help="comma list of grid sizes to time")
     ap.add_argument("--skip-check", action="store_true")
     ap.add_argument("--skip-timing", action="store_true")
     ap.add_argument("--teams", action="store_true")
