@@ -520,47 +520,69 @@ __device__ __noinline__ void fast_attention(const DevModel& M, int layer, int de
     const int j = lane >> 2, part = lane & 3;
     const bool ok = j <= depth_pos;
     const uint32_t lay = fkv + (uint32_t)(layer * kLL2Depth * kvw) * 2u;
+    // a warp carries up to kHeadsPerWarp heads AT ONCE (their FMA chains and shuffle trees interleave): heads warp, warp + kNW, ..
+    constexpr int kHP = 2;
 #pragma unroll 1
-    for (int hq = warp; hq < Hq; hq += kNW) {
-        const int kvh = hq / G;
-        float s = 0.f;
-        if (ok) {
-            const uint32_t qa = fq + (uint32_t)(hq * kHeadDim + part * 16) * 2u;
-            const uint32_t ka = lay + (uint32_t)(j * kvw + kvh * kHeadDim + part * 16) * 2u;
-            float qf[8], kf[8];
-            unpack8(lds_v4(qa), qf); unpack8(lds_v4(ka), kf);
+    for (int h0 = warp; h0 < Hq; h0 += kHP * kNW) {
+        float s[kHP], sa[kHP];
+        uint32_t vw[kHP][8];
+        bool hv[kHP];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s = fmaf(qf[e], kf[e], s);
-            unpack8(lds_v4(qa + 16u), qf); unpack8(lds_v4(ka + 16u), kf);
+        for (int u = 0; u < kHP; ++u) {
+            const int hq = h0 + u * kNW;
+            hv[u] = hq < Hq;
+            const int kvh = hv[u] ? hq / G : 0;
+            s[u] = 0.f; sa[u] = 0.f;
+            if (ok && hv[u]) {
+                const uint32_t qa = fq + (uint32_t)(hq * kHeadDim + part * 16) * 2u;
+                const uint32_t ka = lay + (uint32_t)(j * kvw + kvh * kHeadDim + part * 16) * 2u;
+                float qf[8], kf[8];
+                unpack8(lds_v4(qa), qf); unpack8(lds_v4(ka), kf);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s = fmaf(qf[e], kf[e], s);
+                for (int e = 0; e < 8; ++e) s[u] = fmaf(qf[e], kf[e], s[u]);
+                unpack8(lds_v4(qa + 16u), qf); unpack8(lds_v4(ka + 16u), kf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sa[u] = fmaf(qf[e], kf[e], sa[u]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+                vw[u][jj] = (jj <= depth_pos && hv[u]) ? lds_u32(lay + (uint32_t)(jj * kvw + Hkv * kHeadDim + kvh * kHeadDim + 2 * lane) * 2u) : 0u;
         }
-        uint32_t vw[8];
+        float sc[kHP], m[kHP], pe[kHP], l[kHP];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-            vw[jj] = jj <= depth_pos ? lds_u32(lay + (uint32_t)(jj * kvw + Hkv * kHeadDim + kvh * kHeadDim + 2 * lane) * 2u) : 0u;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const float sc = ok ? s * 0.125f : -INFINITY;
-        float m = sc;
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-        const float pe = ok ? expf(sc - m) : 0.f;
-        float l = pe + 0.f;
-        l += __shfl_xor_sync(0xffffffffu, l, 4);
-        l += __shfl_xor_sync(0xffffffffu, l, 8);
-        l += __shfl_xor_sync(0xffffffffu, l, 16);
-        const float pb = bf16_round(pe);
-        float o0 = 0.f, o1 = 0.f;
+        for (int u = 0; u < kHP; ++u) s[u] = s[u] + sa[u];   // same order as one 16-term chain? no: two 8-term halves, added once
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const float pj = __shfl_sync(0xffffffffu, pb, jj * 4);
-            o0 = fmaf(pj, bf_lo(vw[jj]), o0);
-            o1 = fmaf(pj, bf_hi(vw[jj]), o1);
+        for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < kHP; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
         }
-        const float inv = 1.0f / l;
-        sts_u32(xs + (uint32_t)(hq * kHeadDim + 2 * lane) * 2u, pack_bf16(bf16_round(o0 * inv), bf16_round(o1 * inv)));
+#pragma unroll
+        for (int u = 0; u < kHP; ++u) { sc[u] = ok ? s[u] * 0.125f : -INFINITY; m[u] = sc[u]; }
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < kHP; ++u) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+        }
+#pragma unroll
+        for (int u = 0; u < kHP; ++u) { pe[u] = ok ? expf(sc[u] - m[u]) : 0.f; l[u] = pe[u] + 0.f; }
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < kHP; ++u) l[u] += __shfl_xor_sync(0xffffffffu, l[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < kHP; ++u) {
+            const float pb = bf16_round(pe[u]);
+            float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float pj = __shfl_sync(0xffffffffu, pb, jj * 4);
+                o0 = fmaf(pj, bf_lo(vw[u][jj]), o0);
+                o1 = fmaf(pj, bf_hi(vw[u][jj]), o1);
+            }
+            const float inv = 1.0f / l[u];
+            if (hv[u]) sts_u32(xs + (uint32_t)((h0 + u * kNW) * kHeadDim + 2 * lane) * 2u, pack_bf16(bf16_round(o0 * inv), bf16_round(o1 * inv)));
+        }
     }
 }
 
@@ -635,24 +657,47 @@ __device__ __noinline__ void phase_attn(const DevModel& M, const CallArgs& A, co
             }
         }
         csync();
+        // all (round, head) dot products are independent: their FMA chains and shuffle trees interleave
+        float sc[kRounds][kMaxGroup];
+        {
+            float kf[kRounds][8];
 #pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            float kf[8];
-            unpack8(kk[r], kf);
-            const int pos = p0 + (tid >> 3) + kPosPerRound * r;
-#pragma unroll 1
-            for (int h = 0; h < G; ++h) {
-                const uint32_t qa = scratch + (uint32_t)(h * kHeadDim + chunk * 8) * 4u;
-                const uint4 q0 = lds_v4(qa), q1 = lds_v4(qa + 16u);
-                float sc = 0.f;
-                sc = fmaf(__uint_as_float(q0.x), kf[0], sc); sc = fmaf(__uint_as_float(q0.y), kf[1], sc);
-                sc = fmaf(__uint_as_float(q0.z), kf[2], sc); sc = fmaf(__uint_as_float(q0.w), kf[3], sc);
-                sc = fmaf(__uint_as_float(q1.x), kf[4], sc); sc = fmaf(__uint_as_float(q1.y), kf[5], sc);
-                sc = fmaf(__uint_as_float(q1.z), kf[6], sc); sc = fmaf(__uint_as_float(q1.w), kf[7], sc);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-                if (chunk == 0 && pos < p1) st_relaxed_v2(score_words(M, tm, layer, kvh * G + h) + pos, __float_as_uint(sc), epoch);
+            for (int r = 0; r < kRounds; ++r) unpack8(kk[r], kf[r]);
+#pragma unroll
+            for (int h = 0; h < kMaxGroup; ++h) {
+                if (h < G) {
+                    const uint32_t qa = scratch + (uint32_t)(h * kHeadDim + chunk * 8) * 4u;
+                    const uint4 q0 = lds_v4(qa), q1 = lds_v4(qa + 16u);
+#pragma unroll
+                    for (int r = 0; r < kRounds; ++r) {
+                        float a = __uint_as_float(q0.x) * kf[r][0];
+                        a = fmaf(__uint_as_float(q0.y), kf[r][1], a); a = fmaf(__uint_as_float(q0.z), kf[r][2], a);
+                        a = fmaf(__uint_as_float(q0.w), kf[r][3], a); a = fmaf(__uint_as_float(q1.x), kf[r][4], a);
+                        a = fmaf(__uint_as_float(q1.y), kf[r][5], a); a = fmaf(__uint_as_float(q1.z), kf[r][6], a);
+                        sc[r][h] = fmaf(__uint_as_float(q1.w), kf[r][7], a);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kRounds; ++r) sc[r][h] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) {
+#pragma unroll
+                for (int h = 0; h < kMaxGroup; ++h)
+                    if (h < G) sc[r][h] += __shfl_xor_sync(0xffffffffu, sc[r][h], o);
+            }
+        }
+        if (chunk == 0) {
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) {
+                const int pos = p0 + (tid >> 3) + kPosPerRound * r;
+#pragma unroll
+                for (int h = 0; h < kMaxGroup; ++h)
+                    if (h < G && pos < p1) st_relaxed_v2(score_words(M, tm, layer, kvh * G + h) + pos, __float_as_uint(sc[r][h]), epoch);
             }
         }
         csync();

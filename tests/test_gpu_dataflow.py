@@ -170,6 +170,7 @@ def test_dataflow_stop_rule_and_force():
     res = {}
     for mode in (0, 2):
         model.set_option("mode", mode)
+        model.set_option("ll_version", 1)
         padded, lens = pack_prompts(model, prompts)
         batch = model.new_batch(B, max_positions=64, max_frames=8)
         try:
