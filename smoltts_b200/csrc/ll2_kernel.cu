@@ -508,13 +508,34 @@ __device__ __noinline__ void fast_attention(const DevModel& M, int layer, int de
     const int Hq = M.fn_head, Hkv = M.fn_kv, G = Hq / Hkv;
     const int q_rows = Hq * kHeadDim, kvw = 2 * Hkv * kHeadDim;  // elements
     const uint32_t slot = fkv + (uint32_t)((layer * kLL2Depth + depth_pos) * kvw) * 2u;
-    for (int i = tid; i < (q_rows + kvw) / 4; i += kCons) {  // 4 elements = 2 words = one 16-byte load
-        uint4 v = ld_relaxed_v4(qkv + 2 * i);
+    {   // 4 elements = 2 words = one 16-byte load; all of a thread's polls are in flight together
+        constexpr int kPer = (1024 / 4 + 512 / 4 + kCons - 1) / kCons;   // up to 16 q heads + 8 kv heads
+        const int n_it = (q_rows + kvw) / 4;
+        uint4 v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kCons;
+            v[k] = make_uint4(0u, e_qkv, 0u, e_qkv);
+            if (i < n_it) v[k] = ld_relaxed_v4(qkv + 2 * i);
+        }
         uint32_t spins = 0;
-        while (v.y != e_qkv || v.w != e_qkv) { LL2_SPIN_GUARD(spins); v = ld_relaxed_v4(qkv + 2 * i); }
-        const int e = 4 * i;
-        const uint32_t dst = e < q_rows ? fq + (uint32_t)e * 2u : slot + (uint32_t)(e - q_rows) * 2u;
-        sts_v2(dst, v.x, v.z);
+        for (;;) {
+            bool ready = true;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k)
+                if (v[k].y != e_qkv || v[k].w != e_qkv) { ready = false; v[k] = ld_relaxed_v4(qkv + 2 * (tid + k * kCons)); }
+            if (ready) break;
+            LL2_SPIN_GUARD(spins);
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kCons;
+            if (i < n_it) {
+                const int e = 4 * i;
+                const uint32_t dst = e < q_rows ? fq + (uint32_t)e * 2u : slot + (uint32_t)(e - q_rows) * 2u;
+                sts_v2(dst, v[k].x, v[k].z);
+            }
+        }
     }
     csync();
     const int j = lane >> 2, part = lane & 3;
