@@ -118,7 +118,8 @@ def pack_prompts(model: RQTransformer, prompts: Sequence[torch.Tensor]):
     """list of [R, S_i] -> (padded [B, R, s_max] int32 device, lengths [B] int32 device)."""
     R = model.config.n_rows
     s_max = max(int(p.shape[-1]) for p in prompts)
-    out = torch.zeros(len(prompts), R, s_max, dtype=torch.int32)
+    pin = model.device.type == "cuda"      # page-locked staging: the copy below is one asynchronous DMA
+    out = torch.zeros(len(prompts), R, s_max, dtype=torch.int32, pin_memory=pin)
     lens = []
     for b, p in enumerate(prompts):
         p2 = p if p.ndim == 2 else p[0]
@@ -126,7 +127,8 @@ def pack_prompts(model: RQTransformer, prompts: Sequence[torch.Tensor]):
             raise ValueError(f"prompt {b} has {p2.shape[0]} rows, model expects {R}")
         out[b, :, : p2.shape[1]] = p2.to(torch.int32).cpu()
         lens.append(int(p2.shape[1]))
-    return out.to(model.device), torch.tensor(lens, dtype=torch.int32, device=model.device)
+    lens_h = torch.tensor(lens, dtype=torch.int32, pin_memory=pin)
+    return out.to(model.device, non_blocking=pin), lens_h.to(model.device, non_blocking=pin)
 
 
 def generate_batch(model: RQTransformer, prompts: Sequence[torch.Tensor], generation_settings: GenerationSettings,

@@ -78,7 +78,7 @@ def _prefill_and_frames(model, prompts, n_frames, tc_min_batch, mode=2, prefill_
     model.set_option("prefill_tile", prefill_tile)
     B = len(prompts)
     padded, lens = pack_prompts(model, prompts)
-    batch = model.new_batch(B, max_positions=256, max_frames=n_frames)
+    batch = model.new_batch(B, max_positions=max(256, int(max(lens)) + n_frames + 2), max_frames=n_frames)
     try:
         pages = torch.tensor(batch.pages, device=model.device)
         model.kv_view()[pages] = 0
@@ -137,6 +137,13 @@ def test_tc_prefill_tile_sizes_and_batch_composition_bit_identical():
     for tile in (40, 16):
         b = _prefill_and_frames(model, prompts[20:21], 3, 9, prefill_tile=tile)
         assert torch.equal(a["kv"].view(torch.int16), b["kv"].view(torch.int16)), f"prefill tile {tile}"
+        assert torch.equal(a["codes"], b["codes"])
+    # a long prompt: one iteration of 4 row tiles (up to 512 positions) against 128- and 100-position iterations
+    long_prompt = [prompt_grid(byte_prompt(420, seed=77), cfg)]
+    a = _prefill_and_frames(model, long_prompt, 2, 9)
+    for tile in (128, 100):
+        b = _prefill_and_frames(model, long_prompt, 2, 9, prefill_tile=tile)
+        assert torch.equal(a["kv"].view(torch.int16), b["kv"].view(torch.int16)), f"long prompt, prefill tile {tile}"
         assert torch.equal(a["codes"], b["codes"])
 
 
