@@ -14,8 +14,7 @@
 namespace smol {
 
 constexpr int kTcRows = umma::kM;
-constexpr int kTcSplit = 128;  // cached positions per attention split of the batch attention (CallArgs.tc_split overrides it;
-                               // measured 64 / 128 / 256 at L = 100 / 420 / 2200: gpurun_out/attn_split_ab.log)
+constexpr int kTcSplit = 128;  // cached positions per attention split of the batch attention (CallArgs.tc_split overrides it)
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -198,14 +197,62 @@ __device__ void tc_fast_attention(const DevModel& M, const CallArgs& A, const Ct
     }
 }
 
-// Decode attention over the paged cache for a batch: one WARP per (row, kv head, split of kTcSplit positions); each
-// 8-lane group owns one cached position per step, four steps (16 positions, their K and V) in flight per iteration.
+// ---- batch attention on the tensor cores -------------------------------------------------------------------------
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32): the 16 rows of the A operand are the query rows that share one kv head's
+// cached K/V -- the G query heads of the kv head (GQA) times, in a prefill iteration, up to 16/G consecutive prompt
+// positions of the sequence -- so one pass over a position's 256 bytes of K|V serves all of them.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// Split schedule of the batch attention: ABSOLUTE position ranges, the same for every row whatever its length -- 16
+// splits of s0 positions, then splits of 2*s0 -- so that rows of different lengths (the consecutive prompt positions of a
+// prefill group) share their K/V passes and a row's result is still a function of its own context only (it combines, in
+// split order, the splits that start below its length).  s0 = 128 covers 6144 positions with kMaxSplits = 32 splits.
+struct SplitPlan {
+    int s0, wide_from;   // splits [0, wide_from) hold s0 positions, later ones 2*s0
+    __device__ __forceinline__ int lo(int k) const { return k <= wide_from ? k * s0 : wide_from * s0 + (k - wide_from) * 2 * s0; }
+    __device__ __forceinline__ int count(int L) const {   // splits that start below position L
+        if (L <= wide_from * s0) return (L + s0 - 1) / s0;
+        return wide_from + (L - wide_from * s0 + 2 * s0 - 1) / (2 * s0);
+    }
+};
+__device__ __forceinline__ SplitPlan split_plan(const CallArgs& A, int cap) {
+    SplitPlan sp;
+    if (A.tc_split >= 16) {   // the caller's override (tests): uniform splits, widened only if kMaxSplits would not cover cap
+        sp.s0 = max(A.tc_split & ~15, (((cap + kMaxSplits - 1) / kMaxSplits) + 15) & ~15);
+        sp.wide_from = kMaxSplits;
+        return sp;
+    }
+    sp.s0 = kTcSplit;
+    sp.wide_from = kMaxSplits / 2;
+    while (sp.lo(kMaxSplits) < cap) sp.s0 *= 2;
+    return sp;
+}
+
+// Decode / prefill attention over the paged cache for a batch.  Unit = one WARP per (query group, kv head, split); a
+// query group is one decode row, or up to 16/G consecutive prompt positions of one sequence.  Per 16 cached positions:
+// S = Q K^T (2 n-tiles x 4 k-steps), online softmax in base 2 with P rounded to bf16 for the PV product as the reference's
+// SDPA does (P:559-566; the denominator sums the unrounded fp32 values), O += P V (8 n-tiles).  K, V and Q fragments are
+// loaded straight from global memory with 16-byte loads: the k index of the QK product and the n index of the PV product
+// are permuted so that every thread's fragment words are contiguous in memory (a dot product does not care about the
+// order of its dims as long as both operands use the same one).
 // Splits of a long row meet through M.partial / M.split_count; the last arriver combines them in split order.
 __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx& c, const Phase& ph) {
-    constexpr int GM = kMaxGroup;
     const int Hq = M.n_head, Hkv = M.n_kv, ps = M.page_size, G = Hq / Hkv;
-    const int dch = c.lane & 7, psub = c.lane >> 3;
     const int cap = A.b.max_pages * ps;
+    const int T = A.tile_t > 1 ? A.tile_t : 1;
+    const int P = T > 1 ? 16 / G : 1;              // query positions per unit
+    const int gps = (T + P - 1) / P;               // units (groups) per sequence
+    const int n_groups = (A.batch / T) * gps;
+    const int gq = c.lane >> 2, tq = c.lane & 3;   // fragment coordinates of this lane
     // splits to enumerate: enough for the longest row of the batch (one pass over seq_len; rows with fewer splits skip)
     if (c.tid == 0) g_flag = 1;
     __syncthreads();
@@ -220,193 +267,209 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
         if (c.lane == 0) atomicMax(&g_flag, lmax);
     }
     __syncthreads();
-    // split length: a function of the row's own length only (64 positions up to 256 cached positions, 128 beyond:
-    // measured at L = 100 / 420 / 2200, gpurun_out/attn_split_ab.log), or the caller's override
-    const int forced = A.tc_split >= 16 ? (A.tc_split & ~15) : 0;
-    auto split_of = [&](int L) { return forced ? forced : (L <= 4 * kSplitMin ? kSplitMin : kTcSplit); };
-    const int lmax = min(g_flag, cap);
-    int s_cap = max((lmax + split_of(lmax) - 1) / split_of(lmax), (min(lmax, 4 * kSplitMin) + split_of(1) - 1) / split_of(1));
-    if (s_cap > kMaxSplits) s_cap = kMaxSplits;
-    if (s_cap < 1) s_cap = 1;
-    const int n_tasks = A.batch * Hkv * s_cap;
+    const SplitPlan sp = split_plan(A, cap);
+    const int s_cap = min(sp.count(min(g_flag, cap)), kMaxSplits);
+    const int n_tasks = n_groups * Hkv * s_cap;
     const size_t head_stride = (size_t)ps * kHeadDim;
-    for (int t = c.cta * kWarps + c.warp; t < n_tasks; t += c.n_ctas * kWarps) {
-        const int s = t % s_cap, kvh = (t / s_cap) % Hkv, b = t / (s_cap * Hkv);
-        const int bs = row_seq(A, b);
-        int Lb = ldcg_i32(A.b.seq_len + bs) + row_off(A, b) + 1;
-        if (Lb > cap) Lb = cap;
-        int ns = (Lb + split_of(Lb) - 1) / split_of(Lb);
-        if (ns > kMaxSplits) ns = kMaxSplits;
-        if (s >= ns) continue;
-        int chunk = (Lb + ns - 1) / ns;
-        chunk = (chunk + 15) & ~15;
-        const int p0 = s * chunk, p1 = min(Lb, p0 + chunk);
+    const size_t page_stride = (size_t)M.n_layer * 2 * Hkv * head_stride;
+    constexpr float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e): softmax in base 2
 
-        float qf[GM][8];
-#pragma unroll
-        for (int g = 0; g < GM; ++g) {
-            if (g >= G) continue;
-            unpack8(ldcg_v4(M.q + (size_t)b * Hq * kHeadDim + (kvh * G + g) * kHeadDim + dch * 8), qf[g]);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) qf[g][e] *= 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e): softmax in base 2
+    for (int t = c.cta * kWarps + c.warp; t < n_tasks; t += c.n_ctas * kWarps) {
+        const int s = t % s_cap, kvh = (t / s_cap) % Hkv, grp = t / (s_cap * Hkv);
+        const int b0 = (grp / gps) * T + (grp % gps) * P;            // first batch row of the group
+        const int nq = min(P, T - (grp % gps) * P);                   // its live query positions
+        const int bs = row_seq(A, b0);
+        const int len0 = ldcg_i32(A.b.seq_len + bs);
+        const int L0 = len0 + row_off(A, b0) + 1;                     // context of the first row (its own position included)
+        const int Lg = min(L0 + nq - 1, cap);                         // ... of the last one
+        const int p0 = sp.lo(s);
+        if (p0 >= Lg) continue;
+        // cached positions that hold data: everything up to the group's last ACTIVE row (rows past the end of a prompt do
+        // not append; their stale slots must not reach the PV product of the active rows as 0 x garbage)
+        int Lload = Lg;
+        if (A.mode == 1) {
+            const int act = ldcg_i32(A.prompt_len + bs) - 1 - (A.iter_base + c.iter * T);
+            Lload = min(Lg, len0 + max(0, min(act, T)));
         }
-        float m[GM], l[GM], acc[GM][8];
-#pragma unroll
-        for (int g = 0; g < GM; ++g) {
-            m[g] = -INFINITY; l[g] = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
+        const int p1 = min(Lg, sp.lo(s + 1));
+        const int pl = min(p1, Lload);
+        // the two query rows of this lane: row r = (query position r / G, head r % G)
+        const int ra = gq, rb = gq + 8;
+        const int ia = ra / G, ib = rb / G;
+        const bool va = ia < nq, vb = ib < nq;
+        const int La = min(L0 + ia, cap), Lb = min(L0 + ib, cap);     // causal limits (positions < L are visible)
+        uint32_t qa[4][4];
+        {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const uint16_t* qpa = M.q + ((size_t)(b0 + ia) * Hq + kvh * G + (ra - ia * G)) * kHeadDim + tq * 8;
+            const uint16_t* qpb = M.q + ((size_t)(b0 + ib) * Hq + kvh * G + (rb - ib * G)) * kHeadDim + tq * 8;
+            const uint4 a0 = va ? ldcg_v4(qpa) : z, a1 = va ? ldcg_v4(qpa + 32) : z;
+            const uint4 c0 = vb ? ldcg_v4(qpb) : z, c1 = vb ? ldcg_v4(qpb + 32) : z;
+            // k-step ks covers the dims {32 (ks >> 1) + 8 tq + 4 (ks & 1) + 0..3} of this lane (K uses the same map)
+            qa[0][0] = a0.x; qa[0][1] = c0.x; qa[0][2] = a0.y; qa[0][3] = c0.y;
+            qa[1][0] = a0.z; qa[1][1] = c0.z; qa[1][2] = a0.w; qa[1][3] = c0.w;
+            qa[2][0] = a1.x; qa[2][1] = c1.x; qa[2][2] = a1.y; qa[2][3] = c1.y;
+            qa[3][0] = a1.z; qa[3][1] = c1.z; qa[3][2] = a1.w; qa[3][3] = c1.w;
         }
+        float o[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { o[n][0] = 0.f; o[n][1] = 0.f; o[n][2] = 0.f; o[n][3] = 0.f; }
+        float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;      // running max (quad-uniform), this lane's share of the sums
         const int32_t* bt = A.b.block_table + (size_t)bs * A.b.max_pages;
-        const size_t layer_off = ((size_t)ph.layer * 2 * Hkv + kvh) * head_stride + (size_t)dch * 8;
-        const size_t page_stride = (size_t)M.n_layer * 2 * Hkv * head_stride;
-        // page ids of the split: lane i holds the id of the i-th page the split touches (one coalesced load; longer
-        // splits -- contexts beyond 32 x 64 positions -- reload every 32 pages)
-        const int pg0 = p0 / ps;
-        int pg_base = pg0;
-        int my_page = (pg_base + c.lane) * ps < p1 ? ldcg_i32(bt + pg_base + c.lane) : 0;
+        const size_t layer_off = ((size_t)ph.layer * 2 * Hkv + kvh) * head_stride;
+        // page ids of the split: lane i holds the id of the i-th page the split touches (one coalesced load; a split longer
+        // than 32 pages reloads).  A 16-position group never straddles a page (pages hold 16 or 32 positions).
+        int pg_base = p0 / ps;
+        int my_page = (pg_base + c.lane) * ps < pl ? ldcg_i32(bt + pg_base + c.lane) : 0;
         for (int pb = p0; pb < p1; pb += 16) {
-            uint4 kk[4], vv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int p = pb + j * 4 + psub;
-                const int pg = min(p, p1 - 1) / ps;
-                const int page = __shfl_sync(0xffffffffu, my_page, (pg - pg_base) & 31);
-                kk[j] = make_uint4(0u, 0u, 0u, 0u); vv[j] = kk[j];
-                if (p < p1) {
-                    const uint16_t* kp = M.kv_pool + (size_t)page * page_stride + layer_off + (size_t)(p % ps) * kHeadDim;
-                    kk[j] = ldcg_v4(kp);
-                    vv[j] = ldcg_v4(kp + (size_t)Hkv * head_stride);
-                }
+            if (pb / ps - pg_base >= 32) {
+                pg_base = pb / ps;
+                my_page = (pg_base + c.lane) * ps < pl ? ldcg_i32(bt + pg_base + c.lane) : 0;
             }
-            if ((pb + 16) / ps - pg_base >= 31 && pb + 16 < p1) {  // next group may leave the window of 32 cached page ids
-                pg_base = (pb + 16) / ps;
-                my_page = (pg_base + c.lane) * ps < p1 ? ldcg_i32(bt + pg_base + c.lane) : 0;
-            }
-            // scores of the group's four positions for every head (log2 domain: q carries 1/8 * log2 e), then ONE
-            // running-max update per head and iteration -- a third fewer instructions than an update per position,
-            // and the phase is issue-bound (profiles/r1c: ~600 instructions per lane and 16 positions before)
-            float sc[GM][4];
+            const int page = __shfl_sync(0xffffffffu, my_page, (pb / ps - pg_base) & 31);
+            const uint16_t* kbase = M.kv_pool + (size_t)page * page_stride + layer_off + (size_t)(pb % ps) * kHeadDim;
+            const uint16_t* vbase = kbase + (size_t)Hkv * head_stride;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            uint4 kk[2][2], vv[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool valid = pb + j * 4 + psub < p1;
-                float kf[8];
-                unpack8(kk[j], kf);
-#pragma unroll
-                for (int g = 0; g < GM; ++g) {
-                    if (g >= G) continue;
-                    float t = 0.f;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) t = fmaf(qf[g][e], kf[e], t);
-                    t += __shfl_xor_sync(0xffffffffu, t, 1);
-                    t += __shfl_xor_sync(0xffffffffu, t, 2);
-                    t += __shfl_xor_sync(0xffffffffu, t, 4);
-                    sc[g][j] = valid ? t : -INFINITY;
-                }
+            for (int j = 0; j < 2; ++j) {      // K rows of n-tile j: position pb + 8 j + gq, this lane's 2 x 8 dims
+                const bool ok = pb + 8 * j + gq < pl;
+                const uint16_t* kp = kbase + (size_t)(8 * j + gq) * kHeadDim + tq * 8;
+                kk[j][0] = ok ? ldcg_v4(kp) : z;
+                kk[j][1] = ok ? ldcg_v4(kp + 32) : z;
             }
 #pragma unroll
-            for (int g = 0; g < GM; ++g) {
-                if (g >= G) continue;
-                const float mn = fmaxf(fmaxf(m[g], fmaxf(sc[g][0], sc[g][1])), fmaxf(sc[g][2], sc[g][3]));
-                const float mref = (mn == -INFINITY) ? 0.f : mn;   // nothing seen yet: every factor below becomes 0
-                const float corr = ex2(m[g] - mref);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sc[g][j] = ex2(sc[g][j] - mref);
-                l[g] = fmaf(l[g], corr, (sc[g][0] + sc[g][1]) + (sc[g][2] + sc[g][3]));
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[g][e] *= corr;
-                m[g] = mn;
+            for (int j = 0; j < 4; ++j) {      // V rows pb + {2 tq, 2 tq + 1, 2 tq + 8, 2 tq + 9}, dims 8 gq .. 8 gq + 7
+                const int r = 2 * tq + (j & 1) + 8 * (j >> 1);
+                vv[j] = pb + r < pl ? ldcg_v4(vbase + (size_t)r * kHeadDim + gq * 8) : z;
             }
+            float sc[2][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float vf[8];
-                unpack8(vv[j], vf);
+            for (int j = 0; j < 2; ++j) {
+                sc[j][0] = 0.f; sc[j][1] = 0.f; sc[j][2] = 0.f; sc[j][3] = 0.f;
+                mma16816(sc[j], qa[0], kk[j][0].x, kk[j][0].y);
+                mma16816(sc[j], qa[1], kk[j][0].z, kk[j][0].w);
+                mma16816(sc[j], qa[2], kk[j][1].x, kk[j][1].y);
+                mma16816(sc[j], qa[3], kk[j][1].z, kk[j][1].w);
+            }
+            // scores in the log2 domain, causal mask per row, one running-max update per row and 16 positions
+            float mna = ma, mnb = mb;
 #pragma unroll
-                for (int g = 0; g < GM; ++g) {
-                    if (g >= G) continue;
+            for (int j = 0; j < 2; ++j) {
+                const int pc = pb + 8 * j + 2 * tq;
+                sc[j][0] = pc < La ? sc[j][0] * kScale : -INFINITY;
+                sc[j][1] = pc + 1 < La ? sc[j][1] * kScale : -INFINITY;
+                sc[j][2] = pc < Lb ? sc[j][2] * kScale : -INFINITY;
+                sc[j][3] = pc + 1 < Lb ? sc[j][3] * kScale : -INFINITY;
+                mna = fmaxf(mna, fmaxf(sc[j][0], sc[j][1]));
+                mnb = fmaxf(mnb, fmaxf(sc[j][2], sc[j][3]));
+            }
+            mna = fmaxf(mna, __shfl_xor_sync(0xffffffffu, mna, 1));
+            mna = fmaxf(mna, __shfl_xor_sync(0xffffffffu, mna, 2));
+            mnb = fmaxf(mnb, __shfl_xor_sync(0xffffffffu, mnb, 1));
+            mnb = fmaxf(mnb, __shfl_xor_sync(0xffffffffu, mnb, 2));
+            const float refa = (mna == -INFINITY) ? 0.f : mna, refb = (mnb == -INFINITY) ? 0.f : mnb;   // nothing visible yet: all factors 0
+            const float ca = ex2(ma - refa), cb = ex2(mb - refb);
+            ma = mna; mb = mnb;
+            float sa = 0.f, sb = 0.f;
+            uint32_t pa[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(sc[g][j], vf[e], acc[g][e]);
+            for (int j = 0; j < 2; ++j) {
+                const float e0 = ex2(sc[j][0] - refa), e1 = ex2(sc[j][1] - refa);
+                const float e2 = ex2(sc[j][2] - refb), e3 = ex2(sc[j][3] - refb);
+                sa += e0 + e1; sb += e2 + e3;
+                pa[2 * j] = pack_bf16(e0, e1);       // row a, k = 8 j + 2 tq, + 1
+                pa[2 * j + 1] = pack_bf16(e2, e3);   // row b
+            }
+            la = fmaf(la, ca, sa); lb = fmaf(lb, cb, sb);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) { o[n][0] *= ca; o[n][1] *= ca; o[n][2] *= cb; o[n][3] *= cb; }
+            // O += P V: n-tile n, column gq of the B fragment = dim 8 gq + n; k pairs (2 tq, 2 tq + 1) and (2 tq + 8, 2 tq + 9)
+            const uint32_t v0[4] = {vv[0].x, vv[0].y, vv[0].z, vv[0].w}, v1[4] = {vv[1].x, vv[1].y, vv[1].z, vv[1].w};
+            const uint32_t v2[4] = {vv[2].x, vv[2].y, vv[2].z, vv[2].w}, v3[4] = {vv[3].x, vv[3].y, vv[3].z, vv[3].w};
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const uint32_t sel = (n & 1) ? 0x7632u : 0x5410u;
+                mma16816(o[n], pa, prmt(v0[n >> 1], v1[n >> 1], sel), prmt(v2[n >> 1], v3[n >> 1], sel));
+            }
+        }
+        la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
+        lb += __shfl_xor_sync(0xffffffffu, lb, 1); lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+        // this lane holds, for rows a and b, the dims 16 tq + n (o[n][0], o[n][2]) and 16 tq + 8 + n (o[n][1], o[n][3])
+        bool need_count = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool valid = h ? vb : va;
+            const int r = h ? rb : ra, i = h ? ib : ia, Lr = h ? Lb : La;
+            if (!valid || Lr <= p0) continue;            // padding row, or a row that ends before this split starts
+            const int row = b0 + i, hq = kvh * G + (r - i * G);
+            const float lsum = h ? lb : la, mrow = h ? mb : ma;
+            if (sp.count(Lr) == 1) {
+                float x0[8], x1[8];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) { x0[n] = o[n][2 * h] / lsum; x1[n] = o[n][2 * h + 1] / lsum; }
+                uint16_t* dst = M.attn + (size_t)row * Hq * kHeadDim + hq * kHeadDim + 16 * tq;
+                *reinterpret_cast<uint4*>(dst) = pack8(x0);
+                *reinterpret_cast<uint4*>(dst + 8) = pack8(x1);
+            } else {
+                need_count = true;
+                float* dst = M.partial + (((size_t)row * Hq + hq) * kMaxSplits + s) * kPartialStride;
+                if (tq == 0) { dst[0] = mrow; dst[1] = lsum; }
+#pragma unroll
+                for (int n = 0; n < 8; n += 2) {
+                    *reinterpret_cast<float2*>(dst + 2 + 16 * tq + n) = make_float2(o[n][2 * h], o[n + 1][2 * h]);
+                    *reinterpret_cast<float2*>(dst + 2 + 16 * tq + 8 + n) = make_float2(o[n][2 * h + 1], o[n + 1][2 * h + 1]);
                 }
             }
         }
-        // merge the four position groups of the warp
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
-#pragma unroll
-            for (int g = 0; g < GM; ++g) {
-                if (g >= G) continue;
-                const float mo = __shfl_xor_sync(0xffffffffu, m[g], o);
-                const float lo = __shfl_xor_sync(0xffffffffu, l[g], o);
-                const float mn = fmaxf(m[g], mo);
-                const float c1 = (m[g] == -INFINITY) ? 0.f : ex2(m[g] - mn);
-                const float c2 = (mo == -INFINITY) ? 0.f : ex2(mo - mn);
-                l[g] = fmaf(l[g], c1, __fmul_rn(lo, c2));
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float ao = __shfl_xor_sync(0xffffffffu, acc[g][e], o);
-                    acc[g][e] = fmaf(acc[g][e], c1, __fmul_rn(ao, c2));
-                }
-                m[g] = mn;
-            }
-        }
-        if (ns == 1) {
-            if (psub == 0) {
-#pragma unroll
-                for (int g = 0; g < GM; ++g) {
-                    if (g >= G) continue;
-                    float o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = acc[g][e] / l[g];
-                    *reinterpret_cast<uint4*>(M.attn + (size_t)b * Hq * kHeadDim + (kvh * G + g) * kHeadDim + dch * 8) = pack8(o);
-                }
-            }
-            continue;
-        }
-        if (psub == 0) {
-#pragma unroll
-            for (int g = 0; g < GM; ++g) {
-                if (g >= G) continue;
-                float* dst = M.partial + (((size_t)b * Hq + kvh * G + g) * kMaxSplits + s) * kPartialStride;
-                if (dch == 0) { dst[0] = m[g]; dst[1] = l[g]; }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dst[2 + dch * 8 + e] = acc[g][e];
-            }
-        }
+        if (!__any_sync(0xffffffffu, need_count)) continue;
         __threadfence();
         __syncwarp();
+        // one arrival per (row, kv head); the last split of a row combines all of its splits in split order
+        int ns_row = 0;
         uint32_t old = 0;
-        if (c.lane == 0) old = atomicAdd(M.split_count + (size_t)b * Hkv + kvh, 1u);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old != (uint32_t)(ns - 1)) continue;
-        __threadfence();  // last split of this (row, kv head): combine all splits in split order
-        for (int g = 0; g < G; ++g) {  // lane i holds split i's (m, l); outputs: lane owns dims 2*lane, 2*lane+1
-            const int hq = kvh * G + g;
-            const float* base = M.partial + ((size_t)b * Hq + hq) * kMaxSplits * kPartialStride;
-            const float m_l = c.lane < ns ? ldcg_f32(base + c.lane * kPartialStride) : -INFINITY;
-            const float l_l = c.lane < ns ? ldcg_f32(base + c.lane * kPartialStride + 1) : 0.f;
-            const float Mg = warp_max(m_l);
-            const float sc_l = (m_l == -INFINITY) ? 0.f : ex2(m_l - Mg);
-            float Lg = 0.f, O0 = 0.f, O1 = 0.f;
-            for (int si = 0; si < ns; si += 4) {
-                float2 o[4];
+        if (c.lane < nq) {
+            const int Lr = min(L0 + c.lane, cap);
+            ns_row = sp.count(Lr);
+            if (ns_row > 1 && Lr > p0) old = atomicAdd(M.split_count + (size_t)(b0 + c.lane) * Hkv + kvh, 1u);
+            else ns_row = 0;
+        }
+        uint32_t last = __ballot_sync(0xffffffffu, ns_row > 1 && old == (uint32_t)(ns_row - 1));
+        if (!last) continue;
+        __threadfence();
+        while (last) {
+            const int i = __ffs(last) - 1;
+            last &= last - 1;
+            const int row = b0 + i, ns = __shfl_sync(0xffffffffu, ns_row, i);
+            for (int g = 0; g < G; ++g) {  // lane j holds split j's (m, l); outputs: lane owns dims 2*lane, 2*lane+1
+                const int hq = kvh * G + g;
+                const float* base = M.partial + ((size_t)row * Hq + hq) * kMaxSplits * kPartialStride;
+                const float m_l = c.lane < ns ? ldcg_f32(base + c.lane * kPartialStride) : -INFINITY;
+                const float l_l = c.lane < ns ? ldcg_f32(base + c.lane * kPartialStride + 1) : 0.f;
+                const float Mg = warp_max(m_l);
+                const float sc_l = (m_l == -INFINITY) ? 0.f : ex2(m_l - Mg);
+                float Lsum = 0.f, O0 = 0.f, O1 = 0.f;
+                for (int si = 0; si < ns; si += 4) {
+                    float2 ov[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    o[u] = si + u < ns ? __ldcg(reinterpret_cast<const float2*>(base + (si + u) * kPartialStride + 2 + 2 * c.lane))
-                                       : make_float2(0.f, 0.f);
+                    for (int u = 0; u < 4; ++u)
+                        ov[u] = si + u < ns ? __ldcg(reinterpret_cast<const float2*>(base + (si + u) * kPartialStride + 2 + 2 * c.lane))
+                                            : make_float2(0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float sc = __shfl_sync(0xffffffffu, sc_l, (si + u) & 31);
-                    const float ll = __shfl_sync(0xffffffffu, l_l, (si + u) & 31);
-                    if (si + u < ns) {
-                        Lg = fmaf(ll, sc, Lg);
-                        O0 = fmaf(o[u].x, sc, O0);
-                        O1 = fmaf(o[u].y, sc, O1);
+                    for (int u = 0; u < 4; ++u) {
+                        const float scu = __shfl_sync(0xffffffffu, sc_l, (si + u) & 31);
+                        const float ll = __shfl_sync(0xffffffffu, l_l, (si + u) & 31);
+                        if (si + u < ns) {
+                            Lsum = fmaf(ll, scu, Lsum);
+                            O0 = fmaf(ov[u].x, scu, O0);
+                            O1 = fmaf(ov[u].y, scu, O1);
+                        }
                     }
                 }
+                *reinterpret_cast<uint32_t*>(M.attn + (size_t)row * Hq * kHeadDim + hq * kHeadDim + 2 * c.lane) = pack_bf16(O0 / Lsum, O1 / Lsum);
             }
-            *reinterpret_cast<uint32_t*>(M.attn + (size_t)b * Hq * kHeadDim + hq * kHeadDim + 2 * c.lane) = pack_bf16(O0 / Lg, O1 / Lg);
+            if (c.lane == 0) M.split_count[(size_t)row * Hkv + kvh] = 0u;
         }
-        if (c.lane == 0) M.split_count[(size_t)b * Hkv + kvh] = 0u;
     }
 }
 
