@@ -441,7 +441,7 @@ def measure(work: Work, args, steps: int, warmup: int, ctx) -> dict:
 
     dataflow = args.mode == 2 and work.batch <= model.get_option("ll_max_batch")
     tensor = not dataflow and work.batch >= model.get_option("tc_min_batch") > 0
-    kernel_name = (("smol_ll2_kernel (tensor-core GEMV, LL flag words)" if model.get_option("ll_version") == 2 else "smol_ll_kernel") if dataflow
+    kernel_name = ("smol_ll2_kernel (tensor-core GEMV, LL flag words)" if dataflow
                    else "smol_decode_kernel<0> (tcgen05 tiles, TMA operand ring)" if tensor else "smol_decode_kernel")
     traffic = load_traffic() or {}
     tr = (traffic.get(work.key) or {}).get("dram_bytes_per_frame") if work.model == "smoltts_byte_150m" else None

@@ -27,13 +27,7 @@ cudaError_t sample_launch(const float* logits, int n, int batch, const SmolSampl
 cudaError_t store_codes_launch(int32_t* frame_tokens, const int32_t* codes, int batch, int n_rows, int row,
                                cudaStream_t stream);
 cudaError_t silu_lut_launch(uint16_t* lut, cudaStream_t stream);
-// data-flow kernel (ll_kernel.cu)
-size_t ll_smem_plan(const DevModel& M, int bt, int n_ctas, int* xs_bytes, int* res_bytes, int* scratch_bytes, int* ring_bytes);
-cudaError_t ll_configure(int bt, size_t smem);
-cudaError_t ll_max_ctas(int bt, size_t smem, int* per_sm);
-cudaError_t ll_launch(const DevModel& M, const CallArgs& A, int bt, int n_ctas, size_t smem, int xs_bytes, int res_bytes,
-                      int scratch_bytes, int ring_bytes, cudaStream_t stream);
-// second-generation data-flow kernel (ll2_kernel.cu)
+// data-flow kernel (ll2_kernel.cu)
 namespace ll2 { using SmemPlan = LL2SmemPlan; }
 bool ll2_plan(const DevModel& M, int holdoff, int flags, ll2::SmemPlan* sp, size_t* smem);
 cudaError_t ll2_configure(size_t smem);
@@ -59,10 +53,6 @@ struct SmolModel {
     int device = 0, n_sms = 0, n_ctas = 0, n_ctas_override = 0;
     size_t smem[9] = {0}, xs_bytes[9] = {0};  // indexed by batch tile (1, 2, 4, 8)
     bool tile_ready[9] = {false};
-    // data-flow kernel, indexed by batch tile
-    size_t ll_smem[9] = {0};
-    int ll_xs[9] = {0}, ll_res[9] = {0}, ll_scratch[9] = {0}, ll_ring[9] = {0};
-    int ll_state[9] = {0};  // 0 unknown, 1 ready, -1 does not fit
     int mode = 2;
     int repeat = 0;
     int prefill_tile = 0;  // option: cap of prompt positions per prefill iteration (0 = as many as fit)
@@ -70,8 +60,7 @@ struct SmolModel {
     int tc_min_batch = 9;  // rows (sequences, or prompt positions of a prefill tile) from which the tcgen05 variant runs:
                            // measured crossover (150m, us per frame): bs 8: 2276 CUDA-core vs 2566 tensor-core; bs 12: 3642 vs 2577
     int ll_flags = 0;  // data-flow kernel: A/B switches and hold-off override (tools/ll_ncu.py)
-    // second-generation data-flow kernel
-    int ll_version = 2;        // option: 1 = first-generation kernel (A/B), 2 = ll2_kernel.cu
+    // data-flow kernel
     int ll2_state = 0;         // 0 unknown, 1 ready, -1 does not fit this model
     int ll2_holdoff = 400;     // option "ll_holdoff": cycles between the end of a phase and the first poll of the next
     int ll2_max_batch = 8;     // option: sequences (teams of CTAs) the kernel carries per launch; larger batches go to the
@@ -111,7 +100,7 @@ static int imax(int a, int b) { return a > b ? a : b; }
 
 struct WsLayout {
     size_t x, h, xf, q, attn, act, xn, silu_lut, tmaps, kpart, fkv, token_logits, depth_logits, frame_tokens, partial, split_count, barrier;
-    size_t ll, ll_partial, ll_tok, ll_cand, ll_epoch, ll2_score, ll2_tok, ll2_cand, packed, total;
+    size_t ll, ll_epoch, ll2_score, ll2_tok, ll2_cand, packed, total;
 };
 
 static int ll_batch_of(const SmolConfig& c) { (void)c; return smol::kLL2MaxTeams; }  // word regions for up to 8 teams
@@ -180,9 +169,6 @@ static WsLayout ws_layout(const SmolConfig& c, int depth) {
     L.barrier = take(256);
     const int bl = ll_batch_of(c);
     L.ll = take(ll_regions(c, depth, bl, nullptr, nullptr) * 8);
-    L.ll_partial = take((size_t)2 * bl * c.n_head * smol::kMaxSplits * smol::kPartialStride * 8);
-    L.ll_tok = take((size_t)bl * (1 + depth) * smol::kLLMaxCtas * 8);
-    L.ll_cand = take((size_t)(1 + depth) * smol::kLLRep * smol::kLLMaxCtas * 8);
     L.ll_epoch = take(256);
     L.ll2_score = take((size_t)bl * 2 * c.n_head * ll2_score_len(c) * 8);
     L.ll2_tok = take((size_t)bl * (1 + depth) * smol::kLLMaxCtas * 8);
@@ -324,9 +310,7 @@ int smol_bind_workspace(SmolModel* m, void* d_workspace, size_t bytes) {
     d.frame_tokens = (int32_t*)(base + L.frame_tokens);
     d.partial = (float*)(base + L.partial); d.split_count = (uint32_t*)(base + L.split_count);
     d.barrier = (uint32_t*)(base + L.barrier);
-    d.ll = (unsigned long long*)(base + L.ll); d.ll_partial = (unsigned long long*)(base + L.ll_partial);
-    d.ll_tok = (unsigned long long*)(base + L.ll_tok); d.ll_epoch = (uint32_t*)(base + L.ll_epoch);
-    d.ll_cand = (unsigned long long*)(base + L.ll_cand);
+    d.ll = (unsigned long long*)(base + L.ll); d.ll_epoch = (uint32_t*)(base + L.ll_epoch);
     d.ll2_score = (unsigned long long*)(base + L.ll2_score); d.ll2_tok = (unsigned long long*)(base + L.ll2_tok);
     d.ll2_cand = (unsigned long long*)(base + L.ll2_cand); d.ll2_score_len = ll2_score_len(m->cfg);
     m->packed_ready = false;
@@ -372,7 +356,7 @@ static int ensure_configured(SmolModel* m) {
     if (!coop) return fail(SMOL_ERR_UNSUPPORTED, "device does not support cooperative launch");
     m->n_ctas = m->n_sms;
     if (m->n_ctas_override > 0 && m->n_ctas_override < m->n_ctas) m->n_ctas = m->n_ctas_override;
-    for (int i = 0; i < 9; ++i) { m->tile_ready[i] = false; m->ll_state[i] = 0; }
+    for (int i = 0; i < 9; ++i) m->tile_ready[i] = false;
     if (m->ll2_state > 0) m->ll2_state = 0;
     m->configured = true;
     return SMOL_OK;
@@ -512,18 +496,6 @@ static int check_batch(const SmolModel* m, const SmolBatch* b, int batch) {
 
 // Enqueue `n_iter` iterations of phases [begin, end).  mode 0: one cooperative launch.
 // mode 1: one launch per phase (optionally the caller wraps a frame in a graph).
-// Shared-memory plan of the data-flow kernel for this batch tile; ll_state -1 = it does not fit this model.
-static int ensure_ll_tile(SmolModel* m, int bt) {
-    if (m->ll_state[bt] != 0) return SMOL_OK;
-    m->ll_smem[bt] = smol::ll_smem_plan(m->dm, bt, m->n_ctas, &m->ll_xs[bt], &m->ll_res[bt], &m->ll_scratch[bt], &m->ll_ring[bt]);
-    if (m->ll_smem[bt] == 0 || m->n_ctas > smol::kLLMaxCtas) { m->ll_state[bt] = -1; return SMOL_OK; }
-    CU(smol::ll_configure(bt, m->ll_smem[bt]));
-    int per_sm = 0;
-    CU(smol::ll_max_ctas(bt, m->ll_smem[bt], &per_sm));
-    m->ll_state[bt] = per_sm >= 1 ? 1 : -1;
-    return SMOL_OK;
-}
-
 // whole_iters: the call runs complete frames / complete prefill positions (what the data-flow kernel carries).
 static bool use_tc(const SmolModel* m, int rows) {
     return m->tc_min_batch > 0 && rows >= m->tc_min_batch && tc_eligible(m->cfg);
@@ -534,7 +506,7 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
     int rc;
     A.repeat = m->repeat;
     A.tc_split = m->tc_attn_split;
-    if (m->mode == 2 && whole_iters && A.mode == 0 && m->ll_version == 2 && A.batch <= m->ll2_max_batch && A.batch <= smol::kLL2MaxTeams &&
+    if (m->mode == 2 && whole_iters && A.mode == 0 && A.batch <= m->ll2_max_batch && A.batch <= smol::kLL2MaxTeams &&
         A.batch <= m->n_ctas) {
         if ((rc = ensure_ll2(m))) return rc;
         if (m->ll2_state == 1) {
@@ -543,17 +515,6 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
             m->ll2_sp.holdoff = m->ll2_holdoff;
             m->ll2_sp.flags = m->ll_flags;
             CU(smol::ll2_launch(m->dm, A, m->ll2_sp, m->ll2_smem, A.team_ctas * A.batch, stream));
-            m->launches += 1;
-            return SMOL_OK;
-        }
-    }
-    if (m->mode == 2 && whole_iters && m->ll_version == 1 && A.batch <= smol::kLLMaxBatch && A.batch <= m->dm.ll_batch) {
-        if ((rc = ensure_ll_tile(m, bt))) return rc;
-        if (m->ll_state[bt] == 1) {
-            if (A.n_iter == 0 && !A.finalize) return SMOL_OK;
-            A.repeat = m->ll_flags;  // the data-flow kernel reads its switches from this field
-            CU(smol::ll_launch(m->dm, A, bt, m->n_ctas, m->ll_smem[bt], m->ll_xs[bt], m->ll_res[bt], m->ll_scratch[bt],
-                               m->ll_ring[bt], stream));
             m->launches += 1;
             return SMOL_OK;
         }
@@ -828,11 +789,6 @@ int smol_set_option(SmolModel* m, const char* name, int64_t value) {
         m->ll_flags = (int)value;
         return SMOL_OK;
     }
-    if (!std::strcmp(name, "ll_version")) {
-        if (value != 1 && value != 2) return fail(SMOL_ERR_INVALID, "ll_version must be 1 or 2");
-        m->ll_version = (int)value;
-        return SMOL_OK;
-    }
     if (!std::strcmp(name, "ll_holdoff")) {
         m->ll2_holdoff = value > 0 ? (int)value : 0;
         return SMOL_OK;
@@ -860,15 +816,11 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!std::strcmp(name, "smem_bytes")) return (int64_t)m->smem[1];
     if (!std::strcmp(name, "tc_min_batch")) return m->tc_min_batch;
     if (!std::strcmp(name, "tc_ready")) return m->tile_ready[0] ? 1 : 0;
-    if (!std::strcmp(name, "ll_smem_bytes")) return (int64_t)m->ll_smem[1];
-    if (!std::strcmp(name, "ll_ring_bytes")) return (int64_t)m->ll_ring[1];
-    if (!std::strcmp(name, "ll_ready")) return (int64_t)(m->ll_version == 2 ? m->ll2_state : m->ll_state[1]);
-    if (!std::strcmp(name, "ll_max_batch")) return (int64_t)(m->ll_version == 2 ? m->ll2_max_batch : 1);
-    if (!std::strcmp(name, "ll1_ready")) return (int64_t)m->ll_state[1];
-    if (!std::strcmp(name, "ll_version")) return (int64_t)m->ll_version;
+    if (!std::strcmp(name, "ll_smem_bytes")) return (int64_t)m->ll2_smem;
+    if (!std::strcmp(name, "ll_ready")) return (int64_t)m->ll2_state;
+    if (!std::strcmp(name, "ll_max_batch")) return (int64_t)m->ll2_max_batch;
     if (!std::strcmp(name, "ll_holdoff")) return (int64_t)m->ll2_holdoff;
-    if (!std::strcmp(name, "ll2_smem_bytes")) return (int64_t)m->ll2_smem;
-    if (!std::strcmp(name, "ll2_slots")) return (int64_t)m->ll2_sp.n_slots;
+    if (!std::strcmp(name, "ll_slots")) return (int64_t)m->ll2_sp.n_slots;
     return -1;
 }
 

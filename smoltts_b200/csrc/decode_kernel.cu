@@ -554,8 +554,10 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
                     const float corr = (m[g] == -INFINITY) ? 0.f : expf(m[g] - mn);
                     const float pe = expf(sc - mn);
                     l[g] = fmaf(l[g], corr, pe);
+                    // the reference's SDPA rounds P to bf16 for the PV product and sums the unrounded values (P:559-566)
+                    const float pq = bf16_round(pe);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(acc[g][e], corr, pe * vf[e]);
+                    for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(acc[g][e], corr, pq * vf[e]);
                     m[g] = mn;
                 }
             }
@@ -571,7 +573,7 @@ __device__ void phase_attn_g(const DevModel& M, const CallArgs& A, const Ctx& c,
                 const float mn = fmaxf(m[g], mo);
                 const float c1 = (m[g] == -INFINITY) ? 0.f : expf(m[g] - mn);
                 const float c2 = (mo == -INFINITY) ? 0.f : expf(mo - mn);
-                l[g] = fmaf(l[g], c1, __fmul_rn(lo, c2));  // explicit: ll_kernel.cu must contract identically
+                l[g] = fmaf(l[g], c1, __fmul_rn(lo, c2));
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float ao = __shfl_xor_sync(0xffffffffu, acc[g][e], o);

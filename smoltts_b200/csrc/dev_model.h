@@ -20,15 +20,9 @@ constexpr int kPartialStride = 66;     // (m, l, o[64]) per attention partial
 constexpr int kMaxProg = 512;          // phases of one frame's program
 constexpr int kMaxRows = kMaxDepth + 1; // rows of one token column
 
-// ---- data-flow ("LL") decode kernel (ll_kernel.cu) ----
-constexpr int kLLWarps = 11;             // consumer warps of the data-flow kernel; warp 11 is the TMA producer
-constexpr int kLLThreads = (kLLWarps + 1) * 32;  // 12 warps: 3 per scheduler -> 168 registers per thread, no spills (local
-                                         // memory misses L1 next to 227 KB of shared memory: a spill costs an L2 round trip)
-constexpr int kLLMaxBatch = 1;         // sequences the data-flow kernel carries (the bs=1 latency path)
+// ---- data-flow ("LL") decode kernel (ll2_kernel.cu): tensor-core GEMV, one team of CTAs per sequence ----
 constexpr int kLLRep = 8;              // replicas of every broadcast vector (spreads the polls over L2 slices)
 constexpr int kLLMaxCtas = 256;        // token words are published once per CTA
-
-// ---- data-flow kernel, second generation (ll2_kernel.cu): tensor-core GEMV, team of CTAs per sequence ----
 #ifndef LL2_WARPS
 #define LL2_WARPS 7
 #endif
@@ -125,16 +119,12 @@ struct DevModel {
     // data-flow kernel: every phase publishes its output as 8-byte words {payload, epoch} that the
     // consumers poll ("LL" protocol: the flag travels with the data, no barrier, no fence)
     unsigned long long* ll;          // phase p, sequence b, replica r: ll + ll_off[p] + (b * kLLRep + r) * ll_len[p]
-    unsigned long long* ll_partial;  // split-KV partials [2][ll_batch][n_head][kMaxSplits][66] words
-    unsigned long long* ll_tok;      // sampled ids [ll_batch][n_rows][kLLMaxCtas] words
-    unsigned long long* ll_cand;     // greedy candidates (best logit | index) of every CTA [n_rows][kLLRep][kLLMaxCtas] words
     uint32_t* ll_epoch;              // [0] phases executed by earlier launches (epochs never repeat)
     int ll_batch;
     uint32_t ll_step_words;          // words between the regions of the same phase of two consecutive depth steps
     uint32_t ll_off[kMaxProg];
     uint16_t ll_len[kMaxProg];
 
-    // second-generation data-flow kernel
     const uint16_t* pk_head;         // packed LM head
     const uint16_t* pk_fast_output;  // packed depth heads (row groups in checkpoint order)
     unsigned long long* ll2_score;   // attention scores {fp32 bits, epoch} [teams][2][n_head][ll2_score_len] words

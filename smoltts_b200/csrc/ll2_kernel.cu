@@ -1,19 +1,23 @@
-// The DualAR decode step as a DATA-FLOW persistent kernel, second generation (sm_100a) -- the latency path.
+// The DualAR decode step as a DATA-FLOW persistent kernel (sm_100a) -- the latency path (batches 1..8).
 //
 // A frame at batch 1 is a chain of ~200 dependent matrix-vector products; what bounds it is the hand-off between them
-// and the dependent instruction chain inside a CTA, not bytes.  Same protocol as the first generation (ll_kernel.cu:
+// and the dependent instruction chain inside a CTA, not bytes.  No grid barrier anywhere:
 // every phase publishes 8-byte words {payload | epoch}, consumers poll exactly the words they need, weights stream
-// through a shared-memory ring fed by a TMA producer warp that never waits for activations) with a different body:
+// through a shared-memory ring fed by a TMA producer warp that never waits for activations.  (The round-1 kernel used the
+// same protocol with CUDA-core GEMVs, one warp per two rows; it is in the git history, ll_kernel.cu.)
 //
 //  * GEMV on the tensor cores.  mma.sync m16n8k16 (bf16 in, fp32 accumulate): the 16 rows of a tile are weight rows,
-//    the 8 columns all carry the one activation vector.  Weights are packed at bind time as
-//    [group of 8 rows][K / 32][8 rows][32 elements], so that a warp's A fragment of a 32-element k-block is ONE
-//    conflict-free 16-byte shared-memory load per lane and a CTA's rows of a phase are one contiguous bulk copy per
-//    8-row group.  A 16 x 768 tile costs a warp ~15 instructions per 96 elements of K instead of ~200 FMA/unpack
-//    instructions per row pair; the 8 consumer warps split K, partial sums meet in shared memory in warp order.
-//  * Everybody polls, nobody computes alone: the 256 consumer threads poll two words each (one 16-byte load), so the
-//    staging of the input vector, the sum of squares of RMSNorm (per-warp partials, summed in warp order) and the
-//    normalisation of each warp's own K slice (kept in registers as B fragments) are a few instructions per thread.
+//    the 8 columns all carry the one activation vector.  Weights are packed once at bind time (smol_pack_kernel) as
+//    ready-made A fragments, [tile of 16 rows][K / 32][MMA step 2][lane 32][16 bytes] (gated MLP: a tile = 8 rows of w1
+//    over the same 8 rows of w3), so that a warp's A fragment is ONE conflict-free 16-byte shared-memory load per lane and
+//    a CTA's tiles of a phase are one contiguous run of 24 KB ring stages (one bulk copy each).  The 7 consumer warps
+//    split K; a pass carries up to 4 tiles through one K sweep (the B fragments -- the activation -- are loaded once),
+//    partial sums meet in shared memory and are added in warp order by a warp that rotates from pass to pass.
+//    A 16 x 768 tile costs a warp ~15 instructions per 96 elements of K instead of ~200 FMA/unpack instructions per
+//    row pair on the CUDA cores (the round-1 kernel).
+//  * Everybody polls, nobody computes alone: all 224 consumer threads poll the input vector (16-byte loads, two words
+//    each), every thread normalises four elements in place (RMSNorm: per-warp sums of squares, added in warp order),
+//    so staging + norm are a few instructions per thread instead of one warp's 1 200-cycle chain.
 //  * A precise hold-off (clock-based) before the first poll of a phase: a poll issued before the producers' stores can
 //    have reached L2 only adds L2 traffic and one wasted round trip.
 //  * Slow attention with the reference's softmax semantics (torch CPU SDPA, which the oracle runs): score units

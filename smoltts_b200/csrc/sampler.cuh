@@ -11,7 +11,7 @@
 #include "common.cuh"
 #include "dev_model.h"
 
-// Block barrier over the kThreads sampling threads.  The data-flow kernel (ll_kernel.cu) runs an extra
+// Block barrier over the kThreads sampling threads.  The data-flow kernel (ll2_kernel.cu) runs an extra
 // producer warp next to them and substitutes a named barrier.
 #ifndef SMOL_BLOCK_SYNC
 #define SMOL_BLOCK_SYNC() __syncthreads()

@@ -316,33 +316,57 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
         for (int n = 0; n < 8; ++n) { o[n][0] = 0.f; o[n][1] = 0.f; o[n][2] = 0.f; o[n][3] = 0.f; }
         float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;      // running max (quad-uniform), this lane's share of the sums
         const int32_t* bt = A.b.block_table + (size_t)bs * A.b.max_pages;
-        const size_t layer_off = ((size_t)ph.layer * 2 * Hkv + kvh) * head_stride;
         // page ids of the split: lane i holds the id of the i-th page the split touches (one coalesced load; a split longer
         // than 32 pages reloads).  A 16-position group never straddles a page (pages hold 16 or 32 positions).
-        int pg_base = p0 / ps;
-        int my_page = (pg_base + c.lane) * ps < pl ? ldcg_i32(bt + pg_base + c.lane) : 0;
+        const int psh = ps == 32 ? 5 : 4;
+        int pg_base = p0 >> psh;
+        int my_page = ((pg_base + c.lane) << psh) < pl ? ldcg_i32(bt + pg_base + c.lane) : 0;
+        // Addressing is the hot loop's other half (the phase is issue-bound): everything per-lane is a byte offset fixed
+        // before the loop, a group costs one shuffle and one 64-bit multiply-add, full groups load without predicates.
+        const char* pool = reinterpret_cast<const char*>(M.kv_pool) + ((size_t)ph.layer * 2 * Hkv + kvh) * head_stride * 2;
+        const size_t page_bytes = page_stride * 2, v_delta = (size_t)Hkv * head_stride * 2;
+        const uint32_t koff = (uint32_t)(gq * kHeadDim + tq * 8) * 2;        // K row gq (n-tile 1: + 8 rows), this lane's dims 8 tq .. (+ 32)
+        const uint32_t voff = (uint32_t)(2 * tq * kHeadDim + gq * 8) * 2;    // V rows 2 tq (+ 1, + 8, + 9), dims 8 gq ..
+        auto group_base = [&](int pb) -> const char* {
+            const int pg = pb >> psh;
+            if (pg - pg_base >= 32) {
+                pg_base = pg;
+                my_page = ((pg_base + c.lane) << psh) < pl ? ldcg_i32(bt + pg_base + c.lane) : 0;
+            }
+            const int page = __shfl_sync(0xffffffffu, my_page, (pg - pg_base) & 31);
+            return pool + (size_t)page * page_bytes + ((size_t)(pb & (ps - 1)) << 7);
+        };
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        uint4 kk[2][2], vv[4];
+        auto load_k = [&](const char* gb, int pb) {      // K rows of n-tile j: position pb + 8 j + gq, this lane's 2 x 8 dims
+            const char* kp = gb + koff;
+            if (pb + 16 <= pl) {
+                kk[0][0] = ldcg_v4(kp); kk[0][1] = ldcg_v4(kp + 64);
+                kk[1][0] = ldcg_v4(kp + 1024); kk[1][1] = ldcg_v4(kp + 1088);
+            } else {
+                const bool ok0 = pb + gq < pl, ok1 = pb + 8 + gq < pl;
+                kk[0][0] = ok0 ? ldcg_v4(kp) : z; kk[0][1] = ok0 ? ldcg_v4(kp + 64) : z;
+                kk[1][0] = ok1 ? ldcg_v4(kp + 1024) : z; kk[1][1] = ok1 ? ldcg_v4(kp + 1088) : z;
+            }
+        };
+        auto load_v = [&](const char* gb, int pb) {      // V rows pb + {2 tq, 2 tq + 1, 2 tq + 8, 2 tq + 9}, dims 8 gq .. 8 gq + 7
+            const char* vp = gb + v_delta + voff;
+            if (pb + 16 <= pl) {
+                vv[0] = ldcg_v4(vp); vv[1] = ldcg_v4(vp + 128); vv[2] = ldcg_v4(vp + 1024); vv[3] = ldcg_v4(vp + 1152);
+            } else {
+                const int r = pb + 2 * tq;
+                vv[0] = r < pl ? ldcg_v4(vp) : z; vv[1] = r + 1 < pl ? ldcg_v4(vp + 128) : z;
+                vv[2] = r + 8 < pl ? ldcg_v4(vp + 1024) : z; vv[3] = r + 9 < pl ? ldcg_v4(vp + 1152) : z;
+            }
+        };
+        // software pipeline without extra registers: the K fragments are dead after the QK products and the V fragments
+        // after the PV products, so the next group's K loads are issued right after QK (covered by the softmax and PV of
+        // this group) and its V loads right after PV (covered by the next group's QK and softmax)
+        const char* gb = group_base(p0);
+        load_k(gb, p0);
+        load_v(gb, p0);
         for (int pb = p0; pb < p1; pb += 16) {
-            if (pb / ps - pg_base >= 32) {
-                pg_base = pb / ps;
-                my_page = (pg_base + c.lane) * ps < pl ? ldcg_i32(bt + pg_base + c.lane) : 0;
-            }
-            const int page = __shfl_sync(0xffffffffu, my_page, (pb / ps - pg_base) & 31);
-            const uint16_t* kbase = M.kv_pool + (size_t)page * page_stride + layer_off + (size_t)(pb % ps) * kHeadDim;
-            const uint16_t* vbase = kbase + (size_t)Hkv * head_stride;
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            uint4 kk[2][2], vv[4];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {      // K rows of n-tile j: position pb + 8 j + gq, this lane's 2 x 8 dims
-                const bool ok = pb + 8 * j + gq < pl;
-                const uint16_t* kp = kbase + (size_t)(8 * j + gq) * kHeadDim + tq * 8;
-                kk[j][0] = ok ? ldcg_v4(kp) : z;
-                kk[j][1] = ok ? ldcg_v4(kp + 32) : z;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {      // V rows pb + {2 tq, 2 tq + 1, 2 tq + 8, 2 tq + 9}, dims 8 gq .. 8 gq + 7
-                const int r = 2 * tq + (j & 1) + 8 * (j >> 1);
-                vv[j] = pb + r < pl ? ldcg_v4(vbase + (size_t)r * kHeadDim + gq * 8) : z;
-            }
+            const bool more = pb + 16 < p1;
             float sc[2][4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -352,6 +376,7 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
                 mma16816(sc[j], qa[2], kk[j][1].x, kk[j][1].y);
                 mma16816(sc[j], qa[3], kk[j][1].z, kk[j][1].w);
             }
+            if (more) { gb = group_base(pb + 16); load_k(gb, pb + 16); }
             // scores in the log2 domain, causal mask per row, one running-max update per row and 16 positions
             float mna = ma, mnb = mb;
 #pragma unroll
@@ -382,8 +407,10 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
                 pa[2 * j + 1] = pack_bf16(e2, e3);   // row b
             }
             la = fmaf(la, ca, sa); lb = fmaf(lb, cb, sb);
+            if (__any_sync(0xffffffffu, (ca != 1.f) | (cb != 1.f))) {   // a row's maximum moved (rare after the first groups)
 #pragma unroll
-            for (int n = 0; n < 8; ++n) { o[n][0] *= ca; o[n][1] *= ca; o[n][2] *= cb; o[n][3] *= cb; }
+                for (int n = 0; n < 8; ++n) { o[n][0] *= ca; o[n][1] *= ca; o[n][2] *= cb; o[n][3] *= cb; }
+            }
             // O += P V: n-tile n, column gq of the B fragment = dim 8 gq + n; k pairs (2 tq, 2 tq + 1) and (2 tq + 8, 2 tq + 9)
             const uint32_t v0[4] = {vv[0].x, vv[0].y, vv[0].z, vv[0].w}, v1[4] = {vv[1].x, vv[1].y, vv[1].z, vv[1].w};
             const uint32_t v2[4] = {vv[2].x, vv[2].y, vv[2].z, vv[2].w}, v3[4] = {vv[3].x, vv[3].y, vv[3].z, vv[3].w};
@@ -392,6 +419,7 @@ __device__ void phase_attn_batch(const DevModel& M, const CallArgs& A, const Ctx
                 const uint32_t sel = (n & 1) ? 0x7632u : 0x5410u;
                 mma16816(o[n], pa, prmt(v0[n >> 1], v1[n >> 1], sel), prmt(v2[n >> 1], v3[n >> 1], sel));
             }
+            if (more) load_v(gb, pb + 16);
         }
         la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
         lb += __shfl_xor_sync(0xffffffffu, lb, 1); lb += __shfl_xor_sync(0xffffffffu, lb, 2);

@@ -198,6 +198,45 @@ def _modes_and_composition(model, prompts, gs):
     assert torch.equal(trio[1], ref[4])
 
 
+@pytest.mark.parametrize("size,lens", [("smoltts_byte_tiny", [45]), ("smoltts_byte_70m", [70]), ("smoltts_byte_tiny", [33, 9, 58])])
+def test_prefill_tiles_and_modes_write_identical_kv(size, lens):
+    """Prefill on the CUDA-core barrier kernel (fewer than 9 rows) -- 8 / 3 / 1 prompt positions per iteration, one
+    cooperative launch or one launch per phase -- then two frames: bit-identical K/V, seq_len, pending tokens and codes,
+    also for ragged prompt lengths (rows of a tile past the end of a prompt are inert)."""
+    from smoltts_b200.generate import pack_prompts
+
+    cfg, sd, model, orc = model_and_oracle(size)
+    B = len(lens)
+    prompts = [prompt_grid(byte_prompt(n, seed=110 + b), cfg) for b, n in enumerate(lens)]
+    variants = [(0, 8 // B), (0, 1), (1, 8 // B)] + ([(0, 3)] if B == 1 else [])
+    got = []
+    model.set_option("ll_max_batch", 0)       # the two frames on the barrier kernel too
+    try:
+        for mode, tile in variants:
+            model.set_option("mode", mode)
+            model.set_option("prefill_tile", tile)
+            padded, lens_t = pack_prompts(model, prompts)
+            batch = model.new_batch(B, max_positions=128, max_frames=4)
+            try:
+                pages = torch.tensor(batch.pages, device=model.device)
+                model.kv_view()[pages] = 0
+                model.prefill(batch, padded, lens_t)
+                model.decode_frames(batch, model.sampling(ignore_stop=True), 2)
+                torch.cuda.synchronize()
+                got.append((model.kv_view()[pages].clone(), batch.seq_len.clone(), batch.tokens.clone(), batch.out_codes.clone()))
+            finally:
+                batch.release()
+    finally:
+        model.set_option("mode", 2)
+        model.set_option("prefill_tile", 0)
+        model.set_option("ll_max_batch", 8)
+    assert got[0][1].tolist() == [n + 12 - 1 + 2 for n in lens]
+    for (mode, tile), g in zip(variants[1:], got[1:]):
+        assert torch.equal(g[0].view(torch.int16), got[0][0].view(torch.int16)), f"KV differs (mode {mode}, tile {tile})"
+        for a, b in zip(g[1:], got[0][1:]):
+            assert torch.equal(a, b), f"state differs (mode {mode}, tile {tile})"
+
+
 @pytest.mark.parametrize("cfgset", [
     dict(temp=0.0, fast_temp=0.0),
     dict(temp=0.7, fast_temp=0.7),

@@ -37,7 +37,7 @@ def _run(model, prompt, n_frames, chunks, seq_ids=None, **skw):
             torch.cuda.synchronize()
             logits.append((model.debug_buffer("token_logits", 1).clone(), model.debug_buffer("depth_logits", 1).clone()))
         assert sum(chunks) == n_frames
-        assert model.get_option("ll_ready") == 1 and model.get_option("ll_version") == 2, "the ll2 kernel did not run"
+        assert model.get_option("ll_ready") == 1, "the data-flow kernel did not run"
         return dict(codes=batch.out_codes.clone(), tokens=batch.tokens.clone(), seq_len=batch.seq_len.clone(), step=batch.step.clone(),
                     kv=model.kv_view()[pages].clone(), last_logits=logits[-1])
     finally:

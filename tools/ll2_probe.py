@@ -55,8 +55,8 @@ def check(size, n_frames, n_prompt):
     model.set_option("mode", 2)
     got = generate_batch(model, [prompt], gs, audio_only=False, fixed_frames=n_frames)[0]
     torch.cuda.synchronize()
-    print(f"[{size}] ll_ready={model.get_option('ll_ready')} ll_version={model.get_option('ll_version')} "
-          f"slots={model.get_option('ll2_slots')} smem={model.get_option('ll2_smem_bytes')}")
+    print(f"[{size}] ll_ready={model.get_option('ll_ready')} "
+          f"slots={model.get_option('ll_slots')} smem={model.get_option('ll_smem_bytes')}")
     orc = DualAROracle(cfg, sd, dtype=torch.bfloat16, max_seq_len=max(256, n_prompt + n_frames + 32))
     with torch.no_grad():
         frames = orc.generate(prompt, OracleSettings(default_temp=0.0, default_fast_temp=0.0), fixed_frames=n_frames)
@@ -102,27 +102,23 @@ def timing(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3 / n
 
-    for version, holdoffs in ((1, [0]), (2, [int(h) for h in args.holdoffs.split(",")])):
-        model.set_option("ll_version", version)
-        for h in holdoffs:
-            for st in ([0] if version == 1 else [int(x) for x in args.staggers.split(",")]):
-                model.set_option("ll_holdoff", h)
-                model.set_option("ll_flags", st)
-                run(8)
-                us = [run(args.frames) for _ in range(3)]
-                codes = int(batch.out_codes.sum().item())
-                print(f"ll_version={version} holdoff={h:5d} stagger={st:4d} cycles: {min(us):8.1f} us/frame (runs {', '.join(f'{u:.1f}' for u in us)}) check={codes}")
+    for h in [int(h) for h in args.holdoffs.split(",")]:
+        for st in [int(x) for x in args.staggers.split(",")]:
+            model.set_option("ll_holdoff", h)
+            model.set_option("ll_flags", st)
+            run(8)
+            us = [run(args.frames) for _ in range(3)]
+            codes = int(batch.out_codes.sum().item())
+            print(f"holdoff={h:5d} stagger={st:4d} cycles: {min(us):8.1f} us/frame (runs {', '.join(f'{u:.1f}' for u in us)}) check={codes}")
     model.set_option("ll_flags", args.trace_stagger)
-    model.set_option("ll_version", 2)
     model.set_option("ll_holdoff", args.trace_holdoff)
     for n in [int(x) for x in args.n_ctas.split(",") if x]:
         model.set_option("n_ctas", n)
         run(8)
         us = [run(args.frames) for _ in range(2)]
-        print(f"ll_version=2 n_ctas={n:4d}: {min(us):8.1f} us/frame")
+        print(f"n_ctas={n:4d}: {min(us):8.1f} us/frame")
     model.set_option("n_ctas", 0)
     # cycle trace at the default hold-off
-    model.set_option("ll_version", 2)
     model.set_option("ll_holdoff", args.trace_holdoff)
     run(8)
     prof = model.set_profile(True)

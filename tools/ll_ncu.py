@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small fixed workload for ncu captures of the decode kernel: prefill, a warm-up launch, then ONE
-launch of --frames frames (the one to capture: ncu -k regex:smol_ll_kernel --launch-skip 2 --launch-count 1)."""
+launch of --frames frames (the one to capture: ncu -k regex:smol_ll2_kernel --launch-skip 1 --launch-count 1)."""
 from __future__ import annotations
 
 import argparse
@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--prompt-bytes", type=int, default=200)
     ap.add_argument("--mode", type=int, default=2)
     ap.add_argument("--n-ctas", type=int, default=0)
-    ap.add_argument("--flags", type=int, nargs="*", default=[0], help="A/B switches of the data-flow kernel (option \"ll_flags\": 1 no K split, 2 sampler CTA for greedy rows, 4 no end-of-phase barrier, 8 no unit rotation, n<<8 hold-off in 64 ns units, 255<<8 none)")
+    ap.add_argument("--flags", type=int, nargs="*", default=[0], help="values of the engine option \"ll_flags\" to A/B (a spare switch word the data-flow kernel receives in its shared-memory plan; the shipped kernel ignores it)")
     a = ap.parse_args()
     cfg = named_config(a.model)
     need = a.prompt_bytes + 12 + 2 * a.frames + 16
