@@ -11,6 +11,22 @@
 // the tensor core's.
 #pragma once
 
+// L2 policy of the weight boxes: 0 default, 1 evict_first, 2 evict_last.  Measured at bs=256 (profiles/r2_l2_policy_ab.txt):
+// the hints (evict_last on the depth transformer, evict_first on the slow one) cost 9 % MORE DRAM traffic than no hint
+// and no time either way, so the tiles carry none.  (The data-flow kernel keeps its hints: there they hold the depth
+// weights in L2, 235 MB of DRAM traffic per frame against 271 MB of weights.)
+#ifndef SMOL_TC_FAST_POLICY
+#define SMOL_TC_FAST_POLICY umma::kWeightsDefault
+#endif
+#ifndef SMOL_TC_SLOW_POLICY
+#define SMOL_TC_SLOW_POLICY umma::kWeightsDefault
+#endif
+// Unit -> CTA order: 1 = the row tiles that share a weight block run on neighbouring CTAs (prefill iterations of 4 row
+// tiles: 20 % less DRAM traffic, same time), 0 = row tile major.
+#ifndef SMOL_TC_UNIT_ORDER
+#define SMOL_TC_UNIT_ORDER 1
+#endif
+
 namespace smol {
 
 constexpr int kTcRows = umma::kM;
@@ -581,8 +597,13 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
     const int n_units = (A.tc_part == 0 || A.tc_part == 2) ? m_tiles * n_blocks * n_split : 0;
 
     for (int u = c.cta; u < n_units; u += c.n_ctas) {
+#if SMOL_TC_UNIT_ORDER
+        const int mt = u % m_tiles, un = u / m_tiles;       // the row tiles that share a weight block on neighbouring CTAs
+        const int ks = un % n_split, nb = un / n_split;
+#else
         const int ks = u % n_split, un = u / n_split;
         const int mt = un / n_blocks, nb = un - mt * n_blocks;
+#endif
         const int m0 = mt * kTcRows, n0 = nb * blk;
         if (kind == PH_QKV && c.tid < kTcRows) {
             const int bg = min(m0 + c.tid, A.batch - 1);
@@ -597,7 +618,7 @@ __device__ void phase_gemm_tc(const DevModel& M, const CallArgs& A, const Ctx& c
         // slow weights are read once per frame (evict first), the depth transformer's by every depth step (keep in L2):
         // measured DRAM reads 937 -> 891 MB per frame at bs=256, time unchanged (gpurun_out/l2hint_dram.csv)
         umma::tile_mma_tma<kThreads>(ring, bars, pipe, k_len, tm_a, m0, b0, b1, ks * k_len, a_rows,
-                                            fast ? umma::kWeightsKeep : umma::kWeightsStream);
+                                            fast ? SMOL_TC_FAST_POLICY : SMOL_TC_SLOW_POLICY);
         if (prof) { const unsigned long long t = globaltimer_ns(); seg[2] += t - ts; ts = t; }
 
         if (kind == PH_W13) {
