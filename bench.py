@@ -418,7 +418,7 @@ def measure(work: Work, args, steps: int, warmup: int, ctx) -> dict:
 
     def e2e_step():
         outs = generate_batch(model, host_prompts, gs, audio_only=False, fixed_frames=work.frames, chunk=work.frames, seq_ids=seq_ids)
-        return gather_utterances(outs, gloo) if world > 1 else outs
+        return gather_utterances(outs, dist, group=gloo) if world > 1 else outs
 
     for _ in range(max(1, min(warmup, 2))):
         e2e_step()

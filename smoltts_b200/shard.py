@@ -29,14 +29,16 @@ def shard(items: Sequence, rank: int, world: int) -> Tuple[list, List[int]]:
     return list(items[lo:hi]), list(range(lo, hi))
 
 
-def gather_utterances(local: Sequence[torch.Tensor], dist=None, dst: int = 0) -> Optional[List[torch.Tensor]]:
-    """Host-side gather of per-utterance code tensors (ragged) onto ``dst`` in global utterance order."""
+def gather_utterances(local: Sequence[torch.Tensor], dist=None, dst: int = 0, group=None) -> Optional[List[torch.Tensor]]:
+    """Host-side gather of per-utterance code tensors (ragged) onto ``dst`` in global utterance order.
+    ``dist`` is the ``torch.distributed`` module; ``group`` an optional process group of it (a gloo group when the default
+    one is NCCL: the codes are host tensors)."""
     local = [t.cpu() for t in local]
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
     bucket = [None] * world if rank == dst else None
-    dist.gather_object(local, bucket, dst=dst)
+    dist.gather_object(local, bucket, dst=dst, group=group)
     if rank != dst:
         return None
     return [t for part in bucket for t in part]

@@ -55,6 +55,11 @@ def _worker(rank, world, port, n_frames, q):
         outs = _decode_slice(mine, ids, n_frames)
         dist.barrier()
         gathered = gather_utterances(outs, dist)
+        side = dist.new_group(backend="gloo")      # bench.py gathers through a gloo side group next to the NCCL default group
+        again = gather_utterances(outs, dist, group=side)
+        assert (again is None) == (gathered is None)
+        if gathered is not None:
+            assert all(torch.equal(a, b) for a, b in zip(gathered, again))
         t = max_over_ranks([float(rank + 1), 10.0 - rank], dist)
         if rank == 0:
             q.put(([g.tolist() for g in gathered], t, ids))
