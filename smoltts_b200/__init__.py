@@ -21,6 +21,7 @@ from .model import (  # noqa: F401
     make_prompt_cache,
 )
 
+from .serving import ContinuousBatcher, PromptEncoder, byte_level_tokenizer  # noqa: F401,E402
 from .shard import ShardedGenerator, generate_sharded  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -70,6 +70,31 @@ def test_checkpoint_layout_and_normalisation():
     assert torch.equal(sd["fast_output.weight"][1 * cfg.codebook_size + 5], w3[1, :, 5])
 
 
+def test_convert_cli_round_trip(tmp_path):
+    """python -m smoltts_b200.convert: trainer checkpoint (.pt, 3-D fast_output, _orig_mod. prefixes) -> config.json +
+    model.safetensors in the exported layout; wrong shapes are refused (train/convert_safetensors.py:6-16 hard-codes 768)."""
+    from safetensors.torch import load_file
+
+    from smoltts_b200.convert import main as convert_main
+
+    cfg = named_config("smoltts_byte_tiny")          # hidden size 128: the reference converter would mis-shape this one
+    sd = make_state_dict(cfg, seed=5)
+    raw = {"_orig_mod." + k: (flat_to_depthwise(v, cfg) if k == "fast_output.weight" else v).float() for k, v in sd.items()}
+    ckpt = tmp_path / "checkpoint.pt"
+    torch.save({"model_state_dict": raw, "step": 7}, ckpt)
+    cfg.save(str(tmp_path / "config.json"))
+    out = tmp_path / "export"
+    assert convert_main([str(ckpt), "--config", str(tmp_path / "config.json"), "-o", str(out)]) == 0
+    got = load_file(str(out / "model.safetensors"))
+    assert set(got) == set(sd) and (out / "config.json").exists()
+    for k in sd:
+        assert got[k].dtype == torch.bfloat16 and torch.equal(got[k], sd[k]), k
+    raw["_orig_mod.norm.weight"] = torch.ones(cfg.dim + 1)
+    torch.save(raw, ckpt)                              # a bare state dict is accepted too; the bad shape is not
+    with pytest.raises(ValueError, match="norm.weight"):
+        convert_main([str(ckpt), "--config", str(tmp_path / "config.json"), "-o", str(out)])
+
+
 def test_synthetic_inputs_are_deterministic_and_well_formed():
     cfg = named_config("smoltts_byte_150m")
     p = byte_prompt(200, seed=1)
