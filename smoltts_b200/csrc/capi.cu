@@ -132,11 +132,11 @@ static size_t packed_bytes(const SmolConfig& c, int depth) {
     return c.n_layer * align_up(slow, 256) + c.n_fast_layer * align_up(fast, 256) + align_up(heads, 256) + 4096;
 }
 
-// Rows of the activation workspace: a prefill iteration carries up to this many rows (sequences x prompt positions, four
-// 128-row tensor-core tiles): an iteration costs about the same from 128 to 512 rows (it is bound by the per-phase fixed
-// costs), so the prompt of a batch of 256 is cached two positions at a time instead of one, that
-// of a batch of 32 sixteen at a time instead of four.
-constexpr int kPrefillRows = 512;
+// Rows of the activation workspace: a prefill iteration carries up to this many rows (sequences x prompt positions, eight
+// 128-row tensor-core tiles).  An iteration costs about the same from 128 to 512 rows and ~1.4x at 1024 (it is bound by
+// the per-phase fixed costs), so the prompt of a batch of 256 is cached four positions at a time
+// instead of one, that of a batch of 32 thirty-two at a time instead of four.  Costs ~0.4 GB of workspace.
+constexpr int kPrefillRows = 1024;
 static int ws_rows(const SmolConfig& c) { return c.max_batch > kPrefillRows ? c.max_batch : kPrefillRows; }
 
 static WsLayout ws_layout(const SmolConfig& c, int depth) {

@@ -138,7 +138,7 @@ def test_tc_prefill_tile_sizes_and_batch_composition_bit_identical():
         b = _prefill_and_frames(model, prompts[20:21], 3, 9, prefill_tile=tile)
         assert torch.equal(a["kv"].view(torch.int16), b["kv"].view(torch.int16)), f"prefill tile {tile}"
         assert torch.equal(a["codes"], b["codes"])
-    # a long prompt: one iteration of 4 row tiles (up to 512 positions) against 128- and 100-position iterations
+    # a long prompt: one iteration of 4 row tiles (420 positions; up to 1024 fit) against 128- and 100-position iterations
     long_prompt = [prompt_grid(byte_prompt(420, seed=77), cfg)]
     a = _prefill_and_frames(model, long_prompt, 2, 9)
     for tile in (128, 100):
