@@ -467,6 +467,20 @@ static int ensure_ll2(SmolModel* m) {
     return SMOL_OK;
 }
 
+// Grid of a SOLO decode on the data-flow kernel.  Fewer CTAs make every exchange cheaper as long as no phase needs more
+// tiles per CTA, and a phase whose tiles divide evenly has no early finishers polling for words that cannot be there yet.
+// Measured on 150m, 1024 frames (profiles/r2_ll2_grid_size_sweep.txt): 128 CTAs -- the gated-MLP phase's 384 tiles are 3 per
+// CTA exactly -- 617.5 us per frame, 148 CTAs 626.2, 136: 626.2, 120: 630.5; 70m (192 tiles): 148 = 128 = 593.5.  Rule: the
+// largest grid within 15 % of the SM count that divides the gated-MLP tile count, else one CTA per SM.  Results do not depend
+// on the grid (bit-identical, tests/test_gpu_ll2.py); the caller's "n_ctas" option overrides.
+static int ll2_solo_ctas(const SmolModel* m) {
+    if (m->n_ctas_override > 0 || m->n_ctas <= 0) return m->n_ctas;
+    const int tiles = m->cfg.intermediate_size / 8;
+    for (int n = m->n_ctas; n * 100 >= m->n_ctas * 85; --n)
+        if (tiles % n == 0) return n;
+    return m->n_ctas;
+}
+
 // Shared-memory budget and function attributes of the kernel variant for this batch tile.
 static int ensure_tile(SmolModel* m, int bt) {
     if (bt == 0) {
@@ -511,7 +525,7 @@ static int enqueue(SmolModel* m, CallArgs A, cudaStream_t stream, bool whole_ite
         if ((rc = ensure_ll2(m))) return rc;
         if (m->ll2_state == 1) {
             if (A.n_iter == 0) return SMOL_OK;
-            A.team_ctas = m->n_ctas / A.batch;
+            A.team_ctas = A.batch == 1 ? ll2_solo_ctas(m) : m->n_ctas / A.batch;
             m->ll2_sp.holdoff = m->ll2_holdoff;
             m->ll2_sp.flags = m->ll_flags;
             CU(smol::ll2_launch(m->dm, A, m->ll2_sp, m->ll2_smem, A.team_ctas * A.batch, stream));
@@ -821,6 +835,7 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!std::strcmp(name, "ll_max_batch")) return (int64_t)m->ll2_max_batch;
     if (!std::strcmp(name, "ll_holdoff")) return (int64_t)m->ll2_holdoff;
     if (!std::strcmp(name, "ll_slots")) return (int64_t)m->ll2_sp.n_slots;
+    if (!std::strcmp(name, "ll_solo_ctas")) return (int64_t)ll2_solo_ctas(m);
     return -1;
 }
 
