@@ -467,12 +467,12 @@ static int ensure_ll2(SmolModel* m) {
     return SMOL_OK;
 }
 
-// Grid of a SOLO decode on the data-flow kernel.  Fewer CTAs make every exchange cheaper as long as no phase needs more
-// tiles per CTA, and a phase whose tiles divide evenly has no early finishers polling for words that cannot be there yet.
-// Measured on 150m, 1024 frames (profiles/r2_ll2_grid_size_sweep.txt): 128 CTAs -- the gated-MLP phase's 384 tiles are 3 per
-// CTA exactly -- 617.5 us per frame, 148 CTAs 626.2, 136: 626.2, 120: 630.5; 70m (192 tiles): 148 = 128 = 593.5.  Rule: the
-// largest grid within 15 % of the SM count that divides the gated-MLP tile count, else one CTA per SM.  Results do not depend
-// on the grid (bit-identical, tests/test_gpu_ll2.py); the caller's "n_ctas" option overrides.
+// Grid of a SOLO decode on the data-flow kernel.  An exchange has as many participants as the grid has CTAs, a phase takes as
+// long as its busiest CTA.  Measured on 150m, 1024 frames (profiles/r2_ll2_grid_size_sweep.txt): 128 CTAs -- the gated-MLP
+// phase's 384 tiles are 3 per CTA exactly, the same maximum as on 148 -- 617.5 us per frame, 148 CTAs 626.2, 136: 626.2, 120:
+// 630.5; 70m (192 tiles): 148 = 128 = 593.5.  Rule: the largest grid within 15 % of the SM count that divides the gated-MLP
+// tile count, else one CTA per SM.  Results do not depend on the grid (bit-identical, tests/test_gpu_ll2.py); the caller's
+// "n_ctas" option overrides.
 static int ll2_solo_ctas(const SmolModel* m) {
     if (m->n_ctas_override > 0 || m->n_ctas <= 0) return m->n_ctas;
     const int tiles = m->cfg.intermediate_size / 8;

@@ -190,7 +190,9 @@ def teams(args):
         outs = generate_batch(model, prompts[:B], gs, audio_only=False, fixed_frames=12, seq_ids=list(range(B)))
         same = [bool(torch.equal(outs[b], solo[b])) for b in range(B)]
         print(f"teams: batch of {B}: rows identical to their solo decode: {same}")
-    for B in (1, 2, 4, 8):
+    grids = [int(x) for x in args.n_ctas.split(",") if x] or [0]
+    for B, n_ctas in [(B, n) for n in grids for B in (1, 2, 3, 4, 6, 8)]:
+        model.set_option("n_ctas", n_ctas)
         padded, lens = pack_prompts(model, prompts[:B])
         batch = model.new_batch(B, max_positions=need, max_frames=64)
         s = _sampling(model, gs, True, ignore_stop=True)
@@ -203,8 +205,9 @@ def teams(args):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 48
-        print(f"teams: bs={B}: {us:8.1f} us per frame step -> {B / us * 1e6:9.0f} frames/s")
+        print(f"teams: bs={B} grid {model.get_option('n_ctas')}: {us:8.1f} us per frame step -> {B / us * 1e6:9.0f} frames/s")
         batch.release()
+    model.set_option("n_ctas", 0)
 
 
 def main():
