@@ -158,3 +158,78 @@ def teacher_grid(cfg: RQTransformerModelArgs, n_text: int, n_audio: int, batch: 
         else:
             grid[:, 0, n_text:] = TOK_SEMANTIC0 + torch.randint(0, C, (batch, n_audio), generator=g)
     return grid
+
+
+# ---- Mimi decoder: seeded weights under kyutai/mimi's state-dict keys ----------------------------------
+def mimi_state_dict_shapes(n_q: int = 8, codebook_size: int = 2048, codebook_dim: int = 256, dim: int = 512, n_layers: int = 8,
+                           ffn: int = 2048, n_filters: int = 64, ratios=(8, 6, 5, 4), kernel: int = 7, res_kernel: int = 3,
+                           last_kernel: int = 3) -> Dict[str, tuple]:
+    """Key -> shape of the decode half of kyutai/mimi's model.safetensors (the keys the reference's load_mimi() maps onto
+    its module tree, mlx_inference/src/smoltts_mlx/codec/mimi.py:107-156; torch layouts: Conv1d [out, in, k],
+    ConvTranspose1d [in, out, k])."""
+    s: Dict[str, tuple] = {}
+    for half, n in (("semantic", 1), ("acoustic", n_q - 1)):
+        p = f"quantizer.{half}_residual_vector_quantizer"
+        for i in range(n):
+            s[f"{p}.layers.{i}.codebook.embed_sum"] = (codebook_size, codebook_dim)
+            s[f"{p}.layers.{i}.codebook.cluster_usage"] = (codebook_size,)
+        s[f"{p}.output_proj.weight"] = (dim, codebook_dim, 1)
+    s["upsample.conv.weight"] = (dim, 1, 4)
+    for l in range(n_layers):
+        p = f"decoder_transformer.layers.{l}"
+        for w in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            s[f"{p}.self_attn.{w}.weight"] = (dim, dim)
+        s[f"{p}.mlp.fc1.weight"] = (ffn, dim)
+        s[f"{p}.mlp.fc2.weight"] = (dim, ffn)
+        for nm in ("input_layernorm", "post_attention_layernorm"):
+            s[f"{p}.{nm}.weight"] = (dim,)
+            s[f"{p}.{nm}.bias"] = (dim,)
+        s[f"{p}.self_attn_layer_scale.scale"] = (dim,)
+        s[f"{p}.mlp_layer_scale.scale"] = (dim,)
+    ch = n_filters * 2 ** len(ratios)
+    s["decoder.layers.0.conv.weight"] = (ch, dim, kernel)
+    s["decoder.layers.0.conv.bias"] = (ch,)
+    idx = 1
+    for r in ratios:
+        s[f"decoder.layers.{idx + 1}.conv.weight"] = (ch, ch // 2, 2 * r)
+        s[f"decoder.layers.{idx + 1}.conv.bias"] = (ch // 2,)
+        ch //= 2
+        s[f"decoder.layers.{idx + 2}.block.1.conv.weight"] = (ch // 2, ch, res_kernel)
+        s[f"decoder.layers.{idx + 2}.block.1.conv.bias"] = (ch // 2,)
+        s[f"decoder.layers.{idx + 2}.block.3.conv.weight"] = (ch, ch // 2, 1)
+        s[f"decoder.layers.{idx + 2}.block.3.conv.bias"] = (ch,)
+        idx += 3
+    s[f"decoder.layers.{idx + 1}.conv.weight"] = (1, ch, last_kernel)
+    s[f"decoder.layers.{idx + 1}.conv.bias"] = (1,)
+    return s
+
+
+def make_mimi_state_dict(seed: int = 0, **dims) -> Dict[str, torch.Tensor]:
+    """Seeded fp32 weights of the Mimi decoder.  Scales keep every stage O(1) (fan-in scaled weights, layer scales of
+    0.1 .. 0.3 instead of the trained 0.01 .. so that all eight transformer layers matter in a parity check)."""
+    out: Dict[str, torch.Tensor] = {}
+    for name, shape in mimi_state_dict_shapes(**dims).items():
+        g = torch.Generator(device="cpu")
+        g.manual_seed(_key_seed("mimi." + name, seed))
+        if name.endswith("cluster_usage"):
+            t = 0.5 + 1.5 * torch.rand(*shape, generator=g)
+        elif name.endswith("layer_scale.scale"):
+            t = 0.1 + 0.2 * torch.rand(*shape, generator=g)
+        elif name.endswith("layernorm.weight"):
+            t = 1.0 + 0.1 * torch.randn(*shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.05 * torch.randn(*shape, generator=g)
+        elif name.endswith("embed_sum"):
+            t = torch.randn(*shape, generator=g)
+        elif name == "upsample.conv.weight":
+            t = 0.7 * torch.randn(*shape, generator=g)
+        else:
+            if name.startswith("decoder.") and len(shape) == 3:
+                # Conv1d [out, in, k]: fan-in = in * k; ConvTranspose1d [in, out, k = 2 stride]: two taps per output
+                is_tr = shape[2] >= 8 and not name.startswith("decoder.layers.0.")
+                fan = shape[0] * 2 if is_tr else shape[1] * shape[2]
+            else:
+                fan = shape[1] * (shape[2] if len(shape) == 3 else 1)
+            t = torch.randn(*shape, generator=g) * (1.4 / fan ** 0.5)
+        out[name] = t.to(torch.float32).contiguous()
+    return out
