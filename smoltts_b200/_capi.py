@@ -58,7 +58,40 @@ class SmolSampling(C.Structure):
         ("min_p", C.c_float), ("seed", C.c_uint64), ("audio_only", C.c_int32), ("ignore_stop", C.c_int32)]
 
 
-# name -> (restype, argtypes); every symbol the header declares
+# ---- include/smoltts_b200_mimi.h ----
+SMOL_MIMI_MAX_LAYERS = 16
+SMOL_MIMI_MAX_RATIOS = 8
+SMOL_MIMI_MAX_Q = 32
+
+
+class SmolMimiConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_q", "codebook_size", "codebook_dim", "dim", "n_layers", "n_heads", "head_dim", "ffn", "n_filters", "n_ratios")] + [
+        ("ratios", C.c_int32 * SMOL_MIMI_MAX_RATIOS)] + [(n, C.c_int32) for n in (
+            "kernel", "res_kernel", "last_kernel", "max_streams", "max_positions", "window", "upsample_carry", "use_graph")] + [
+        ("norm_eps", C.c_float), ("codebook_eps", C.c_float)]
+
+
+class SmolMimiLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("q_proj", "k_proj", "v_proj", "o_proj", "fc1", "fc2", "ln1_w", "ln1_b", "ln2_w", "ln2_b",
+                                          "scale_attn", "scale_mlp")]
+
+
+class SmolMimiConv(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class SmolMimiWeights(C.Structure):
+    _fields_ = [
+        ("embed_sum", C.c_void_p * SMOL_MIMI_MAX_Q), ("cluster_usage", C.c_void_p * SMOL_MIMI_MAX_Q),
+        ("semantic_output_proj", C.c_void_p), ("acoustic_output_proj", C.c_void_p), ("upsample", C.c_void_p),
+        ("layers", SmolMimiLayerWeights * SMOL_MIMI_MAX_LAYERS),
+        ("conv_in", SmolMimiConv), ("convtr", SmolMimiConv * SMOL_MIMI_MAX_RATIOS),
+        ("res_conv1", SmolMimiConv * SMOL_MIMI_MAX_RATIOS), ("res_conv2", SmolMimiConv * SMOL_MIMI_MAX_RATIOS),
+        ("conv_out", SmolMimiConv), ("rope", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol the headers declare
 PROTOTYPES = {
     "smol_abi_version": (C.c_int, []),
     "smol_last_error": (C.c_char_p, []),
@@ -89,6 +122,17 @@ PROTOTYPES = {
     "smol_debug_buffer": (C.c_void_p, [C.c_void_p, C.c_char_p]),
     "smol_launches_per_frame": (C.c_int32, [C.c_void_p]),
     "smol_launch_count": (C.c_int64, [C.c_void_p]),
+    # include/smoltts_b200_mimi.h
+    "smol_mimi_create": (C.c_int, [C.POINTER(SmolMimiConfig), C.POINTER(C.c_void_p)]),
+    "smol_mimi_destroy": (None, [C.c_void_p]),
+    "smol_mimi_samples_per_frame": (C.c_int32, [C.c_void_p]),
+    "smol_mimi_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "smol_mimi_bind": (C.c_int, [C.c_void_p, C.POINTER(SmolMimiWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smol_mimi_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "smol_mimi_decode_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "smol_mimi_debug_buffer": (C.c_void_p, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "smol_mimi_launches_per_step": (C.c_int32, [C.c_void_p]),
+    "smol_mimi_error_word": (C.c_void_p, [C.c_void_p]),
 }
 
 _lib = None

@@ -89,6 +89,11 @@ static int cuda_fail(cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return SMOL_ERR_CUDA;
 }
+namespace smol {
+// the same error channel for the other translation units of the library (mimi_kernels.cu)
+int capi_fail(int code, const std::string& msg) { return fail(code, msg); }
+int capi_cuda_fail(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+}  // namespace smol
 #define CU(call)                                         \
     do {                                                 \
         cudaError_t e__ = (call);                        \

@@ -1,0 +1,743 @@
+// The Mimi streaming decoder (codes -> PCM) for sm_100a: the step after the DualAR decode step.
+//
+// One frame of one stream: 8 codes -> RVQ rows summed and projected (512) -> 2 upsampled positions -> 8 transformer
+// layers against the stream's KV cache -> SEANet decoder (conv k7, then 4 x [ELU, transposed conv x8/x6/x5/x4, residual
+// block], ELU, conv k3) with carried convolution state -> 1920 fp32 samples.  The reference computes all of it in fp32
+// (load_mimi(format="fp32")), so do these kernels: fp32 FMA, fixed summation orders, no atomics -- a stream decodes to the
+// same bits alone or in any batch.
+//
+// At streaming batch sizes every stage is a handful of rows (2 .. 1920 per stream) against a weight matrix that is read
+// once: weight-streaming "row" products.  ONE kernel shape carries them all (rows_kernel): a CTA stages up to 16 input
+// rows in shared memory -- gathered straight from the producer's buffer, im2col of a causal convolution = a contiguous run
+// of (kernel x channels) floats that begins in the carried history rows; ELU or LayerNorm applied while staging -- and every
+// warp streams one weight row with 16-byte loads against all staged rows, finishing with a shuffle reduction and a fused
+// epilogue (bias, GELU, layer scale + residual, residual, or the upsampler).  Transposed convolutions (kernel = 2 stride)
+// are the same product with K = (previous | current input row) x channels and N = (phase, channel): their outputs land
+// contiguously.  Everything a stream carries (convolution history rows, the upsampler's previous embedding, KV cache,
+// position) lives in per-slot arenas of the caller's workspace; a step is ~57 launches, replayed as one CUDA graph.
+//
+// Reference map (C = mlx_inference/src/smoltts_mlx/codec/): RVQ decode C/rvq.py:118-130,171-186; upsample C/conv.py:225-282;
+// transformer C/transformer.py:36-150; Conv1d.step C/conv.py:133-160; ConvTranspose1d.step C/conv.py:207-221; residual
+// block C/seanet.py:9-50; decoder C/seanet.py:99-161; decode_step C/mimi.py:73-104.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smoltts_b200.h"
+#include "../../include/smoltts_b200_mimi.h"
+
+namespace smol {
+int capi_fail(int code, const std::string& msg);              // capi.cu: sets smol_last_error()
+int capi_cuda_fail(cudaError_t e, const char* what);
+
+namespace mimi {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kStageFloats = 8192;   // shared-memory staging area of rows_kernel: R rows x (8192 / R) floats
+constexpr int kMaxBufs = 24;
+
+enum { PRO_NONE = 0, PRO_ELU = 1, PRO_LN = 2 };
+enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_SCALE_RES = 2, EPI_RES = 3, EPI_UPSAMPLE = 4 };
+
+struct RowOp {
+    // input rows: slot arena + in_off, `in_hs` history rows before the step's T rows, in_c floats per row;
+    // element k of row (slot, t) = in[(in_hs + t + tap0 + (k / in_c) * tapstep) * in_c + k % in_c]
+    const float* in; long long in_stride; int in_hs, in_c, tap0, tapstep, T;
+    const float* W; const float* bias; int N, K, bias_mod;
+    float* out; long long out_stride; int out_off0, out_by_row;
+    const float* res; long long res_stride; int res_off0;
+    int pro, epi;
+    const float* ln_w; const float* ln_b; float eps;
+    const float* scale;
+    const float* wup; float* up_prev; int carry;   // EPI_UPSAMPLE
+    const int32_t* slots; int batch;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Y[row][n] = epilogue( sum_k A(row, k) W[n][k] ): R staged rows per CTA, one weight row per warp.
+template <int R>
+__global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
+    __shared__ __align__(16) float As[kStageFloats];
+    __shared__ float s_mean[R], s_rstd[R];
+    constexpr int KC = kStageFloats / R;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rows = op.batch * op.T;
+    const int row0 = blockIdx.y * R;
+    const int n = blockIdx.x * kWarps + warp;
+    const bool n_ok = n < op.N;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+
+    for (int kc = 0; kc < op.K; kc += KC) {
+        const int kcur = min(KC, op.K - kc);
+        // ---- stage R rows x kcur (16-byte pieces: in_c and K are multiples of 4) ----
+        const int q4 = kcur >> 2;
+        for (int idx = tid; idx < R * q4; idx += kThreads) {
+            const int r = idx / q4, k = kc + ((idx - r * q4) << 2);
+            const int row = row0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows) {
+                const int b = row / op.T, t = row - b * op.T;
+                const int slot = op.slots ? op.slots[b] : b;
+                const int j = k / op.in_c, c = k - j * op.in_c;
+                const float* src = op.in + (long long)slot * op.in_stride + (long long)(op.in_hs + t + op.tap0 + j * op.tapstep) * op.in_c + c;
+                v = *reinterpret_cast<const float4*>(src);
+                if (op.pro == PRO_ELU) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+            }
+            *reinterpret_cast<float4*>(&As[r * KC + ((idx - r * q4) << 2)]) = v;
+        }
+        __syncthreads();
+        if (op.pro == PRO_LN) {   // LayerNorm over the whole row (K <= KC, checked on the host): two passes, as torch does
+            for (int r = warp; r < R; r += kWarps) {
+                float s = 0.f;
+                for (int k = lane; k < kcur; k += 32) s += As[r * KC + k];
+                const float mean = warp_sum(s) / (float)kcur;
+                float d2 = 0.f;
+                for (int k = lane; k < kcur; k += 32) { const float d = As[r * KC + k] - mean; d2 = fmaf(d, d, d2); }
+                const float var = warp_sum(d2) / (float)kcur;
+                if (lane == 0) { s_mean[r] = mean; s_rstd[r] = 1.0f / sqrtf(var + op.eps); }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < R * kcur; idx += kThreads) {
+                const int r = idx / kcur, k = idx - r * kcur;
+                As[r * KC + k] = (As[r * KC + k] - s_mean[r]) * s_rstd[r] * op.ln_w[k] + op.ln_b[k];
+            }
+            __syncthreads();
+        }
+        // ---- one weight row per warp against all staged rows ----
+        if (n_ok) {
+            const float* wrow = op.W + (long long)n * op.K + kc;
+#pragma unroll 4
+            for (int k4 = lane * 4; k4 < kcur; k4 += 128) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k4));
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 a = *reinterpret_cast<const float4*>(&As[r * KC + k4]);
+                    acc[r] = fmaf(a.x, w.x, acc[r]); acc[r] = fmaf(a.y, w.y, acc[r]);
+                    acc[r] = fmaf(a.z, w.z, acc[r]); acc[r] = fmaf(a.w, w.w, acc[r]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- reduce over the lanes; lane r finishes row r ----
+    float mine = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float v = warp_sum(acc[r]);
+        if (lane == r) mine = v;
+    }
+    const int row = row0 + lane;
+    if (!n_ok || lane >= R || row >= rows) return;
+    const int b = row / op.T, t = row - b * op.T;
+    const int slot = op.slots ? op.slots[b] : b;
+    float y = mine + (op.bias ? op.bias[n % op.bias_mod] : 0.f);
+    if (op.epi == EPI_UPSAMPLE) {
+        // grouped transposed convolution, kernel 4, stride 2 (conv.py:271-282): outputs 2 t + j take tap j of this frame and,
+        // with `carry`, tap 2 + j of the previous one; decode_step upsamples every frame alone (carry = 0)
+        const float4 wu = *reinterpret_cast<const float4*>(op.wup + 4 * n);
+        float o0 = y * wu.x, o1 = y * wu.y;
+        if (op.carry) {
+            float* pp = op.up_prev + (long long)slot * op.N + n;
+            const float pv = *pp;
+            o0 = fmaf(pv, wu.z, o0); o1 = fmaf(pv, wu.w, o1);
+            *pp = y;
+        }
+        float* o = op.out + (long long)slot * op.out_stride + op.out_off0 + n;
+        o[0] = o0; o[op.N] = o1;
+        return;
+    }
+    const long long e = (long long)op.out_off0 + (long long)t * op.N + n;
+    float* o = op.out + (long long)(op.out_by_row ? b : slot) * op.out_stride + e;
+    if (op.epi == EPI_GELU) y = gelu_erf(y);
+    else if (op.epi == EPI_SCALE_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)t * op.N + n] + y * op.scale[n];
+    else if (op.epi == EPI_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)t * op.N + n] + y;
+    *o = y;
+}
+
+// RVQ decode (rvq.py:118-130, 171-186): the semantic codebook's row | the sum of the acoustic codebooks' rows, in order.
+struct EmbedArgs {
+    const float* books;   // [n_q][codebook_size][cdim], rows already divided by max(cluster_usage, eps)
+    const int32_t* codes; const int32_t* slots; float* q; long long q_stride;
+    int n_q, cb_size, cdim;
+};
+__global__ void embed_kernel(const EmbedArgs a) {
+    const int b = blockIdx.x, slot = a.slots ? a.slots[b] : b;
+    for (int k = threadIdx.x; k < 2 * a.cdim; k += blockDim.x) {
+        float v;
+        if (k < a.cdim) {
+            int c = a.codes[b * a.n_q]; c = min(max(c, 0), a.cb_size - 1);
+            v = a.books[(long long)c * a.cdim + k];
+        } else {
+            v = 0.f;
+            for (int i = 1; i < a.n_q; ++i) {
+                int c = a.codes[b * a.n_q + i]; c = min(max(c, 0), a.cb_size - 1);
+                const float e = a.books[((long long)i * a.cb_size + c) * a.cdim + (k - a.cdim)];
+                v = i == 1 ? e : v + e;
+            }
+        }
+        a.q[(long long)slot * a.q_stride + k] = v;
+    }
+}
+
+// Attention of one (stream, head): the step's two positions against the stream's cache (transformer.py:62-91).
+// Half-split RoPE (nn.RoPE traditional=False) from the table, K/V appended, scores by one thread per position, softmax,
+// P V by (dim, position parity) threads; fixed orders throughout.
+struct AttnArgs {
+    const float* qkv; long long qkv_stride;      // [2][3 dim]
+    float* att; long long att_stride;            // [2][dim]
+    float* kv; long long kv_slot_stride, kv_layer_stride;   // [slot][layer][2][max_pos][dim]
+    const float* rope; const int32_t* pos; const int32_t* slots; int32_t* err;
+    int layer, dim, hd, max_pos, window;
+};
+__global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+    const int slot = a.slots ? a.slots[b] : b;
+    const int hd = a.hd, half = hd >> 1;
+    const int p0 = 2 * a.pos[slot];
+    if (p0 + 2 > a.max_pos) { if (tid == 0) *a.err = 1; return; }
+    float* q = sm;                // [2][hd], pre-scaled
+    float* red = sm + 2 * hd;     // [kThreads * 2] scratch
+    float* S = red + 2 * kThreads;   // [2][L]
+    const int L = p0 + 2;
+    float* kc = a.kv + (long long)slot * a.kv_slot_stride + (long long)a.layer * a.kv_layer_stride;
+    float* vc = kc + (long long)a.max_pos * a.dim;
+    const float* src = a.qkv + (long long)slot * a.qkv_stride;
+    const float scale = rsqrtf((float)hd);
+    for (int i = tid; i < 2 * half; i += kThreads) {   // (position t, pair i)
+        const int t = i / half, j = i - t * half;
+        const float* row = src + (long long)t * 3 * a.dim + h * hd;
+        const float cs = a.rope[(long long)(p0 + t) * hd + j], sn = a.rope[(long long)(p0 + t) * hd + half + j];
+        const float q1 = row[j], q2 = row[j + half];
+        q[t * hd + j] = (q1 * cs - q2 * sn) * scale;
+        q[t * hd + j + half] = (q2 * cs + q1 * sn) * scale;
+        const float k1 = row[a.dim + j], k2 = row[a.dim + j + half];
+        float* kd = kc + (long long)(p0 + t) * a.dim + h * hd;
+        kd[j] = k1 * cs - k2 * sn;
+        kd[j + half] = k2 * cs + k1 * sn;
+        float* vd = vc + (long long)(p0 + t) * a.dim + h * hd;
+        vd[j] = row[2 * a.dim + j];
+        vd[j + half] = row[2 * a.dim + j + half];
+    }
+    __syncthreads();
+    // visible positions: query t sees lo_t .. p0 + t
+    const int lo0 = a.window > 0 ? max(0, p0 + 1 - a.window) : 0;
+    const int lo1 = a.window > 0 ? max(0, p0 + 2 - a.window) : 0;
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int p = lo0 + tid; p < L; p += kThreads) {
+        const float4* kr = reinterpret_cast<const float4*>(kc + (long long)p * a.dim + h * hd);
+        float s0 = 0.f, s1 = 0.f;
+        for (int i = 0; i < hd / 4; ++i) {
+            const float4 kk = kr[i];
+            const float4 qa = *reinterpret_cast<const float4*>(q + 4 * i), qb = *reinterpret_cast<const float4*>(q + hd + 4 * i);
+            s0 = fmaf(qa.x, kk.x, s0); s0 = fmaf(qa.y, kk.y, s0); s0 = fmaf(qa.z, kk.z, s0); s0 = fmaf(qa.w, kk.w, s0);
+            s1 = fmaf(qb.x, kk.x, s1); s1 = fmaf(qb.y, kk.y, s1); s1 = fmaf(qb.z, kk.z, s1); s1 = fmaf(qb.w, kk.w, s1);
+        }
+        if (p > p0) s0 = -INFINITY;
+        if (p < lo1) s1 = -INFINITY;
+        S[p] = s0; S[L + p] = s1;
+        m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1);
+    }
+    red[tid] = m0; red[kThreads + tid] = m1;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (tid < o) { red[tid] = fmaxf(red[tid], red[tid + o]); red[kThreads + tid] = fmaxf(red[kThreads + tid], red[kThreads + tid + o]); }
+        __syncthreads();
+    }
+    m0 = red[0]; m1 = red[kThreads];
+    __syncthreads();
+    float l0 = 0.f, l1 = 0.f;
+    for (int p = lo0 + tid; p < L; p += kThreads) {
+        const float e0 = expf(S[p] - m0), e1 = expf(S[L + p] - m1);   // exp(-inf) = 0 for masked positions
+        S[p] = e0; S[L + p] = e1;
+        l0 += e0; l1 += e1;
+    }
+    red[tid] = l0; red[kThreads + tid] = l1;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (tid < o) { red[tid] += red[tid + o]; red[kThreads + tid] += red[kThreads + tid + o]; }
+        __syncthreads();
+    }
+    l0 = red[0]; l1 = red[kThreads];
+    __syncthreads();
+    // P V: thread = (dim d, position class g of kThreads / hd)
+    const int G = kThreads / hd, d = tid % hd, g = tid / hd;
+    float o0 = 0.f, o1 = 0.f;
+    if (g < G) {
+        for (int p = lo0 + g; p < L; p += G) {
+            const float v = vc[(long long)p * a.dim + h * hd + d];
+            o0 = fmaf(S[p], v, o0); o1 = fmaf(S[L + p], v, o1);
+        }
+    }
+    red[tid] = o0; red[kThreads + tid] = o1;
+    __syncthreads();
+    if (tid < hd) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int gg = 0; gg < G; ++gg) { s0 += red[gg * hd + tid]; s1 += red[kThreads + gg * hd + tid]; }
+        float* dst = a.att + (long long)slot * a.att_stride + h * hd + tid;
+        dst[0] = s0 / l0;
+        dst[a.dim] = s1 / l1;
+    }
+}
+
+// End of a step: the last `hs` rows of every history-carrying buffer move to its front; the position advances.
+struct BufDesc { int off, hs, T, C; };
+struct ShiftArgs {
+    float* arena; long long stride; const int32_t* slots; int32_t* pos; float* up_prev; int dim;
+    int n_bufs; BufDesc bufs[kMaxBufs];
+    int reset;   // 1: zero the history rows, the upsampler's carry and the position instead
+};
+__global__ void __launch_bounds__(kThreads) shift_kernel(const ShiftArgs a) {
+    __shared__ float tmp[4096];
+    const int b = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
+    const int slot = a.slots ? a.slots[b] : b;
+    if (i == a.n_bufs) {
+        if (a.reset) {
+            for (int k = tid; k < a.dim; k += kThreads) a.up_prev[(long long)slot * a.dim + k] = 0.f;
+            if (tid == 0) a.pos[slot] = 0;
+        } else if (tid == 0) a.pos[slot] += 1;
+        return;
+    }
+    const BufDesc d = a.bufs[i];
+    float* base = a.arena + (long long)slot * a.stride + d.off;
+    const int n = d.hs * d.C;
+    if (a.reset) { for (int k = tid; k < n; k += kThreads) base[k] = 0.f; return; }
+    const float* src = base + (long long)d.T * d.C;   // rows T .. T + hs
+    for (int k0 = 0; k0 < n; k0 += 4096) {   // (source and destination overlap when T < hs: staged through shared memory)
+        const int m = min(4096, n - k0);
+        for (int k = tid; k < m; k += kThreads) tmp[k] = src[k0 + k];
+        __syncthreads();
+        for (int k = tid; k < m; k += kThreads) base[k0 + k] = tmp[k];
+        __syncthreads();
+    }
+}
+
+// ---- bind-time packing ---------------------------------------------------------------------------------------------
+__global__ void pack_codebook_kernel(float* dst, const float* es, const float* cu, int rows, int dim, float eps) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * dim; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = es[i] / fmaxf(cu[i / dim], eps);
+}
+// Conv1d [Co][Ci][k] -> [Co][j * Ci + ci]
+__global__ void pack_conv_kernel(float* dst, const float* w, int Co, int Ci, int k) {
+    const long long total = (long long)Co * Ci * k;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Ci); const long long r = i / Ci; const int j = (int)(r % k); const int co = (int)(r / k);
+        dst[i] = w[((long long)co * Ci + ci) * k + j];
+    }
+}
+// ConvTranspose1d [Ci][Co][2 s] -> [(r, co)][(u, ci)] = w[ci][co][r + u s]   (u = 0: this input row, u = 1: the previous one)
+__global__ void pack_convtr_kernel(float* dst, const float* w, int Ci, int Co, int s) {
+    const long long total = (long long)s * Co * 2 * Ci;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Ci); long long r = i / Ci; const int u = (int)(r % 2); r /= 2; const int co = (int)(r % Co); const int ph = (int)(r / Co);
+        dst[i] = w[((long long)ci * Co + co) * (2 * s) + ph + u * s];
+    }
+}
+// two [N][K1] matrices side by side -> [N][2 K1]
+__global__ void pack_hcat_kernel(float* dst, const float* a, const float* b, int N, int K1) {
+    const long long total = (long long)N * 2 * K1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % (2 * K1)); const int n = (int)(i / (2 * K1));
+        dst[i] = k < K1 ? a[(long long)n * K1 + k] : b[(long long)n * K1 + (k - K1)];
+    }
+}
+
+}  // namespace mimi
+}  // namespace smol
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+using namespace smol::mimi;
+
+struct MimiBuf { size_t off; int hs, T, C; };   // per-slot arena buffer (floats)
+
+struct SmolMimi {
+    SmolMimiConfig cfg{};
+    int spf = 0;                       // samples per frame
+    int ch0 = 0;                       // channels after conv_in
+    // per-slot arena
+    std::vector<MimiBuf> bufs;
+    int bX0 = 0, bQ = 0, bQKV = 0, bATT = 0, bFF = 0, bA0 = 0;
+    int bCT[SMOL_MIMI_MAX_RATIOS], bH[SMOL_MIMI_MAX_RATIOS], bR[SMOL_MIMI_MAX_RATIOS];
+    size_t arena_floats = 0;
+    // workspace layout (bytes)
+    size_t o_books = 0, o_wcat = 0, o_up = 0, o_rope = 0, o_small = 0, o_conv_in = 0, o_conv_out = 0;
+    size_t o_qkv[SMOL_MIMI_MAX_LAYERS], o_o[SMOL_MIMI_MAX_LAYERS], o_fc1[SMOL_MIMI_MAX_LAYERS], o_fc2[SMOL_MIMI_MAX_LAYERS], o_vec[SMOL_MIMI_MAX_LAYERS];
+    size_t o_ct[SMOL_MIMI_MAX_RATIOS], o_r1[SMOL_MIMI_MAX_RATIOS], o_r2[SMOL_MIMI_MAX_RATIOS], o_bias = 0;
+    size_t o_arena = 0, o_kv = 0, o_pos = 0, o_upprev = 0, o_err = 0, total = 0;
+    unsigned char* ws = nullptr;
+    bool bound = false;
+    int launches = 0;
+    size_t attn_smem = 0;
+    // cached graph of one step
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    const void* g_codes = nullptr; const void* g_slots = nullptr; const void* g_pcm = nullptr; int g_batch = -1;
+};
+
+static size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+static int mimi_plan(SmolMimi* m) {
+    const SmolMimiConfig& c = m->cfg;
+    m->bufs.clear();
+    size_t off = 0;
+    auto add = [&](int hs, int T, int C) { m->bufs.push_back({off, hs, T, C}); off += (size_t)(hs + T) * C; off = (off + 3) / 4 * 4; return (int)m->bufs.size() - 1; };
+    m->ch0 = c.n_filters << c.n_ratios;
+    m->bX0 = add(c.kernel - 1, 2, c.dim);
+    m->bQ = add(0, 1, 2 * c.codebook_dim);
+    m->bQKV = add(0, 2, 3 * c.dim);
+    m->bATT = add(0, 2, c.dim);
+    m->bFF = add(0, 2, c.ffn);
+    m->bA0 = add(1, 2, m->ch0);
+    int T = 2, ch = m->ch0;
+    for (int i = 0; i < c.n_ratios; ++i) {
+        T *= c.ratios[i]; ch /= 2;
+        m->bCT[i] = add(c.res_kernel - 1, T, ch);
+        m->bH[i] = add(0, T, ch / 2);
+        m->bR[i] = add(i + 1 < c.n_ratios ? 1 : c.last_kernel - 1, T, ch);
+    }
+    m->spf = T;
+    m->arena_floats = (off + 63) / 64 * 64;
+    if ((int)m->bufs.size() > kMaxBufs) return -1;
+    // workspace
+    size_t o = 0;
+    auto take = [&](size_t floats) { const size_t r = o; o = al(o + floats * 4); return r; };
+    m->o_books = take((size_t)c.n_q * c.codebook_size * c.codebook_dim);
+    m->o_wcat = take((size_t)c.dim * 2 * c.codebook_dim);
+    m->o_up = take((size_t)c.dim * 4);
+    m->o_rope = take((size_t)c.max_positions * c.head_dim);
+    for (int l = 0; l < c.n_layers; ++l) {
+        m->o_qkv[l] = take((size_t)3 * c.dim * c.dim);
+        m->o_o[l] = take((size_t)c.dim * c.dim);
+        m->o_fc1[l] = take((size_t)c.ffn * c.dim);
+        m->o_fc2[l] = take((size_t)c.dim * c.ffn);
+        m->o_vec[l] = take((size_t)6 * c.dim);   // ln1 w|b, ln2 w|b, scale_attn, scale_mlp
+    }
+    m->o_conv_in = take((size_t)m->ch0 * c.dim * c.kernel);
+    ch = m->ch0;
+    for (int i = 0; i < c.n_ratios; ++i) {
+        m->o_ct[i] = take((size_t)ch * (ch / 2) * 2 * c.ratios[i]);
+        ch /= 2;
+        m->o_r1[i] = take((size_t)(ch / 2) * ch * c.res_kernel);
+        m->o_r2[i] = take((size_t)ch * (ch / 2));
+    }
+    m->o_conv_out = take((size_t)ch * c.last_kernel);
+    m->o_bias = take((size_t)4 * m->ch0 + 16);   // all SEANet biases, back to back
+    m->o_arena = take(m->arena_floats * (size_t)c.max_streams);
+    m->o_kv = take((size_t)c.max_streams * c.n_layers * 2 * c.max_positions * c.dim);
+    m->o_pos = take((size_t)c.max_streams);
+    m->o_upprev = take((size_t)c.max_streams * c.dim);
+    m->o_err = take(4);
+    m->total = o;
+    m->attn_smem = (size_t)(2 * c.head_dim + 2 * kThreads + 2 * c.max_positions) * 4;
+    return 0;
+}
+
+extern "C" int smol_mimi_create(const SmolMimiConfig* cfg, SmolMimi** out) {
+    if (!cfg || !out) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_create: null argument");
+    const SmolMimiConfig& c = *cfg;
+    if (c.n_q < 2 || c.n_q > SMOL_MIMI_MAX_Q) return smol::capi_fail(SMOL_ERR_INVALID, "mimi: n_q must be 2 .. 32 (one semantic + acoustic codebooks)");
+    if (c.n_layers < 1 || c.n_layers > SMOL_MIMI_MAX_LAYERS) return smol::capi_fail(SMOL_ERR_INVALID, "mimi: n_layers out of range");
+    if (c.n_ratios < 1 || c.n_ratios > SMOL_MIMI_MAX_RATIOS) return smol::capi_fail(SMOL_ERR_INVALID, "mimi: n_ratios out of range");
+    if (c.dim != c.n_heads * c.head_dim) return smol::capi_fail(SMOL_ERR_INVALID, "mimi: dim != n_heads * head_dim");
+    if (c.head_dim % 8 || c.head_dim > kThreads || kThreads % c.head_dim) return smol::capi_fail(SMOL_ERR_UNSUPPORTED, "mimi: head_dim must divide 256 and be a multiple of 8");
+    if (c.dim % 4 || c.ffn % 4 || c.codebook_dim % 4 || (c.n_filters % 8)) return smol::capi_fail(SMOL_ERR_UNSUPPORTED, "mimi: channel counts must be multiples of 4 (n_filters of 8)");
+    if (c.dim > kStageFloats / 16) return smol::capi_fail(SMOL_ERR_UNSUPPORTED, "mimi: dim above 512 does not fit the LayerNorm staging");
+    if (c.kernel < 1 || c.res_kernel < 1 || c.last_kernel < 1) return smol::capi_fail(SMOL_ERR_INVALID, "mimi: kernel sizes");
+    for (int i = 0; i < c.n_ratios; ++i) if (c.ratios[i] < 1) return smol::capi_fail(SMOL_ERR_INVALID, "mimi: ratios must be positive");
+    if (c.max_streams < 1 || c.max_positions < 2 || (c.max_positions & 1)) return smol::capi_fail(SMOL_ERR_INVALID, "mimi: max_streams >= 1, max_positions even and >= 2");
+    SmolMimi* m = new SmolMimi();
+    m->cfg = c;
+    if (mimi_plan(m) != 0) { delete m; return smol::capi_fail(SMOL_ERR_UNSUPPORTED, "mimi: too many buffers"); }
+    if (m->attn_smem > 227 * 1024) { delete m; return smol::capi_fail(SMOL_ERR_CAPACITY, "mimi: max_positions too large for the attention kernel's score buffer (about 28 000)"); }
+    *out = m;
+    return SMOL_OK;
+}
+
+extern "C" void smol_mimi_destroy(SmolMimi* m) {
+    if (!m) return;
+    if (m->graph) cudaGraphExecDestroy(m->graph);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+    delete m;
+}
+extern "C" int32_t smol_mimi_samples_per_frame(const SmolMimi* m) { return m ? m->spf : 0; }
+extern "C" size_t smol_mimi_workspace_bytes(const SmolMimi* m) { return m ? m->total : 0; }
+extern "C" int32_t smol_mimi_launches_per_step(const SmolMimi* m) { return m ? m->launches : 0; }
+extern "C" int32_t* smol_mimi_error_word(SmolMimi* m) { return (m && m->bound) ? reinterpret_cast<int32_t*>(m->ws + m->o_err) : nullptr; }
+
+#define MCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return smol::capi_cuda_fail(e__, #call); } while (0)
+
+static float* wsf(SmolMimi* m, size_t off) { return reinterpret_cast<float*>(m->ws + off); }
+
+static ShiftArgs shift_args(SmolMimi* m, const int32_t* slots, int reset) {
+    ShiftArgs a{};
+    a.arena = wsf(m, m->o_arena); a.stride = (long long)m->arena_floats; a.slots = slots;
+    a.pos = reinterpret_cast<int32_t*>(m->ws + m->o_pos); a.up_prev = wsf(m, m->o_upprev); a.dim = m->cfg.dim;
+    a.n_bufs = 0; a.reset = reset;
+    for (const MimiBuf& b : m->bufs) if (b.hs > 0) a.bufs[a.n_bufs++] = BufDesc{(int)b.off, b.hs, b.T, b.C};
+    return a;
+}
+
+extern "C" int smol_mimi_reset(SmolMimi* m, const int32_t* d_slots, int32_t n, void* stream) {
+    if (!m) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_reset: null model");
+    if (!m->bound) return smol::capi_fail(SMOL_ERR_UNBOUND, "smol_mimi_reset: weights / workspace not bound");
+    if (n < 1 || n > m->cfg.max_streams) return smol::capi_fail(SMOL_ERR_CAPACITY, "smol_mimi_reset: n outside 1 .. max_streams");
+    const ShiftArgs a = shift_args(m, d_slots, 1);
+    shift_kernel<<<dim3(n, a.n_bufs + 1), kThreads, 0, (cudaStream_t)stream>>>(a);
+    MCU(cudaGetLastError());
+    return SMOL_OK;
+}
+
+extern "C" int smol_mimi_bind(SmolMimi* m, const SmolMimiWeights* w, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!m || !w || !d_workspace) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_bind: null argument");
+    if (workspace_bytes < m->total) return smol::capi_fail(SMOL_ERR_CAPACITY, "smol_mimi_bind: workspace smaller than smol_mimi_workspace_bytes()");
+    if ((uintptr_t)d_workspace % 256) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_bind: workspace must be 256-byte aligned");
+    const SmolMimiConfig& c = m->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto need = [&](const void* p) { return p != nullptr; };
+    bool ok = need(w->semantic_output_proj) && need(w->acoustic_output_proj) && need(w->upsample) && need(w->rope) &&
+              need(w->conv_in.weight) && need(w->conv_in.bias) && need(w->conv_out.weight) && need(w->conv_out.bias);
+    for (int i = 0; i < c.n_q; ++i) ok = ok && need(w->embed_sum[i]) && need(w->cluster_usage[i]);
+    for (int l = 0; l < c.n_layers; ++l) {
+        const SmolMimiLayerWeights& L = w->layers[l];
+        ok = ok && need(L.q_proj) && need(L.k_proj) && need(L.v_proj) && need(L.o_proj) && need(L.fc1) && need(L.fc2) && need(L.ln1_w) &&
+             need(L.ln1_b) && need(L.ln2_w) && need(L.ln2_b) && need(L.scale_attn) && need(L.scale_mlp);
+    }
+    for (int i = 0; i < c.n_ratios; ++i)
+        ok = ok && need(w->convtr[i].weight) && need(w->convtr[i].bias) && need(w->res_conv1[i].weight) && need(w->res_conv1[i].bias) &&
+             need(w->res_conv2[i].weight) && need(w->res_conv2[i].bias);
+    if (!ok) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_bind: a weight pointer is null");
+    m->ws = reinterpret_cast<unsigned char*>(d_workspace);
+    if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; m->g_batch = -1; }
+    const size_t f4 = sizeof(float);
+    auto d2d = [&](size_t off, const float* src, size_t floats) { return cudaMemcpyAsync(m->ws + off, src, floats * f4, cudaMemcpyDeviceToDevice, st); };
+    for (int i = 0; i < c.n_q; ++i)
+        pack_codebook_kernel<<<256, 256, 0, st>>>(wsf(m, m->o_books) + (size_t)i * c.codebook_size * c.codebook_dim, w->embed_sum[i],
+                                                   w->cluster_usage[i], c.codebook_size, c.codebook_dim, c.codebook_eps);
+    pack_hcat_kernel<<<256, 256, 0, st>>>(wsf(m, m->o_wcat), w->semantic_output_proj, w->acoustic_output_proj, c.dim, c.codebook_dim);
+    MCU(d2d(m->o_up, w->upsample, (size_t)c.dim * 4));
+    MCU(d2d(m->o_rope, w->rope, (size_t)c.max_positions * c.head_dim));
+    for (int l = 0; l < c.n_layers; ++l) {
+        const SmolMimiLayerWeights& L = w->layers[l];
+        const size_t dd = (size_t)c.dim * c.dim;
+        MCU(d2d(m->o_qkv[l], L.q_proj, dd));
+        MCU(d2d(m->o_qkv[l] + dd * f4, L.k_proj, dd));
+        MCU(d2d(m->o_qkv[l] + 2 * dd * f4, L.v_proj, dd));
+        MCU(d2d(m->o_o[l], L.o_proj, dd));
+        MCU(d2d(m->o_fc1[l], L.fc1, (size_t)c.ffn * c.dim));
+        MCU(d2d(m->o_fc2[l], L.fc2, (size_t)c.ffn * c.dim));
+        const float* vecs[6] = {L.ln1_w, L.ln1_b, L.ln2_w, L.ln2_b, L.scale_attn, L.scale_mlp};
+        for (int i = 0; i < 6; ++i) MCU(d2d(m->o_vec[l] + (size_t)i * c.dim * f4, vecs[i], c.dim));
+    }
+    pack_conv_kernel<<<512, 256, 0, st>>>(wsf(m, m->o_conv_in), w->conv_in.weight, m->ch0, c.dim, c.kernel);
+    size_t bo = m->o_bias;
+    MCU(d2d(bo, w->conv_in.bias, m->ch0)); bo += (size_t)m->ch0 * f4;
+    int ch = m->ch0;
+    for (int i = 0; i < c.n_ratios; ++i) {
+        pack_convtr_kernel<<<512, 256, 0, st>>>(wsf(m, m->o_ct[i]), w->convtr[i].weight, ch, ch / 2, c.ratios[i]);
+        ch /= 2;
+        pack_conv_kernel<<<256, 256, 0, st>>>(wsf(m, m->o_r1[i]), w->res_conv1[i].weight, ch / 2, ch, c.res_kernel);
+        MCU(d2d(m->o_r2[i], w->res_conv2[i].weight, (size_t)ch * (ch / 2)));
+        MCU(d2d(bo, w->convtr[i].bias, ch)); bo += (size_t)ch * f4;
+        MCU(d2d(bo, w->res_conv1[i].bias, ch / 2)); bo += (size_t)(ch / 2) * f4;
+        MCU(d2d(bo, w->res_conv2[i].bias, ch)); bo += (size_t)ch * f4;
+    }
+    pack_conv_kernel<<<16, 256, 0, st>>>(wsf(m, m->o_conv_out), w->conv_out.weight, 1, ch, c.last_kernel);
+    MCU(d2d(bo, w->conv_out.bias, 1));
+    MCU(cudaGetLastError());
+    MCU(cudaMemsetAsync(m->ws + m->o_err, 0, 16, st));
+    if (m->attn_smem > 48 * 1024) MCU(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->attn_smem));
+    m->bound = true;
+    return smol_mimi_reset(m, nullptr, c.max_streams, stream);
+}
+
+static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
+    const int rows = op.batch * op.T;
+    const int R = rows <= 2 ? 2 : rows <= 4 ? 4 : rows <= 8 ? 8 : 16;
+    const dim3 grid((op.N + kWarps - 1) / kWarps, (rows + R - 1) / R);
+    switch (R) {
+        case 2: rows_kernel<2><<<grid, kThreads, 0, st>>>(op); break;
+        case 4: rows_kernel<4><<<grid, kThreads, 0, st>>>(op); break;
+        case 8: rows_kernel<8><<<grid, kThreads, 0, st>>>(op); break;
+        default: rows_kernel<16><<<grid, kThreads, 0, st>>>(op); break;
+    }
+    return cudaGetLastError();
+}
+
+// every launch of one step, in order
+static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_slots, int batch, float* d_pcm, cudaStream_t st) {
+    const SmolMimiConfig& c = m->cfg;
+    float* arena = wsf(m, m->o_arena);
+    const long long AS = (long long)m->arena_floats;
+    int n_launch = 0;
+    auto buf = [&](int i) -> const MimiBuf& { return m->bufs[i]; };
+    auto base_op = [&]() { RowOp op{}; op.slots = d_slots; op.batch = batch; op.in_stride = AS; op.out_stride = AS; op.res_stride = AS; op.bias_mod = 1; op.tapstep = 1; return op; };
+    // input of an op: buffer bi, `taps` rows ending at the current one (conv) or {current, previous} (transposed conv)
+    auto set_in = [&](RowOp& op, int bi, int taps, bool transposed) {
+        const MimiBuf& b = buf(bi);
+        op.in = arena + b.off; op.in_hs = b.hs; op.in_c = b.C; op.T = b.T; op.K = taps * b.C;
+        op.tap0 = transposed ? 0 : -(taps - 1); op.tapstep = transposed ? -1 : 1;
+    };
+    auto set_out = [&](RowOp& op, int bi) { const MimiBuf& b = buf(bi); op.out = arena + b.off; op.out_off0 = b.hs * b.C; };
+    auto set_res = [&](RowOp& op, int bi) { const MimiBuf& b = buf(bi); op.res = arena + b.off; op.res_off0 = b.hs * b.C; };
+
+    {   // RVQ rows -> Q; projection + upsample -> the residual stream (current rows of X0)
+        EmbedArgs e{wsf(m, m->o_books), d_codes, d_slots, arena + buf(m->bQ).off, AS, c.n_q, c.codebook_size, c.codebook_dim};
+        embed_kernel<<<batch, 256, 0, st>>>(e);
+        MCU(cudaGetLastError()); ++n_launch;
+        RowOp op = base_op();
+        set_in(op, m->bQ, 1, false);
+        op.W = wsf(m, m->o_wcat); op.N = c.dim; op.epi = EPI_UPSAMPLE; op.wup = wsf(m, m->o_up);
+        op.up_prev = wsf(m, m->o_upprev); op.carry = c.upsample_carry;
+        set_out(op, m->bX0);
+        MCU(launch_rows(op, st)); ++n_launch;
+    }
+    for (int l = 0; l < c.n_layers; ++l) {
+        const float* vec = wsf(m, m->o_vec[l]);
+        {   // LayerNorm -> q | k | v
+            RowOp op = base_op();
+            set_in(op, m->bX0, 1, false);
+            op.pro = PRO_LN; op.ln_w = vec; op.ln_b = vec + c.dim; op.eps = c.norm_eps;
+            op.W = wsf(m, m->o_qkv[l]); op.N = 3 * c.dim; op.epi = EPI_BIAS;
+            set_out(op, m->bQKV);
+            MCU(launch_rows(op, st)); ++n_launch;
+        }
+        {
+            AttnArgs a{};
+            a.qkv = arena + buf(m->bQKV).off; a.qkv_stride = AS; a.att = arena + buf(m->bATT).off; a.att_stride = AS;
+            a.kv = wsf(m, m->o_kv); a.kv_layer_stride = (long long)2 * c.max_positions * c.dim; a.kv_slot_stride = a.kv_layer_stride * c.n_layers;
+            a.rope = wsf(m, m->o_rope); a.pos = reinterpret_cast<const int32_t*>(m->ws + m->o_pos); a.slots = d_slots;
+            a.err = reinterpret_cast<int32_t*>(m->ws + m->o_err);
+            a.layer = l; a.dim = c.dim; a.hd = c.head_dim; a.max_pos = c.max_positions; a.window = c.window;
+            attn_kernel<<<dim3(batch, c.n_heads), kThreads, m->attn_smem, st>>>(a);
+            MCU(cudaGetLastError()); ++n_launch;
+        }
+        {   // o_proj, layer scale, residual (in place on the stream)
+            RowOp op = base_op();
+            set_in(op, m->bATT, 1, false);
+            op.W = wsf(m, m->o_o[l]); op.N = c.dim; op.epi = EPI_SCALE_RES; op.scale = vec + 4 * c.dim;
+            set_out(op, m->bX0); set_res(op, m->bX0);
+            MCU(launch_rows(op, st)); ++n_launch;
+        }
+        {   // LayerNorm -> fc1 -> GELU
+            RowOp op = base_op();
+            set_in(op, m->bX0, 1, false);
+            op.pro = PRO_LN; op.ln_w = vec + 2 * c.dim; op.ln_b = vec + 3 * c.dim; op.eps = c.norm_eps;
+            op.W = wsf(m, m->o_fc1[l]); op.N = c.ffn; op.epi = EPI_GELU;
+            set_out(op, m->bFF);
+            MCU(launch_rows(op, st)); ++n_launch;
+        }
+        {   // fc2, layer scale, residual
+            RowOp op = base_op();
+            set_in(op, m->bFF, 1, false);
+            op.W = wsf(m, m->o_fc2[l]); op.N = c.dim; op.epi = EPI_SCALE_RES; op.scale = vec + 5 * c.dim;
+            set_out(op, m->bX0); set_res(op, m->bX0);
+            MCU(launch_rows(op, st)); ++n_launch;
+        }
+    }
+    // ---- SEANet decoder ----
+    const float* bias = wsf(m, m->o_bias);
+    {
+        RowOp op = base_op();
+        set_in(op, m->bX0, c.kernel, false);
+        op.W = wsf(m, m->o_conv_in); op.N = m->ch0; op.bias = bias; op.bias_mod = m->ch0; op.epi = EPI_BIAS;
+        set_out(op, m->bA0);
+        MCU(launch_rows(op, st)); ++n_launch;
+        bias += m->ch0;
+    }
+    int ch = m->ch0, prev = m->bA0;
+    for (int i = 0; i < c.n_ratios; ++i) {
+        const int r = c.ratios[i];
+        ch /= 2;
+        {   // ELU -> transposed convolution (kernel 2 r, stride r): row t -> r output rows, contiguous
+            RowOp op = base_op();
+            set_in(op, prev, 2, true);
+            op.pro = PRO_ELU; op.W = wsf(m, m->o_ct[i]); op.N = r * ch; op.bias = bias; op.bias_mod = ch; op.epi = EPI_BIAS;
+            set_out(op, m->bCT[i]);
+            MCU(launch_rows(op, st)); ++n_launch;
+            bias += ch;
+        }
+        {   // residual block: ELU -> conv k3 -> ELU -> conv k1, + skip
+            RowOp op = base_op();
+            set_in(op, m->bCT[i], c.res_kernel, false);
+            op.pro = PRO_ELU; op.W = wsf(m, m->o_r1[i]); op.N = ch / 2; op.bias = bias; op.bias_mod = ch / 2; op.epi = EPI_BIAS;
+            set_out(op, m->bH[i]);
+            MCU(launch_rows(op, st)); ++n_launch;
+            bias += ch / 2;
+            RowOp o2 = base_op();
+            set_in(o2, m->bH[i], 1, false);
+            o2.pro = PRO_ELU; o2.W = wsf(m, m->o_r2[i]); o2.N = ch; o2.bias = bias; o2.bias_mod = ch; o2.epi = EPI_RES;
+            set_out(o2, m->bR[i]); set_res(o2, m->bCT[i]);
+            MCU(launch_rows(o2, st)); ++n_launch;
+            bias += ch;
+        }
+        prev = m->bR[i];
+    }
+    {   // ELU -> conv k3 -> PCM (the caller's buffer, row b)
+        RowOp op = base_op();
+        set_in(op, prev, c.last_kernel, false);
+        op.pro = PRO_ELU; op.W = wsf(m, m->o_conv_out); op.N = 1; op.bias = bias; op.bias_mod = 1; op.epi = EPI_BIAS;
+        op.out = d_pcm; op.out_stride = m->spf; op.out_off0 = 0; op.out_by_row = 1;
+        MCU(launch_rows(op, st)); ++n_launch;
+    }
+    {
+        const ShiftArgs a = shift_args(m, d_slots, 0);
+        shift_kernel<<<dim3(batch, a.n_bufs + 1), kThreads, 0, st>>>(a);
+        MCU(cudaGetLastError()); ++n_launch;
+    }
+    m->launches = n_launch;
+    return SMOL_OK;
+}
+
+extern "C" int smol_mimi_decode_step(SmolMimi* m, const int32_t* d_codes, const int32_t* d_slots, int32_t batch, float* d_pcm, void* stream) {
+    if (!m || !d_codes || !d_pcm) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_decode_step: null argument");
+    if (!m->bound) return smol::capi_fail(SMOL_ERR_UNBOUND, "smol_mimi_decode_step: weights / workspace not bound");
+    if (batch < 1 || batch > m->cfg.max_streams) return smol::capi_fail(SMOL_ERR_CAPACITY, "smol_mimi_decode_step: batch outside 1 .. max_streams");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!m->cfg.use_graph) return mimi_enqueue(m, d_codes, d_slots, batch, d_pcm, st);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+        return mimi_enqueue(m, d_codes, d_slots, batch, d_pcm, st);   // the caller is capturing: become part of its graph
+    if (!(m->graph && m->g_codes == d_codes && m->g_slots == d_slots && m->g_pcm == d_pcm && m->g_batch == batch)) {
+        if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
+        if (!m->cap_stream) MCU(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        MCU(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = mimi_enqueue(m, d_codes, d_slots, batch, d_pcm, m->cap_stream);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(m->cap_stream, &g);
+        if (rc != SMOL_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        MCU(ee);
+        const cudaError_t ei = cudaGraphInstantiate(&m->graph, g, 0);
+        cudaGraphDestroy(g);
+        MCU(ei);
+        m->g_codes = d_codes; m->g_slots = d_slots; m->g_pcm = d_pcm; m->g_batch = batch;
+    }
+    MCU(cudaGraphLaunch(m->graph, st));
+    return SMOL_OK;
+}
+
+extern "C" void* smol_mimi_debug_buffer(SmolMimi* m, const char* name, int64_t* slot_stride_floats) {
+    if (!m || !m->bound || !name) return nullptr;
+    if (slot_stride_floats) *slot_stride_floats = (int64_t)m->arena_floats;
+    float* arena = wsf(m, m->o_arena);
+    auto cur = [&](int bi) { const MimiBuf& b = m->bufs[bi]; return (void*)(arena + b.off + (size_t)b.hs * b.C); };
+    if (!strcmp(name, "xf") || !strcmp(name, "emb")) return cur(m->bX0);   // (emb: valid with n_layers' launches skipped; see tests)
+    if (!strcmp(name, "q")) return cur(m->bQ);
+    if (!strcmp(name, "conv_in")) return cur(m->bA0);
+    if (!strcmp(name, "res_last")) return cur(m->bR[m->cfg.n_ratios - 1]);
+    if (!strcmp(name, "pos")) return (void*)(m->ws + m->o_pos);
+    return nullptr;
+}

@@ -8,7 +8,7 @@ from conftest import ROOT
 
 
 def _declared():
-    text = open(os.path.join(ROOT, "include", "smoltts_b200.h")).read()
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))) if h.endswith(".h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(smol_[a-z_0-9]+)\s*\(", text)))
 
@@ -60,3 +60,33 @@ def test_create_validates_shapes_without_a_gpu():
     assert lib.smol_create(ctypes.byref(make(fast_dim=512, fast_n_head=8)), ctypes.byref(h2)) == _capi.SMOL_ERR_UNSUPPORTED
     assert b"fast_project_in" in lib.smol_last_error()
     assert lib.smol_create(ctypes.byref(make(head_dim=128)), ctypes.byref(h2)) == _capi.SMOL_ERR_UNSUPPORTED
+
+
+def test_mimi_create_validates_shapes_without_a_gpu():
+    """smol_mimi_create is pure host code too."""
+    from smoltts_b200 import _capi
+
+    lib = _capi.load()
+
+    def make(**over):
+        c = _capi.SmolMimiConfig(n_q=8, codebook_size=2048, codebook_dim=256, dim=512, n_layers=8, n_heads=8, head_dim=64, ffn=2048,
+                                 n_filters=64, n_ratios=4, kernel=7, res_kernel=3, last_kernel=3, max_streams=2, max_positions=512,
+                                 window=0, upsample_carry=0, use_graph=1, norm_eps=1e-5, codebook_eps=1e-5)
+        for i, r in enumerate((8, 6, 5, 4)):
+            c.ratios[i] = r
+        for k, v in over.items():
+            setattr(c, k, v)
+        return c
+
+    h = ctypes.c_void_p()
+    assert lib.smol_mimi_create(ctypes.byref(make()), ctypes.byref(h)) == 0
+    assert lib.smol_mimi_samples_per_frame(h) == 1920
+    ws = lib.smol_mimi_workspace_bytes(h)
+    # packed weights of the decode half (44.4 M parameters) + two streams' KV caches and arenas
+    assert 44.3e6 * 4 < ws < 44.3e6 * 4 + 2 * (8 * 2 * 512 * 512 * 4 + 3.0e6) + 4e6
+    assert lib.smol_mimi_decode_step(h, ctypes.c_void_p(8), None, 1, ctypes.c_void_p(8), None) == _capi.SMOL_ERR_UNBOUND
+    lib.smol_mimi_destroy(h)
+    h2 = ctypes.c_void_p()
+    assert lib.smol_mimi_create(ctypes.byref(make(head_dim=48)), ctypes.byref(h2)) == _capi.SMOL_ERR_INVALID
+    assert lib.smol_mimi_create(ctypes.byref(make(max_positions=7)), ctypes.byref(h2)) == _capi.SMOL_ERR_INVALID
+    assert lib.smol_mimi_create(ctypes.byref(make(max_positions=60000)), ctypes.byref(h2)) == _capi.SMOL_ERR_CAPACITY

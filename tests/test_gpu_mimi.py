@@ -1,0 +1,142 @@
+"""Mimi streaming decoder on the GPU (csrc/mimi_kernels.cu through include/smoltts_b200_mimi.h) against the goldens made from
+transformers' MimiModel and against the CPU oracle (oracle/mimi_oracle.py) on the same seeded weights.
+
+Tolerance: everything is fp32 on both sides and differs only in summation order (dot products of up to 3584 terms):
+max |error| <= 1e-4 x max |reference| over the compared tensor (measured: a few 1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+_CACHE = {}
+
+
+def _sd():
+    from smoltts_b200.synth import make_mimi_state_dict
+
+    if "sd" not in _CACHE:
+        _CACHE["sd"] = make_mimi_state_dict(0)
+    return _CACHE["sd"]
+
+
+def _model(**kw):
+    from smoltts_b200.mimi import MimiModel
+
+    key = tuple(sorted(kw.items()))
+    if key not in _CACHE:
+        m = MimiModel(**kw)
+        m.load_state_dict(_sd())
+        _CACHE[key] = m
+    return _CACHE[key]
+
+
+def _close(name, got, want, rel=REL):
+    got = torch.as_tensor(got).float().cpu()
+    want = torch.as_tensor(want).float().cpu()
+    assert got.shape == want.shape, (name, tuple(got.shape), tuple(want.shape))
+    assert torch.isfinite(got).all(), f"{name}: non-finite samples"
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item()
+    print(f"{name}: max abs error {err:.3g} (scale {scale:.3g}, rel {err / scale:.2g})")
+    assert err <= rel * scale, f"{name}: max abs error {err:.3g} vs scale {scale:.3g}"
+
+
+def _run(m, codes, caches=None):
+    """codes [B, n_q, T] through decode_step, frame by frame."""
+    own = caches is None
+    caches = caches or [m.make_cache() for _ in range(codes.shape[0])]
+    out = [m.decode_step(codes[:, :, t:t + 1].cuda(), caches).clone() for t in range(codes.shape[-1])]
+    if own:
+        for c in caches:
+            m.release_cache(c)
+    return torch.cat(out, dim=-1)
+
+
+def test_steps_match_transformers_goldens_under_both_upsampling_rules():
+    g = np.load(f"{GOLDEN_DIR}/mimi.npz")
+    codes = torch.from_numpy(g["codes"]).long()
+    ref_rule = _model(max_streams=4, max_frames=64)
+    pcm = _run(ref_rule, codes)
+    assert pcm.shape == (2, 1, 4 * 1920)
+    _close("decode_step rule vs transformers (frame-wise upsample)", pcm, g["stream"])
+    assert ref_rule.launches_per_step == 2 + 5 * 8 + 1 + 3 * 4 + 1 + 1
+    carry = _model(max_streams=4, max_frames=64, upsample_carry=True)
+    _close("carry rule vs MimiModel.decode", _run(carry, codes), g["full"])
+    _close("decode() helper", carry.decode(codes), g["full"])
+
+
+def test_transformer_output_matches_goldens():
+    g = np.load(f"{GOLDEN_DIR}/mimi.npz")
+    codes = torch.from_numpy(g["codes"]).long()
+    m = _model(max_streams=4, max_frames=64)
+    caches = [m.make_cache() for _ in range(2)]
+    for t in range(codes.shape[-1]):
+        m.decode_step(codes[:, :, t:t + 1].cuda(), caches)
+        for b, c in enumerate(caches):
+            _close(f"xf frame {t} row {b}", m.debug_rows("xf", c.slot, 2, 512), g["xf_stream"][b, 2 * t: 2 * t + 2])
+    for c in caches:
+        m.release_cache(c)
+
+
+def test_long_run_matches_the_oracle_with_and_without_window():
+    from oracle.mimi_oracle import MimiOracle, StreamState
+
+    gen = torch.Generator().manual_seed(11)
+    T = 24
+    codes = torch.randint(0, 2048, (1, 8, T), generator=gen)
+    for window in (0, 6):
+        orc = MimiOracle(_sd(), window=window)
+        st = StreamState()
+        with torch.no_grad():
+            want = torch.cat([orc.decode_step(codes[:, :, t:t + 1], st) for t in range(T)], dim=-1)
+        m = _model(max_streams=2, max_frames=32, window=window)
+        _close(f"{T} frames, window {window}", _run(m, codes), want)
+    # the window really bites
+    assert not torch.allclose(_run(_model(max_streams=2, max_frames=32, window=6), codes), _run(_model(max_streams=2, max_frames=32, window=0), codes))
+
+
+def test_a_stream_decodes_to_the_same_bits_alone_in_any_batch_slot_and_launch_mode():
+    gen = torch.Generator().manual_seed(5)
+    B, T = 9, 5
+    codes = torch.randint(0, 2048, (B, 8, T), generator=gen)
+    m = _model(max_streams=12, max_frames=16)
+    batch = _run(m, codes)                       # 9 streams: 18 transformer rows, 17280 SEANet rows (ragged 16-row chunks)
+    eager = _model(max_streams=12, max_frames=16, use_graph=False)
+    assert torch.equal(_run(eager, codes), batch), "graph replay and plain launches differ"
+    for b in (0, 4, 8):
+        assert torch.equal(_run(m, codes[b:b + 1]), batch[b:b + 1]), f"stream {b} decodes differently alone"
+    # slots in a different order, neighbours changing from step to step
+    caches = [m.make_cache() for _ in range(B)]
+    perm = [3, 0, 8, 1, 7, 2, 6, 4, 5]
+    out = []
+    for t in range(T):
+        if t % 2 == 0:
+            out.append(m.decode_step(codes[perm, :, t:t + 1].cuda(), [caches[i] for i in perm]).clone()[torch.argsort(torch.tensor(perm)).cuda()])
+        else:   # two calls of different batch sizes
+            a = m.decode_step(codes[:4, :, t:t + 1].cuda(), caches[:4]).clone()
+            b2 = m.decode_step(codes[4:, :, t:t + 1].cuda(), caches[4:]).clone()
+            out.append(torch.cat([a, b2], dim=0))
+    assert torch.equal(torch.cat(out, dim=-1), batch)
+    for c in caches:
+        m.release_cache(c)
+
+
+def test_slot_reuse_and_capacity():
+    gen = torch.Generator().manual_seed(3)
+    codes = torch.randint(0, 2048, (1, 8, 4), generator=gen)
+    m = _model(max_streams=1, max_frames=4)
+    first = _run(m, codes)
+    assert torch.equal(_run(m, codes), first), "a reused slot remembers its previous stream"
+    c = m.make_cache()
+    for t in range(4):
+        m.decode_step(codes[:, :, t:t + 1].cuda(), c)
+    with pytest.raises(RuntimeError, match="max_frames"):
+        m.decode_step(codes[:, :, :1].cuda(), c)
+    with pytest.raises(RuntimeError, match="slots are in use"):
+        m.make_cache()
+    m.release_cache(c)
+    assert not m.overflowed()
