@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -66,17 +67,57 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// Y[row][n] = epilogue( sum_k A(row, k) W[n][k] ): R staged rows per CTA, one weight row per warp.
-template <int R>
+// Programmatic dependent launch: every kernel of a step is launched with the programmatic-serialization attribute, so its
+// CTAs may start while the previous kernel still runs.  Before pdl_wait() a kernel touches only what no kernel of the step
+// writes (weights: prefetched into L2); pdl_wait() returns when the previous kernel has completed and its writes are
+// visible; pdl_go() lets the next kernel's CTAs start their own prefetch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_go() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Y[row][n] = epilogue( sum_k A(row, k) W[n][k] ): R staged rows per CTA; a weight row is streamed by KS warps (lanes of the
+// KS warps interleave over K, partial sums meet in shared memory and are added in warp order), 8 / KS weight rows per CTA.
+template <int R, int KS>
 __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
     __shared__ __align__(16) float As[kStageFloats];
     __shared__ float s_mean[R], s_rstd[R];
+    __shared__ float s_red[kWarps * R];
+    __shared__ int s_slot[R], s_t[R], s_b[R];   // slot, row inside the step and batch row of every staged row
     constexpr int KC = kStageFloats / R;
+    constexpr int CW = kWarps / KS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ks = warp % KS;
     const int rows = op.batch * op.T;
     const int row0 = blockIdx.y * R;
-    const int n = blockIdx.x * kWarps + warp;
+    const int n = blockIdx.x * CW + warp / KS;
     const bool n_ok = n < op.N;
+    if (tid < R) {   // (the slot table is constant during a step: read before the wait too)
+        const int row = row0 + tid;
+        int b = 0, t = 0, slot = -1;
+        if (row < rows) { b = row / op.T; t = row - b * op.T; slot = op.slots ? op.slots[b] : b; }
+        s_slot[tid] = slot; s_t[tid] = t; s_b[tid] = b;
+    }
+    if (n_ok && blockIdx.y == 0) {   // weights do not depend on the previous kernel: pull this warp's share of the row into L2
+        const char* wr = reinterpret_cast<const char*>(op.W + (long long)n * op.K);
+        const int lines = (op.K * 4 + 127) >> 7;
+        for (int l = lane + 32 * ks; l < lines; l += 32 * KS) prefetch_l2(wr + ((long long)l << 7));
+    }
+    // ... and the first four 16-byte pieces of this lane straight into registers: their HBM latency overlaps the wait for
+    // the previous kernel and the staging of the input rows
+    constexpr int kPre = 4;
+    float4 wpre[kPre];
+    {
+        const int k0 = min(kStageFloats / R, op.K);
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int k4 = (lane + 32 * ks) * 4 + i * 128 * KS;
+            wpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n_ok && k4 < k0) wpre[i] = __ldg(reinterpret_cast<const float4*>(op.W + (long long)n * op.K + k4));
+        }
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_go();
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
@@ -87,11 +128,9 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
         const int q4 = kcur >> 2;
         for (int idx = tid; idx < R * q4; idx += kThreads) {
             const int r = idx / q4, k = kc + ((idx - r * q4) << 2);
-            const int row = row0 + r;
+            const int slot = s_slot[r], t = s_t[r];
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < rows) {
-                const int b = row / op.T, t = row - b * op.T;
-                const int slot = op.slots ? op.slots[b] : b;
+            if (slot >= 0) {
                 const int j = k / op.in_c, c = k - j * op.in_c;
                 const float* src = op.in + (long long)slot * op.in_stride + (long long)(op.in_hs + t + op.tap0 + j * op.tapstep) * op.in_c + c;
                 v = *reinterpret_cast<const float4*>(src);
@@ -117,11 +156,26 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
             }
             __syncthreads();
         }
-        // ---- one weight row per warp against all staged rows ----
+        // ---- the weight row against all staged rows ----
         if (n_ok) {
             const float* wrow = op.W + (long long)n * op.K + kc;
+            int k4 = (lane + 32 * ks) * 4;
+            if (kc == 0) {   // the pieces fetched before the wait (same order of additions as the loop below)
+#pragma unroll
+                for (int i = 0; i < kPre; ++i) {
+                    if (k4 < kcur) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float4 a = *reinterpret_cast<const float4*>(&As[r * KC + k4]);
+                            acc[r] = fmaf(a.x, wpre[i].x, acc[r]); acc[r] = fmaf(a.y, wpre[i].y, acc[r]);
+                            acc[r] = fmaf(a.z, wpre[i].z, acc[r]); acc[r] = fmaf(a.w, wpre[i].w, acc[r]);
+                        }
+                        k4 += 128 * KS;
+                    }
+                }
+            }
 #pragma unroll 4
-            for (int k4 = lane * 4; k4 < kcur; k4 += 128) {
+            for (; k4 < kcur; k4 += 128 * KS) {
                 const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k4));
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -133,17 +187,25 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
         }
         __syncthreads();
     }
-    // ---- reduce over the lanes; lane r finishes row r ----
+    // ---- reduce over the lanes, then over the KS warps of the row (in warp order); lane r finishes row r ----
     float mine = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const float v = warp_sum(acc[r]);
         if (lane == r) mine = v;
     }
-    const int row = row0 + lane;
-    if (!n_ok || lane >= R || row >= rows) return;
-    const int b = row / op.T, t = row - b * op.T;
-    const int slot = op.slots ? op.slots[b] : b;
+    if (KS > 1) {
+        if (lane < R) s_red[warp * R + lane] = mine;
+        __syncthreads();
+        if (ks != 0) return;
+        if (lane < R) {
+            mine = 0.f;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) mine += s_red[(warp + j) * R + lane];
+        }
+    }
+    if (!n_ok || lane >= R || s_slot[lane] < 0) return;
+    const int b = s_b[lane], t = s_t[lane], slot = s_slot[lane];
     float y = mine + (op.bias ? op.bias[n % op.bias_mod] : 0.f);
     if (op.epi == EPI_UPSAMPLE) {
         // grouped transposed convolution, kernel 4, stride 2 (conv.py:271-282): outputs 2 t + j take tap j of this frame and,
@@ -175,6 +237,8 @@ struct EmbedArgs {
     int n_q, cb_size, cdim;
 };
 __global__ void embed_kernel(const EmbedArgs a) {
+    pdl_wait();
+    pdl_go();
     const int b = blockIdx.x, slot = a.slots ? a.slots[b] : b;
     for (int k = threadIdx.x; k < 2 * a.cdim; k += blockDim.x) {
         float v;
@@ -205,6 +269,8 @@ struct AttnArgs {
 };
 __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_go();
     const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int slot = a.slots ? a.slots[b] : b;
     const int hd = a.hd, half = hd >> 1;
@@ -252,13 +318,14 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
         S[p] = s0; S[L + p] = s1;
         m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1);
     }
-    red[tid] = m0; red[kThreads + tid] = m1;
+    // block maximum: shuffles inside a warp, the eight warp values through shared memory (max is order-independent)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o)); }
+    if ((tid & 31) == 0) { red[tid >> 5] = m0; red[kWarps + (tid >> 5)] = m1; }
     __syncthreads();
-    for (int o = kThreads / 2; o > 0; o >>= 1) {
-        if (tid < o) { red[tid] = fmaxf(red[tid], red[tid + o]); red[kThreads + tid] = fmaxf(red[kThreads + tid], red[kThreads + tid + o]); }
-        __syncthreads();
-    }
-    m0 = red[0]; m1 = red[kThreads];
+    m0 = red[0]; m1 = red[kWarps];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) { m0 = fmaxf(m0, red[w]); m1 = fmaxf(m1, red[kWarps + w]); }
     __syncthreads();
     float l0 = 0.f, l1 = 0.f;
     for (int p = lo0 + tid; p < L; p += kThreads) {
@@ -266,13 +333,13 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
         S[p] = e0; S[L + p] = e1;
         l0 += e0; l1 += e1;
     }
-    red[tid] = l0; red[kThreads + tid] = l1;
+    // block sum: fixed shuffle tree inside a warp, warp sums added in warp order
+    l0 = warp_sum(l0); l1 = warp_sum(l1);
+    if ((tid & 31) == 0) { red[tid >> 5] = l0; red[kWarps + (tid >> 5)] = l1; }
     __syncthreads();
-    for (int o = kThreads / 2; o > 0; o >>= 1) {
-        if (tid < o) { red[tid] += red[tid + o]; red[kThreads + tid] += red[kThreads + tid + o]; }
-        __syncthreads();
-    }
-    l0 = red[0]; l1 = red[kThreads];
+    l0 = red[0]; l1 = red[kWarps];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) { l0 += red[w]; l1 += red[kWarps + w]; }
     __syncthreads();
     // P V: thread = (dim d, position class g of kThreads / hd)
     const int G = kThreads / hd, d = tid % hd, g = tid / hd;
@@ -303,6 +370,8 @@ struct ShiftArgs {
 };
 __global__ void __launch_bounds__(kThreads) shift_kernel(const ShiftArgs a) {
     __shared__ float tmp[4096];
+    pdl_wait();
+    pdl_go();
     const int b = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
     const int slot = a.slots ? a.slots[b] : b;
     if (i == a.n_bufs) {
@@ -564,17 +633,54 @@ extern "C" int smol_mimi_bind(SmolMimi* m, const SmolMimiWeights* w, void* d_wor
     return smol_mimi_reset(m, nullptr, c.max_streams, stream);
 }
 
+// Launch with the programmatic-serialization attribute (see pdl_wait); SMOL_MIMI_PDL=0 launches plainly (A/B).
+static bool g_pdl = true;
+template <class Args>
+static cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Args& a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+// K split of an op: a function of the op's shape only (never of the batch), so that results do not depend on the batch
+// (Measured on B200: splitting a weight row over 2 .. 8 warps to get 256+ CTAs per op changed nothing at one stream --
+//  510 vs 513 us per step, the ops are latency chains, not bandwidth -- and cost 20 .. 45 % at 8 .. 64 streams, where every
+//  extra CTA re-stages the same input rows.  SMOL_MIMI_KS=1 re-enables the heuristic for A/B runs.)
+static int rows_ks(int N, int K, int T) {
+    static const bool on = [] { const char* e = getenv("SMOL_MIMI_KS"); return e && e[0] == '1'; }();
+    if (!on) return 1;
+    int ks = 1;
+    const int chunks = (T + 15) / 16;
+    while (ks < kWarps && ((N + kWarps / ks - 1) / (kWarps / ks)) * chunks < 256 && K / (ks * 2) >= 128) ks *= 2;
+    return ks;
+}
+
+template <int R>
+static cudaError_t launch_rows_r(const RowOp& op, int ks, dim3 grid, cudaStream_t st) {
+    switch (ks) {
+        case 1: return launch_pdl(rows_kernel<R, 1>, grid, dim3(kThreads), 0, st, op);
+        case 2: return launch_pdl(rows_kernel<R, 2>, grid, dim3(kThreads), 0, st, op);
+        case 4: return launch_pdl(rows_kernel<R, 4>, grid, dim3(kThreads), 0, st, op);
+        default: return launch_pdl(rows_kernel<R, 8>, grid, dim3(kThreads), 0, st, op);
+    }
+}
+
 static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
     const int rows = op.batch * op.T;
     const int R = rows <= 2 ? 2 : rows <= 4 ? 4 : rows <= 8 ? 8 : 16;
-    const dim3 grid((op.N + kWarps - 1) / kWarps, (rows + R - 1) / R);
+    const int ks = rows_ks(op.N, op.K, op.T);
+    const int cw = kWarps / ks;
+    const dim3 grid((op.N + cw - 1) / cw, (rows + R - 1) / R);
     switch (R) {
-        case 2: rows_kernel<2><<<grid, kThreads, 0, st>>>(op); break;
-        case 4: rows_kernel<4><<<grid, kThreads, 0, st>>>(op); break;
-        case 8: rows_kernel<8><<<grid, kThreads, 0, st>>>(op); break;
-        default: rows_kernel<16><<<grid, kThreads, 0, st>>>(op); break;
+        case 2: return launch_rows_r<2>(op, ks, grid, st);
+        case 4: return launch_rows_r<4>(op, ks, grid, st);
+        case 8: return launch_rows_r<8>(op, ks, grid, st);
+        default: return launch_rows_r<16>(op, ks, grid, st);
     }
-    return cudaGetLastError();
 }
 
 // every launch of one step, in order
@@ -596,8 +702,7 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
 
     {   // RVQ rows -> Q; projection + upsample -> the residual stream (current rows of X0)
         EmbedArgs e{wsf(m, m->o_books), d_codes, d_slots, arena + buf(m->bQ).off, AS, c.n_q, c.codebook_size, c.codebook_dim};
-        embed_kernel<<<batch, 256, 0, st>>>(e);
-        MCU(cudaGetLastError()); ++n_launch;
+        MCU(launch_pdl(embed_kernel, dim3(batch), dim3(256), 0, st, e)); ++n_launch;
         RowOp op = base_op();
         set_in(op, m->bQ, 1, false);
         op.W = wsf(m, m->o_wcat); op.N = c.dim; op.epi = EPI_UPSAMPLE; op.wup = wsf(m, m->o_up);
@@ -622,8 +727,7 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
             a.rope = wsf(m, m->o_rope); a.pos = reinterpret_cast<const int32_t*>(m->ws + m->o_pos); a.slots = d_slots;
             a.err = reinterpret_cast<int32_t*>(m->ws + m->o_err);
             a.layer = l; a.dim = c.dim; a.hd = c.head_dim; a.max_pos = c.max_positions; a.window = c.window;
-            attn_kernel<<<dim3(batch, c.n_heads), kThreads, m->attn_smem, st>>>(a);
-            MCU(cudaGetLastError()); ++n_launch;
+            MCU(launch_pdl(attn_kernel, dim3(batch, c.n_heads), dim3(kThreads), m->attn_smem, st, a)); ++n_launch;
         }
         {   // o_proj, layer scale, residual (in place on the stream)
             RowOp op = base_op();
@@ -695,8 +799,7 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
     }
     {
         const ShiftArgs a = shift_args(m, d_slots, 0);
-        shift_kernel<<<dim3(batch, a.n_bufs + 1), kThreads, 0, st>>>(a);
-        MCU(cudaGetLastError()); ++n_launch;
+        MCU(launch_pdl(shift_kernel, dim3(batch, a.n_bufs + 1), dim3(kThreads), 0, st, a)); ++n_launch;
     }
     m->launches = n_launch;
     return SMOL_OK;
@@ -707,6 +810,10 @@ extern "C" int smol_mimi_decode_step(SmolMimi* m, const int32_t* d_codes, const 
     if (!m->bound) return smol::capi_fail(SMOL_ERR_UNBOUND, "smol_mimi_decode_step: weights / workspace not bound");
     if (batch < 1 || batch > m->cfg.max_streams) return smol::capi_fail(SMOL_ERR_CAPACITY, "smol_mimi_decode_step: batch outside 1 .. max_streams");
     cudaStream_t st = (cudaStream_t)stream;
+    // programmatic dependent launch pays for plain stream launches (632 -> 549 us per step at one stream) and costs a
+    // little inside a replayed graph (510 -> 536): on for the former, off for the latter; SMOL_MIMI_PDL=0/1 forces it
+    const char* pe = getenv("SMOL_MIMI_PDL");
+    g_pdl = pe ? pe[0] != '0' : !m->cfg.use_graph;
     if (!m->cfg.use_graph) return mimi_enqueue(m, d_codes, d_slots, batch, d_pcm, st);
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
