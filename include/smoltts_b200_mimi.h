@@ -40,7 +40,8 @@ typedef struct SmolMimiConfig {
                                   n > 0: kyutai's sliding window of n positions (transformer.context, unused by the reference) */
     int32_t upsample_carry;    /* 0: decode_step's rule -- every frame upsampled alone (C/mimi.py:73-86, C/conv.py:271-282);
                                   1: carry the transposed convolution's trailing taps: a run of steps == decode() of the sequence */
-    int32_t use_graph;         /* 1: a step's launches are captured once per (batch, pointers) and replayed as a CUDA graph */
+    int32_t use_graph;         /* 1: a step's launches are captured once per (batch, pointers) and replayed as a CUDA graph;
+                                  0: plain launches (programmatic dependent launch), e.g. inside the caller's own capture */
     float norm_eps, codebook_eps;
 } SmolMimiConfig;
 

@@ -14,7 +14,7 @@
 // epilogue (bias, GELU, layer scale + residual, residual, or the upsampler).  Transposed convolutions (kernel = 2 stride)
 // are the same product with K = (previous | current input row) x channels and N = (phase, channel): their outputs land
 // contiguously.  Everything a stream carries (convolution history rows, the upsampler's previous embedding, KV cache,
-// position) lives in per-slot arenas of the caller's workspace; a step is ~57 launches, replayed as one CUDA graph.
+// position) lives in per-slot arenas of the caller's workspace; a step is 57 launches, replayed as one CUDA graph.
 //
 // Reference map (C = mlx_inference/src/smoltts_mlx/codec/): RVQ decode C/rvq.py:118-130,171-186; upsample C/conv.py:225-282;
 // transformer C/transformer.py:36-150; Conv1d.step C/conv.py:133-160; ConvTranspose1d.step C/conv.py:207-221; residual
@@ -75,49 +75,49 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_go() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Y[row][n] = epilogue( sum_k A(row, k) W[n][k] ): R staged rows per CTA; a weight row is streamed by KS warps (lanes of the
-// KS warps interleave over K, partial sums meet in shared memory and are added in warp order), 8 / KS weight rows per CTA.
-template <int R, int KS>
-__global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
-    __shared__ __align__(16) float As[kStageFloats];
-    __shared__ float s_mean[R], s_rstd[R];
-    __shared__ float s_red[kWarps * R];
-    __shared__ int s_slot[R], s_t[R], s_b[R];   // slot, row inside the step and batch row of every staged row
+// Y[row][n] = epilogue( sum_k A(row, k) W[n][k] ): R staged rows per CTA, one weight row per warp (8 per CTA).
+// Work item (bx, by) = (group of 8 weight rows, chunk of R input rows).
+struct RowsSmem {
+    float As[kStageFloats];
+    float mean[16], rstd[16];
+    int slot[16], t[16], b[16];   // slot, row inside the step and batch row of every staged row
+};
+
+template <int R, bool kPdl>
+__device__ __forceinline__ void rows_body(const RowOp& op, int bx, int by, RowsSmem& S) {
     constexpr int KC = kStageFloats / R;
-    constexpr int CW = kWarps / KS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ks = warp % KS;
     const int rows = op.batch * op.T;
-    const int row0 = blockIdx.y * R;
-    const int n = blockIdx.x * CW + warp / KS;
+    const int row0 = by * R;
+    const int n = bx * kWarps + warp;
     const bool n_ok = n < op.N;
-    if (tid < R) {   // (the slot table is constant during a step: read before the wait too)
+    if (tid < R) {   // (the slot table is constant during a step: read before the dependency wait)
         const int row = row0 + tid;
         int b = 0, t = 0, slot = -1;
         if (row < rows) { b = row / op.T; t = row - b * op.T; slot = op.slots ? op.slots[b] : b; }
-        s_slot[tid] = slot; s_t[tid] = t; s_b[tid] = b;
+        S.slot[tid] = slot; S.t[tid] = t; S.b[tid] = b;
     }
-    if (n_ok && blockIdx.y == 0) {   // weights do not depend on the previous kernel: pull this warp's share of the row into L2
+    // weights do not depend on the previous kernel / phase: the first four 16-byte pieces of this lane go straight into
+    // registers (their latency overlaps the wait and the staging of the input rows) and the warp pulls its whole weight
+    // row into L2
+    if (kPdl && n_ok && by == 0) {
         const char* wr = reinterpret_cast<const char*>(op.W + (long long)n * op.K);
         const int lines = (op.K * 4 + 127) >> 7;
-        for (int l = lane + 32 * ks; l < lines; l += 32 * KS) prefetch_l2(wr + ((long long)l << 7));
+        for (int l = lane; l < lines; l += 32) prefetch_l2(wr + ((long long)l << 7));
     }
-    // ... and the first four 16-byte pieces of this lane straight into registers: their HBM latency overlaps the wait for
-    // the previous kernel and the staging of the input rows
     constexpr int kPre = 4;
     float4 wpre[kPre];
     {
-        const int k0 = min(kStageFloats / R, op.K);
+        const int k0 = min(KC, op.K);
 #pragma unroll
         for (int i = 0; i < kPre; ++i) {
-            const int k4 = (lane + 32 * ks) * 4 + i * 128 * KS;
+            const int k4 = lane * 4 + i * 128;
             wpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (n_ok && k4 < k0) wpre[i] = __ldg(reinterpret_cast<const float4*>(op.W + (long long)n * op.K + k4));
         }
     }
     __syncthreads();
-    pdl_wait();
-    pdl_go();
+    if (kPdl) { pdl_wait(); pdl_go(); }
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
@@ -125,10 +125,12 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
     for (int kc = 0; kc < op.K; kc += KC) {
         const int kcur = min(KC, op.K - kc);
         // ---- stage R rows x kcur (16-byte pieces: in_c and K are multiples of 4) ----
+        // (A division-free form of this loop -- one unrolled pass per row, contiguous im2col runs -- and LayerNorm statistics
+        //  spread over all warps were measured: 500 -> 689 us per step at one stream; this is the faster form.)
         const int q4 = kcur >> 2;
         for (int idx = tid; idx < R * q4; idx += kThreads) {
             const int r = idx / q4, k = kc + ((idx - r * q4) << 2);
-            const int slot = s_slot[r], t = s_t[r];
+            const int slot = S.slot[r], t = S.t[r];
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (slot >= 0) {
                 const int j = k / op.in_c, c = k - j * op.in_c;
@@ -136,50 +138,51 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
                 v = *reinterpret_cast<const float4*>(src);
                 if (op.pro == PRO_ELU) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
             }
-            *reinterpret_cast<float4*>(&As[r * KC + ((idx - r * q4) << 2)]) = v;
+            *reinterpret_cast<float4*>(&S.As[r * KC + ((idx - r * q4) << 2)]) = v;
         }
         __syncthreads();
         if (op.pro == PRO_LN) {   // LayerNorm over the whole row (K <= KC, checked on the host): two passes, as torch does
             for (int r = warp; r < R; r += kWarps) {
                 float s = 0.f;
-                for (int k = lane; k < kcur; k += 32) s += As[r * KC + k];
+                for (int k = lane; k < kcur; k += 32) s += S.As[r * KC + k];
                 const float mean = warp_sum(s) / (float)kcur;
                 float d2 = 0.f;
-                for (int k = lane; k < kcur; k += 32) { const float d = As[r * KC + k] - mean; d2 = fmaf(d, d, d2); }
+                for (int k = lane; k < kcur; k += 32) { const float d = S.As[r * KC + k] - mean; d2 = fmaf(d, d, d2); }
                 const float var = warp_sum(d2) / (float)kcur;
-                if (lane == 0) { s_mean[r] = mean; s_rstd[r] = 1.0f / sqrtf(var + op.eps); }
+                if (lane == 0) { S.mean[r] = mean; S.rstd[r] = 1.0f / sqrtf(var + op.eps); }
             }
             __syncthreads();
-            for (int idx = tid; idx < R * kcur; idx += kThreads) {
-                const int r = idx / kcur, k = idx - r * kcur;
-                As[r * KC + k] = (As[r * KC + k] - s_mean[r]) * s_rstd[r] * op.ln_w[k] + op.ln_b[k];
+            for (int k = tid; k < kcur; k += kThreads) {
+                const float w = op.ln_w[k], bb = op.ln_b[k];
+#pragma unroll
+                for (int r = 0; r < R; ++r) S.As[r * KC + k] = (S.As[r * KC + k] - S.mean[r]) * S.rstd[r] * w + bb;
             }
             __syncthreads();
         }
         // ---- the weight row against all staged rows ----
         if (n_ok) {
             const float* wrow = op.W + (long long)n * op.K + kc;
-            int k4 = (lane + 32 * ks) * 4;
+            int k4 = lane * 4;
             if (kc == 0) {   // the pieces fetched before the wait (same order of additions as the loop below)
 #pragma unroll
                 for (int i = 0; i < kPre; ++i) {
                     if (k4 < kcur) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const float4 a = *reinterpret_cast<const float4*>(&As[r * KC + k4]);
+                            const float4 a = *reinterpret_cast<const float4*>(&S.As[r * KC + k4]);
                             acc[r] = fmaf(a.x, wpre[i].x, acc[r]); acc[r] = fmaf(a.y, wpre[i].y, acc[r]);
                             acc[r] = fmaf(a.z, wpre[i].z, acc[r]); acc[r] = fmaf(a.w, wpre[i].w, acc[r]);
                         }
-                        k4 += 128 * KS;
+                        k4 += 128;
                     }
                 }
             }
 #pragma unroll 4
-            for (; k4 < kcur; k4 += 128 * KS) {
+            for (; k4 < kcur; k4 += 128) {
                 const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k4));
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const float4 a = *reinterpret_cast<const float4*>(&As[r * KC + k4]);
+                    const float4 a = *reinterpret_cast<const float4*>(&S.As[r * KC + k4]);
                     acc[r] = fmaf(a.x, w.x, acc[r]); acc[r] = fmaf(a.y, w.y, acc[r]);
                     acc[r] = fmaf(a.z, w.z, acc[r]); acc[r] = fmaf(a.w, w.w, acc[r]);
                 }
@@ -187,59 +190,55 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
         }
         __syncthreads();
     }
-    // ---- reduce over the lanes, then over the KS warps of the row (in warp order); lane r finishes row r ----
+    // ---- reduce over the lanes; lane r finishes row r ----
     float mine = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const float v = warp_sum(acc[r]);
         if (lane == r) mine = v;
     }
-    if (KS > 1) {
-        if (lane < R) s_red[warp * R + lane] = mine;
-        __syncthreads();
-        if (ks != 0) return;
-        if (lane < R) {
-            mine = 0.f;
-#pragma unroll
-            for (int j = 0; j < KS; ++j) mine += s_red[(warp + j) * R + lane];
+    if (n_ok && lane < R && S.slot[lane] >= 0) {
+        const int b = S.b[lane], t = S.t[lane], slot = S.slot[lane];
+        float y = mine + (op.bias ? op.bias[n % op.bias_mod] : 0.f);
+        if (op.epi == EPI_UPSAMPLE) {
+            // grouped transposed convolution, kernel 4, stride 2 (conv.py:271-282): outputs 2 t + j take tap j of this frame
+            // and, with `carry`, tap 2 + j of the previous one; decode_step upsamples every frame alone (carry = 0)
+            const float4 wu = *reinterpret_cast<const float4*>(op.wup + 4 * n);
+            float o0 = y * wu.x, o1 = y * wu.y;
+            if (op.carry) {
+                float* pp = op.up_prev + (long long)slot * op.N + n;
+                const float pv = *pp;
+                o0 = fmaf(pv, wu.z, o0); o1 = fmaf(pv, wu.w, o1);
+                *pp = y;
+            }
+            float* o = op.out + (long long)slot * op.out_stride + op.out_off0 + n;
+            o[0] = o0; o[op.N] = o1;
+        } else {
+            const long long e = (long long)op.out_off0 + (long long)t * op.N + n;
+            float* o = op.out + (long long)(op.out_by_row ? b : slot) * op.out_stride + e;
+            if (op.epi == EPI_GELU) y = gelu_erf(y);
+            else if (op.epi == EPI_SCALE_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)t * op.N + n] + y * op.scale[n];
+            else if (op.epi == EPI_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)t * op.N + n] + y;
+            *o = y;
         }
     }
-    if (!n_ok || lane >= R || s_slot[lane] < 0) return;
-    const int b = s_b[lane], t = s_t[lane], slot = s_slot[lane];
-    float y = mine + (op.bias ? op.bias[n % op.bias_mod] : 0.f);
-    if (op.epi == EPI_UPSAMPLE) {
-        // grouped transposed convolution, kernel 4, stride 2 (conv.py:271-282): outputs 2 t + j take tap j of this frame and,
-        // with `carry`, tap 2 + j of the previous one; decode_step upsamples every frame alone (carry = 0)
-        const float4 wu = *reinterpret_cast<const float4*>(op.wup + 4 * n);
-        float o0 = y * wu.x, o1 = y * wu.y;
-        if (op.carry) {
-            float* pp = op.up_prev + (long long)slot * op.N + n;
-            const float pv = *pp;
-            o0 = fmaf(pv, wu.z, o0); o1 = fmaf(pv, wu.w, o1);
-            *pp = y;
-        }
-        float* o = op.out + (long long)slot * op.out_stride + op.out_off0 + n;
-        o[0] = o0; o[op.N] = o1;
-        return;
-    }
-    const long long e = (long long)op.out_off0 + (long long)t * op.N + n;
-    float* o = op.out + (long long)(op.out_by_row ? b : slot) * op.out_stride + e;
-    if (op.epi == EPI_GELU) y = gelu_erf(y);
-    else if (op.epi == EPI_SCALE_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)t * op.N + n] + y * op.scale[n];
-    else if (op.epi == EPI_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)t * op.N + n] + y;
-    *o = y;
+    __syncthreads();   // S is reused by the next work item
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
+    __shared__ __align__(16) RowsSmem S;
+    rows_body<R, true>(op, blockIdx.x, blockIdx.y, S);
 }
 
 // RVQ decode (rvq.py:118-130, 171-186): the semantic codebook's row | the sum of the acoustic codebooks' rows, in order.
 struct EmbedArgs {
     const float* books;   // [n_q][codebook_size][cdim], rows already divided by max(cluster_usage, eps)
     const int32_t* codes; const int32_t* slots; float* q; long long q_stride;
-    int n_q, cb_size, cdim;
+    int n_q, cb_size, cdim, batch;
 };
-__global__ void embed_kernel(const EmbedArgs a) {
-    pdl_wait();
-    pdl_go();
-    const int b = blockIdx.x, slot = a.slots ? a.slots[b] : b;
+__device__ __forceinline__ void embed_body(const EmbedArgs& a, int b) {
+    const int slot = a.slots ? a.slots[b] : b;
     for (int k = threadIdx.x; k < 2 * a.cdim; k += blockDim.x) {
         float v;
         if (k < a.cdim) {
@@ -256,28 +255,30 @@ __global__ void embed_kernel(const EmbedArgs a) {
         a.q[(long long)slot * a.q_stride + k] = v;
     }
 }
+__global__ void embed_kernel(const EmbedArgs a) {
+    pdl_wait();
+    pdl_go();
+    embed_body(a, blockIdx.x);
+}
 
 // Attention of one (stream, head): the step's two positions against the stream's cache (transformer.py:62-91).
 // Half-split RoPE (nn.RoPE traditional=False) from the table, K/V appended, scores by one thread per position, softmax,
-// P V by (dim, position parity) threads; fixed orders throughout.
+// P V by (dim, position class) threads; fixed orders throughout.
 struct AttnArgs {
     const float* qkv; long long qkv_stride;      // [2][3 dim]
     float* att; long long att_stride;            // [2][dim]
     float* kv; long long kv_slot_stride, kv_layer_stride;   // [slot][layer][2][max_pos][dim]
     const float* rope; const int32_t* pos; const int32_t* slots; int32_t* err;
-    int layer, dim, hd, max_pos, window;
+    int layer, dim, hd, max_pos, window, batch, heads;
 };
-__global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
-    extern __shared__ __align__(16) float sm[];
-    pdl_wait();
-    pdl_go();
-    const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+__device__ __forceinline__ void attn_body(const AttnArgs& a, int b, int h, float* sm) {
+    const int tid = threadIdx.x;
     const int slot = a.slots ? a.slots[b] : b;
     const int hd = a.hd, half = hd >> 1;
     const int p0 = 2 * a.pos[slot];
-    if (p0 + 2 > a.max_pos) { if (tid == 0) *a.err = 1; return; }
+    if (p0 + 2 > a.max_pos) { if (tid == 0) *a.err = 1; return; }   // (uniform over the CTA)
     float* q = sm;                // [2][hd], pre-scaled
-    float* red = sm + 2 * hd;     // [kThreads * 2] scratch
+    float* red = sm + 2 * hd;     // [2 * kThreads] scratch
     float* S = red + 2 * kThreads;   // [2][L]
     const int L = p0 + 2;
     float* kc = a.kv + (long long)slot * a.kv_slot_stride + (long long)a.layer * a.kv_layer_stride;
@@ -359,20 +360,25 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
         dst[0] = s0 / l0;
         dst[a.dim] = s1 / l1;
     }
+    __syncthreads();   // sm is reused by the next work item
+}
+__global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_go();
+    attn_body(a, blockIdx.x, blockIdx.y, sm);
 }
 
 // End of a step: the last `hs` rows of every history-carrying buffer move to its front; the position advances.
 struct BufDesc { int off, hs, T, C; };
 struct ShiftArgs {
     float* arena; long long stride; const int32_t* slots; int32_t* pos; float* up_prev; int dim;
-    int n_bufs; BufDesc bufs[kMaxBufs];
-    int reset;   // 1: zero the history rows, the upsampler's carry and the position instead
+    int n_bufs; int reset;   // reset = 1: zero the history rows, the upsampler's carry and the position instead
+    int batch, pad;
+    BufDesc bufs[kMaxBufs];
 };
-__global__ void __launch_bounds__(kThreads) shift_kernel(const ShiftArgs a) {
-    __shared__ float tmp[4096];
-    pdl_wait();
-    pdl_go();
-    const int b = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
+__device__ __forceinline__ void shift_body(const ShiftArgs& a, int b, int i, float* tmp /* 4096 floats */) {
+    const int tid = threadIdx.x;
     const int slot = a.slots ? a.slots[b] : b;
     if (i == a.n_bufs) {
         if (a.reset) {
@@ -394,6 +400,24 @@ __global__ void __launch_bounds__(kThreads) shift_kernel(const ShiftArgs a) {
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(kThreads) shift_kernel(const ShiftArgs a) {
+    __shared__ float tmp[4096];
+    pdl_wait();
+    pdl_go();
+    shift_body(a, blockIdx.x, blockIdx.y, tmp);
+}
+
+// A step = a program of operations, one launch each (replayed as a CUDA graph).
+// (Measured and dropped: the whole program inside ONE persistent cooperative kernel -- 296 co-resident CTAs walking 512-byte
+//  operation records, a grid barrier after every operation, the next operation's weight rows prefetched into L2 before the
+//  barrier.  Bit-identical, but 760 us per step against 500 us for the graph at one stream, 1.79 vs 1.37 ms at 8, and worse
+//  on 148 or 74 CTAs (1 102 / 1 509 us): an operation is a chain of dependent instructions and L2 round trips inside a
+//  CTA, which a barrier does not shorten, while the graph's kernel boundaries cost less than a 296-CTA barrier.)
+enum { OP_ROWS = 0, OP_ATTN = 1, OP_EMBED = 2, OP_SHIFT = 3 };
+struct OpRec {
+    int kind, R;
+    union { RowOp row; AttnArgs attn; EmbedArgs emb; ShiftArgs shift; };
+};
 
 // ---- bind-time packing ---------------------------------------------------------------------------------------------
 __global__ void pack_codebook_kernel(float* dst, const float* es, const float* cu, int rows, int dim, float eps) {
@@ -455,6 +479,7 @@ struct SmolMimi {
     cudaGraphExec_t graph = nullptr;
     cudaStream_t cap_stream = nullptr;
     const void* g_codes = nullptr; const void* g_slots = nullptr; const void* g_pcm = nullptr; int g_batch = -1;
+    std::vector<OpRec> prog;   // the step's program (rebuilt when the batch or a pointer changes)
 };
 
 static size_t al(size_t v) { return (v + 255) / 256 * 256; }
@@ -564,7 +589,8 @@ extern "C" int smol_mimi_reset(SmolMimi* m, const int32_t* d_slots, int32_t n, v
     if (!m) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_reset: null model");
     if (!m->bound) return smol::capi_fail(SMOL_ERR_UNBOUND, "smol_mimi_reset: weights / workspace not bound");
     if (n < 1 || n > m->cfg.max_streams) return smol::capi_fail(SMOL_ERR_CAPACITY, "smol_mimi_reset: n outside 1 .. max_streams");
-    const ShiftArgs a = shift_args(m, d_slots, 1);
+    ShiftArgs a = shift_args(m, d_slots, 1);
+    a.batch = n;
     shift_kernel<<<dim3(n, a.n_bufs + 1), kThreads, 0, (cudaStream_t)stream>>>(a);
     MCU(cudaGetLastError());
     return SMOL_OK;
@@ -629,6 +655,7 @@ extern "C" int smol_mimi_bind(SmolMimi* m, const SmolMimiWeights* w, void* d_wor
     MCU(cudaGetLastError());
     MCU(cudaMemsetAsync(m->ws + m->o_err, 0, 16, st));
     if (m->attn_smem > 48 * 1024) MCU(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->attn_smem));
+    m->g_batch = -1;
     m->bound = true;
     return smol_mimi_reset(m, nullptr, c.max_streams, stream);
 }
@@ -645,50 +672,30 @@ static cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, dim3 block, s
     cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
+// (Measured and dropped: splitting a weight row over 2 .. 8 warps to get 256+ CTAs per operation changed nothing at one
+//  stream -- 510 vs 513 us per step: the operations are latency chains, not bandwidth -- and cost 20 .. 45 % at 8 .. 64
+//  streams, where every extra CTA re-stages the same input rows.)
 
-// K split of an op: a function of the op's shape only (never of the batch), so that results do not depend on the batch
-// (Measured on B200: splitting a weight row over 2 .. 8 warps to get 256+ CTAs per op changed nothing at one stream --
-//  510 vs 513 us per step, the ops are latency chains, not bandwidth -- and cost 20 .. 45 % at 8 .. 64 streams, where every
-//  extra CTA re-stages the same input rows.  SMOL_MIMI_KS=1 re-enables the heuristic for A/B runs.)
-static int rows_ks(int N, int K, int T) {
-    static const bool on = [] { const char* e = getenv("SMOL_MIMI_KS"); return e && e[0] == '1'; }();
-    if (!on) return 1;
-    int ks = 1;
-    const int chunks = (T + 15) / 16;
-    while (ks < kWarps && ((N + kWarps / ks - 1) / (kWarps / ks)) * chunks < 256 && K / (ks * 2) >= 128) ks *= 2;
-    return ks;
-}
-
-template <int R>
-static cudaError_t launch_rows_r(const RowOp& op, int ks, dim3 grid, cudaStream_t st) {
-    switch (ks) {
-        case 1: return launch_pdl(rows_kernel<R, 1>, grid, dim3(kThreads), 0, st, op);
-        case 2: return launch_pdl(rows_kernel<R, 2>, grid, dim3(kThreads), 0, st, op);
-        case 4: return launch_pdl(rows_kernel<R, 4>, grid, dim3(kThreads), 0, st, op);
-        default: return launch_pdl(rows_kernel<R, 8>, grid, dim3(kThreads), 0, st, op);
-    }
-}
+static int rows_R(int rows) { return rows <= 2 ? 2 : rows <= 4 ? 4 : rows <= 8 ? 8 : 16; }
 
 static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
     const int rows = op.batch * op.T;
-    const int R = rows <= 2 ? 2 : rows <= 4 ? 4 : rows <= 8 ? 8 : 16;
-    const int ks = rows_ks(op.N, op.K, op.T);
-    const int cw = kWarps / ks;
-    const dim3 grid((op.N + cw - 1) / cw, (rows + R - 1) / R);
+    const int R = rows_R(rows);
+    const dim3 grid((op.N + kWarps - 1) / kWarps, (rows + R - 1) / R);
     switch (R) {
-        case 2: return launch_rows_r<2>(op, ks, grid, st);
-        case 4: return launch_rows_r<4>(op, ks, grid, st);
-        case 8: return launch_rows_r<8>(op, ks, grid, st);
-        default: return launch_rows_r<16>(op, ks, grid, st);
+        case 2: return launch_pdl(rows_kernel<2>, grid, dim3(kThreads), 0, st, op);
+        case 4: return launch_pdl(rows_kernel<4>, grid, dim3(kThreads), 0, st, op);
+        case 8: return launch_pdl(rows_kernel<8>, grid, dim3(kThreads), 0, st, op);
+        default: return launch_pdl(rows_kernel<16>, grid, dim3(kThreads), 0, st, op);
     }
 }
 
-// every launch of one step, in order
-static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_slots, int batch, float* d_pcm, cudaStream_t st) {
+// The step as a program: every operation in order (executed by one launch each, or by the persistent kernel).
+static void mimi_program(SmolMimi* m, const int32_t* d_codes, const int32_t* d_slots, int batch, float* d_pcm, std::vector<OpRec>& prog) {
     const SmolMimiConfig& c = m->cfg;
     float* arena = wsf(m, m->o_arena);
     const long long AS = (long long)m->arena_floats;
-    int n_launch = 0;
+    prog.clear();
     auto buf = [&](int i) -> const MimiBuf& { return m->bufs[i]; };
     auto base_op = [&]() { RowOp op{}; op.slots = d_slots; op.batch = batch; op.in_stride = AS; op.out_stride = AS; op.res_stride = AS; op.bias_mod = 1; op.tapstep = 1; return op; };
     // input of an op: buffer bi, `taps` rows ending at the current one (conv) or {current, previous} (transposed conv)
@@ -699,16 +706,18 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
     };
     auto set_out = [&](RowOp& op, int bi) { const MimiBuf& b = buf(bi); op.out = arena + b.off; op.out_off0 = b.hs * b.C; };
     auto set_res = [&](RowOp& op, int bi) { const MimiBuf& b = buf(bi); op.res = arena + b.off; op.res_off0 = b.hs * b.C; };
+    auto push_rows = [&](const RowOp& op) { OpRec r{}; r.kind = OP_ROWS; r.R = rows_R(op.batch * op.T); r.row = op; prog.push_back(r); };
 
     {   // RVQ rows -> Q; projection + upsample -> the residual stream (current rows of X0)
-        EmbedArgs e{wsf(m, m->o_books), d_codes, d_slots, arena + buf(m->bQ).off, AS, c.n_q, c.codebook_size, c.codebook_dim};
-        MCU(launch_pdl(embed_kernel, dim3(batch), dim3(256), 0, st, e)); ++n_launch;
+        OpRec r{}; r.kind = OP_EMBED;
+        r.emb = EmbedArgs{wsf(m, m->o_books), d_codes, d_slots, arena + buf(m->bQ).off, AS, c.n_q, c.codebook_size, c.codebook_dim, batch};
+        prog.push_back(r);
         RowOp op = base_op();
         set_in(op, m->bQ, 1, false);
         op.W = wsf(m, m->o_wcat); op.N = c.dim; op.epi = EPI_UPSAMPLE; op.wup = wsf(m, m->o_up);
         op.up_prev = wsf(m, m->o_upprev); op.carry = c.upsample_carry;
         set_out(op, m->bX0);
-        MCU(launch_rows(op, st)); ++n_launch;
+        push_rows(op);
     }
     for (int l = 0; l < c.n_layers; ++l) {
         const float* vec = wsf(m, m->o_vec[l]);
@@ -718,23 +727,24 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
             op.pro = PRO_LN; op.ln_w = vec; op.ln_b = vec + c.dim; op.eps = c.norm_eps;
             op.W = wsf(m, m->o_qkv[l]); op.N = 3 * c.dim; op.epi = EPI_BIAS;
             set_out(op, m->bQKV);
-            MCU(launch_rows(op, st)); ++n_launch;
+            push_rows(op);
         }
         {
-            AttnArgs a{};
+            OpRec r{}; r.kind = OP_ATTN;
+            AttnArgs& a = r.attn;
             a.qkv = arena + buf(m->bQKV).off; a.qkv_stride = AS; a.att = arena + buf(m->bATT).off; a.att_stride = AS;
             a.kv = wsf(m, m->o_kv); a.kv_layer_stride = (long long)2 * c.max_positions * c.dim; a.kv_slot_stride = a.kv_layer_stride * c.n_layers;
             a.rope = wsf(m, m->o_rope); a.pos = reinterpret_cast<const int32_t*>(m->ws + m->o_pos); a.slots = d_slots;
             a.err = reinterpret_cast<int32_t*>(m->ws + m->o_err);
-            a.layer = l; a.dim = c.dim; a.hd = c.head_dim; a.max_pos = c.max_positions; a.window = c.window;
-            MCU(launch_pdl(attn_kernel, dim3(batch, c.n_heads), dim3(kThreads), m->attn_smem, st, a)); ++n_launch;
+            a.layer = l; a.dim = c.dim; a.hd = c.head_dim; a.max_pos = c.max_positions; a.window = c.window; a.batch = batch; a.heads = c.n_heads;
+            prog.push_back(r);
         }
         {   // o_proj, layer scale, residual (in place on the stream)
             RowOp op = base_op();
             set_in(op, m->bATT, 1, false);
             op.W = wsf(m, m->o_o[l]); op.N = c.dim; op.epi = EPI_SCALE_RES; op.scale = vec + 4 * c.dim;
             set_out(op, m->bX0); set_res(op, m->bX0);
-            MCU(launch_rows(op, st)); ++n_launch;
+            push_rows(op);
         }
         {   // LayerNorm -> fc1 -> GELU
             RowOp op = base_op();
@@ -742,14 +752,14 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
             op.pro = PRO_LN; op.ln_w = vec + 2 * c.dim; op.ln_b = vec + 3 * c.dim; op.eps = c.norm_eps;
             op.W = wsf(m, m->o_fc1[l]); op.N = c.ffn; op.epi = EPI_GELU;
             set_out(op, m->bFF);
-            MCU(launch_rows(op, st)); ++n_launch;
+            push_rows(op);
         }
         {   // fc2, layer scale, residual
             RowOp op = base_op();
             set_in(op, m->bFF, 1, false);
             op.W = wsf(m, m->o_fc2[l]); op.N = c.dim; op.epi = EPI_SCALE_RES; op.scale = vec + 5 * c.dim;
             set_out(op, m->bX0); set_res(op, m->bX0);
-            MCU(launch_rows(op, st)); ++n_launch;
+            push_rows(op);
         }
     }
     // ---- SEANet decoder ----
@@ -759,7 +769,7 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
         set_in(op, m->bX0, c.kernel, false);
         op.W = wsf(m, m->o_conv_in); op.N = m->ch0; op.bias = bias; op.bias_mod = m->ch0; op.epi = EPI_BIAS;
         set_out(op, m->bA0);
-        MCU(launch_rows(op, st)); ++n_launch;
+        push_rows(op);
         bias += m->ch0;
     }
     int ch = m->ch0, prev = m->bA0;
@@ -771,7 +781,7 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
             set_in(op, prev, 2, true);
             op.pro = PRO_ELU; op.W = wsf(m, m->o_ct[i]); op.N = r * ch; op.bias = bias; op.bias_mod = ch; op.epi = EPI_BIAS;
             set_out(op, m->bCT[i]);
-            MCU(launch_rows(op, st)); ++n_launch;
+            push_rows(op);
             bias += ch;
         }
         {   // residual block: ELU -> conv k3 -> ELU -> conv k1, + skip
@@ -779,13 +789,13 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
             set_in(op, m->bCT[i], c.res_kernel, false);
             op.pro = PRO_ELU; op.W = wsf(m, m->o_r1[i]); op.N = ch / 2; op.bias = bias; op.bias_mod = ch / 2; op.epi = EPI_BIAS;
             set_out(op, m->bH[i]);
-            MCU(launch_rows(op, st)); ++n_launch;
+            push_rows(op);
             bias += ch / 2;
             RowOp o2 = base_op();
             set_in(o2, m->bH[i], 1, false);
             o2.pro = PRO_ELU; o2.W = wsf(m, m->o_r2[i]); o2.N = ch; o2.bias = bias; o2.bias_mod = ch; o2.epi = EPI_RES;
             set_out(o2, m->bR[i]); set_res(o2, m->bCT[i]);
-            MCU(launch_rows(o2, st)); ++n_launch;
+            push_rows(o2);
             bias += ch;
         }
         prev = m->bR[i];
@@ -795,13 +805,27 @@ static int mimi_enqueue(SmolMimi* m, const int32_t* d_codes, const int32_t* d_sl
         set_in(op, prev, c.last_kernel, false);
         op.pro = PRO_ELU; op.W = wsf(m, m->o_conv_out); op.N = 1; op.bias = bias; op.bias_mod = 1; op.epi = EPI_BIAS;
         op.out = d_pcm; op.out_stride = m->spf; op.out_off0 = 0; op.out_by_row = 1;
-        MCU(launch_rows(op, st)); ++n_launch;
+        push_rows(op);
     }
     {
-        const ShiftArgs a = shift_args(m, d_slots, 0);
-        MCU(launch_pdl(shift_kernel, dim3(batch, a.n_bufs + 1), dim3(kThreads), 0, st, a)); ++n_launch;
+        OpRec r{}; r.kind = OP_SHIFT;
+        r.shift = shift_args(m, d_slots, 0);
+        r.shift.batch = batch;
+        prog.push_back(r);
     }
-    m->launches = n_launch;
+}
+
+// one launch per operation, in order
+static int mimi_enqueue(SmolMimi* m, const std::vector<OpRec>& prog, cudaStream_t st) {
+    for (const OpRec& r : prog) {
+        switch (r.kind) {
+            case OP_ROWS: MCU(launch_rows(r.row, st)); break;
+            case OP_ATTN: MCU(launch_pdl(attn_kernel, dim3(r.attn.batch, r.attn.heads), dim3(kThreads), m->attn_smem, st, r.attn)); break;
+            case OP_EMBED: MCU(launch_pdl(embed_kernel, dim3(r.emb.batch), dim3(256), 0, st, r.emb)); break;
+            default: MCU(launch_pdl(shift_kernel, dim3(r.shift.batch, r.shift.n_bufs + 1), dim3(kThreads), 0, st, r.shift)); break;
+        }
+    }
+    m->launches = (int)prog.size();
     return SMOL_OK;
 }
 
@@ -810,19 +834,24 @@ extern "C" int smol_mimi_decode_step(SmolMimi* m, const int32_t* d_codes, const 
     if (!m->bound) return smol::capi_fail(SMOL_ERR_UNBOUND, "smol_mimi_decode_step: weights / workspace not bound");
     if (batch < 1 || batch > m->cfg.max_streams) return smol::capi_fail(SMOL_ERR_CAPACITY, "smol_mimi_decode_step: batch outside 1 .. max_streams");
     cudaStream_t st = (cudaStream_t)stream;
+    const int mode = m->cfg.use_graph;   // 0: one launch per operation; 1: those launches replayed as a CUDA graph
     // programmatic dependent launch pays for plain stream launches (632 -> 549 us per step at one stream) and costs a
     // little inside a replayed graph (510 -> 536): on for the former, off for the latter; SMOL_MIMI_PDL=0/1 forces it
     const char* pe = getenv("SMOL_MIMI_PDL");
-    g_pdl = pe ? pe[0] != '0' : !m->cfg.use_graph;
-    if (!m->cfg.use_graph) return mimi_enqueue(m, d_codes, d_slots, batch, d_pcm, st);
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
-        return mimi_enqueue(m, d_codes, d_slots, batch, d_pcm, st);   // the caller is capturing: become part of its graph
-    if (!(m->graph && m->g_codes == d_codes && m->g_slots == d_slots && m->g_pcm == d_pcm && m->g_batch == batch)) {
+    g_pdl = pe ? pe[0] != '0' : mode == 0;
+    const bool same = m->g_codes == d_codes && m->g_slots == d_slots && m->g_pcm == d_pcm && m->g_batch == batch;
+    if (!same) {
+        mimi_program(m, d_codes, d_slots, batch, d_pcm, m->prog);
         if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
+        m->g_codes = d_codes; m->g_slots = d_slots; m->g_pcm = d_pcm; m->g_batch = batch;
+    }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+    if (mode == 0 || capturing) return mimi_enqueue(m, m->prog, st);   // (capturing: become part of the caller's graph)
+    if (!m->graph) {
         if (!m->cap_stream) MCU(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
         MCU(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = mimi_enqueue(m, d_codes, d_slots, batch, d_pcm, m->cap_stream);
+        const int rc = mimi_enqueue(m, m->prog, m->cap_stream);
         cudaGraph_t g = nullptr;
         const cudaError_t ee = cudaStreamEndCapture(m->cap_stream, &g);
         if (rc != SMOL_OK) { if (g) cudaGraphDestroy(g); return rc; }
@@ -830,7 +859,6 @@ extern "C" int smol_mimi_decode_step(SmolMimi* m, const int32_t* d_codes, const 
         const cudaError_t ei = cudaGraphInstantiate(&m->graph, g, 0);
         cudaGraphDestroy(g);
         MCU(ei);
-        m->g_codes = d_codes; m->g_slots = d_slots; m->g_pcm = d_pcm; m->g_batch = batch;
     }
     MCU(cudaGraphLaunch(m->graph, st));
     return SMOL_OK;

@@ -92,7 +92,10 @@ class MimiModel:
     """The decode half of the reference's ``MimiModel`` on one CUDA device."""
 
     def __init__(self, config: Optional[MimiConfig] = None, num_codebooks: int = 8, max_streams: int = 1, max_frames: int = 2048,
-                 window: int = 0, upsample_carry: bool = False, use_graph: bool = True, device: Union[str, torch.device, None] = None):
+                 window: int = 0, upsample_carry: bool = False, mode: str = "graph", device: Union[str, torch.device, None] = None):
+        """mode: "graph" -- a step's 57 launches are captured once per (batch, buffers) and replayed as one CUDA graph (the
+        default); "eager" -- plain launches with programmatic dependent launch (also what a caller's own graph capture
+        records).  Both compute the same bits."""
         if not torch.cuda.is_available():
             raise RuntimeError("smoltts_b200.MimiModel needs a CUDA device (there is no CPU path)")
         self.config = config or MimiConfig()
@@ -116,7 +119,10 @@ class MimiModel:
             cfg.ratios[i] = r
         cfg.kernel, cfg.res_kernel, cfg.last_kernel = c.seanet.kernel_size, c.seanet.residual_kernel_size, c.seanet.last_kernel_size
         cfg.max_streams, cfg.max_positions = max_streams, 2 * max_frames
-        cfg.window, cfg.upsample_carry, cfg.use_graph = window, int(upsample_carry), int(use_graph)
+        if mode not in ("graph", "eager"):
+            raise ValueError(f"MimiModel: unknown mode {mode!r}")
+        self.mode = mode
+        cfg.window, cfg.upsample_carry, cfg.use_graph = window, int(upsample_carry), {"eager": 0, "graph": 1}[mode]
         cfg.norm_eps, cfg.codebook_eps = c.transformer.norm_eps, 1e-5
         self._cfg = cfg
         h = C.c_void_p()

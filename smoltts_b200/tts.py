@@ -1,0 +1,99 @@
+"""Text -> PCM: the reference's ``SmolTTS`` front object (mlx_inference/src/smoltts_mlx/__init__.py:25-151) over the two
+B200 engines -- the DualAR decode step (``RQTransformer``) and the Mimi streaming decoder (``MimiModel``).
+
+Same call surface: ``SmolTTS(...)(text, voice)`` returns the flattened PCM of one utterance (:64-83), ``stream(text,
+voice)`` yields one 80 ms chunk per generated frame (:85-95: a fresh Mimi cache per utterance, ``decode_step`` on the
+frame's codes).  ``synthesize_batch`` is new: B utterances decode together (``generate_batch``), then their frames go
+through the codec as one batch of B streams per step.
+
+Parity note: the reference's ``__call__`` decodes the whole code sequence with ``codec.decode`` (the upsampler sees the
+sequence) while its ``stream`` upsamples every frame alone (codec/mimi.py:73-104): the two give different audio in the
+reference, and so do they here -- ``__call__`` uses a codec stream with the upsampler's carry, ``stream`` one without.
+"""
+from __future__ import annotations
+
+from typing import Iterator, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .generate import GenerationSettings, SingleBatchGenerator, generate_batch, generate_blocking
+from .mimi import MimiModel
+from .model import RQTransformer
+from .serving import PromptEncoder
+
+VOICES = ["heart", "bella", "nova", "sky", "sarah", "michael", "fenrir", "liam", "emma", "isabella", "fable"]   # :127-143
+
+
+class SmolTTS:
+    def __init__(self, lm: RQTransformer, prompt_encoder: PromptEncoder, codec_stream: MimiModel, codec_full: Optional[MimiModel] = None,
+                 settings: Optional[GenerationSettings] = None):
+        """codec_stream: a MimiModel with the reference's decode_step rule (upsample_carry=False); codec_full: one with
+        upsample_carry=True for ``__call__`` / ``synthesize_batch`` (defaults to codec_stream if it already carries)."""
+        self.lm = lm
+        self.prompt_encoder = prompt_encoder
+        self.codec = codec_stream
+        self.codec_full = codec_full if codec_full is not None else codec_stream
+        self.settings = settings or GenerationSettings()
+        self.sampling_rate = 24_000
+
+    # ---- prompt assembly (:123-151) ----
+    def _get_prompt(self, input: str, voice: str, sysprompt: Optional[torch.Tensor] = None) -> torch.Tensor:
+        voice_id = VOICES.index(voice) if voice in VOICES else 0
+        return self.prompt_encoder.tts_prompt(input, speaker=voice_id, sysprompt=sysprompt)[None]
+
+    def create_speaker(self, samples: Sequence[dict], system_prompt: Optional[str] = None) -> torch.Tensor:
+        return self.prompt_encoder.create_speaker(samples, system_prompt)
+
+    # ---- one utterance (:64-83) ----
+    def __call__(self, input: str, voice: Optional[str] = "heart", speaker: Optional[torch.Tensor] = None) -> np.ndarray:
+        prompt = self._get_prompt(input, voice if voice is not None else "heart", sysprompt=speaker)
+        codes = generate_blocking(self.lm, prompt, self.settings)          # [1, N, T]
+        if codes.shape[-1] == 0:
+            return np.zeros(0, dtype=np.float32)
+        pcm = self.codec_full.decode(codes.to(torch.int64))
+        return pcm.flatten().cpu().numpy()
+
+    # ---- streaming (:85-95) ----
+    def stream(self, input: str, voice: Optional[str] = "heart") -> Iterator[np.ndarray]:
+        prompt = self._get_prompt(input, voice if voice is not None else "0")
+        frame_gen = SingleBatchGenerator(self.lm, prompt, self.settings)
+        cache = self.codec.make_cache()
+        try:
+            for frame in frame_gen:
+                if frame.audio_codes is None:      # the <|im_end|> frame (the reference would hand None to the codec here)
+                    continue
+                if cache.frames >= self.codec.max_frames:
+                    break
+                yield self.codec.decode_step(frame.audio_codes, cache).flatten().cpu().numpy()
+        finally:
+            self.codec.release_cache(cache)
+
+    # ---- many utterances at once (new) ----
+    def synthesize_batch(self, inputs: Sequence[str], voices: Optional[Sequence[str]] = None, fixed_frames: Optional[int] = None) -> List[np.ndarray]:
+        voices = list(voices) if voices is not None else ["heart"] * len(inputs)
+        prompts = [self._get_prompt(t, v)[0] for t, v in zip(inputs, voices)]
+        codes = generate_batch(self.lm, prompts, self.settings, fixed_frames=fixed_frames)   # list of [N, T_b]
+        return self.decode_codes(codes)
+
+    def decode_codes(self, codes: Sequence[torch.Tensor]) -> List[np.ndarray]:
+        """Ragged code sequences [N, T_b] -> PCM, all streams stepping together while they last."""
+        codec = self.codec_full
+        B = len(codes)
+        if B > codec.max_streams:
+            raise ValueError(f"decode_codes: {B} utterances, the codec was built for {codec.max_streams} streams")
+        lens = [int(c.shape[-1]) for c in codes]
+        caches = [codec.make_cache() for _ in range(B)]
+        spf = codec.samples_per_frame
+        outs = [torch.empty(n * spf, dtype=torch.float32, device=codec.device) for n in lens]
+        order = sorted(range(B), key=lambda b: -lens[b])          # live streams are always a prefix of this order
+        dev_codes = [c.to(codec.device) for c in codes]
+        for t in range(max(lens) if lens else 0):
+            live = [b for b in order if lens[b] > t]
+            frame = torch.stack([dev_codes[b][:, t] for b in live], dim=0)   # [B_live, N]
+            pcm = codec.decode_step(frame, [caches[b] for b in live])
+            for i, b in enumerate(live):
+                outs[b][t * spf:(t + 1) * spf] = pcm[i, 0]
+        for c in caches:
+            codec.release_cache(c)
+        return [o.cpu().numpy() for o in outs]

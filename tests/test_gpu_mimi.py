@@ -105,8 +105,7 @@ def test_a_stream_decodes_to_the_same_bits_alone_in_any_batch_slot_and_launch_mo
     codes = torch.randint(0, 2048, (B, 8, T), generator=gen)
     m = _model(max_streams=12, max_frames=16)
     batch = _run(m, codes)                       # 9 streams: 18 transformer rows, 17280 SEANet rows (ragged 16-row chunks)
-    eager = _model(max_streams=12, max_frames=16, use_graph=False)
-    assert torch.equal(_run(eager, codes), batch), "graph replay and plain launches differ"
+    assert torch.equal(_run(_model(max_streams=12, max_frames=16, mode="eager"), codes), batch), "graph replay and plain launches differ"
     for b in (0, 4, 8):
         assert torch.equal(_run(m, codes[b:b + 1]), batch[b:b + 1]), f"stream {b} decodes differently alone"
     # slots in a different order, neighbours changing from step to step

@@ -1,0 +1,70 @@
+"""Text -> PCM through both engines (smoltts_b200/tts.py: SmolTTS, the mirror of the reference's front object): the codes of
+the DualAR decode step go through the Mimi streaming decoder, checked against the Mimi oracle on the same codes."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import model_and_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _tts(max_streams=4, max_frames=32):
+    from smoltts_b200 import GenerationSettings, MimiModel, PromptEncoder, SmolTTS, byte_level_tokenizer
+    from smoltts_b200.synth import make_mimi_state_dict
+
+    cfg, sd, lm, _ = model_and_oracle("smoltts_byte_tiny", max_batch=8, max_seq_len=256)
+    enc = PromptEncoder.from_model(byte_level_tokenizer(cfg.codebook_size), lm)
+    msd = make_mimi_state_dict(0)
+    stream = MimiModel(max_streams=max_streams, max_frames=max_frames)
+    stream.load_state_dict(msd)
+    full = MimiModel(max_streams=max_streams, max_frames=max_frames, upsample_carry=True)
+    full.load_state_dict(msd)
+    gs = GenerationSettings(default_temp=0.0, default_fast_temp=0.0, max_new_tokens=9)
+    return SmolTTS(lm, enc, stream, full, gs), msd
+
+
+def _audio_codes(tts, text, voice):
+    from smoltts_b200 import generate_blocking
+
+    return generate_blocking(tts.lm, tts._get_prompt(text, voice), tts.settings).cpu().long()   # [1, 8, T]
+
+
+def test_call_and_stream_follow_the_two_codec_rules_of_the_reference():
+    from oracle.mimi_oracle import MimiOracle, StreamState
+
+    tts, msd = _tts()
+    orc = MimiOracle(msd)
+    text, voice = "Hello there, B200.", "nova"
+    codes = _audio_codes(tts, text, voice)
+    T = codes.shape[-1]
+    assert T >= 1, "the tiny random-init model emitted no audio frame; pick another text"
+    with torch.no_grad():
+        want_full = orc.decode(codes).flatten().numpy()
+        st = StreamState()
+        want_stream = [orc.decode_step(codes[:, :, t:t + 1], st).flatten().numpy() for t in range(T)]
+    pcm = tts(text, voice)
+    assert pcm.shape == (T * 1920,) and pcm.dtype == np.float32
+    assert np.abs(pcm - want_full).max() <= 1e-4 * np.abs(want_full).max()
+    chunks = list(tts.stream(text, voice))
+    assert len(chunks) == T and all(c.shape == (1920,) for c in chunks)
+    for t, (c, w) in enumerate(zip(chunks, want_stream)):
+        assert np.abs(c - w).max() <= 1e-4 * np.abs(np.concatenate(want_stream)).max(), f"chunk {t}"
+    assert len(tts.codec._free) == tts.codec.max_streams, "stream() must give its codec slot back"
+
+
+def test_batch_synthesis_equals_one_utterance_at_a_time():
+    tts, _ = _tts()
+    texts = ["One.", "A second, longer utterance.", "Three!"]
+    voices = ["heart", "sky", "liam"]
+    outs = tts.synthesize_batch(texts, voices, fixed_frames=6)
+    assert len(outs) == 3
+    from smoltts_b200 import generate_batch
+
+    prompts = [tts._get_prompt(t, v)[0] for t, v in zip(texts, voices)]
+    codes = generate_batch(tts.lm, prompts, tts.settings, fixed_frames=6)
+    assert any(c.shape[-1] > 0 for c in codes)
+    for b in range(3):
+        solo = tts.decode_codes([codes[b]])[0]
+        assert outs[b].shape == (codes[b].shape[-1] * 1920,)
+        assert np.array_equal(outs[b], solo), f"utterance {b}: PCM differs between the batch of streams and a stream alone"

@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--batch", default="1,8,64")
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--window", type=int, default=0)
-    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"])
     args = ap.parse_args()
     from smoltts_b200.mimi import MimiModel
     from smoltts_b200.synth import make_mimi_state_dict
@@ -37,7 +37,7 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm = float(peaks.get("hbm_gbs", 6450.9))
     for B in [int(x) for x in args.batch.split(",")]:
-        m = MimiModel(max_streams=B, max_frames=args.frames + 8, window=args.window, use_graph=not args.no_graph)
+        m = MimiModel(max_streams=B, max_frames=args.frames + 8, window=args.window, mode=args.mode)
         m.load_state_dict(sd)
         caches = [m.make_cache() for _ in range(B)]
         g = torch.Generator().manual_seed(1)
@@ -55,7 +55,7 @@ def main():
         mean_pos = 2 * (4 + args.frames / 2)
         kv = B * 8 * 2 * 512 * 4 * (2 * (mean_pos if args.window == 0 else min(mean_pos, args.window)) + 2)
         bytes_step = wb + kv
-        print(json.dumps({"workload": f"mimi decode_step bs={B}, {args.frames} frames, window {args.window}", "us_per_step": round(us, 1),
+        print(json.dumps({"workload": f"mimi decode_step bs={B}, {args.frames} frames, window {args.window}, {args.mode}", "us_per_step": round(us, 1),
                           "frames_per_s": round(B * 1e6 / us, 1), "realtime_factor": round(B * 1e6 / us / 12.5, 1),
                           "launches_per_step": m.launches_per_step, "algorithmic_bytes_per_step": int(bytes_step),
                           "roofline": {"bound": "hbm", "achieved": round(bytes_step / us / 1e3, 1), "peak": hbm, "unit": "GB/s",
