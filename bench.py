@@ -14,7 +14,8 @@ codes, and for N > 1 the host-side gather of every rank's codes on rank 0), for 
 
 The same line carries ``"configs"``: the other BASELINE.json configurations measured the same way in the same run
 (configs[2] bs=64 sampled, configs[3] bs=256 per GPU at two prompt lengths, configs[4] long-form bs=32 at the
-workload's mean context), each with its own ``roofline`` and ``e2e``.  Under ``--gpus N > 1`` every entry is the
+workload's mean context), each with its own ``roofline`` and ``e2e``, and two entries for the step AFTER the path
+(the Mimi streaming decoder: ``mimi_bs1``, ``mimi_bs64`` -- codes to PCM, frames/s).  Under ``--gpus N > 1`` every entry is the
 per-GPU batch sharded over the N ranks (weak scaling), so the bs=256/GPU 1 -> 8 curve is in the driver's records.
 
 Roofline: algorithmic bytes (unique weight bytes + KV bytes of the mean context) or flops per launch over
@@ -465,6 +466,104 @@ def measure(work: Work, args, steps: int, warmup: int, ctx) -> dict:
     return res
 
 
+def measure_mimi(key: str, batch: int, frames: int, args, steps: int, warmup: int, ctx) -> dict:
+    """The step after the path: Mimi streaming decoder, `batch` streams x `frames` decode_step calls per
+    bench step.  value: codes resident in HBM; e2e: codes from pinned host memory, PCM back to pinned host memory, through
+    MimiModel.decode_step.  Roofline: every packed fp32 weight once per decode_step + the KV the step touches."""
+    import torch
+
+    from smoltts_b200.mimi import MimiModel
+    from smoltts_b200.synth import make_mimi_state_dict
+
+    dist, rank, world, local = ctx["dist"], ctx["rank"], ctx["world"], ctx["local"]
+    sd = ctx["mimi_weights"]()
+    m = MimiModel(max_streams=batch, max_frames=frames + 8)
+    m.load_state_dict(sd)
+    dev = m.device
+    g = torch.Generator().manual_seed(100 + rank)
+    codes_h = torch.randint(0, 2048, (frames, batch, 8), generator=g, dtype=torch.int32).pin_memory()
+    codes_d = codes_h.to(dev)
+    pcm_h = torch.empty(frames, batch, m.samples_per_frame, dtype=torch.float32).pin_memory()
+    caches = [m.make_cache() for _ in range(batch)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(resident: bool):
+        m._reset([c.slot for c in caches])
+        for t in range(frames):
+            pcm = m.decode_step(codes_d[t] if resident else codes_h[t].to(dev, non_blocking=True), caches)
+            if not resident:
+                pcm_h[t].copy_(pcm[:, 0], non_blocking=True)
+        return pcm
+
+    for _ in range(warmup):
+        run(True)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        last = run(True)
+    stop.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = start.elapsed_time(stop)
+    check = float(last.abs().sum().item())
+    for _ in range(max(1, min(warmup, 2))):
+        run(False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run(False)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = (float(v) for v in t.tolist())
+    wbytes = sum(v.numel() * 4 for k, v in sd.items() if "codebook" not in k) + 8 * 256 * 4
+    mean_pos = frames + 1            # 2 positions per frame, mean over the run
+    kv = batch * 8 * 2 * 512 * 4 * (mean_pos + 2)
+    us_step = 1e3 * total_ms / (steps * frames)
+    hbm, src = load_peaks()
+    ach = (wbytes + kv) / (us_step * 1e-6) / 1e9
+    res = {
+        "key": key, "workload": f"Mimi streaming decoder (kyutai/mimi shape, seeded fp32 weights): {batch} stream(s) x {frames} decode_step calls per step",
+        "note": "SURVEY 8(f)-2: codes [B, 8] -> 1920 fp32 samples per frame; 57 launches per decode_step replayed as one CUDA graph",
+        "value": steps * frames * batch * world / (total_ms * 1e-3), "unit": "frames/s", "ms_per_step": total_ms / steps, "steps": steps,
+        "warmup": warmup, "us_per_frame_step": us_step,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src, "traffic": None,
+                     "kernel": "smol::mimi::rows_kernel (weight-streaming row products, fp32 FMA)",
+                     "algorithmic_bytes_per_launch": wbytes + kv,
+                     "bytes_model": "packed fp32 weights of the decode half once per decode_step + KV cache read/written"},
+        "e2e": {"value": steps * frames * batch * world / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frames * batch * 8 * 4,
+                "d2h_bytes_per_step": frames * batch * m.samples_per_frame * 4, "steps": steps},
+        "clocks": clocks, "gpu_launches": steps * frames * m.launches_per_step, "launch_mode": "57 launches per decode_step, CUDA-graph replay",
+        "realtime_factor": steps * frames * batch * world / (total_ms * 1e-3) / 12.5, "check": check,
+    }
+    if rank == 0 and world == 1 and batch == 1 and not args.no_cpu_baseline:
+        from oracle.mimi_oracle import MimiOracle, StreamState   # CPU leg only (the checker, never the product)
+
+        orc, st = MimiOracle(sd), StreamState()
+        n = 24
+        with torch.no_grad():
+            orc.decode_step(codes_h[0][0:1].long()[:, :, None], st)      # warm-up call (allocator, thread pool)
+            t1 = time.perf_counter()
+            for t in range(1, 1 + n):
+                orc.decode_step(codes_h[t % frames][0:1].long()[:, :, None], st)
+            cpu_s = time.perf_counter() - t1
+        res["cpu_baseline"] = {"value": n / cpu_s, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{n} decode_step calls of one stream (oracle/mimi_oracle.py, torch CPU fp32)"}
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
 
@@ -492,7 +591,14 @@ def run_ours(args):
             wcache[name] = make_state_dict(named_config(name), seed=0)
         return wcache[name]
 
-    ctx = {"dist": dist, "gloo": gloo, "rank": rank, "world": world, "local": local, "weights": weights}
+    def mimi_weights():
+        if "mimi" not in wcache:
+            from smoltts_b200.synth import make_mimi_state_dict
+
+            wcache["mimi"] = make_mimi_state_dict(0)
+        return wcache["mimi"]
+
+    ctx = {"dist": dist, "gloo": gloo, "rank": rank, "world": world, "local": local, "weights": weights, "mimi_weights": mimi_weights}
     head = headline_work(args)
     main = measure(head, args, args.steps, args.warmup, ctx)
     entries = []
@@ -503,6 +609,9 @@ def run_ours(args):
                 r = measure(w, args, max(1, min(args.steps, args.config_steps)), 3, ctx)
                 r["key"] = w.key
                 entries.append(r)
+        for key, b, f in (("mimi_bs1", 1, 256), ("mimi_bs64", 64, 32)):     # the step after the path: codes -> PCM
+            if wanted is None or key in wanted:
+                entries.append(measure_mimi(key, b, f, args, max(1, min(args.steps, args.config_steps)), 3, ctx))
 
     if rank == 0:
         cfg_pub = dict(main["config"])  # identical in both arms (ours / --impl reference): the configuration measured
@@ -515,7 +624,8 @@ def run_ours(args):
             "latency": {"us_per_frame": main["us_per_frame_step"], "frame_latency_bs1": main["frame_latency_bs1"]},
             "detail": {"launch_mode": main["launch_mode"], "e2e_includes": main["e2e"]["includes"]},
             "configs": [{k: e[k] for k in ("key", "workload", "note", "value", "unit", "ms_per_step", "steps", "warmup",
-                                           "us_per_frame_step", "roofline", "e2e", "clocks", "gpu_launches", "launch_mode")}
+                                           "us_per_frame_step", "roofline", "e2e", "clocks", "gpu_launches", "launch_mode",
+                                           "realtime_factor", "cpu_baseline") if k in e}
                         for e in entries],
         }
         if world == 1 and not args.no_cpu_baseline:

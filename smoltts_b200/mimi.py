@@ -134,6 +134,7 @@ class MimiModel:
         self._free = list(range(max_streams - 1, -1, -1))
         self._frames = [0] * max_streams
         self._io: Dict[int, tuple] = {}   # batch -> (codes, slots, pcm) device buffers with stable addresses (graph replay)
+        self._io_slots: Dict[int, tuple] = {}
 
     def __del__(self):
         try:
@@ -266,7 +267,10 @@ class MimiModel:
                 raise RuntimeError(f"MimiModel: stream in slot {c.slot} is at max_frames = {self.max_frames}")
         d_codes, d_slots, d_pcm = self._buffers(B)
         d_codes.copy_(codes.to(torch.int32), non_blocking=True)
-        d_slots.copy_(torch.tensor([c.slot for c in caches], dtype=torch.int32), non_blocking=True)
+        slots = tuple(c.slot for c in caches)
+        if self._io_slots.get(B) != slots:      # the slot table of this batch size changes only when streams come and go
+            d_slots.copy_(torch.tensor(slots, dtype=torch.int32), non_blocking=True)
+            self._io_slots[B] = slots
         _capi.check(self._lib.smol_mimi_decode_step(self._h, C.c_void_p(d_codes.data_ptr()), C.c_void_p(d_slots.data_ptr()), B,
                                                     C.c_void_p(d_pcm.data_ptr()), C.c_void_p(self._stream())))
         for c in caches:
