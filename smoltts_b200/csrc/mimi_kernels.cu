@@ -231,6 +231,90 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
     rows_body<R, true>(op, blockIdx.x, blockIdx.y, S);
 }
 
+// The same product for MANY rows (8+ streams x the 16 .. 1920 rows of a SEANet stage): a 64 x 64 output tile per CTA, K in
+// steps of 16 through shared memory, 4 x 4 outputs per thread -- 16 FMAs per pair of 16-byte shared-memory loads instead of
+// the 4 of rows_kernel, whose one-weight-row-per-warp shape is built for a handful of rows.  Every output is one sequential
+// FMA chain over k = 0 .. K-1: deterministic and independent of what shares the launch, but a different order than
+// rows_kernel's lane-interleaved sums -- which kernel runs is decided by the BATCH SIZE alone (8+ streams), so a stream's bits
+// are the same in any batch of the same class.  Prologue none | ELU, epilogue bias | bias + residual (the SEANet's ops).
+constexpr int kTM = 64, kTN = 64, kTK = 16;
+__global__ void __launch_bounds__(kThreads, 2) tile_kernel(const RowOp op) {
+    __shared__ __align__(16) float As[kTK][kTM + 4];
+    __shared__ __align__(16) float Ws[kTK][kTN + 4];
+    __shared__ int s_slot[kTM], s_t[kTM], s_b[kTM];
+    const int tid = threadIdx.x;
+    const int rows = op.batch * op.T;
+    const int row0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+    if (tid < kTM) {
+        const int row = row0 + tid;
+        int b = 0, t = 0, slot = -1;
+        if (row < rows) { b = row / op.T; t = row - b * op.T; slot = op.slots ? op.slots[b] : b; }
+        s_slot[tid] = slot; s_t[tid] = t; s_b[tid] = b;
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_go();
+    const int lm = tid >> 2, lk = (tid & 3) << 2;      // this thread's row (of A and of W) and k offset of the 16-byte pieces it loads
+    const int a_slot = s_slot[lm];
+    const float* a_base = op.in + (long long)(a_slot < 0 ? 0 : a_slot) * op.in_stride + (long long)(op.in_hs + s_t[lm] + op.tap0) * op.in_c;
+    const bool w_ok = n0 + lm < op.N;
+    const float* w_base = op.W + (long long)(n0 + lm) * op.K;
+    auto load_a = [&](int k) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a_slot >= 0) {
+            const int j = k / op.in_c, c = k - j * op.in_c;
+            v = *reinterpret_cast<const float4*>(a_base + (long long)j * op.tapstep * op.in_c + c);
+            if (op.pro == PRO_ELU) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+        }
+        return v;
+    };
+    auto load_w = [&](int k) -> float4 {
+        return w_ok ? __ldg(reinterpret_cast<const float4*>(w_base + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 ra = load_a(lk), rw = load_w(lk);
+    for (int k0 = 0; k0 < op.K; k0 += kTK) {
+        As[lk + 0][lm] = ra.x; As[lk + 1][lm] = ra.y; As[lk + 2][lm] = ra.z; As[lk + 3][lm] = ra.w;
+        Ws[lk + 0][lm] = rw.x; Ws[lk + 1][lm] = rw.y; Ws[lk + 2][lm] = rw.z; Ws[lk + 3][lm] = rw.w;
+        __syncthreads();
+        if (k0 + kTK < op.K) { ra = load_a(k0 + kTK + lk); rw = load_w(k0 + kTK + lk); }   // next step's pieces in flight during the FMAs
+#pragma unroll
+        for (int k = 0; k < kTK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]); acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
+            acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]); acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
+            acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]); acc[2][2] = fmaf(a.z, w.z, acc[2][2]); acc[2][3] = fmaf(a.z, w.w, acc[2][3]);
+            acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]); acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx * 4;
+    if (n >= op.N) return;                      // (N is a multiple of 4: the four columns of a thread are all in or all out)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = ty * 4 + i;
+        const int slot = s_slot[m];
+        if (slot < 0) continue;
+        const long long e = (long long)op.out_off0 + (long long)s_t[m] * op.N + n;
+        float4 y = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (op.bias) {
+            y.x += op.bias[n % op.bias_mod]; y.y += op.bias[(n + 1) % op.bias_mod];
+            y.z += op.bias[(n + 2) % op.bias_mod]; y.w += op.bias[(n + 3) % op.bias_mod];
+        }
+        if (op.epi == EPI_RES) {
+            const float4 r = *reinterpret_cast<const float4*>(op.res + (long long)slot * op.res_stride + op.res_off0 + (long long)s_t[m] * op.N + n);
+            y.x = r.x + y.x; y.y = r.y + y.y; y.z = r.z + y.z; y.w = r.w + y.w;
+        }
+        *reinterpret_cast<float4*>(op.out + (long long)(op.out_by_row ? s_b[m] : slot) * op.out_stride + e) = y;
+    }
+}
+
 // RVQ decode (rvq.py:118-130, 171-186): the semantic codebook's row | the sum of the acoustic codebooks' rows, in order.
 struct EmbedArgs {
     const float* books;   // [n_q][codebook_size][cdim], rows already divided by max(cluster_usage, eps)
@@ -678,7 +762,19 @@ static cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, dim3 block, s
 
 static int rows_R(int rows) { return rows <= 2 ? 2 : rows <= 4 ? 4 : rows <= 8 ? 8 : 16; }
 
+// 8+ streams: the many-row stages go through the tile kernel (decided by the batch size alone, see tile_kernel)
+constexpr int kTileMinBatch = 8;
+static bool use_tile(const RowOp& op) {
+    static const int min_batch = [] { const char* e = getenv("SMOL_MIMI_TILE_MIN_BATCH"); return e ? atoi(e) : kTileMinBatch; }();
+    return op.batch >= min_batch && op.T >= 16 && op.N >= 16 && op.N % 4 == 0 && op.K % kTK == 0 &&
+           (op.pro == PRO_NONE || op.pro == PRO_ELU) && (op.epi == EPI_BIAS || op.epi == EPI_RES);
+}
+
 static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
+    if (use_tile(op)) {
+        const dim3 grid((op.N + kTN - 1) / kTN, (op.batch * op.T + kTM - 1) / kTM);
+        return launch_pdl(tile_kernel, grid, dim3(kThreads), 0, st, op);
+    }
     const int rows = op.batch * op.T;
     const int R = rows_R(rows);
     const dim3 grid((op.N + kWarps - 1) / kWarps, (rows + R - 1) / R);
