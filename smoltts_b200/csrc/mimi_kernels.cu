@@ -236,8 +236,11 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
 // the 4 of rows_kernel, whose one-weight-row-per-warp shape is built for a handful of rows.  Every output is one sequential
 // FMA chain over k = 0 .. K-1: deterministic and independent of what shares the launch, but a different order than
 // rows_kernel's lane-interleaved sums -- which kernel runs is decided by the BATCH SIZE alone (8+ streams), so a stream's bits
-// are the same in any batch of the same class.  Prologue none | ELU, epilogue bias | bias + residual (the SEANet's ops).
-constexpr int kTM = 64, kTN = 64, kTK = 16;
+// are the same in any batch of the same class (< 8 streams, 8+).  Prologues none | ELU | LayerNorm (row statistics in a pre-pass), epilogues bias |
+// residual | layer scale + residual | GELU: every operation of a step except the upsampler and the one-channel last convolution
+// (rowdot_kernel below).
+constexpr int kTM = 64, kTN = 64, kTK = 16, kTU = kTK / 16;   // kTU 16-byte pieces of A and of W per thread and K step
+// (K steps of 32: the many-row stages 15 .. 30 % slower -- fewer resident CTAs -- measured at 64 streams.)
 __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const RowOp op) {
     __shared__ __align__(16) float As[kTK][kTM + 4];
     __shared__ __align__(16) float Ws[kTK][kTN + 4];
@@ -277,12 +280,21 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const RowOp op) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    float4 ra = load_a(lk), rw = load_w(lk);
+    float4 ra[kTU], rw[kTU];
+#pragma unroll
+    for (int u = 0; u < kTU; ++u) { ra[u] = load_a(lk + 16 * u); rw[u] = load_w(lk + 16 * u); }
     for (int k0 = 0; k0 < op.K; k0 += kTK) {
-        As[lk + 0][lm] = ra.x; As[lk + 1][lm] = ra.y; As[lk + 2][lm] = ra.z; As[lk + 3][lm] = ra.w;
-        Ws[lk + 0][lm] = rw.x; Ws[lk + 1][lm] = rw.y; Ws[lk + 2][lm] = rw.z; Ws[lk + 3][lm] = rw.w;
+#pragma unroll
+        for (int u = 0; u < kTU; ++u) {
+            const int kk = lk + 16 * u;
+            As[kk + 0][lm] = ra[u].x; As[kk + 1][lm] = ra[u].y; As[kk + 2][lm] = ra[u].z; As[kk + 3][lm] = ra[u].w;
+            Ws[kk + 0][lm] = rw[u].x; Ws[kk + 1][lm] = rw[u].y; Ws[kk + 2][lm] = rw[u].z; Ws[kk + 3][lm] = rw[u].w;
+        }
         __syncthreads();
-        if (k0 + kTK < op.K) { ra = load_a(k0 + kTK + lk); rw = load_w(k0 + kTK + lk); }   // next step's pieces in flight during the FMAs
+        if (k0 + kTK < op.K) {   // next step's pieces in flight during the FMAs
+#pragma unroll
+            for (int u = 0; u < kTU; ++u) { ra[u] = load_a(k0 + kTK + lk + 16 * u); rw[u] = load_w(k0 + kTK + lk + 16 * u); }
+        }
 #pragma unroll
         for (int k = 0; k < kTK; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -313,6 +325,29 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(const RowOp op) {
         }
         *reinterpret_cast<float4*>(op.out + (long long)(op.out_by_row ? s_b[m] : slot) * op.out_stride + e) = y;
     }
+}
+
+// The last convolution (one output channel) for many rows: one thread per output sample, the weight vector in shared memory.
+__global__ void __launch_bounds__(kThreads) rowdot_kernel(const RowOp op) {
+    __shared__ __align__(16) float w[1024];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < op.K; k += kThreads) w[k] = op.W[k];
+    __syncthreads();
+    pdl_wait();
+    pdl_go();
+    const int row = blockIdx.x * kThreads + tid;
+    if (row >= op.batch * op.T) return;
+    const int b = row / op.T, t = row - b * op.T;
+    const int slot = op.slots ? op.slots[b] : b;
+    const float* a = op.in + (long long)slot * op.in_stride + (long long)(op.in_hs + t + op.tap0) * op.in_c;   // contiguous im2col run
+    float acc = 0.f;
+    for (int k = 0; k < op.K; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(a + k);
+        if (op.pro == PRO_ELU) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+        const float4 ww = *reinterpret_cast<const float4*>(&w[k]);
+        acc = fmaf(v.x, ww.x, acc); acc = fmaf(v.y, ww.y, acc); acc = fmaf(v.z, ww.z, acc); acc = fmaf(v.w, ww.w, acc);
+    }
+    op.out[(long long)(op.out_by_row ? b : slot) * op.out_stride + op.out_off0 + t] = acc + (op.bias ? op.bias[0] : 0.f);
 }
 
 // RVQ decode (rvq.py:118-130, 171-186): the semantic codebook's row | the sum of the acoustic codebooks' rows, in order.
@@ -769,12 +804,17 @@ static bool use_tile(const RowOp& op) {
     return op.batch >= min_batch && op.T >= 16 && op.N >= 16 && op.N % 4 == 0 && op.K % kTK == 0 &&
            (op.pro == PRO_NONE || op.pro == PRO_ELU) && (op.epi == EPI_BIAS || op.epi == EPI_RES);
 }
+static bool use_rowdot(const RowOp& op) {
+    static const int min_batch = [] { const char* e = getenv("SMOL_MIMI_TILE_MIN_BATCH"); return e ? atoi(e) : kTileMinBatch; }();
+    return op.batch >= min_batch && op.N == 1 && op.K <= 1024 && op.K % 4 == 0 && op.tapstep > 0 && op.epi == EPI_BIAS && op.pro != PRO_LN;
+}
 
 static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
     if (use_tile(op)) {
         const dim3 grid((op.N + kTN - 1) / kTN, (op.batch * op.T + kTM - 1) / kTM);
         return launch_pdl(tile_kernel, grid, dim3(kThreads), 0, st, op);
     }
+    if (use_rowdot(op)) return launch_pdl(rowdot_kernel, dim3((op.batch * op.T + kThreads - 1) / kThreads), dim3(kThreads), 0, st, op);
     const int rows = op.batch * op.T;
     const int R = rows_R(rows);
     const dim3 grid((op.N + kWarps - 1) / kWarps, (rows + R - 1) / R);

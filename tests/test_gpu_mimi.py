@@ -99,29 +99,50 @@ def test_long_run_matches_the_oracle_with_and_without_window():
     assert not torch.allclose(_run(_model(max_streams=2, max_frames=32, window=6), codes), _run(_model(max_streams=2, max_frames=32, window=0), codes))
 
 
-def test_a_stream_decodes_to_the_same_bits_alone_in_any_batch_slot_and_launch_mode():
-    gen = torch.Generator().manual_seed(5)
-    B, T = 9, 5
-    codes = torch.randint(0, 2048, (B, 8, T), generator=gen)
-    m = _model(max_streams=12, max_frames=16)
-    batch = _run(m, codes)                       # 9 streams: 18 transformer rows, 17280 SEANet rows (ragged 16-row chunks)
-    assert torch.equal(_run(_model(max_streams=12, max_frames=16, mode="eager"), codes), batch), "graph replay and plain launches differ"
-    for b in (0, 4, 8):
-        assert torch.equal(_run(m, codes[b:b + 1]), batch[b:b + 1]), f"stream {b} decodes differently alone"
-    # slots in a different order, neighbours changing from step to step
+def _shuffled_run(m, codes, perm, split):
+    """The same streams stepped in permuted row order on even frames and as two separate calls on odd frames."""
+    B, T = codes.shape[0], codes.shape[-1]
     caches = [m.make_cache() for _ in range(B)]
-    perm = [3, 0, 8, 1, 7, 2, 6, 4, 5]
+    inv = torch.argsort(torch.tensor(perm)).cuda()
     out = []
     for t in range(T):
         if t % 2 == 0:
-            out.append(m.decode_step(codes[perm, :, t:t + 1].cuda(), [caches[i] for i in perm]).clone()[torch.argsort(torch.tensor(perm)).cuda()])
-        else:   # two calls of different batch sizes
-            a = m.decode_step(codes[:4, :, t:t + 1].cuda(), caches[:4]).clone()
-            b2 = m.decode_step(codes[4:, :, t:t + 1].cuda(), caches[4:]).clone()
+            out.append(m.decode_step(codes[perm, :, t:t + 1].cuda(), [caches[i] for i in perm]).clone()[inv])
+        else:
+            a = m.decode_step(codes[:split, :, t:t + 1].cuda(), caches[:split]).clone()
+            b2 = m.decode_step(codes[split:, :, t:t + 1].cuda(), caches[split:]).clone()
             out.append(torch.cat([a, b2], dim=0))
-    assert torch.equal(torch.cat(out, dim=-1), batch)
     for c in caches:
         m.release_cache(c)
+    return torch.cat(out, dim=-1)
+
+
+def test_a_stream_decodes_to_the_same_bits_alone_in_any_batch_slot_and_launch_mode():
+    """Two kernel classes, chosen by the batch size alone: fewer than 8 streams (rows_kernel everywhere) and 8+ (the SEANet's
+    many-row stages on tile_kernel, the last convolution on rowdot_kernel).  Inside a class a stream's PCM is bit-identical
+    whatever shares the launch; across the classes only the summation order differs."""
+    gen = torch.Generator().manual_seed(5)
+    T = 5
+    m = _model(max_streams=40, max_frames=16)
+    eager = _model(max_streams=40, max_frames=16, mode="eager")
+    # ---- few streams ----
+    codes = torch.randint(0, 2048, (5, 8, T), generator=gen)
+    batch = _run(m, codes)
+    assert torch.equal(_run(eager, codes), batch), "graph replay and plain launches differ"
+    for b in (0, 2, 4):
+        assert torch.equal(_run(m, codes[b:b + 1]), batch[b:b + 1]), f"stream {b} decodes differently alone"
+    assert torch.equal(_shuffled_run(m, codes, [3, 0, 4, 1, 2], 2), batch)
+    # ---- many streams: 17 (ragged 64-row tiles and 16-row chunks), split 8 + 9 on odd frames ----
+    codes17 = torch.cat([codes, torch.randint(0, 2048, (12, 8, T), generator=gen)], dim=0)
+    big = _run(m, codes17)
+    assert torch.equal(_run(eager, codes17), big), "graph replay and plain launches differ (tile kernel)"
+    assert torch.equal(_run(m, codes17[:8]), big[:8]) and torch.equal(_run(m, codes17[8:]), big[8:])
+    assert torch.equal(_shuffled_run(m, codes17, [3, 0, 8, 1, 7, 2, 6, 4, 5, 16, 9, 15, 10, 14, 11, 13, 12], 8), big)
+    codes37 = torch.cat([codes17, torch.randint(0, 2048, (20, 8, T), generator=gen)], dim=0)
+    huge = _run(m, codes37)
+    assert torch.equal(huge[:17], big), "streams decode differently in a batch of 37 than in one of 17"
+    # ---- across the classes: same streams, different summation order ----
+    _close("5 streams inside a batch of 17 vs their own batch", big[:5], batch, rel=1e-5)
 
 
 def test_slot_reuse_and_capacity():
