@@ -382,28 +382,42 @@ __global__ void embed_kernel(const EmbedArgs a) {
 
 // Attention of one (stream, head): the step's two positions against the stream's cache (transformer.py:62-91).
 // Half-split RoPE (nn.RoPE traditional=False) from the table, K/V appended, scores by one thread per position, softmax,
-// P V by (dim, position class) threads; fixed orders throughout.
+// P V by (dim, position class) threads; fixed orders throughout.  The reference's cache never forgets (no window), so a long
+// stream's history is cut into SPLITS of kAttnChunk positions, one CTA each (grid z; CTAs past the stream's length leave at
+// once): a split leaves (max, sum, unnormalised P V) per query, the last split to arrive combines them in split order.  A
+// history of one split (<= 512 positions) writes its result directly.
+constexpr int kAttnChunk = 512;
 struct AttnArgs {
     const float* qkv; long long qkv_stride;      // [2][3 dim]
     float* att; long long att_stride;            // [2][dim]
     float* kv; long long kv_slot_stride, kv_layer_stride;   // [slot][layer][2][max_pos][dim]
     const float* rope; const int32_t* pos; const int32_t* slots; int32_t* err;
-    int layer, dim, hd, max_pos, window, batch, heads;
+    float* part; unsigned int* arrive;           // [slot][head][split][2][hd + 2], [slot][head]
+    int layer, dim, hd, max_pos, window, batch, heads, max_splits;
 };
-__device__ __forceinline__ void attn_body(const AttnArgs& a, int b, int h, float* sm) {
+__device__ __forceinline__ void attn_body(const AttnArgs& a, int b, int h, int sp, float* sm) {
+    __shared__ int s_last;
     const int tid = threadIdx.x;
     const int slot = a.slots ? a.slots[b] : b;
     const int hd = a.hd, half = hd >> 1;
     const int p0 = 2 * a.pos[slot];
-    if (p0 + 2 > a.max_pos) { if (tid == 0) *a.err = 1; return; }   // (uniform over the CTA)
+    if (p0 + 2 > a.max_pos) { if (tid == 0 && sp == 0) *a.err = 1; return; }   // (uniform over the CTA)
+    const int L = p0 + 2;
+    // visible positions: query t sees lo_t .. p0 + t
+    const int lo0 = a.window > 0 ? max(0, p0 + 1 - a.window) : 0;
+    const int lo1 = a.window > 0 ? max(0, p0 + 2 - a.window) : 0;
+    const int s_first = lo0 / kAttnChunk, s_end = (L + kAttnChunk - 1) / kAttnChunk;   // splits that hold visible positions
+    if (sp < s_first || sp >= s_end) return;
+    const int n_part = s_end - s_first;
+    const int pa = max(lo0, sp * kAttnChunk), pe = min(L, (sp + 1) * kAttnChunk);       // this split's positions
     float* q = sm;                // [2][hd], pre-scaled
     float* red = sm + 2 * hd;     // [2 * kThreads] scratch
-    float* S = red + 2 * kThreads;   // [2][L]
-    const int L = p0 + 2;
+    float* S = red + 2 * kThreads;   // [2][kAttnChunk]
     float* kc = a.kv + (long long)slot * a.kv_slot_stride + (long long)a.layer * a.kv_layer_stride;
     float* vc = kc + (long long)a.max_pos * a.dim;
     const float* src = a.qkv + (long long)slot * a.qkv_stride;
     const float scale = rsqrtf((float)hd);
+    const bool newest = sp == s_end - 1;          // the split that holds the step's own two positions appends them
     for (int i = tid; i < 2 * half; i += kThreads) {   // (position t, pair i)
         const int t = i / half, j = i - t * half;
         const float* row = src + (long long)t * 3 * a.dim + h * hd;
@@ -411,20 +425,19 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, int b, int h, float
         const float q1 = row[j], q2 = row[j + half];
         q[t * hd + j] = (q1 * cs - q2 * sn) * scale;
         q[t * hd + j + half] = (q2 * cs + q1 * sn) * scale;
-        const float k1 = row[a.dim + j], k2 = row[a.dim + j + half];
-        float* kd = kc + (long long)(p0 + t) * a.dim + h * hd;
-        kd[j] = k1 * cs - k2 * sn;
-        kd[j + half] = k2 * cs + k1 * sn;
-        float* vd = vc + (long long)(p0 + t) * a.dim + h * hd;
-        vd[j] = row[2 * a.dim + j];
-        vd[j + half] = row[2 * a.dim + j + half];
+        if (newest) {
+            const float k1 = row[a.dim + j], k2 = row[a.dim + j + half];
+            float* kd = kc + (long long)(p0 + t) * a.dim + h * hd;
+            kd[j] = k1 * cs - k2 * sn;
+            kd[j + half] = k2 * cs + k1 * sn;
+            float* vd = vc + (long long)(p0 + t) * a.dim + h * hd;
+            vd[j] = row[2 * a.dim + j];
+            vd[j + half] = row[2 * a.dim + j + half];
+        }
     }
     __syncthreads();
-    // visible positions: query t sees lo_t .. p0 + t
-    const int lo0 = a.window > 0 ? max(0, p0 + 1 - a.window) : 0;
-    const int lo1 = a.window > 0 ? max(0, p0 + 2 - a.window) : 0;
     float m0 = -INFINITY, m1 = -INFINITY;
-    for (int p = lo0 + tid; p < L; p += kThreads) {
+    for (int p = pa + tid; p < pe; p += kThreads) {
         const float4* kr = reinterpret_cast<const float4*>(kc + (long long)p * a.dim + h * hd);
         float s0 = 0.f, s1 = 0.f;
         for (int i = 0; i < hd / 4; ++i) {
@@ -435,7 +448,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, int b, int h, float
         }
         if (p > p0) s0 = -INFINITY;
         if (p < lo1) s1 = -INFINITY;
-        S[p] = s0; S[L + p] = s1;
+        S[p - pa] = s0; S[kAttnChunk + p - pa] = s1;
         m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1);
     }
     // block maximum: shuffles inside a warp, the eight warp values through shared memory (max is order-independent)
@@ -448,9 +461,9 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, int b, int h, float
     for (int w = 1; w < kWarps; ++w) { m0 = fmaxf(m0, red[w]); m1 = fmaxf(m1, red[kWarps + w]); }
     __syncthreads();
     float l0 = 0.f, l1 = 0.f;
-    for (int p = lo0 + tid; p < L; p += kThreads) {
-        const float e0 = expf(S[p] - m0), e1 = expf(S[L + p] - m1);   // exp(-inf) = 0 for masked positions
-        S[p] = e0; S[L + p] = e1;
+    for (int p = pa + tid; p < pe; p += kThreads) {   // (a split in which a query sees nothing has max -inf: its terms are 0)
+        const float e0 = m0 == -INFINITY ? 0.f : expf(S[p - pa] - m0), e1 = m1 == -INFINITY ? 0.f : expf(S[kAttnChunk + p - pa] - m1);
+        S[p - pa] = e0; S[kAttnChunk + p - pa] = e1;
         l0 += e0; l1 += e1;
     }
     // block sum: fixed shuffle tree inside a warp, warp sums added in warp order
@@ -465,19 +478,53 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, int b, int h, float
     const int G = kThreads / hd, d = tid % hd, g = tid / hd;
     float o0 = 0.f, o1 = 0.f;
     if (g < G) {
-        for (int p = lo0 + g; p < L; p += G) {
+        for (int p = pa + g; p < pe; p += G) {
             const float v = vc[(long long)p * a.dim + h * hd + d];
-            o0 = fmaf(S[p], v, o0); o1 = fmaf(S[L + p], v, o1);
+            o0 = fmaf(S[p - pa], v, o0); o1 = fmaf(S[kAttnChunk + p - pa], v, o1);
         }
     }
     red[tid] = o0; red[kThreads + tid] = o1;
     __syncthreads();
+    float* dst = a.att + (long long)slot * a.att_stride + h * hd;
+    float* mypart = a.part + (((long long)slot * a.heads + h) * a.max_splits) * (2 * (hd + 2));
     if (tid < hd) {
         float s0 = 0.f, s1 = 0.f;
         for (int gg = 0; gg < G; ++gg) { s0 += red[gg * hd + tid]; s1 += red[kThreads + gg * hd + tid]; }
-        float* dst = a.att + (long long)slot * a.att_stride + h * hd + tid;
-        dst[0] = s0 / l0;
-        dst[a.dim] = s1 / l1;
+        if (n_part == 1) {
+            dst[tid] = s0 / l0;
+            dst[a.dim + tid] = s1 / l1;
+        } else {
+            float* pp = mypart + (long long)sp * (2 * (hd + 2));
+            pp[2 + tid] = s0; pp[(hd + 2) + 2 + tid] = s1;
+            if (tid == 0) { pp[0] = m0; pp[1] = l0; pp[hd + 2] = m1; pp[hd + 3] = l1; }
+        }
+    }
+    if (n_part > 1) {   // one arrival per split; the last one combines all of them in split order
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int old = atomicAdd(a.arrive + (long long)slot * a.heads + h, 1u);
+            s_last = old == (unsigned int)(n_part - 1);
+            if (s_last) a.arrive[(long long)slot * a.heads + h] = 0u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (tid < 2 * hd) {
+                const int qi = tid / hd, dd = tid - qi * hd;
+                float M = -INFINITY;
+                for (int s = s_first; s < s_end; ++s) M = fmaxf(M, __ldcg(mypart + (long long)s * (2 * (hd + 2)) + qi * (hd + 2)));
+                float Ls = 0.f, O = 0.f;
+                for (int s = s_first; s < s_end; ++s) {
+                    const float* pp = mypart + (long long)s * (2 * (hd + 2)) + qi * (hd + 2);
+                    const float ms = __ldcg(pp);
+                    const float c = ms == -INFINITY ? 0.f : expf(ms - M);
+                    Ls = fmaf(__ldcg(pp + 1), c, Ls);
+                    O = fmaf(__ldcg(pp + 2 + dd), c, O);
+                }
+                dst[qi * a.dim + dd] = O / Ls;
+            }
+        }
     }
     __syncthreads();   // sm is reused by the next work item
 }
@@ -485,7 +532,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) float sm[];
     pdl_wait();
     pdl_go();
-    attn_body(a, blockIdx.x, blockIdx.y, sm);
+    attn_body(a, blockIdx.x, blockIdx.y, blockIdx.z, sm);
 }
 
 // End of a step: the last `hs` rows of every history-carrying buffer move to its front; the position advances.
@@ -593,7 +640,8 @@ struct SmolMimi {
     unsigned char* ws = nullptr;
     bool bound = false;
     int launches = 0;
-    size_t attn_smem = 0;
+    size_t attn_smem = 0, o_part = 0, o_arrive = 0;
+    int max_splits = 1;
     // cached graph of one step
     cudaGraphExec_t graph = nullptr;
     cudaStream_t cap_stream = nullptr;
@@ -654,8 +702,12 @@ static int mimi_plan(SmolMimi* m) {
     m->o_pos = take((size_t)c.max_streams);
     m->o_upprev = take((size_t)c.max_streams * c.dim);
     m->o_err = take(4);
+    m->max_splits = (c.max_positions + kAttnChunk - 1) / kAttnChunk;
+    m->o_part = take((size_t)c.max_streams * c.n_heads * m->max_splits * 2 * (c.head_dim + 2));
+    m->o_arrive = take((size_t)c.max_streams * c.n_heads);
     m->total = o;
-    m->attn_smem = (size_t)(2 * c.head_dim + 2 * kThreads + 2 * c.max_positions) * 4;
+    m->attn_smem = (size_t)(2 * c.head_dim + 2 * kThreads + 2 * kAttnChunk) * 4;
+    m->max_splits = (c.max_positions + kAttnChunk - 1) / kAttnChunk;
     return 0;
 }
 
@@ -675,7 +727,7 @@ extern "C" int smol_mimi_create(const SmolMimiConfig* cfg, SmolMimi** out) {
     SmolMimi* m = new SmolMimi();
     m->cfg = c;
     if (mimi_plan(m) != 0) { delete m; return smol::capi_fail(SMOL_ERR_UNSUPPORTED, "mimi: too many buffers"); }
-    if (m->attn_smem > 227 * 1024) { delete m; return smol::capi_fail(SMOL_ERR_CAPACITY, "mimi: max_positions too large for the attention kernel's score buffer (about 28 000)"); }
+    if (c.max_positions > (1 << 20)) { delete m; return smol::capi_fail(SMOL_ERR_CAPACITY, "mimi: max_positions above 1 048 576"); }
     *out = m;
     return SMOL_OK;
 }
@@ -773,6 +825,7 @@ extern "C" int smol_mimi_bind(SmolMimi* m, const SmolMimiWeights* w, void* d_wor
     MCU(d2d(bo, w->conv_out.bias, 1));
     MCU(cudaGetLastError());
     MCU(cudaMemsetAsync(m->ws + m->o_err, 0, 16, st));
+    MCU(cudaMemsetAsync(m->ws + m->o_arrive, 0, (size_t)c.max_streams * c.n_heads * 4, st));
     if (m->attn_smem > 48 * 1024) MCU(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->attn_smem));
     m->g_batch = -1;
     m->bound = true;
@@ -872,6 +925,7 @@ static void mimi_program(SmolMimi* m, const int32_t* d_codes, const int32_t* d_s
             a.kv = wsf(m, m->o_kv); a.kv_layer_stride = (long long)2 * c.max_positions * c.dim; a.kv_slot_stride = a.kv_layer_stride * c.n_layers;
             a.rope = wsf(m, m->o_rope); a.pos = reinterpret_cast<const int32_t*>(m->ws + m->o_pos); a.slots = d_slots;
             a.err = reinterpret_cast<int32_t*>(m->ws + m->o_err);
+            a.part = wsf(m, m->o_part); a.arrive = reinterpret_cast<unsigned int*>(m->ws + m->o_arrive); a.max_splits = m->max_splits;
             a.layer = l; a.dim = c.dim; a.hd = c.head_dim; a.max_pos = c.max_positions; a.window = c.window; a.batch = batch; a.heads = c.n_heads;
             prog.push_back(r);
         }
@@ -956,7 +1010,7 @@ static int mimi_enqueue(SmolMimi* m, const std::vector<OpRec>& prog, cudaStream_
     for (const OpRec& r : prog) {
         switch (r.kind) {
             case OP_ROWS: MCU(launch_rows(r.row, st)); break;
-            case OP_ATTN: MCU(launch_pdl(attn_kernel, dim3(r.attn.batch, r.attn.heads), dim3(kThreads), m->attn_smem, st, r.attn)); break;
+            case OP_ATTN: MCU(launch_pdl(attn_kernel, dim3(r.attn.batch, r.attn.heads, r.attn.max_splits), dim3(kThreads), m->attn_smem, st, r.attn)); break;
             case OP_EMBED: MCU(launch_pdl(embed_kernel, dim3(r.emb.batch), dim3(256), 0, st, r.emb)); break;
             default: MCU(launch_pdl(shift_kernel, dim3(r.shift.batch, r.shift.n_bufs + 1), dim3(kThreads), 0, st, r.shift)); break;
         }

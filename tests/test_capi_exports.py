@@ -89,4 +89,4 @@ def test_mimi_create_validates_shapes_without_a_gpu():
     h2 = ctypes.c_void_p()
     assert lib.smol_mimi_create(ctypes.byref(make(head_dim=48)), ctypes.byref(h2)) == _capi.SMOL_ERR_INVALID
     assert lib.smol_mimi_create(ctypes.byref(make(max_positions=7)), ctypes.byref(h2)) == _capi.SMOL_ERR_INVALID
-    assert lib.smol_mimi_create(ctypes.byref(make(max_positions=60000)), ctypes.byref(h2)) == _capi.SMOL_ERR_CAPACITY
+    assert lib.smol_mimi_create(ctypes.byref(make(max_positions=4000000)), ctypes.byref(h2)) == _capi.SMOL_ERR_CAPACITY

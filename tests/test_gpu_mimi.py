@@ -117,6 +117,26 @@ def _shuffled_run(m, codes, perm, split):
     return torch.cat(out, dim=-1)
 
 
+def test_history_longer_than_one_attention_split_matches_the_oracle():
+    """270 frames = 540 positions: the history crosses the 512-position split of the attention kernel (two CTAs per head whose
+    partial softmaxes are combined), without a window and with one of 20 positions that slides past the first split."""
+    from oracle.mimi_oracle import MimiOracle, StreamState
+
+    gen = torch.Generator().manual_seed(13)
+    T = 270
+    codes = torch.randint(0, 2048, (1, 8, T), generator=gen)
+    for window in (0, 20):
+        orc = MimiOracle(_sd(), window=window)
+        st = StreamState()
+        with torch.no_grad():
+            want = torch.cat([orc.decode_step(codes[:, :, t:t + 1], st) for t in range(T)], dim=-1)
+        m = _model(max_streams=2, max_frames=272, window=window)
+        got = _run(m, codes)
+        _close(f"{T} frames, window {window}: all", got, want)
+        _close(f"{T} frames, window {window}: frames past position 512", got[..., 257 * 1920:], want[..., 257 * 1920:])
+        assert not m.overflowed()
+
+
 def test_a_stream_decodes_to_the_same_bits_alone_in_any_batch_slot_and_launch_mode():
     """Two kernel classes, chosen by the batch size alone: fewer than 8 streams (rows_kernel everywhere) and 8+ (the SEANet's
     many-row stages on tile_kernel, the last convolution on rowdot_kernel).  Inside a class a stream's PCM is bit-identical
