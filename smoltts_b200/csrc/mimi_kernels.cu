@@ -83,14 +83,18 @@ struct RowsSmem {
     int slot[16], t[16], b[16];   // slot, row inside the step and batch row of every staged row
 };
 
-template <int R, bool kPdl>
+// CPW weight rows per warp: 1 at streaming batch sizes; 4 from 64 rows on, where an operation is many CTAs deep and every
+// CTA pays the same latency chain -- four rows per warp reuse the staged input rows (16 FMAs per shared-memory load instead of 4)
+// and cut the CTA count by four.  A column's arithmetic (lane-interleaved sums, shuffle tree) is the same for any CPW.
+template <int R, bool kPdl, int CPW>
 __device__ __forceinline__ void rows_body(const RowOp& op, int bx, int by, RowsSmem& S) {
     constexpr int KC = kStageFloats / R;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows = op.batch * op.T;
     const int row0 = by * R;
-    const int n = bx * kWarps + warp;
-    const bool n_ok = n < op.N;
+    const int n0 = (bx * kWarps + warp) * CPW;         // first of this warp's CPW weight rows
+    const bool n_ok = n0 < op.N;
+    const int n = n0;
     if (tid < R) {   // (the slot table is constant during a step: read before the dependency wait)
         const int row = row0 + tid;
         int b = 0, t = 0, slot = -1;
@@ -102,11 +106,11 @@ __device__ __forceinline__ void rows_body(const RowOp& op, int bx, int by, RowsS
     // row into L2
     if (kPdl && n_ok && by == 0) {
         const char* wr = reinterpret_cast<const char*>(op.W + (long long)n * op.K);
-        const int lines = (op.K * 4 + 127) >> 7;
+        const int lines = (min(CPW, op.N - n) * op.K * 4 + 127) >> 7;     // (the warp's rows are contiguous)
         for (int l = lane; l < lines; l += 32) prefetch_l2(wr + ((long long)l << 7));
     }
-    constexpr int kPre = 4;
-    float4 wpre[kPre];
+    constexpr int kPre = CPW == 1 ? 4 : 0;
+    float4 wpre[kPre > 0 ? kPre : 1];
     {
         const int k0 = min(KC, op.K);
 #pragma unroll
@@ -118,9 +122,11 @@ __device__ __forceinline__ void rows_body(const RowOp& op, int bx, int by, RowsS
     }
     __syncthreads();
     if (kPdl) { pdl_wait(); pdl_go(); }
-    float acc[R];
+    float acc[CPW][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int c = 0; c < CPW; ++c)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[c][r] = 0.f;
 
     for (int kc = 0; kc < op.K; kc += KC) {
         const int kcur = min(KC, op.K - kc);
@@ -170,34 +176,43 @@ __device__ __forceinline__ void rows_body(const RowOp& op, int bx, int by, RowsS
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const float4 a = *reinterpret_cast<const float4*>(&S.As[r * KC + k4]);
-                            acc[r] = fmaf(a.x, wpre[i].x, acc[r]); acc[r] = fmaf(a.y, wpre[i].y, acc[r]);
-                            acc[r] = fmaf(a.z, wpre[i].z, acc[r]); acc[r] = fmaf(a.w, wpre[i].w, acc[r]);
+                            acc[0][r] = fmaf(a.x, wpre[i].x, acc[0][r]); acc[0][r] = fmaf(a.y, wpre[i].y, acc[0][r]);
+                            acc[0][r] = fmaf(a.z, wpre[i].z, acc[0][r]); acc[0][r] = fmaf(a.w, wpre[i].w, acc[0][r]);
                         }
                         k4 += 128;
                     }
                 }
             }
-#pragma unroll 4
+#pragma unroll(CPW == 1 ? 4 : 1)
             for (; k4 < kcur; k4 += 128) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k4));
+                float4 w[CPW];
+#pragma unroll
+                for (int c = 0; c < CPW; ++c)
+                    w[c] = (n + c < op.N) ? __ldg(reinterpret_cast<const float4*>(wrow + (long long)c * op.K + k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const float4 a = *reinterpret_cast<const float4*>(&S.As[r * KC + k4]);
-                    acc[r] = fmaf(a.x, w.x, acc[r]); acc[r] = fmaf(a.y, w.y, acc[r]);
-                    acc[r] = fmaf(a.z, w.z, acc[r]); acc[r] = fmaf(a.w, w.w, acc[r]);
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) {
+                        acc[c][r] = fmaf(a.x, w[c].x, acc[c][r]); acc[c][r] = fmaf(a.y, w[c].y, acc[c][r]);
+                        acc[c][r] = fmaf(a.z, w[c].z, acc[c][r]); acc[c][r] = fmaf(a.w, w[c].w, acc[c][r]);
+                    }
                 }
             }
         }
         __syncthreads();
     }
     // ---- reduce over the lanes; lane r finishes row r ----
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) {
+    const int n = n0 + cc;
     float mine = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const float v = warp_sum(acc[r]);
+        const float v = warp_sum(acc[cc][r]);
         if (lane == r) mine = v;
     }
-    if (n_ok && lane < R && S.slot[lane] >= 0) {
+    if (n < op.N && lane < R && S.slot[lane] >= 0) {
         const int b = S.b[lane], t = S.t[lane], slot = S.slot[lane];
         float y = mine + (op.bias ? op.bias[n % op.bias_mod] : 0.f);
         if (op.epi == EPI_UPSAMPLE) {
@@ -222,13 +237,14 @@ __device__ __forceinline__ void rows_body(const RowOp& op, int bx, int by, RowsS
             *o = y;
         }
     }
+    }
     __syncthreads();   // S is reused by the next work item
 }
 
-template <int R>
+template <int R, int CPW>
 __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
     __shared__ __align__(16) RowsSmem S;
-    rows_body<R, true>(op, blockIdx.x, blockIdx.y, S);
+    rows_body<R, true, CPW>(op, blockIdx.x, blockIdx.y, S);
 }
 
 // The same product for MANY rows (8+ streams x the 16 .. 1920 rows of a SEANet stage): a 64 x 64 output tile per CTA, K in
@@ -870,12 +886,19 @@ static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
     if (use_rowdot(op)) return launch_pdl(rowdot_kernel, dim3((op.batch * op.T + kThreads - 1) / kThreads), dim3(kThreads), 0, st, op);
     const int rows = op.batch * op.T;
     const int R = rows_R(rows);
+    static const int min_batch = [] { const char* e = getenv("SMOL_MIMI_TILE_MIN_BATCH"); return e ? atoi(e) : kTileMinBatch; }();
+    // 64+ rows (32+ streams of a two-row operation): four weight rows per warp -- the same bits, fewer and fatter CTAs
+    // (measured per step: 32 streams 1.99 -> 1.73 ms, 64 streams 3.22 -> 2.41 ms; at 8 streams 1.24 -> 1.39 ms, hence the bar)
+    if (R == 16 && op.batch >= min_batch && rows >= 64 && op.N >= 256) {
+        const dim3 grid4((op.N + 4 * kWarps - 1) / (4 * kWarps), (rows + R - 1) / R);
+        return launch_pdl(rows_kernel<16, 4>, grid4, dim3(kThreads), 0, st, op);
+    }
     const dim3 grid((op.N + kWarps - 1) / kWarps, (rows + R - 1) / R);
     switch (R) {
-        case 2: return launch_pdl(rows_kernel<2>, grid, dim3(kThreads), 0, st, op);
-        case 4: return launch_pdl(rows_kernel<4>, grid, dim3(kThreads), 0, st, op);
-        case 8: return launch_pdl(rows_kernel<8>, grid, dim3(kThreads), 0, st, op);
-        default: return launch_pdl(rows_kernel<16>, grid, dim3(kThreads), 0, st, op);
+        case 2: return launch_pdl(rows_kernel<2, 1>, grid, dim3(kThreads), 0, st, op);
+        case 4: return launch_pdl(rows_kernel<4, 1>, grid, dim3(kThreads), 0, st, op);
+        case 8: return launch_pdl(rows_kernel<8, 1>, grid, dim3(kThreads), 0, st, op);
+        default: return launch_pdl(rows_kernel<16, 1>, grid, dim3(kThreads), 0, st, op);
     }
 }
 

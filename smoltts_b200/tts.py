@@ -76,6 +76,26 @@ class SmolTTS:
         codes = generate_batch(self.lm, prompts, self.settings, fixed_frames=fixed_frames)   # list of [N, T_b]
         return self.decode_codes(codes)
 
+    def serve(self, inputs: Sequence[str], voices: Optional[Sequence[str]] = None, slots: int = 8, chunk: int = 16,
+              max_prompt: int = 512) -> Iterator[tuple]:
+        """Continuous batching with audio out (replaces the one-blocking-call-per-request loop of server/tts_core.py:28-47):
+        the utterances share ``slots`` rows of one resident decode batch (``ContinuousBatcher``); whatever retires at a chunk
+        boundary goes through the codec together, as one batch of streams.  Yields ``(index, pcm)`` in retirement order."""
+        from .serving import ContinuousBatcher
+
+        voices = list(voices) if voices is not None else ["heart"] * len(inputs)
+        cb = ContinuousBatcher(self.lm, self.settings, slots=slots, max_prompt=max_prompt, chunk=chunk)
+        try:
+            uid_to_index = {cb.submit(self._get_prompt(t, v)[0]): i for i, (t, v) in enumerate(zip(inputs, voices))}
+            while cb.pending or cb.running:
+                done = cb.step_chunk()
+                for g0 in range(0, len(done), self.codec_full.max_streams):
+                    group = done[g0:g0 + self.codec_full.max_streams]
+                    for (uid, _), pcm in zip(group, self.decode_codes([c for _, c in group])):
+                        yield uid_to_index[uid], pcm
+        finally:
+            cb.close()
+
     def decode_codes(self, codes: Sequence[torch.Tensor]) -> List[np.ndarray]:
         """Ragged code sequences [N, T_b] -> PCM, all streams stepping together while they last."""
         codec = self.codec_full

@@ -68,3 +68,18 @@ def test_batch_synthesis_equals_one_utterance_at_a_time():
         solo = tts.decode_codes([codes[b]])[0]
         assert outs[b].shape == (codes[b].shape[-1] * 1920,)
         assert np.array_equal(outs[b], solo), f"utterance {b}: PCM differs between the batch of streams and a stream alone"
+
+
+def test_serving_with_continuous_batching_yields_the_same_audio():
+    """SmolTTS.serve: 7 utterances through 3 decode slots (admitted late, retired early) and then the codec, against
+    synthesize_batch of the same texts -- the same PCM, bit for bit (greedy decoding, both code paths keep an utterance's codes
+    and every codec call here stays below 8 streams, one kernel class)."""
+    tts, _ = _tts()
+    texts = [f"Utterance number {i}, of some length {'.' * (3 * i)}" for i in range(7)]
+    voices = ["heart", "bella", "nova", "sky", "sarah", "michael", "liam"]
+    got = dict(tts.serve(texts, voices, slots=3, chunk=4, max_prompt=128))
+    assert sorted(got) == list(range(7))
+    want = tts.synthesize_batch(texts[:4], voices[:4]) + tts.synthesize_batch(texts[4:], voices[4:])
+    for i in range(7):
+        assert got[i].shape == want[i].shape, (i, got[i].shape, want[i].shape)
+        assert np.array_equal(got[i], want[i]), f"utterance {i}: served audio differs from batch synthesis"
