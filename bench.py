@@ -15,7 +15,8 @@ codes, and for N > 1 the host-side gather of every rank's codes on rank 0), for 
 The same line carries ``"configs"``: the other BASELINE.json configurations measured the same way in the same run
 (configs[2] bs=64 sampled, configs[3] bs=256 per GPU at two prompt lengths, configs[4] long-form bs=32 at the
 workload's mean context), each with its own ``roofline`` and ``e2e``, and two entries for the step AFTER the path
-(the Mimi streaming decoder: ``mimi_bs1``, ``mimi_bs64`` -- codes to PCM, frames/s).  Under ``--gpus N > 1`` every entry is the
+(the Mimi streaming decoder: ``mimi_bs1``, ``mimi_bs64`` -- codes to PCM, frames/s) and one for the
+reference's streaming loop through both engines (``tts_stream_bs1``: text to PCM chunks, one frame per host iteration).  Under ``--gpus N > 1`` every entry is the
 per-GPU batch sharded over the N ranks (weak scaling), so the bs=256/GPU 1 -> 8 curve is in the driver's records.
 
 Roofline: algorithmic bytes (unique weight bytes + KV bytes of the mean context) or flops per launch over
@@ -564,6 +565,79 @@ def measure_mimi(key: str, batch: int, frames: int, args, steps: int, warmup: in
     return res
 
 
+def measure_tts_stream(args, steps: int, warmup: int, ctx, frames: int = 128) -> dict:
+    """The reference's streaming loop end to end (smoltts_mlx/__init__.py:85-95) at one utterance: prompt -> one frame per
+    SingleBatchGenerator.__next__ (one launch of the data-flow kernel, ids read back by the host) -> MimiModel.decode_step ->
+    the 80 ms PCM chunk on the host.  There is no device-resident form of this loop: value == e2e."""
+    import torch
+
+    from smoltts_b200 import GenerationSettings, MimiModel, PromptEncoder, RQTransformer, SmolTTS, byte_level_tokenizer, named_config
+
+    dist, rank, world, local = ctx["dist"], ctx["rank"], ctx["world"], ctx["local"]
+    cfg = named_config(args.model)
+    lm = RQTransformer(cfg, max_batch=1, max_seq_len=512 + frames)
+    lm.load_state_dict(ctx["weights"](args.model))
+    codec = MimiModel(max_streams=1, max_frames=frames + 8)
+    codec.load_state_dict(ctx["mimi_weights"]())
+    enc = PromptEncoder.from_model(byte_level_tokenizer(cfg.codebook_size), lm)
+    tts = SmolTTS(lm, enc, codec, settings=GenerationSettings(default_temp=0.0, default_fast_temp=0.0, max_new_tokens=frames - 1))
+    text = "The quick brown fox jumps over the lazy dog. " * 4          # 180 bytes
+
+    from smoltts_b200 import SingleBatchGenerator
+
+    def run():
+        # the body of SmolTTS.stream, with the frames counted: random-init weights emit non-audio ids now and then (they
+        # skip the codec, as in the reference) and may hit <|im_end|> early
+        n_gen, n_pcm = 0, 0
+        gen = SingleBatchGenerator(tts.lm, tts._get_prompt(text, "nova"), tts.settings)
+        cache = codec.make_cache()
+        for frame in gen:
+            n_gen += 1
+            if frame.audio_codes is not None:
+                codec.decode_step(frame.audio_codes, cache).flatten().cpu().numpy()
+                n_pcm += 1
+        codec.release_cache(cache)
+        return n_gen, n_pcm
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(warmup, 2))):
+        n_gen, n_pcm = run()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        n_gen, n_pcm = run()
+    torch.cuda.synchronize()
+    frames = n_gen
+    ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=lm.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = steps * frames * world / (ms * 1e-3)
+    res = {
+        "key": "tts_stream_bs1", "workload": f"SmolTTS.stream: {args.model} greedy + Mimi decoder, one utterance, {frames} frames per step, one frame per host iteration",
+        "note": "the reference's streaming loop (generator.__next__ -> codec.decode_step -> numpy chunk), prefill included; "
+                f"{n_pcm} of {frames} frames were audio frames and went through the codec",
+        "value": value, "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "us_per_frame_step": 1e3 * ms / (steps * frames),
+        "roofline": None,
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": frames * (cfg.n_rows * 4) + n_pcm * 1920 * 4, "steps": steps},
+        "clocks": clocks, "gpu_launches": steps * (frames * lm.get_option("ll_ready") + n_pcm * codec.launches_per_step),
+        "launch_mode": "one data-flow kernel launch per frame + 57 codec launches per audio frame (CUDA-graph replay)",
+        "realtime_factor": value / 12.5,
+    }
+    del tts, lm, codec
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
 
@@ -612,6 +686,8 @@ def run_ours(args):
         for key, b, f in (("mimi_bs1", 1, 256), ("mimi_bs64", 64, 32)):     # the step after the path: codes -> PCM
             if wanted is None or key in wanted:
                 entries.append(measure_mimi(key, b, f, args, max(1, min(args.steps, args.config_steps)), 3, ctx))
+        if (wanted is None or "tts_stream_bs1" in wanted) and args.model == "smoltts_byte_150m":
+            entries.append(measure_tts_stream(args, max(1, min(args.steps, 3)), 2, ctx))
 
     if rank == 0:
         cfg_pub = dict(main["config"])  # identical in both arms (ours / --impl reference): the configuration measured

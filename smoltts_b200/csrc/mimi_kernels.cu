@@ -10,11 +10,14 @@
 // once: weight-streaming "row" products.  ONE kernel shape carries them all (rows_kernel): a CTA stages up to 16 input
 // rows in shared memory -- gathered straight from the producer's buffer, im2col of a causal convolution = a contiguous run
 // of (kernel x channels) floats that begins in the carried history rows; ELU or LayerNorm applied while staging -- and every
-// warp streams one weight row with 16-byte loads against all staged rows, finishing with a shuffle reduction and a fused
-// epilogue (bias, GELU, layer scale + residual, residual, or the upsampler).  Transposed convolutions (kernel = 2 stride)
-// are the same product with K = (previous | current input row) x channels and N = (phase, channel): their outputs land
-// contiguously.  Everything a stream carries (convolution history rows, the upsampler's previous embedding, KV cache,
-// position) lives in per-slot arenas of the caller's workspace; a step is 57 launches, replayed as one CUDA graph.
+// warp streams one weight row (four from 64 rows on) with 16-byte loads against all staged rows, finishing with a shuffle
+// reduction and a fused epilogue (bias, GELU, layer scale + residual, residual, or the upsampler).  Transposed convolutions
+// (kernel = 2 stride) are the same product with K = (previous | current input row) x channels and N = (phase, channel): their
+// outputs land contiguously.  From 8 streams on the SEANet's many-row stages run as 64 x 64 register tiles (tile_kernel) and
+// the one-channel last convolution as one thread per sample (rowdot_kernel).  Attention: one CTA per (stream, head, split
+// of 512 cached positions), partial softmaxes combined in split order.  Everything a stream carries (convolution history
+// rows, the upsampler's previous embedding, KV cache, position) lives in per-slot arenas of the caller's workspace; a step is
+// a program of 57 operations, one launch each, replayed as one CUDA graph.
 //
 // Reference map (C = mlx_inference/src/smoltts_mlx/codec/): RVQ decode C/rvq.py:118-130,171-186; upsample C/conv.py:225-282;
 // transformer C/transformer.py:36-150; Conv1d.step C/conv.py:133-160; ConvTranspose1d.step C/conv.py:207-221; residual
