@@ -662,11 +662,14 @@ struct SmolMimi {
     size_t attn_smem = 0, o_part = 0, o_arrive = 0;
     int max_splits = 1;
     // cached graph of one step
-    cudaGraphExec_t graph = nullptr;
     cudaStream_t cap_stream = nullptr;
-    const void* g_codes = nullptr; const void* g_slots = nullptr; const void* g_pcm = nullptr; int g_batch = -1;
-    std::vector<OpRec> prog;   // the step's program (rebuilt when the batch or a pointer changes)
+    // captured steps, keyed by (batch, buffers): a serving loop alternates between a few batch sizes
+    struct Step { const void* codes; const void* slots; const void* pcm; int batch; std::vector<OpRec> prog; cudaGraphExec_t graph; uint64_t used; };
+    std::vector<Step> steps;
+    uint64_t tick = 0;
+    void drop_steps() { for (Step& s : steps) if (s.graph) cudaGraphExecDestroy(s.graph); steps.clear(); }
 };
+constexpr size_t kMaxSteps = 16;
 
 static size_t al(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -753,7 +756,7 @@ extern "C" int smol_mimi_create(const SmolMimiConfig* cfg, SmolMimi** out) {
 
 extern "C" void smol_mimi_destroy(SmolMimi* m) {
     if (!m) return;
-    if (m->graph) cudaGraphExecDestroy(m->graph);
+    m->drop_steps();
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     delete m;
 }
@@ -806,7 +809,7 @@ extern "C" int smol_mimi_bind(SmolMimi* m, const SmolMimiWeights* w, void* d_wor
              need(w->res_conv2[i].weight) && need(w->res_conv2[i].bias);
     if (!ok) return smol::capi_fail(SMOL_ERR_INVALID, "smol_mimi_bind: a weight pointer is null");
     m->ws = reinterpret_cast<unsigned char*>(d_workspace);
-    if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; m->g_batch = -1; }
+    m->drop_steps();
     const size_t f4 = sizeof(float);
     auto d2d = [&](size_t off, const float* src, size_t floats) { return cudaMemcpyAsync(m->ws + off, src, floats * f4, cudaMemcpyDeviceToDevice, st); };
     for (int i = 0; i < c.n_q; ++i)
@@ -846,7 +849,6 @@ extern "C" int smol_mimi_bind(SmolMimi* m, const SmolMimiWeights* w, void* d_wor
     MCU(cudaMemsetAsync(m->ws + m->o_err, 0, 16, st));
     MCU(cudaMemsetAsync(m->ws + m->o_arrive, 0, (size_t)c.max_streams * c.n_heads * 4, st));
     if (m->attn_smem > 48 * 1024) MCU(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->attn_smem));
-    m->g_batch = -1;
     m->bound = true;
     return smol_mimi_reset(m, nullptr, c.max_streams, stream);
 }
@@ -1055,28 +1057,37 @@ extern "C" int smol_mimi_decode_step(SmolMimi* m, const int32_t* d_codes, const 
     // little inside a replayed graph (510 -> 536): on for the former, off for the latter; SMOL_MIMI_PDL=0/1 forces it
     const char* pe = getenv("SMOL_MIMI_PDL");
     g_pdl = pe ? pe[0] != '0' : mode == 0;
-    const bool same = m->g_codes == d_codes && m->g_slots == d_slots && m->g_pcm == d_pcm && m->g_batch == batch;
-    if (!same) {
-        mimi_program(m, d_codes, d_slots, batch, d_pcm, m->prog);
-        if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
-        m->g_codes = d_codes; m->g_slots = d_slots; m->g_pcm = d_pcm; m->g_batch = batch;
+    SmolMimi::Step* step = nullptr;
+    for (SmolMimi::Step& c : m->steps)
+        if (c.codes == d_codes && c.slots == d_slots && c.pcm == d_pcm && c.batch == batch) { step = &c; break; }
+    if (!step) {
+        if (m->steps.size() >= kMaxSteps) {   // evict the least recently used
+            size_t lru = 0;
+            for (size_t i = 1; i < m->steps.size(); ++i) if (m->steps[i].used < m->steps[lru].used) lru = i;
+            if (m->steps[lru].graph) cudaGraphExecDestroy(m->steps[lru].graph);
+            m->steps.erase(m->steps.begin() + lru);
+        }
+        m->steps.push_back(SmolMimi::Step{d_codes, d_slots, d_pcm, batch, {}, nullptr, 0});
+        step = &m->steps.back();
+        mimi_program(m, d_codes, d_slots, batch, d_pcm, step->prog);
     }
+    step->used = ++m->tick;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     const bool capturing = st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
-    if (mode == 0 || capturing) return mimi_enqueue(m, m->prog, st);   // (capturing: become part of the caller's graph)
-    if (!m->graph) {
+    if (mode == 0 || capturing) return mimi_enqueue(m, step->prog, st);   // (capturing: become part of the caller's graph)
+    if (!step->graph) {
         if (!m->cap_stream) MCU(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
         MCU(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = mimi_enqueue(m, m->prog, m->cap_stream);
+        const int rc = mimi_enqueue(m, step->prog, m->cap_stream);
         cudaGraph_t g = nullptr;
         const cudaError_t ee = cudaStreamEndCapture(m->cap_stream, &g);
         if (rc != SMOL_OK) { if (g) cudaGraphDestroy(g); return rc; }
         MCU(ee);
-        const cudaError_t ei = cudaGraphInstantiate(&m->graph, g, 0);
+        const cudaError_t ei = cudaGraphInstantiate(&step->graph, g, 0);
         cudaGraphDestroy(g);
         MCU(ei);
     }
-    MCU(cudaGraphLaunch(m->graph, st));
+    MCU(cudaGraphLaunch(step->graph, st));
     return SMOL_OK;
 }
 
