@@ -180,3 +180,33 @@ def test_slot_reuse_and_capacity():
         m.make_cache()
     m.release_cache(c)
     assert not m.overflowed()
+
+
+def test_a_differently_shaped_codec_matches_the_oracle():
+    """Nothing in the kernels is specific to kyutai/mimi's sizes: a small codec (4 codebooks of 64 x 32, d = 128, 2 heads, 3
+    transformer layers, SEANet 8 filters with ratios 4, 3, kernels 5 / 3 / 5: 24 samples per frame, channel counts down to 4)
+    against the oracle, in both kernel classes (2 streams; 9 streams: tile_kernel / rowdot_kernel where they apply)."""
+    from oracle.mimi_oracle import MimiDims, MimiOracle, StreamState
+    from smoltts_b200.mimi import MimiConfig, MimiModel, MimiTransformerConfig, RVQConfig, SeanetConfig
+    from smoltts_b200.synth import make_mimi_state_dict
+
+    sd = make_mimi_state_dict(5, n_q=4, codebook_size=64, codebook_dim=32, dim=128, n_layers=3, ffn=256, n_filters=8, ratios=(4, 3),
+                              kernel=5, res_kernel=3, last_kernel=5)
+    dims = MimiDims(n_q=4, codebook_size=64, codebook_dim=32, dim=128, n_layers=3, n_heads=2, head_dim=64, ffn=256, n_filters=8,
+                    ratios=(4, 3), kernel=5, res_kernel=3, last_kernel=5)
+    cfg = MimiConfig(seanet=SeanetConfig(dimension=128, n_filters=8, kernel_size=5, residual_kernel_size=3, last_kernel_size=5, ratios=[4, 3]),
+                     transformer=MimiTransformerConfig(d_model=128, num_heads=2, head_dim=64, num_layers=3, dim_feedforward=256),
+                     rvq=RVQConfig(codebook_size=64, codebook_dim=32, num_quantizers=4, hidden_dim=128))
+    gen = torch.Generator().manual_seed(17)
+    T = 6
+    for B, carry in ((2, False), (9, True)):
+        codes = torch.randint(0, 64, (B, 4, T), generator=gen)
+        orc, st = MimiOracle(sd, dims), StreamState()
+        with torch.no_grad():
+            want = torch.cat([orc.decode_step(codes[:, :, t:t + 1], st, carry=carry) for t in range(T)], dim=-1)
+        m = MimiModel(cfg, num_codebooks=4, max_streams=B, max_frames=8, upsample_carry=carry)
+        m.load_state_dict(sd)
+        assert m.samples_per_frame == 24
+        got = _run(m, codes)
+        assert got.shape == (B, 1, T * 24)
+        _close(f"small codec, {B} streams, carry {carry}", got, want)
