@@ -108,6 +108,8 @@ def parse_args():
                     "'none'; or a comma list of config3,config4i,config4ii,config5")
     ap.add_argument("--config-steps", type=int, default=5, help="timed steps of each entry of \"configs\" (3 warm-up steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stream-lm-ctas", type=int, default=96, help="tts_stream_bs1: CTAs of the decode kernel while the codec runs beside it")
+    ap.add_argument("--no-stream-overlap", action="store_true", help="tts_stream_bs1: codec step after the decode step instead of beside the next one")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (0 = %d)" % CPU_SAMPLE_FRAMES)
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (smol_set_option), repeatable")
     return ap.parse_args()
@@ -583,21 +585,13 @@ def measure_tts_stream(args, steps: int, warmup: int, ctx, frames: int = 128) ->
     tts = SmolTTS(lm, enc, codec, settings=GenerationSettings(default_temp=0.0, default_fast_temp=0.0, max_new_tokens=frames - 1))
     text = "The quick brown fox jumps over the lazy dog. " * 4          # 180 bytes
 
-    from smoltts_b200 import SingleBatchGenerator
-
     def run():
-        # the body of SmolTTS.stream, with the frames counted: random-init weights emit non-audio ids now and then (they
-        # skip the codec, as in the reference) and may hit <|im_end|> early
-        n_gen, n_pcm = 0, 0
-        gen = SingleBatchGenerator(tts.lm, tts._get_prompt(text, "nova"), tts.settings)
-        cache = codec.make_cache()
-        for frame in gen:
-            n_gen += 1
-            if frame.audio_codes is not None:
-                codec.decode_step(frame.audio_codes, cache).flatten().cpu().numpy()
-                n_pcm += 1
-        codec.release_cache(cache)
-        return n_gen, n_pcm
+        # random-init weights emit non-audio ids now and then (they skip the codec, as in the reference) and may hit
+        # <|im_end|> early: SmolTTS.stream reports what it generated
+        st = {}
+        for chunk in tts.stream(text, "nova", overlap=not args.no_stream_overlap, lm_ctas=args.stream_lm_ctas, stats=st):
+            pass
+        return st["frames"], st["audio_frames"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -630,7 +624,8 @@ def measure_tts_stream(args, steps: int, warmup: int, ctx, frames: int = 128) ->
         "roofline": None,
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": frames * (cfg.n_rows * 4) + n_pcm * 1920 * 4, "steps": steps},
         "clocks": clocks, "gpu_launches": steps * (frames * lm.get_option("ll_ready") + n_pcm * codec.launches_per_step),
-        "launch_mode": "one data-flow kernel launch per frame + 57 codec launches per audio frame (CUDA-graph replay)",
+        "launch_mode": "one data-flow kernel launch per frame + 57 codec launches per audio frame (CUDA-graph replay)"
+                       + ("" if args.no_stream_overlap else "; the codec step of frame t on a side stream beside the decode step of frame t + 1 (96 / 52 SMs)"),
         "realtime_factor": value / 12.5,
     }
     del tts, lm, codec

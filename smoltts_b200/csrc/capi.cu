@@ -831,6 +831,7 @@ int64_t smol_get_option(const SmolModel* m, const char* name) {
     if (!m || !name) return -1;
     if (!std::strcmp(name, "mode")) return m->mode;
     if (!std::strcmp(name, "n_ctas")) return m->n_ctas;
+    if (!std::strcmp(name, "n_ctas_override")) return m->n_ctas_override;
     if (!std::strcmp(name, "n_sms")) return m->n_sms;
     if (!std::strcmp(name, "smem_bytes")) return (int64_t)m->smem[1];
     if (!std::strcmp(name, "tc_min_batch")) return m->tc_min_batch;

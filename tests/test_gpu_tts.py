@@ -51,6 +51,10 @@ def test_call_and_stream_follow_the_two_codec_rules_of_the_reference():
     for t, (c, w) in enumerate(zip(chunks, want_stream)):
         assert np.abs(c - w).max() <= 1e-4 * np.abs(np.concatenate(want_stream)).max(), f"chunk {t}"
     assert len(tts.codec._free) == tts.codec.max_streams, "stream() must give its codec slot back"
+    st = {}
+    plain = list(tts.stream(text, voice, overlap=False, stats=st))      # codec step after the decode step instead of beside the next
+    assert st["audio_frames"] == T and len(plain) == T and all(np.array_equal(a, b) for a, b in zip(plain, chunks))
+    assert tts.lm.get_option("n_ctas_override") == 0, "stream() must restore the decode kernel's grid"
 
 
 def test_batch_synthesis_equals_one_utterance_at_a_time():
