@@ -85,8 +85,8 @@ class SingleBatchGenerator:
         codes_tensor = vq.view(1, -1, 1)
         audio = None
         if tc.semantic_end_id is not None and tc.semantic_start_id <= slow <= tc.semantic_end_id:
-            arr = host[1:] if cfg.duplicate_code_0 else [slow - tc.semantic_start_id, *host[1:]]
-            audio = torch.tensor(arr, dtype=torch.int32, device=model.device).view(1, -1, 1)
+            # (built from the device copy of the column: no host -> device copy per frame on the streaming path)
+            audio = (vq[1:] if cfg.duplicate_code_0 else torch.cat([vq[0:1] - tc.semantic_start_id, vq[1:]])).view(1, -1, 1)
         self.input_pos += 1
         if self.audio_only and slow == tc.im_end_id:
             self.prompt = None
