@@ -543,7 +543,10 @@ def measure_mimi(key: str, batch: int, frames: int, args, steps: int, warmup: in
         "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src, "traffic": None,
                      "kernel": "smol::mimi::rows_kernel (weight-streaming row products, fp32 FMA)",
                      "algorithmic_bytes_per_launch": wbytes + kv,
-                     "bytes_model": "packed fp32 weights of the decode half once per decode_step + KV cache read/written"},
+                     "bytes_model": "packed fp32 weights of the decode half once per decode_step + KV cache read/written",
+                     "fp32_tflops_achieved": batch * m.flops_per_frame() / (us_step * 1e-6) / 1e12,
+                     "fp32_note": "fp32 FMA on CUDA cores (the reference's precision); at 64 streams this, not HBM, is the nearer roof "
+                                  "(B200 nominal ~75 TFLOP/s fp32 non-tensor)"},
         "e2e": {"value": steps * frames * batch * world / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frames * batch * 8 * 4,
                 "d2h_bytes_per_step": frames * batch * m.samples_per_frame * 4, "steps": steps},
         "clocks": clocks, "gpu_launches": steps * frames * m.launches_per_step, "launch_mode": "57 launches per decode_step, CUDA-graph replay",

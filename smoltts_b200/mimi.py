@@ -294,6 +294,21 @@ class MimiModel:
                 self.release_cache(c)
         return out
 
+    def flops_per_frame(self) -> int:
+        """Multiply-adds x 2 of one decode_step of one stream, attention excluded (it grows with the history)."""
+        c, s = self.config, self.config.seanet
+        D, F = c.transformer.d_model, c.transformer.dim_feedforward
+        macs = 2 * c.rvq.codebook_dim * D                                         # output projections
+        macs += 2 * c.transformer.num_layers * (4 * D * D + 2 * D * F)            # two positions per frame
+        ch, T = s.n_filters * 2 ** len(s.ratios), 2
+        macs += T * s.kernel_size * D * ch
+        for r in s.ratios:
+            macs += T * 2 * ch * (r * ch // 2)                                    # transposed convolution: 2 taps per output
+            T, ch = T * r, ch // 2
+            macs += T * (s.residual_kernel_size * ch * (ch // 2) + (ch // 2) * ch)
+        macs += T * s.last_kernel_size * ch
+        return 2 * macs
+
     # ---- test / profiling hooks -----------------------------------------------------------------------------------------
     def _base(self) -> int:
         return (self._ws.data_ptr() + 255) // 256 * 256
