@@ -124,6 +124,7 @@ class _Slot:
     uid: int
     budget: int
     pages: List[int]
+    emitted: int = 0         # frames already handed out by step_chunk_stream
 
 
 class ContinuousBatcher:
@@ -312,6 +313,40 @@ class ContinuousBatcher:
         done = self._retire()
         self.stats["frames_decoded"] += n_run * self.chunk
         return done
+
+    def step_chunk_stream(self) -> List[Tuple[int, torch.Tensor, bool]]:
+        """``step_chunk`` for streaming consumers: ``(uid, codes of the frames this utterance emitted in the chunk, done)`` for
+        every sequence that ran -- the same columns ``step_chunk`` / ``run`` hand out at retirement, a chunk at a time."""
+        self._admit()
+        n_run = self.running
+        if n_run == 0:
+            return []
+        _capi.check(self.model.lib.smol_decode_frames(self.model._h, C.byref(self.c), self.slots, C.byref(self.sampling),
+                                                      self.chunk, self.model._stream()))
+        self.stats["chunks"] += 1
+        self.stats["slot_frames"] += self.slots * self.chunk
+        self.stats["frames_decoded"] += n_run * self.chunk
+        fin = self.finished.cpu().tolist()
+        steps = self.step.cpu().tolist()
+        out: List[Tuple[int, torch.Tensor, bool]] = []
+        gone: List[int] = []
+        for b, slot in enumerate(self._active):
+            if slot is None:
+                continue
+            n = min(steps[b], slot.budget)
+            done = bool(fin[b]) or steps[b] >= slot.budget
+            out.append((slot.uid, self._postprocess(self.out_codes[b, slot.emitted:n].cpu()), done))
+            slot.emitted = n
+            if done:
+                self.model.free_pages(slot.pages)
+                self._active[b] = None
+                gone.append(b)
+        if gone:
+            idx = torch.tensor(gone, device=self.model.device)
+            self.finished[idx] = 1
+            self.block_table[idx] = self._scratch[0]
+            self.stats["retired"] += len(gone)
+        return out
 
     def run(self) -> Iterator[Tuple[int, torch.Tensor]]:
         """Decode until the queue and the slots are empty; yields ``(uid, codes)`` as utterances retire."""

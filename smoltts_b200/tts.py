@@ -135,14 +135,47 @@ class SmolTTS:
         finally:
             cb.close()
 
-    def decode_codes(self, codes: Sequence[torch.Tensor]) -> List[np.ndarray]:
-        """Ragged code sequences [N, T_b] -> PCM, all streams stepping together while they last."""
+    def serve_stream(self, inputs: Sequence[str], voices: Optional[Sequence[str]] = None, slots: int = 8, chunk: int = 16,
+                     max_prompt: int = 512) -> Iterator[tuple]:
+        """``serve`` with audio as it is generated: every utterance in a decode slot owns a codec stream, and after each chunk
+        of ``chunk`` frames the new frames of all running utterances go through the codec together.  Yields ``(index, pcm of
+        the chunk, done)``; the chunks of an utterance concatenate to what ``serve`` / ``synthesize_batch`` return for it."""
+        from .serving import ContinuousBatcher
+
+        codec = self.codec_full
+        if slots > codec.max_streams:
+            raise ValueError(f"serve_stream: {slots} slots, the codec was built for {codec.max_streams} streams")
+        voices = list(voices) if voices is not None else ["heart"] * len(inputs)
+        cb = ContinuousBatcher(self.lm, self.settings, slots=slots, max_prompt=max_prompt, chunk=chunk)
+        caches: dict = {}
+        try:
+            uid_to_index = {cb.submit(self._get_prompt(t, v)[0]): i for i, (t, v) in enumerate(zip(inputs, voices))}
+            while cb.pending or cb.running:
+                items = cb.step_chunk_stream()
+                live = [(uid, codes) for uid, codes, _ in items if codes.shape[-1] > 0]
+                for uid, _ in live:
+                    if uid not in caches:
+                        caches[uid] = codec.make_cache()
+                pcms = dict(zip((u for u, _ in live), self.decode_codes([c for _, c in live], [caches[u] for u, _ in live]))) if live else {}
+                for uid, codes, done in items:
+                    if done and uid in caches:
+                        codec.release_cache(caches.pop(uid))
+                    yield uid_to_index[uid], pcms.get(uid, np.zeros(0, dtype=np.float32)), done
+        finally:
+            for c in caches.values():
+                codec.release_cache(c)
+            cb.close()
+
+    def decode_codes(self, codes: Sequence[torch.Tensor], caches: Optional[Sequence] = None) -> List[np.ndarray]:
+        """Ragged code sequences [N, T_b] -> PCM, all streams stepping together while they last (fresh codec streams, or the
+        given ones continued)."""
         codec = self.codec_full
         B = len(codes)
         if B > codec.max_streams:
             raise ValueError(f"decode_codes: {B} utterances, the codec was built for {codec.max_streams} streams")
         lens = [int(c.shape[-1]) for c in codes]
-        caches = [codec.make_cache() for _ in range(B)]
+        own = caches is None
+        caches = [codec.make_cache() for _ in range(B)] if own else list(caches)
         spf = codec.samples_per_frame
         outs = [torch.empty(n * spf, dtype=torch.float32, device=codec.device) for n in lens]
         order = sorted(range(B), key=lambda b: -lens[b])          # live streams are always a prefix of this order
@@ -153,6 +186,7 @@ class SmolTTS:
             pcm = codec.decode_step(frame, [caches[b] for b in live])
             for i, b in enumerate(live):
                 outs[b][t * spf:(t + 1) * spf] = pcm[i, 0]
-        for c in caches:
-            codec.release_cache(c)
+        if own:
+            for c in caches:
+                codec.release_cache(c)
         return [o.cpu().numpy() for o in outs]

@@ -87,3 +87,26 @@ def test_serving_with_continuous_batching_yields_the_same_audio():
     for i in range(7):
         assert got[i].shape == want[i].shape, (i, got[i].shape, want[i].shape)
         assert np.array_equal(got[i], want[i]), f"utterance {i}: served audio differs from batch synthesis"
+
+
+def test_streamed_serving_chunks_concatenate_to_the_served_audio():
+    """SmolTTS.serve_stream: a codec stream per decode slot, audio handed out after every chunk of 4 frames; the chunks of an
+    utterance concatenate to what serve / synthesize_batch return for it, bit for bit."""
+    tts, _ = _tts()
+    texts = [f"Streamed utterance {i} {'!' * i}" for i in range(5)]
+    voices = ["heart", "nova", "sky", "liam", "emma"]
+    parts, finished = {i: [] for i in range(5)}, set()
+    n_items = 0
+    for i, pcm, done in tts.serve_stream(texts, voices, slots=3, chunk=4, max_prompt=128):
+        assert i not in finished, "audio after an utterance was reported done"
+        parts[i].append(pcm)
+        n_items += 1
+        if done:
+            finished.add(i)
+    assert finished == set(range(5)) and n_items > 5, "every utterance must finish, in more than one chunk"
+    want = tts.synthesize_batch(texts[:3], voices[:3]) + tts.synthesize_batch(texts[3:], voices[3:])
+    for i in range(5):
+        got = np.concatenate(parts[i]) if parts[i] else np.zeros(0, dtype=np.float32)
+        assert got.shape == want[i].shape, (i, got.shape, want[i].shape)
+        assert np.array_equal(got, want[i]), f"utterance {i}: streamed chunks differ from batch synthesis"
+    assert len(tts.codec_full._free) == tts.codec_full.max_streams, "serve_stream must give its codec slots back"
