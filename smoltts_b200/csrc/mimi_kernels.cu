@@ -1136,10 +1136,12 @@ extern "C" int smol_mimi_decode_step(SmolMimi* m, const int32_t* d_codes, const 
     if (batch < 1 || batch > m->cfg.max_streams) return smol::capi_fail(SMOL_ERR_CAPACITY, "smol_mimi_decode_step: batch outside 1 .. max_streams");
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = m->cfg.use_graph;   // 0: one launch per operation; 1: those launches replayed as a CUDA graph
-    // programmatic dependent launch pays for plain stream launches (632 -> 549 us per step at one stream) and costs a
-    // little inside a replayed graph (510 -> 536): on for the former, off for the latter; SMOL_MIMI_PDL=0/1 forces it
+    // programmatic dependent launch: every kernel fetches its first weights and prefetches its rows into L2 before the
+    // dependency wait.  Measured per step at one stream: plain launches 632 -> 549 us; inside the replayed graph 462 -> 434 us
+    // with the final kernels (an earlier, heavier kernel prologue had made it 510 -> 536); at 8 / 64 streams it costs 4 - 5 %
+    // inside the graph (1.23 -> 1.28 ms, 2.40 -> 2.52 ms), so there it is off; SMOL_MIMI_PDL=0/1 forces it
     const char* pe = getenv("SMOL_MIMI_PDL");
-    g_pdl = pe ? pe[0] != '0' : mode == 0;
+    g_pdl = pe ? pe[0] != '0' : (mode == 0 || batch < kTileMinBatch);
     SmolMimi::Step* step = nullptr;
     for (SmolMimi::Step& c : m->steps)
         if (c.codes == d_codes && c.slots == d_slots && c.pcm == d_pcm && c.batch == batch) { step = &c; break; }
