@@ -974,10 +974,11 @@ static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
     if (use_rowdot(op)) return launch_pdl(rowdot_kernel, dim3((op.batch * op.T + kThreads - 1) / kThreads), dim3(kThreads), 0, st, op);
     const int rows = op.batch * op.T;
     const int R = rows_R(rows);
-    static const int min_batch = [] { const char* e = getenv("SMOL_MIMI_TILE_MIN_BATCH"); return e ? atoi(e) : kTileMinBatch; }();
-    // 64+ rows (32+ streams of a two-row operation): four weight rows per warp -- the same bits, fewer and fatter CTAs
-    // (measured per step: 32 streams 1.99 -> 1.73 ms, 64 streams 3.22 -> 2.41 ms; at 8 streams 1.24 -> 1.39 ms, hence the bar)
-    if (R == 16 && op.batch >= min_batch && rows >= 64 && op.N >= 256) {
+    // 64+ rows (the SEANet stages below 8 streams, the two-row operations from 32 streams on): four weight rows per warp -- the
+    // same bits, fewer and fatter CTAs.  Measured per step: 4 streams 825 -> 748 us, 32 streams 1.99 -> 1.73 ms, 64 streams
+    // 3.22 -> 2.41 ms; operations of 16 rows (8 streams' Linears) lose 12 % with it, hence the bar.
+    static const int cpw_n = [] { const char* e = getenv("SMOL_MIMI_CPW_MIN_N"); return e ? atoi(e) : 64; }();
+    if (R == 16 && rows >= 64 && op.N >= cpw_n) {
         const dim3 grid4((op.N + 4 * kWarps - 1) / (4 * kWarps), (rows + R - 1) / R);
         return launch_pdl(rows_kernel<16, 4>, grid4, dim3(kThreads), 0, st, op);
     }
