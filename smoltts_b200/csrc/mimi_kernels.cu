@@ -13,7 +13,7 @@
 // warp streams one weight row (four from 64 rows on) with 16-byte loads against all staged rows, finishing with a shuffle
 // reduction and a fused epilogue (bias, GELU, layer scale + residual, residual, or the upsampler).  Transposed convolutions
 // (kernel = 2 stride) are the same product with K = (previous | current input row) x channels and N = (phase, channel): their
-// outputs land contiguously.  From 8 streams on the SEANet's many-row stages run as 64 x 64 register tiles (tile_kernel) and
+// outputs land contiguously.  From 12 streams on the SEANet's many-row stages run as 64 x 64 register tiles (tile_kernel) and
 // the one-channel last convolution as one thread per sample (rowdot_kernel).  Attention: one CTA per (stream, head, split
 // of 512 cached positions), partial softmaxes combined in split order.  Everything a stream carries (convolution history
 // rows, the upsampler's previous embedding, KV cache, position) lives in per-slot arenas of the caller's workspace; a step is
@@ -319,12 +319,12 @@ __global__ void __launch_bounds__(kThreads) lin2_kernel(const RowOp op) {
     }
 }
 
-// The same product for MANY rows (8+ streams x the 16 .. 1920 rows of a SEANet stage): a 64 x 64 output tile per CTA, K in
+// The same product for MANY rows (12+ streams x the 16 .. 1920 rows of a SEANet stage): a 64 x 64 output tile per CTA, K in
 // steps of 16 through shared memory, 4 x 4 outputs per thread -- 16 FMAs per pair of 16-byte shared-memory loads instead of
 // the 4 of rows_kernel, whose one-weight-row-per-warp shape is built for a handful of rows.  Every output is one sequential
 // FMA chain over k = 0 .. K-1: deterministic and independent of what shares the launch, but a different order than
-// rows_kernel's lane-interleaved sums -- which kernel runs is decided by the BATCH SIZE alone (8+ streams), so a stream's bits
-// are the same in any batch of the same class (< 8 streams, 8+).  Prologues none | ELU | LayerNorm (row statistics in a pre-pass), epilogues bias |
+// rows_kernel's lane-interleaved sums -- which kernel runs is decided by the BATCH SIZE alone (12+ streams), so a stream's bits
+// are the same in any batch of the same class (< 12 streams, 12+).  Prologues none | ELU | LayerNorm (row statistics in a pre-pass), epilogues bias |
 // residual | layer scale + residual | GELU: every operation of a step except the upsampler and the one-channel last convolution
 // (rowdot_kernel below).
 constexpr int kTM = 64, kTN = 64, kTK = 16, kTU = kTK / 16;   // kTU 16-byte pieces of A and of W per thread and K step
@@ -940,8 +940,8 @@ static cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, dim3 block, s
 
 static int rows_R(int rows) { return rows <= 2 ? 2 : rows <= 4 ? 4 : rows <= 8 ? 8 : 16; }
 
-// 8+ streams: the many-row stages go through the tile kernel (decided by the batch size alone, see tile_kernel)
-constexpr int kTileMinBatch = 8;
+// 12+ streams: the many-row stages go through the tile kernel (decided by the batch size alone, see tile_kernel)
+constexpr int kTileMinBatch = 12;   // measured: 8 streams 1.13 ms per step on rows_kernel vs 1.23 on the tiles; 12 streams 1.35 vs 1.30
 static bool use_tile(const RowOp& op) {
     static const int min_batch = [] { const char* e = getenv("SMOL_MIMI_TILE_MIN_BATCH"); return e ? atoi(e) : kTileMinBatch; }();
     return op.batch >= min_batch && op.T >= 16 && op.N >= 16 && op.N % 4 == 0 && op.K % kTK == 0 &&
@@ -974,7 +974,7 @@ static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
     if (use_rowdot(op)) return launch_pdl(rowdot_kernel, dim3((op.batch * op.T + kThreads - 1) / kThreads), dim3(kThreads), 0, st, op);
     const int rows = op.batch * op.T;
     const int R = rows_R(rows);
-    // 64+ rows (the SEANet stages below 8 streams, the two-row operations from 32 streams on): four weight rows per warp -- the
+    // 64+ rows (the SEANet stages below 12 streams, the two-row operations from 32 streams on): four weight rows per warp -- the
     // same bits, fewer and fatter CTAs.  Measured per step: 4 streams 825 -> 748 us, 32 streams 1.99 -> 1.73 ms, 64 streams
     // 3.22 -> 2.41 ms; operations of 16 rows (8 streams' Linears) lose 12 % with it, hence the bar.
     static const int cpw_n = [] { const char* e = getenv("SMOL_MIMI_CPW_MIN_N"); return e ? atoi(e) : 64; }();
@@ -1139,8 +1139,8 @@ extern "C" int smol_mimi_decode_step(SmolMimi* m, const int32_t* d_codes, const 
     const int mode = m->cfg.use_graph;   // 0: one launch per operation; 1: those launches replayed as a CUDA graph
     // programmatic dependent launch: every kernel fetches its first weights and prefetches its rows into L2 before the
     // dependency wait.  Measured per step at one stream: plain launches 632 -> 549 us; inside the replayed graph 462 -> 434 us
-    // with the final kernels (an earlier, heavier kernel prologue had made it 510 -> 536); at 8 / 64 streams it costs 4 - 5 %
-    // inside the graph (1.23 -> 1.28 ms, 2.40 -> 2.52 ms), so there it is off; SMOL_MIMI_PDL=0/1 forces it
+    // with the final kernels (an earlier, heavier kernel prologue had made it 510 -> 536); at 64 streams it costs 5 % inside the graph
+    // (2.40 -> 2.52 ms; nothing either way at 10 streams), so from 12 streams on it is off; SMOL_MIMI_PDL=0/1 forces it
     const char* pe = getenv("SMOL_MIMI_PDL");
     g_pdl = pe ? pe[0] != '0' : (mode == 0 || batch < kTileMinBatch);
     SmolMimi::Step* step = nullptr;

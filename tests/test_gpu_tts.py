@@ -77,7 +77,7 @@ def test_batch_synthesis_equals_one_utterance_at_a_time():
 def test_serving_with_continuous_batching_yields_the_same_audio():
     """SmolTTS.serve: 7 utterances through 3 decode slots (admitted late, retired early) and then the codec, against
     synthesize_batch of the same texts -- the same PCM, bit for bit (greedy decoding, both code paths keep an utterance's codes
-    and every codec call here stays below 8 streams, one kernel class)."""
+    and every codec call here stays below 12 streams, one kernel class)."""
     tts, _ = _tts()
     texts = [f"Utterance number {i}, of some length {'.' * (3 * i)}" for i in range(7)]
     voices = ["heart", "bella", "nova", "sky", "sarah", "michael", "liam"]
