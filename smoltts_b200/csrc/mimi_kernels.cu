@@ -250,17 +250,20 @@ __global__ void __launch_bounds__(kThreads) rows_kernel(const RowOp op) {
     rows_body<R, true, CPW>(op, blockIdx.x, blockIdx.y, S);
 }
 
-// The two-row Linears of ONE stream (the 32 transformer operations of a step at batch 1): rows_kernel<2, 1>'s arithmetic --
-// the same lane-interleaved sums, shuffle trees and LayerNorm loops, hence the same bits -- without its generality: the two
-// input rows are one contiguous run, no im2col, no slot table per row, prologue and epilogue fixed at compile time.  An
-// operation at one stream is bound by the dependent instruction stream of its 8 warps (ncu: ~850 instructions per warp for
-// rows_kernel<2, 1>), not by bytes: fewer instructions per warp is what shortens it.
-template <int PRO, int EPI>
-__global__ void __launch_bounds__(kThreads) lin2_kernel(const RowOp op) {
-    __shared__ __align__(16) float As[2][2048];
-    __shared__ float s_mean[2], s_rstd[2];
+// The two-row Linears of up to 8 streams (the 32 transformer operations of a step): rows_kernel<R, 1>'s arithmetic -- the same
+// lane-interleaved sums, shuffle trees and LayerNorm loops, hence the same bits -- without its generality: a stream's two
+// input rows are one contiguous run, no im2col, prologue and epilogue fixed at compile time.  An operation at streaming batch
+// sizes is bound by the dependent instruction stream of its 8 warps (ncu: ~850 instructions per warp for rows_kernel<2, 1>),
+// not by bytes: fewer instructions per warp is what shortens it (one stream: 492 -> 462 us per step).
+template <int R, int PRO, int EPI>
+__global__ void __launch_bounds__(kThreads) lin_kernel(const RowOp op) {
+    constexpr int KC = kStageFloats / R;                                // floats between staged rows (K <= KC, host)
+    __shared__ __align__(16) float As[kStageFloats];
+    __shared__ float s_mean[R], s_rstd[R];
+    __shared__ int s_slot[R / 2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = op.K, n = blockIdx.x * kWarps + warp;                 // N is a multiple of 8 (host)
+    const int rows = 2 * op.batch;
     const float* wrow = op.W + (long long)n * K;
     float4 wpre[4];
 #pragma unroll
@@ -269,52 +272,72 @@ __global__ void __launch_bounds__(kThreads) lin2_kernel(const RowOp op) {
         const char* wr = reinterpret_cast<const char*>(wrow);
         for (int l = lane; l < (K >> 5); l += 32) prefetch_l2(wr + ((long long)l << 7));
     }
-    const int slot = op.slots ? op.slots[0] : 0;
+    if (tid < R / 2) s_slot[tid] = tid < op.batch ? (op.slots ? op.slots[tid] : tid) : -1;
+    __syncthreads();
     pdl_wait();
     pdl_go();
-    const float4* a4 = reinterpret_cast<const float4*>(op.in + (long long)slot * op.in_stride + (long long)op.in_hs * K);
-    float4* s4 = reinterpret_cast<float4*>(&As[0][0]);
-    for (int i = tid; i < (K >> 1); i += kThreads) s4[(i >= (K >> 2) ? 512 - (K >> 2) : 0) + i] = a4[i];   // row 1 starts at As[1]
+    const int q4 = K >> 2;
+#pragma unroll
+    for (int b = 0; b < R / 2; ++b) {                                   // a stream's two rows: 2 K contiguous floats
+        const int slot = s_slot[b];
+        const float4* a4 = reinterpret_cast<const float4*>(op.in + (long long)(slot < 0 ? 0 : slot) * op.in_stride + (long long)op.in_hs * K);
+        for (int i = tid; i < 2 * q4; i += kThreads) {
+            const int t = i >= q4 ? 1 : 0;
+            *reinterpret_cast<float4*>(&As[(2 * b + t) * KC + ((i - t * q4) << 2)]) = slot < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : a4[i];
+        }
+    }
     __syncthreads();
     if (PRO == PRO_LN) {
-        if (warp < 2) {
+        for (int r = warp; r < R; r += kWarps) {
             float s = 0.f;
-            for (int k = lane; k < K; k += 32) s += As[warp][k];
+            for (int k = lane; k < K; k += 32) s += As[r * KC + k];
             const float mean = warp_sum(s) / (float)K;
             float d2 = 0.f;
-            for (int k = lane; k < K; k += 32) { const float d = As[warp][k] - mean; d2 = fmaf(d, d, d2); }
+            for (int k = lane; k < K; k += 32) { const float d = As[r * KC + k] - mean; d2 = fmaf(d, d, d2); }
             const float var = warp_sum(d2) / (float)K;
-            if (lane == 0) { s_mean[warp] = mean; s_rstd[warp] = 1.0f / sqrtf(var + op.eps); }
+            if (lane == 0) { s_mean[r] = mean; s_rstd[r] = 1.0f / sqrtf(var + op.eps); }
         }
         __syncthreads();
         for (int k = tid; k < K; k += kThreads) {
             const float w = op.ln_w[k], bb = op.ln_b[k];
-            As[0][k] = (As[0][k] - s_mean[0]) * s_rstd[0] * w + bb;
-            As[1][k] = (As[1][k] - s_mean[1]) * s_rstd[1] * w + bb;
+#pragma unroll
+            for (int r = 0; r < R; ++r) As[r * KC + k] = (As[r * KC + k] - s_mean[r]) * s_rstd[r] * w + bb;
         }
         __syncthreads();
     }
-    float c0 = 0.f, c1 = 0.f;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
     int k4 = lane * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i, k4 += 128) {
-        const float4 x0 = *reinterpret_cast<const float4*>(&As[0][k4]), x1 = *reinterpret_cast<const float4*>(&As[1][k4]);
-        c0 = fmaf(x0.x, wpre[i].x, c0); c0 = fmaf(x0.y, wpre[i].y, c0); c0 = fmaf(x0.z, wpre[i].z, c0); c0 = fmaf(x0.w, wpre[i].w, c0);
-        c1 = fmaf(x1.x, wpre[i].x, c1); c1 = fmaf(x1.y, wpre[i].y, c1); c1 = fmaf(x1.z, wpre[i].z, c1); c1 = fmaf(x1.w, wpre[i].w, c1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(&As[r * KC + k4]);
+            acc[r] = fmaf(x.x, wpre[i].x, acc[r]); acc[r] = fmaf(x.y, wpre[i].y, acc[r]); acc[r] = fmaf(x.z, wpre[i].z, acc[r]); acc[r] = fmaf(x.w, wpre[i].w, acc[r]);
+        }
     }
 #pragma unroll 4
     for (; k4 < K; k4 += 128) {
         const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k4));
-        const float4 x0 = *reinterpret_cast<const float4*>(&As[0][k4]), x1 = *reinterpret_cast<const float4*>(&As[1][k4]);
-        c0 = fmaf(x0.x, w.x, c0); c0 = fmaf(x0.y, w.y, c0); c0 = fmaf(x0.z, w.z, c0); c0 = fmaf(x0.w, w.w, c0);
-        c1 = fmaf(x1.x, w.x, c1); c1 = fmaf(x1.y, w.y, c1); c1 = fmaf(x1.z, w.z, c1); c1 = fmaf(x1.w, w.w, c1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(&As[r * KC + k4]);
+            acc[r] = fmaf(x.x, w.x, acc[r]); acc[r] = fmaf(x.y, w.y, acc[r]); acc[r] = fmaf(x.z, w.z, acc[r]); acc[r] = fmaf(x.w, w.w, acc[r]);
+        }
     }
-    c0 = warp_sum(c0); c1 = warp_sum(c1);
-    if (lane < 2) {
-        float y = lane ? c1 : c0;
-        const long long e = (long long)slot * op.out_stride + op.out_off0 + (long long)lane * op.N + n;
+    float mine = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float v = warp_sum(acc[r]);
+        if (lane == r) mine = v;
+    }
+    if (lane < rows) {
+        const int slot = s_slot[lane >> 1], t = lane & 1;
+        float y = mine;
+        const long long e = (long long)slot * op.out_stride + op.out_off0 + (long long)t * op.N + n;
         if (EPI == EPI_GELU) y = gelu_erf(y);
-        else if (EPI == EPI_SCALE_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)lane * op.N + n] + y * op.scale[n];
+        else if (EPI == EPI_SCALE_RES) y = op.res[(long long)slot * op.res_stride + op.res_off0 + (long long)t * op.N + n] + y * op.scale[n];
         op.out[e] = y;
     }
 }
@@ -952,20 +975,30 @@ static bool use_rowdot(const RowOp& op) {
     return op.batch >= min_batch && op.N == 1 && op.K <= 1024 && op.K % 4 == 0 && op.tapstep > 0 && op.epi == EPI_BIAS && op.pro != PRO_LN;
 }
 
-// one stream's two-row Linears: the lean form of rows_kernel<2, 1> (same bits)
-static bool use_lin2(const RowOp& op) {
+// the two-row Linears of up to 8 streams: the lean form of rows_kernel<R, 1> (same bits)
+static bool use_lin(const RowOp& op) {
     static const bool off = [] { const char* e = getenv("SMOL_MIMI_LIN2"); return e && e[0] == '0'; }();
-    return !off && op.batch == 1 && op.T == 2 && op.K == op.in_c && op.tapstep > 0 && op.tap0 == 0 && op.N % kWarps == 0 && op.K >= 512 && op.K <= 2048 &&
-           op.K % 128 == 0 && op.bias == nullptr && op.out_by_row == 0 &&
+    const int R = rows_R(op.batch * op.T);
+    return !off && op.batch <= 8 && op.T == 2 && op.K == op.in_c && op.tapstep > 0 && op.tap0 == 0 && op.N % kWarps == 0 && op.K >= 512 &&
+           op.K <= kStageFloats / R && op.K % 128 == 0 && op.bias == nullptr && op.out_by_row == 0 &&
            ((op.pro == PRO_LN && (op.epi == EPI_BIAS || op.epi == EPI_GELU)) || (op.pro == PRO_NONE && op.epi == EPI_SCALE_RES));
+}
+template <int R>
+static cudaError_t launch_lin(const RowOp& op, cudaStream_t st) {
+    const dim3 grid(op.N / kWarps);
+    if (op.pro == PRO_LN && op.epi == EPI_BIAS) return launch_pdl(lin_kernel<R, PRO_LN, EPI_BIAS>, grid, dim3(kThreads), 0, st, op);
+    if (op.pro == PRO_LN) return launch_pdl(lin_kernel<R, PRO_LN, EPI_GELU>, grid, dim3(kThreads), 0, st, op);
+    return launch_pdl(lin_kernel<R, PRO_NONE, EPI_SCALE_RES>, grid, dim3(kThreads), 0, st, op);
 }
 
 static cudaError_t launch_rows(const RowOp& op, cudaStream_t st) {
-    if (use_lin2(op)) {
-        const dim3 grid(op.N / kWarps);
-        if (op.pro == PRO_LN && op.epi == EPI_BIAS) return launch_pdl(lin2_kernel<PRO_LN, EPI_BIAS>, grid, dim3(kThreads), 0, st, op);
-        if (op.pro == PRO_LN) return launch_pdl(lin2_kernel<PRO_LN, EPI_GELU>, grid, dim3(kThreads), 0, st, op);
-        return launch_pdl(lin2_kernel<PRO_NONE, EPI_SCALE_RES>, grid, dim3(kThreads), 0, st, op);
+    if (use_lin(op)) {
+        switch (rows_R(op.batch * op.T)) {
+            case 2: return launch_lin<2>(op, st);
+            case 4: return launch_lin<4>(op, st);
+            case 8: return launch_lin<8>(op, st);
+            default: return launch_lin<16>(op, st);
+        }
     }
     if (use_tile(op)) {
         const dim3 grid((op.N + kTN - 1) / kTN, (op.batch * op.T + kTM - 1) / kTM);
