@@ -57,52 +57,75 @@ class SmolTTS:
     # ---- streaming (:85-95) ----
     def stream(self, input: str, voice: Optional[str] = "heart", overlap: bool = True, lm_ctas: int = 96,
                stats: Optional[dict] = None) -> Iterator[np.ndarray]:
-        """One 80 ms PCM chunk per generated audio frame.  ``overlap`` (default): the codec step of frame t runs on a side
-        stream BESIDE the decode step of frame t + 1 -- the data-flow kernel is told to take ``lm_ctas`` of the GPU's SMs (a
-        bs=1 frame takes the same 600-612 us on 96 .. 148 CTAs), the codec's kernels run on the others --
-        and chunk t is handed out when frame t + 1 is done: one frame of extra latency, throughput bound by the slower of
-        the two engines instead of their sum.  Same chunks, bit for bit, either way."""
+        """One 80 ms PCM chunk per generated audio frame.  ``overlap=False`` is the reference's loop as written: one frame per
+        ``SingleBatchGenerator.__next__`` (launch, host read-back), then the codec step, then the chunk.  ``overlap`` (default)
+        keeps both engines busy: the decode step of frame t + 1 is launched BEFORE the host looks at frame t, and frame t's ids,
+        its codec step and its PCM go through a side stream -- the data-flow kernel is told to take ``lm_ctas`` of the GPU's SMs (a
+        bs=1 frame takes the same 600-612 us on 96 .. 148 CTAs), the codec's kernels run on the others.
+        Throughput is then bound by the slower engine instead of the sum plus the host's time per frame.  Same chunks, bit for bit."""
         prompt = self._get_prompt(input, voice if voice is not None else "0")
-        frame_gen = SingleBatchGenerator(self.lm, prompt, self.settings)
         codec = self.codec
         cache = codec.make_cache()
-        side = torch.cuda.Stream(device=codec.device) if overlap else None
-        old_ctas = None
-        if overlap and lm_ctas > 0:
-            old_ctas = self.lm.get_option("n_ctas_override")
-            self.lm.set_option("n_ctas", lm_ctas)
-        pending = None      # (device PCM of the previous audio frame, event after its codec step)
         n_frames = n_audio = 0
+        old_ctas = None
+        batch = None
         try:
-            for frame in frame_gen:
-                n_frames += 1
-                if frame.audio_codes is None:      # the <|im_end|> frame (the reference would hand None to the codec here)
-                    continue
-                if cache.frames >= codec.max_frames:
-                    break
-                n_audio += 1
-                if side is None:
+            if not overlap:
+                for frame in SingleBatchGenerator(self.lm, prompt, self.settings):
+                    n_frames += 1
+                    if frame.audio_codes is None:      # the <|im_end|> frame (the reference would hand None to the codec here)
+                        continue
+                    if cache.frames >= codec.max_frames:
+                        break
+                    n_audio += 1
                     yield codec.decode_step(frame.audio_codes, cache).flatten().cpu().numpy()
-                    continue
-                out = None
-                if pending is not None:            # its codec step ran beside the decode step that just finished
-                    pending[1].synchronize()
-                    out = pending[0].flatten().cpu().numpy()
-                side.wait_stream(torch.cuda.current_stream(codec.device))     # the frame's codes were written on the main stream
+                return
+            from .generate import _sampling
+
+            lm, s = self.lm, self.settings
+            tc, cfg = lm.token_config, lm.config
+            if lm_ctas > 0:
+                old_ctas = lm.get_option("n_ctas_override")
+                lm.set_option("n_ctas", lm_ctas)
+            budget = s.max_new_tokens + 1                                   # frames of the reference loop (lm/generate.py:60,161)
+            p = prompt.to(device=lm.device, dtype=torch.int32).contiguous()
+            S = int(p.shape[2])
+            batch = lm.new_batch(1, max_positions=min(S + budget + 1, lm.max_seq_len), max_frames=budget)
+            sampling = _sampling(lm, s, audio_only=True)
+            lm.prefill(batch, p, torch.tensor([S], dtype=torch.int32, device=lm.device))
+            main, side = torch.cuda.current_stream(lm.device), torch.cuda.Stream(device=lm.device)
+            done_ev = {}
+
+            def launch(t: int) -> None:
+                lm.decode_frames(batch, sampling, 1)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                done_ev[t] = ev
+
+            launch(0)
+            lo, hi = tc.semantic_start_id, tc.semantic_end_id if tc.semantic_end_id is not None else -1
+            for t in range(budget):
+                if t + 1 < budget:
+                    launch(t + 1)                                            # runs while the host and the codec deal with frame t
                 with torch.cuda.stream(side):
-                    pcm = codec.decode_step(frame.audio_codes, cache)
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                pending = (pcm, ev)
+                    side.wait_event(done_ev.pop(t))
+                    col = batch.out_codes[0, t]
+                    slow = int(col[0].item())                                # (a read on the side stream: it does not wait for frame t + 1)
+                    n_frames += 1
+                    out = None
+                    if lo <= slow <= hi and cache.frames < codec.max_frames:
+                        codes = col[1:] if cfg.duplicate_code_0 else torch.cat([col[0:1] - lo, col[1:]])
+                        out = codec.decode_step(codes.view(1, -1, 1), cache).flatten().cpu().numpy()
+                        n_audio += 1
                 if out is not None:
                     yield out
-            if pending is not None:
-                pending[1].synchronize()
-                yield pending[0].flatten().cpu().numpy()
+                if slow == tc.im_end_id or (lo <= slow <= hi and out is None):
+                    break
         finally:
-            if side is not None:
-                side.synchronize()
+            torch.cuda.synchronize(codec.device)
             codec.release_cache(cache)
+            if batch is not None:
+                batch.release()
             if old_ctas is not None:
                 self.lm.set_option("n_ctas", old_ctas)
             if stats is not None:
