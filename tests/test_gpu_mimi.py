@@ -211,3 +211,26 @@ def test_a_differently_shaped_codec_matches_the_oracle():
         got = _run(m, codes)
         assert got.shape == (B, 1, T * 24)
         _close(f"small codec, {B} streams, carry {carry}", got, want)
+
+
+def test_load_mimi_reads_a_kyutai_style_safetensors_file(tmp_path):
+    """load_mimi(path) (codec/mimi.py:107-156): a model.safetensors with kyutai/mimi's keys -- here the seeded weights plus keys the
+    decode half ignores (encoder, input_proj, `initialized` buffers) -- gives the same PCM as load_state_dict."""
+    from safetensors.torch import save_file
+
+    from smoltts_b200.mimi import load_mimi
+
+    sd = dict(_sd())
+    sd["encoder.layers.0.conv.weight"] = torch.zeros(64, 1, 7)
+    sd["quantizer.semantic_residual_vector_quantizer.input_proj.weight"] = torch.zeros(256, 512, 1)
+    sd["quantizer.semantic_residual_vector_quantizer.layers.0.codebook.initialized"] = torch.ones(1)
+    path = str(tmp_path / "model.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    m = load_mimi(path, max_streams=2, max_frames=8)
+    codes = torch.randint(0, 2048, (2, 8, 3), generator=torch.Generator().manual_seed(21))
+    assert torch.equal(_run(m, codes), _run(_model(max_streams=2, max_frames=8), codes))
+    with pytest.raises(ValueError, match="fp32"):
+        load_mimi(path, format="bf16")
+    bad = {k: v for k, v in sd.items() if k != "upsample.conv.weight"}
+    with pytest.raises(KeyError, match="upsample.conv.weight"):
+        _model(max_streams=2, max_frames=8).load_state_dict(bad)
