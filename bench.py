@@ -628,7 +628,8 @@ def measure_tts_stream(args, steps: int, warmup: int, ctx, frames: int = 128) ->
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": frames * (cfg.n_rows * 4) + n_pcm * 1920 * 4, "steps": steps},
         "clocks": clocks, "gpu_launches": steps * (frames * lm.get_option("ll_ready") + n_pcm * codec.launches_per_step),
         "launch_mode": "one data-flow kernel launch per frame + 57 codec launches per audio frame (CUDA-graph replay)"
-                       + ("" if args.no_stream_overlap else "; the codec step of frame t on a side stream beside the decode step of frame t + 1 (96 / 52 SMs)"),
+                       + ("" if args.no_stream_overlap else "; pipelined: the decode step of frame t + 1 is launched before the host reads frame t, whose ids, "
+                                                              "codec step and PCM go through a side stream (decode kernel on %d of the SMs)" % args.stream_lm_ctas),
         "realtime_factor": value / 12.5,
     }
     del tts, lm, codec
