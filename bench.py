@@ -540,7 +540,8 @@ def measure_mimi(key: str, batch: int, frames: int, args, steps: int, warmup: in
         "note": "SURVEY 8(f)-2: codes [B, 8] -> 1920 fp32 samples per frame; 57 launches per decode_step replayed as one CUDA graph",
         "value": steps * frames * batch * world / (total_ms * 1e-3), "unit": "frames/s", "ms_per_step": total_ms / steps, "steps": steps,
         "warmup": warmup, "us_per_frame_step": us_step,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src,
+                     "traffic": ((load_traffic() or {}).get(key) or {}).get("dram_bytes_per_frame"),   # per decode_step, like algorithmic_bytes_per_launch
                      "kernel": "smol::mimi::rows_kernel (weight-streaming row products, fp32 FMA)",
                      "algorithmic_bytes_per_launch": wbytes + kv,
                      "bytes_model": "packed fp32 weights of the decode half once per decode_step + KV cache read/written",
