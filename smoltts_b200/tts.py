@@ -200,15 +200,24 @@ class SmolTTS:
         own = caches is None
         caches = [codec.make_cache() for _ in range(B)] if own else list(caches)
         spf = codec.samples_per_frame
-        outs = [torch.empty(n * spf, dtype=torch.float32, device=codec.device) for n in lens]
+        t_max = max(lens) if lens else 0
         order = sorted(range(B), key=lambda b: -lens[b])          # live streams are always a prefix of this order
-        dev_codes = [c.to(codec.device) for c in codes]
-        for t in range(max(lens) if lens else 0):
-            live = [b for b in order if lens[b] > t]
-            frame = torch.stack([dev_codes[b][:, t] for b in live], dim=0)   # [B_live, N]
-            pcm = codec.decode_step(frame, [caches[b] for b in live])
-            for i, b in enumerate(live):
-                outs[b][t * spf:(t + 1) * spf] = pcm[i, 0]
+        n_q = codec.num_codebooks
+        grid = torch.zeros(B, n_q, max(t_max, 1), dtype=torch.int32, device=codec.device)   # one padded tensor: one slice per step
+        for i, b in enumerate(order):
+            if lens[b]:
+                grid[i, :, : lens[b]] = codes[b].to(device=codec.device, dtype=torch.int32)
+        pcm_all = torch.empty(B, max(t_max, 1) * spf, dtype=torch.float32, device=codec.device)
+        sorted_caches = [caches[b] for b in order]
+        n_live = B
+        for t in range(t_max):
+            while n_live > 0 and lens[order[n_live - 1]] <= t:
+                n_live -= 1
+            pcm = codec.decode_step(grid[:n_live, :, t], sorted_caches[:n_live])
+            pcm_all[:n_live, t * spf:(t + 1) * spf] = pcm[:, 0]
+        outs = [None] * B
+        for i, b in enumerate(order):
+            outs[b] = pcm_all[i, : lens[b] * spf]
         if own:
             for c in caches:
                 codec.release_cache(c)
